@@ -1,0 +1,229 @@
+"""CPU restatement of the reference EGNO / SEGNO forward (TEST INFRASTRUCTURE).
+
+Plain PyTorch on CPU tensors, functional over a ``params`` dict keyed by the
+reference's own ``state_dict`` names, differentiable (autograd supplies the
+gradients the CUDA backward is checked against).  It runs in fp32 (the
+reference's dtype) or fp64 (a tighter yardstick when judging which of two fp32
+implementations is closer).
+
+Every function cites the reference lines (relative to /root/reference) it
+restates.  Pinned by tests/test_oracle_golden.py against vectors produced by the
+reference's own modules (tests/golden/make_golden.py); the reference itself has
+no tests or golden vectors for this path -> "parity unpinned by reference tests".
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------- helpers
+def silu(x: Tensor) -> Tensor:
+    return x * torch.sigmoid(x)
+
+
+def linear(x: Tensor, p: Dict[str, Tensor], name: str) -> Tensor:
+    return x @ p[name + ".weight"].t() + p[name + ".bias"]
+
+
+def canonical_edges(batch: int, n_nodes: int) -> Tuple[Tensor, Tensor]:
+    """Fully connected edge list, per graph `for i: for j != i`, graphs offset by N*b.
+
+    EGNO/simulation/dataset_simple.py:64-71 (single graph) and :101-111 (batch)."""
+    i = torch.arange(n_nodes).repeat_interleave(n_nodes)
+    j = torch.arange(n_nodes).repeat(n_nodes)
+    keep = i != j
+    i, j = i[keep], j[keep]
+    off = (torch.arange(batch) * n_nodes).repeat_interleave(i.numel())
+    return i.repeat(batch) + off, j.repeat(batch) + off
+
+
+def segment_sum(data: Tensor, idx: Tensor, n: int) -> Tensor:
+    """EGNO/model/basic.py:16-19 (aggregate, sum) == SEGNO/models/models/gcl.py:7-13."""
+    out = data.new_zeros((n, data.shape[1]))
+    return out.index_add(0, idx, data)
+
+
+def segment_mean(data: Tensor, idx: Tensor, n: int) -> Tensor:
+    """EGNO/model/basic.py:22-28: sum / count.clamp(min=1).
+
+    SEGNO's gcl.py:16-23 builds a dense one-hot matrix, L1-normalises its rows and
+    multiplies: the same mean (rows with no edge give 0 in both)."""
+    s = segment_sum(data, idx, n)
+    cnt = segment_sum(torch.ones_like(data), idx, n)
+    return s / cnt.clamp(min=1)
+
+
+# ----------------------------------------------------------------------------- EGNO pieces
+def timestep_embedding(timesteps: Tensor, dim: int, max_positions: int = 10000) -> Tensor:
+    """EGNO/model/layer_no.py:8-17.  timesteps [B,T] -> [B,T,dim] = [sin | cos]."""
+    half = dim // 2
+    scale = math.log(max_positions) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -scale)
+    arg = timesteps.float()[:, :, None] * freq[None, None, :]
+    emb = torch.cat([torch.sin(arg), torch.cos(arg)], dim=-1)
+    if dim % 2 == 1:
+        emb = torch.nn.functional.pad(emb, (0, 1))
+    return emb
+
+
+def spectral_conv(x: Tensor, w: Tensor) -> Tensor:
+    """SpectralConv1d / SpectralConv1d_x forward (layer_no.py:96-109, :151-162).
+
+    x [T, N, ..., Cin]; w [Cin, Cout, modes, 2].  rfft over dim 0, keep the first
+    `modes` coefficients, complex channel mix per mode, irfft back to length T."""
+    T = x.shape[0]
+    modes = w.shape[2]
+    wc = torch.view_as_complex(w.contiguous())
+    xf = torch.fft.rfft(x, dim=0)[:modes]
+    yf = torch.einsum("m...i,iom->m...o", xf, wc.to(xf.dtype))
+    return torch.fft.irfft(yf, n=T, dim=0)
+
+
+def egnn_layer(p: Dict[str, Tensor], pre: str, x: Tensor, h: Tensor, row: Tensor, col: Tensor,
+               edge_fea: Tensor, v: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """EGNN_Layer.forward, EGNO/model/basic.py:167-186 (with_v=True, norm=False, flat=False)."""
+    n = x.shape[0]
+    rij = x[row] - x[col]                                         # :169
+    radial = (rij * rij).sum(-1, keepdim=True)                    # :93 (K=1 Gram matrix)
+    # InvariantScalarNet: [radial | h_row | h_col | edge_fea]      :98, :170
+    z = torch.cat([radial, h[row], h[col], edge_fea], dim=-1)
+    en = pre + ".edge_message_net.scalar_net.mlp"
+    m = silu(linear(silu(linear(z, p, en + ".0")), p, en + ".2"))  # last_act=True :46-51
+    cn = pre + ".coord_net.mlp"
+    c = linear(silu(linear(m, p, cn + ".0")), p, cn + ".2")        # :172
+    f = rij * c                                                    # :173
+    tot_f = segment_mean(f, row, n).clamp(-100, 100)               # :174-175 (clamp AFTER mean)
+    vn = pre + ".node_v_net.mlp"
+    s = linear(silu(linear(h, p, vn + ".0")), p, vn + ".2")
+    x_new = x + s * v + tot_f                                      # :178 (pre-update h)
+    tot_m = segment_sum(m, row, n)                                 # :182
+    nn_ = pre + ".node_net.mlp"
+    h_new = linear(silu(linear(torch.cat([h, tot_m], -1), p, nn_ + ".0")), p, nn_ + ".2")  # :183-185
+    return x_new, v, h_new
+
+
+def egno_forward(p: Dict[str, Tensor], x: Tensor, h: Tensor, row: Tensor, col: Tensor, edge_fea: Tensor,
+                 v: Tensor, loc_mean: Tensor, timesteps_out: Tensor, *, n_layers: int, num_timesteps: int,
+                 time_emb_dim: int = 32, use_time_conv: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """EGNO.forward, EGNO/model/egno.py:37-111, num_inputs == 1.
+
+    Returns (x [T*BN,3], v [T*BN,3], h [T*BN,H]) in t-major node order."""
+    T = num_timesteps
+    nn_ = h.shape[0]
+    ne = row.shape[0]
+    B = timesteps_out.shape[0]
+    temb = timestep_embedding(timesteps_out, time_emb_dim).to(x.dtype)           # :50  [B,T,D]
+    # :66 -- [T,1,B,D].repeat(1, BN/B, 1, 1).reshape(T, BN, D): node k gets batch (k mod B)
+    temb = temb.transpose(0, 1).unsqueeze(1).repeat(1, nn_ // B, 1, 1).reshape(T, -1, time_emb_dim)
+    hh = torch.cat([h.unsqueeze(0).repeat(T, 1, 1), temb], dim=-1).reshape(T * nn_, -1)  # :63,:72,:74
+    hh = linear(hh, p, "embedding")                                               # :76
+    node_off = (torch.arange(T) * nn_).repeat_interleave(ne)                      # :53-55, :91-92
+    rr = row.repeat(T) + node_off
+    cc = col.repeat(T) + node_off
+    xx = x.repeat(T, 1)
+    vv = v.repeat(T, 1)
+    lm = loc_mean.repeat(T, 1)
+    ef = edge_fea.repeat(T, 1)
+    H = hh.shape[-1]
+    for i in range(n_layers):
+        if use_time_conv:
+            # TimeConv: x + LeakyReLU(conv(x))  layer_no.py:121-126
+            h3 = hh.view(T, nn_, H)
+            conv = spectral_conv(h3, p[f"time_conv_modules.{i}.t_conv.weights1"])
+            hh = (h3 + torch.nn.functional.leaky_relu(conv, 0.01)).reshape(T * nn_, H)
+            # TimeConv_x on stack(x - mean, v): x + conv(x), no activation  egno.py:103-108, layer_no.py:173-178
+            X = torch.stack([xx - lm, vv], dim=-1).view(T, nn_, 3, 2)
+            X = X + spectral_conv(X, p[f"time_conv_x_modules.{i}.t_conv.weights1"])
+            xx = X[..., 0].reshape(T * nn_, 3) + lm
+            vv = X[..., 1].reshape(T * nn_, 3)
+        xx, vv, hh = egnn_layer(p, f"layers.{i}", xx, hh, rr, cc, ef, vv)
+    return xx, vv, hh
+
+
+# ----------------------------------------------------------------------------- SEGNO pieces
+def segno_gcl(p: Dict[str, Tensor], h: Tensor, row: Tensor, col: Tensor, x: Tensor, v: Tensor,
+              edge_attr: Tensor, n_layers: int, recurrent: bool = True,
+              coords_weight: float = 1.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """SEGNO_GCL.forward, SEGNO/models/models/gcl.py:111-119 (one 2nd-order sub-step)."""
+    n = x.shape[0]
+    rij = x[row] - x[col]                                            # :106
+    radial = (rij * rij).sum(1, keepdim=True)                        # :107
+    z = torch.cat([h[row], h[col], radial, edge_attr], dim=1)        # :78  (h first)
+    m = silu(linear(silu(linear(z, p, "module.edge_mlp.0")), p, "module.edge_mlp.2"))   # :39-43
+    c = linear(silu(linear(m, p, "module.coord_mlp.0")), p, "module.coord_mlp.2")      # :50-60
+    trans = (rij * c).clamp(-100, 100)                               # :99-100 (clamp per edge, BEFORE mean)
+    agg = segment_mean(trans, row, n) * coords_weight                # :101-102
+    v = v + agg * (1 / n_layers)                                     # :116
+    x = x + v * (1 / n_layers)                                       # :117
+    tot_m = segment_sum(m, row, n)                                   # :87
+    out = linear(silu(linear(torch.cat([h, tot_m], 1), p, "module.node_mlp.0")), p, "module.node_mlp.2")  # :91-92
+    h = h + out if recurrent else out                                # :93-94
+    return h, x, v
+
+
+def segno_forward(p: Dict[str, Tensor], his: Tensor, x: Tensor, row: Tensor, col: Tensor, v: Tensor,
+                  edge_attr: Tensor, T: int, recurrent: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """The *intended* SEGNO forward: forward_step(embedding(his), ...) (SEGNO/models/model.py:73,:95-102).
+
+    (The literal SEGNO.forward at reference HEAD, model.py:53-92, returns its inputs — SURVEY.md §0.)
+    Returns (x, h, v) in the reference's return order."""
+    h = linear(his, p, "embedding")                                   # :73
+    for _ in range(T):                                                # :96-100 (n_layers := T)
+        h, x, v = segno_gcl(p, h, row, col, x, v, edge_attr, n_layers=T, recurrent=recurrent)
+    return x, h, v
+
+
+# ----------------------------------------------------------------------------- featurisation (callers)
+def egno_features(loc: Tensor, vel: Tensor, charges: Tensor, row: Tensor, col: Tensor
+                  ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """prepare_inputs, EGNO/main_simulation_simple_no.py:329-338 (num_inputs == 1).
+
+    loc, vel [B,N,3]; charges [B,N,1] -> (loc[BN,3], vel[BN,3], edge_attr[E,2], nodes[BN,2], loc_mean[BN,3])."""
+    B, N, _ = loc.shape
+    loc_mean = loc.mean(dim=1, keepdim=True).repeat(1, N, 1).view(-1, 3)
+    loc = loc.reshape(-1, 3)
+    vel = vel.reshape(-1, 3)
+    q = charges.reshape(-1, 1)
+    nodes = torch.cat([torch.sqrt((vel ** 2).sum(1, keepdim=True)), q], dim=1)
+    qq = q[row] * q[col]                      # dataset_simple.py:52-53 (edge_attr = q_i q_j)
+    dist = ((loc[row] - loc[col]) ** 2).sum(1, keepdim=True)
+    return loc, vel, torch.cat([qq, dist], 1), nodes, loc_mean
+
+
+def segno_features(loc: Tensor, vel: Tensor, charges: Tensor, row: Tensor, col: Tensor
+                   ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """SEGNO/train_nbody.py:93,119-123.  -> (his[BN,1], loc[BN,3], vel[BN,3], edge_attr[E,2])."""
+    loc = loc.reshape(-1, 3)
+    vel = vel.reshape(-1, 3)
+    q = charges.reshape(-1, 1)
+    his = torch.sqrt((vel ** 2).sum(1, keepdim=True))
+    qq = q[row] * q[col]
+    dist = ((loc[row] - loc[col]) ** 2).sum(1, keepdim=True)
+    return his, loc, vel, torch.cat([qq, dist], 1)
+
+
+# ----------------------------------------------------------------------------- energies (evaluation only)
+def energy_charged(loc: Tensor, vel: Tensor, charges: Tensor) -> Tensor:
+    """utils.py:126-144 (tot_energy_charged_batch): K + 0.5*sum_{i!=j} q_i q_j / |r_ij|.  [B,N,3] -> [B]."""
+    K = 0.5 * (vel ** 2).sum((-1, -2))
+    d = (loc[:, :, None, :] - loc[:, None, :, :]).norm(dim=-1)
+    d = torch.where(d == 0, torch.full_like(d, float("inf")), d)
+    q = charges.reshape(loc.shape[0], -1)
+    U = 0.5 * ((q[:, :, None] * q[:, None, :]) / d).sum((-1, -2))
+    return K + U
+
+
+def energy_gravity(loc: Tensor, vel: Tensor, mass: Tensor, G: float = 1.0) -> Tensor:
+    """utils.py:175-195 (tot_energy_gravity_batch).  [B,N,3], mass [B,N,1] -> [B]."""
+    KE = 0.5 * (mass * vel ** 2).sum((-1, -2))
+    d = (loc[:, :, None, :] - loc[:, None, :, :]).norm(dim=-1)
+    inv = torch.where(d > 0, 1.0 / d, torch.zeros_like(d))
+    m = mass.reshape(loc.shape[0], -1)
+    pe = -(m[:, :, None] * m[:, None, :]) * inv
+    PE = G * torch.triu(pe, 1).sum((-1, -2))
+    return KE + PE

@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import nbody_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+EGNO_CASES = ["egno_n5_t8", "egno_n20_t10", "egno_n5_t6_m4", "egno_n7_t10_m5"]
+SEGNO_CASES = ["segno_n5_t10", "segno_n20_t10_gravity"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    weights = {k[2:]: torch.tensor(d[k]) for k in d if k.startswith("w:")}
+    grads = {k[2:]: torch.tensor(d[k]) for k in d if k.startswith("g:")}
+    return d, weights, grads
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b| / max |b| (scale-relative max error)."""
+    a, b = a.double(), b.double()
+    den = b.abs().max().item()
+    return (a - b).abs().max().item() / (den if den > 0 else 1.0)
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double(), b.double()
+    den = b.norm().item()
+    return (a - b).norm().item() / (den if den > 0 else 1.0)
+
+
+def egno_inputs_from_case(d):
+    n, B, T, L, modes = [int(v) for v in d["meta"]]
+    row, col = O.canonical_edges(B, n)
+    x, v, edge_attr, nodes, loc_mean = O.egno_features(torch.tensor(d["loc"]), torch.tensor(d["vel"]),
+                                                       torch.tensor(d["charges"]), row, col)
+    return dict(n=n, B=B, T=T, L=L, modes=modes, row=row, col=col, x=x, v=v, edge_attr=edge_attr, nodes=nodes,
+                loc_mean=loc_mean, t_out=torch.tensor(d["t_out"]))
+
+
+def segno_inputs_from_case(d):
+    n, B, T = [int(v) for v in d["meta"]]
+    row, col = O.canonical_edges(B, n)
+    his, x, v, edge_attr = O.segno_features(torch.tensor(d["loc"]), torch.tensor(d["vel"]),
+                                            torch.tensor(d["charges"]), row, col)
+    return dict(n=n, B=B, T=T, row=row, col=col, his=his, x=x, v=v, edge_attr=edge_attr)
