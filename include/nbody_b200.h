@@ -1,0 +1,154 @@
+/* nbody_b200.h — C ABI of the B200-native EGNO / SEGNO hot path.
+ *
+ * The reference (simone7monaco/NO-NODE-comparison) has no FFI or plugin layer: its
+ * boundary for this path is two torch.nn.Module classes called from Python
+ * (SURVEY.md §8b).  This header is the C-ABI a drop-in replacement binds instead:
+ * plain pointers and sizes, no torch types.  Each entry point cites the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - all tensors fp32, contiguous, row-major, on ONE CUDA device; indices int64.
+ *  - the callee never allocates, frees or retains device memory: outputs, the
+ *    saved-for-backward buffer and the scratch workspace are caller-owned
+ *    (sizes from the *_floats() queries).
+ *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host
+ *    synchronisation) and are safe under CUDA-graph capture.
+ *  - every function returns 0 on success, <0 on error (nb_last_error() gives a
+ *    thread-local message).  No CPU fallback exists.
+ *  - graphs are the reference's canonical fully connected lists: per graph
+ *    `for i: for j != i`, graphs offset by N*b (EGNO/simulation/dataset_simple.py:64-71,
+ *    :101-111).  nb_check_canonical_edges validates an edge_index on the device.
+ *  - parameters are ONE flat fp32 buffer in the order of the reference module's
+ *    named_parameters() (layouts below); gradients use the same layout.
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_HIDDEN 64      /* hidden_nf the kernels are specialised for (model_confs.yaml:3,23) */
+#define NB_MAX_EDGE_FEA 4 /* in_edge_nf upper bound (reference uses 2) */
+#define NB_MAX_T 16       /* num_timesteps upper bound for EGNO's temporal convolution */
+#define NB_MAX_NODES 100  /* bodies per graph upper bound (BASELINE.json config 5) */
+
+/* Error codes */
+#define NB_OK 0
+#define NB_ERR_INVALID (-1)  /* bad shape / unsupported configuration */
+#define NB_ERR_CUDA (-2)     /* CUDA runtime error */
+
+/* EGNO(**params) as resolved by main.py:133-134 / model_confs.yaml:1-13 (EGNO/model/egno.py:9-35). */
+typedef struct NbEgnoConfig {
+  int32_t B;             /* trajectories (graphs) in the batch */
+  int32_t N;             /* bodies per graph */
+  int32_t T;             /* num_timesteps */
+  int32_t n_layers;
+  int32_t num_modes;     /* after the ctor clamp, <= T/2+1 */
+  int32_t in_node_nf;    /* node features BEFORE the time embedding is appended (2) */
+  int32_t in_edge_nf;    /* 2 */
+  int32_t time_emb_dim;  /* 32 */
+  int32_t use_time_conv; /* 1 */
+} NbEgnoConfig;
+
+/* SEGNO(**params) as resolved by main.py:110-114 / model_confs.yaml:20-29 (SEGNO/models/model.py:7-26). */
+typedef struct NbSegnoConfig {
+  int32_t B;
+  int32_t N;
+  int32_t T;            /* integration sub-steps of this call (forward_step sets n_layers := T, model.py:96-97) */
+  int32_t in_node_nf;   /* 1 */
+  int32_t in_edge_nf;   /* 2 */
+  int32_t recurrent;    /* h += phi_h(...) (gcl.py:93-94) */
+  float coords_weight;  /* gcl.py:102 */
+} NbSegnoConfig;
+
+int nb_version(void);
+const char* nb_last_error(void);
+
+/* --- parameter layout ------------------------------------------------------------
+ * EGNO (EGNO/model/basic.py:189-203, egno.py:28-33), H = 64, F = in_node_nf + time_emb_dim,
+ * E = 1 + 2H + in_edge_nf:
+ *   (note: `layers` is registered before `embedding` in the reference, so it comes first)
+ *   per layer i: edge_message_net.scalar_net.mlp.0.weight[H,E] .bias[H]  (cols: radial | h_row | h_col | edge_fea)
+ *                edge_message_net.scalar_net.mlp.2.weight[H,H] .bias[H]
+ *                coord_net.mlp.0.weight[H,H] .bias[H]  coord_net.mlp.2.weight[1,H] .bias[1]
+ *                node_v_net.mlp.0.weight[H,H] .bias[H] node_v_net.mlp.2.weight[1,H] .bias[1]
+ *                node_net.mlp.0.weight[H,2H] .bias[H]  node_net.mlp.2.weight[H,H] .bias[H]
+ *   embedding.weight[H,F] .bias[H]
+ *   per layer i: time_conv_modules.i.t_conv.weights1[H,H,modes,2]
+ *   per layer i: time_conv_x_modules.i.t_conv.weights1[2,2,modes,2]
+ * SEGNO (SEGNO/models/model.py:19-25, SEGNO/models/models/gcl.py:39-67), E = 2H + 1 + in_edge_nf:
+ *   embedding.weight[H,in_node_nf] .bias[H]
+ *   module.edge_mlp.0.weight[H,E] .bias[H]   (cols: h_row | h_col | radial | edge_attr)
+ *   module.edge_mlp.2.weight[H,H] .bias[H]
+ *   module.node_mlp.0.weight[H,2H] .bias[H]  module.node_mlp.2.weight[H,H] .bias[H]
+ *   module.coord_mlp.0.weight[H,H] .bias[H]  module.coord_mlp.2.weight[1,H] .bias[1]
+ *   module.coord_mlp_vel.0.weight[H,H] .bias[H] module.coord_mlp_vel.2.weight[1,H] .bias[1]  (inert; grads stay 0)
+ */
+int64_t nb_egno_param_count(const NbEgnoConfig* cfg);
+int64_t nb_segno_param_count(const NbSegnoConfig* cfg);
+
+/* floats the caller must provide */
+int64_t nb_egno_saved_floats(const NbEgnoConfig* cfg);
+int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int backward);
+int64_t nb_segno_saved_floats(const NbSegnoConfig* cfg);
+int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int backward);
+
+/* Replaces EGNO.forward (EGNO/model/egno.py:37-111, num_inputs == 1) including every
+ * EGNN_Layer.forward (EGNO/model/basic.py:167-186), aggregate (basic.py:6-31),
+ * TimeConv / TimeConv_x (EGNO/model/layer_no.py:80-178) and get_timestep_embedding (:8-17).
+ *   x[BN,3] nodes[BN,in_node_nf] edge_fea[B*N*(N-1),in_edge_nf] v[BN,3] loc_mean[BN,3]
+ *   timesteps_out[B,T] (int64)  ->  x_out[T*BN,3] v_out[T*BN,3] h_out[T*BN,H]  (t-major)
+ * `saved` may be NULL for inference (then nothing is kept for backward). */
+int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, const float* x, const float* nodes,
+                    const float* edge_fea, const float* v, const float* loc_mean, const int64_t* timesteps_out,
+                    float* x_out, float* v_out, float* h_out, float* saved, float* workspace, void* stream);
+
+/* Backward of the above (the reference relies on autograd).  g_*_out may be NULL (= zero).
+ * grad_params (same layout as params) is OVERWRITTEN; g_x_in / g_v_in [BN,3] may be NULL. */
+int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, const float* nodes, const float* edge_fea,
+                     const float* loc_mean, const int64_t* timesteps_out, const float* saved, const float* g_x_out,
+                     const float* g_v_out, const float* g_h_out, float* grad_params, float* g_x_in, float* g_v_in,
+                     float* workspace, void* stream);
+
+/* Replaces SEGNO.forward_step applied to embedding(his) (SEGNO/models/model.py:73,95-102) with
+ * SEGNO_GCL.forward (SEGNO/models/models/gcl.py:111-119), unsorted_segment_sum / _mean (:7-23).
+ *   his[BN,in_node_nf] x[BN,3] v[BN,3] edge_attr[B*N*(N-1),in_edge_nf] -> x_out[BN,3] h_out[BN,H] v_out[BN,3] */
+int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, const float* his, const float* x, const float* v,
+                     const float* edge_attr, float* x_out, float* h_out, float* v_out, float* saved,
+                     float* workspace, void* stream);
+
+int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, const float* his, const float* edge_attr,
+                      const float* saved, const float* g_x_out, const float* g_h_out, const float* g_v_out,
+                      float* grad_params, float* g_x_in, float* g_v_in, float* workspace, void* stream);
+
+/* Validates that (row, col) is the canonical fully connected list for B graphs of N bodies.
+ * Writes 0 to *flag_dev if so, else the (1-based) index of a mismatching edge.  No host sync. */
+int nb_check_canonical_edges(const int64_t* row, const int64_t* col, int64_t n_edges, int32_t B, int32_t N,
+                             int32_t* flag_dev, void* stream);
+
+/* --- building blocks (exported for unit tests and for callers that fuse their own graph) --------- */
+
+/* Fused E_GCL edge tile, forward.  Replaces basic.py:168-175,182 / gcl.py:104-109,74-83,97-102,87:
+ * coord_diff, radial, phi_e (2 layers, SiLU), phi_x (64->64->1), f = rij*c, and the per-receiver
+ * reductions  M_i = sum_j m_ij ,  Fsum_i = sum_j f_ij  (SEGNO: f clamped to +-100 per edge).
+ * P, Q are the per-node pre-projections of the first edge layer (P = W1[:,h_row] h + b1, Q = W1[:,h_col] h).
+ *   n_gt graph-instances of N bodies (EGNO: T*B, SEGNO: B); edge features indexed by (gt % B).
+ *   w_rad[H], w_ef[in_edge_nf][H] column slices of the first edge layer (stride ldw between output rows). */
+int nb_egcl_edge_forward(int32_t n_gt, int32_t B, int32_t N, int32_t n_edge_fea, int32_t clamp_per_edge,
+                         const float* x, const float* P, const float* Q, const float* edge_fea, const float* w1,
+                         int32_t ldw1, int32_t col_rad, int32_t col_ef, const float* W2, const float* b2,
+                         const float* W3, const float* b3, const float* w4, const float* b4, float* M, float* Fsum,
+                         void* stream);
+
+/* Fused E_GCL edge tile, backward with edge-tile recompute (nothing per-edge is ever stored).
+ * Inputs gM[nodes,H], gFsum[nodes,3]; outputs gP, gQ [nodes,H] (overwritten), gx[nodes,3] (ACCUMULATED into),
+ * and weight gradients written/accumulated into a slice laid out as the parameter buffer (see .cu). */
+int64_t nb_egcl_edge_backward_workspace_floats(int32_t n_gt, int32_t N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_B200_H */

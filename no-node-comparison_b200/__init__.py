@@ -1,0 +1,15 @@
+"""B200-native EGNO / SEGNO hot path (drop-in for the reference's torch.nn.Module classes).
+
+    from no_node_comparison_b200 import EGNO, SEGNO
+
+Host code is Python/PyTorch (device memory, streams, torch.distributed); all arithmetic runs in
+hand-written sm_100a CUDA kernels behind the C ABI of include/nbody_b200.h.  There is no CPU
+fallback: importing is cheap, but constructing a model's forward without the compiled
+`libnbody_b200.so` (see build.py) or without a CUDA device raises.
+"""
+from .egno import EGNO  # noqa: F401
+from .segno import SEGNO  # noqa: F401
+from .build import build_library  # noqa: F401
+from ._lib import load_library, library_path  # noqa: F401
+
+__all__ = ["EGNO", "SEGNO", "build_library", "load_library", "library_path"]

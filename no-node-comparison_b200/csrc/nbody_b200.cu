@@ -1,0 +1,1018 @@
+// nbody_b200.cu — C-ABI implementation: parameter layouts, launch sequencing of the EGNO / SEGNO
+// forward and backward, and the exported building blocks.  See include/nbody_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "nb_common.cuh"
+#include "nb_node.cuh"
+#include "nb_spectral.cuh"
+#include "nb_edge.cuh"
+
+// ============================================================================= errors / device info
+static thread_local char g_err[512] = "";
+
+void nb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int nb_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    nb_set_error("CUDA error after %s: %s", what, cudaGetErrorString(e));
+    return NB_ERR_CUDA;
+  }
+  return NB_OK;
+}
+
+int nb_num_sms() {
+#ifdef NB_EMU
+  return 3;
+#else
+  static thread_local int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached = n > 0 ? n : 148;
+  }
+  return cached;
+#endif
+}
+
+extern "C" int nb_version(void) { return 1; }
+extern "C" const char* nb_last_error(void) { return g_err; }
+
+#define NB_TRY(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != NB_OK) return _rc; \
+  } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int imin(int64_t a, int64_t b) { return (int)(a < b ? a : b); }
+
+// partial-sum scratch shared by all reducing kernels (floats)
+#define NB_PARTIAL_FLOATS ((int64_t)320 * NB_EB_PLEN)
+static inline int wgrad_grid_cap() { return imin(2 * nb_num_sms(), 640); }
+static inline int edge_bwd_grid_cap() { return imin(nb_num_sms(), 320); }
+
+// ============================================================================= launch helpers
+static int launch_gemm(const NbGemmArgs& a, void* st) {
+  if (a.rows <= 0) return NB_OK;
+  const size_t smem = (NB_TILE * NB_LDA + NB_H * NB_H) * sizeof(float);
+  NB_SET_SMEM(k_gemm64, smem);
+  NB_LAUNCH(k_gemm64, (unsigned)cdiv(a.rows, NB_TILE), NB_THREADS, smem, st, a);
+  return nb_check_launch("k_gemm64");
+}
+
+static NbGemmSrc gsrc(const float* A, int lda, int a_silu, const float* W, int64_t sk, int64_t sn, float scale = 1.f) {
+  NbGemmSrc s;
+  s.A = A; s.lda = lda; s.a_silu = a_silu; s.W = W; s.sk = sk; s.sn = sn; s.scale = scale;
+  return s;
+}
+
+static NbGemmArgs gemm_args(int rows) {
+  NbGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows;
+  a.ldu = a.ldr = a.ldo = a.ldp = NB_H;
+  return a;
+}
+
+static int launch_finalize(NbFinArgs& f, void* st) {
+  int total = 0;
+  for (int s = 0; s < f.nseg; ++s) total += f.seg[s].count;
+  f.total = total;
+  NB_LAUNCH(k_finalize, (unsigned)cdiv(total, 256), 256, 0, st, f);
+  return nb_check_launch("k_finalize");
+}
+
+static NbFinSeg fseg(int start, int count, int inner, int64_t dst_off, int64_t so, int64_t si) {
+  NbFinSeg s;
+  s.start = start; s.count = count; s.inner = inner; s.dst_off = dst_off; s.so = so; s.si = si;
+  return s;
+}
+
+// dst[w_off + o*so + k*si] (+)= sum_rows sum_p scale_p G_p[r][o] A_p[r][k];  dst[b_off + o] (+)= colsum(G_0) if b_off >= 0
+static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* partial, float* dst, int64_t w_off,
+                    int64_t so, int64_t si, int64_t b_off, int accumulate, void* st) {
+  if (rows <= 0) return NB_OK;
+  NbWgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows; a.npair = npair; a.pair[0] = p0; a.pair[1] = p1; a.colsum = b_off >= 0; a.partial = partial;
+  int grid = imin(cdiv(rows, NB_TILE), wgrad_grid_cap());
+  const size_t smem = 2 * NB_TILE * NB_LDA * sizeof(float);
+  NB_SET_SMEM(k_wgrad64, smem);
+  NB_LAUNCH(k_wgrad64, (unsigned)grid, NB_THREADS, smem, st, a);
+  NB_TRY(nb_check_launch("k_wgrad64"));
+  NbFinArgs f;
+  memset(&f, 0, sizeof(f));
+  f.partial = partial; f.nparts = grid; f.plen = NB_WGRAD_PLEN; f.dst = dst; f.accumulate = accumulate;
+  f.nseg = 0;
+  f.seg[f.nseg++] = fseg(0, NB_H * NB_H, NB_H, w_off, so, si);
+  if (b_off >= 0) f.seg[f.nseg++] = fseg(NB_H * NB_H, NB_H, NB_H, b_off, 0, 1);
+  return launch_finalize(f, st);
+}
+
+static NbWgradPair wpair(const float* G, const float* A, int a_silu = 0, float scale = 1.f) {
+  NbWgradPair p;
+  p.G = G; p.ldg = NB_H; p.A = A; p.lda = NB_H; p.a_silu = a_silu; p.scale = scale;
+  return p;
+}
+
+static int ew_grid(int64_t n) { return imin(cdiv(n, 256), 8 * nb_num_sms()); }
+
+// ============================================================================= edge tile launches
+static NbEdgeGeom edge_geom(int n_gt, int B, int N, int nef, int clamp_edge) {
+  NbEdgeGeom g;
+  g.N = N; g.EPG = N * (N - 1); g.NGT = n_gt; g.B = B; g.nef = nef; g.clamp_edge = clamp_edge;
+  int G = NB_TILE / g.EPG;            // pack small graphs so a tile is (nearly) full
+  if (G < 1) G = 1;
+  if (G * N > 128) G = 128 / N;
+  if (G < 1) G = 1;
+  g.G = G;
+  g.n_units = (int)cdiv(n_gt, G);
+  return g;
+}
+
+static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
+  const size_t smem = NB_EDGE_FWD_SMEM_FLOATS * sizeof(float);
+  NB_SET_SMEM(k_edge_fwd, smem);
+  int grid = imin(a.g.n_units, 3 * nb_num_sms());
+  NB_LAUNCH(k_edge_fwd, (unsigned)grid, NB_THREADS, smem, st, a);
+  return nb_check_launch("k_edge_fwd");
+}
+
+// grads of the edge-tile weights go to `dst` (parameter-gradient buffer) at the given offsets
+struct EdgeGradDst {
+  int64_t w1, b_unused, W2, b2, W3, b3, w4, b4;
+  int ldw1, col_rad, col_ef;
+};
+
+static int launch_edge_bwd(NbEdgeBwdArgs& a, float* partial, float* dst, const EdgeGradDst& d, int accumulate,
+                           void* st) {
+  const size_t smem = NB_EDGE_BWD_SMEM_FLOATS(a.g.G * a.g.N) * sizeof(float);
+  NB_SET_SMEM(k_edge_bwd, smem);
+  int grid = imin(a.g.n_units, edge_bwd_grid_cap());
+  a.partial = partial;
+  NB_LAUNCH(k_edge_bwd, (unsigned)grid, NB_THREADS, smem, st, a);
+  NB_TRY(nb_check_launch("k_edge_bwd"));
+  NbFinArgs f;
+  memset(&f, 0, sizeof(f));
+  f.partial = partial; f.nparts = grid; f.plen = NB_EB_PLEN; f.dst = dst; f.accumulate = accumulate;
+  f.nseg = 0;
+  f.seg[f.nseg++] = fseg(NB_EB_GW2, NB_H * NB_H, NB_H, d.W2, NB_H, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GW3, NB_H * NB_H, NB_H, d.W3, NB_H, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GB2, NB_H, NB_H, d.b2, 0, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GB3, NB_H, NB_H, d.b3, 0, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GW4, NB_H, NB_H, d.w4, 0, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GWR, NB_H, 1, d.w1 + d.col_rad, d.ldw1, 0);            // column col_rad of W1
+  f.seg[f.nseg++] = fseg(NB_EB_GWE, a.g.nef * NB_H, NB_H, d.w1 + d.col_ef, 1, d.ldw1);  // (f, c) -> W1[c][col_ef + f]
+  f.seg[f.nseg++] = fseg(NB_EB_GB4, 1, 1, d.b4, 0, 0);
+  return launch_finalize(f, st);
+}
+
+// ============================================================================= twiddles
+static int make_twiddle(int T, int modes, NbTwiddle* tw) {
+  if (T < 1 || T > NB_MAX_T || modes < 1 || modes > T / 2 + 1) {
+    nb_set_error("unsupported temporal conv: T=%d (<= %d), modes=%d (<= T/2+1)", T, NB_MAX_T, modes);
+    return NB_ERR_INVALID;
+  }
+  memset(tw, 0, sizeof(*tw));
+  tw->T = T;
+  tw->modes = modes;
+  tw->nyq = (T % 2 == 0 && modes - 1 >= T / 2) ? T / 2 : -1;
+  if (T == 1) tw->nyq = -1;
+  tw->ncoef = 1 + 2 * (modes - 1);
+  for (int m = 0; m < modes; ++m)
+    for (int t = 0; t < T; ++t) {
+      double th = 2.0 * M_PI * (double)((m * t) % T) / (double)T;
+      tw->c[m][t] = (float)cos(th);
+      tw->s[m][t] = (m == 0 || m == tw->nyq) ? 0.f : (float)sin(th);
+    }
+  return NB_OK;
+}
+
+// ============================================================================= EGNO
+#define NB_MAX_LAYERS 32
+struct EgnoLayerOff {
+  int64_t e_w1, e_b1, e_w2, e_b2, c_w1, c_b1, c_w2, c_b2, v_w1, v_b1, v_w2, v_b2, n_w1, n_b1, n_w2, n_b2, tc, tcx;
+};
+struct EgnoLayout {
+  int F, E;  // embedding inputs, first edge layer inputs
+  int64_t emb_w, emb_b, total;
+  EgnoLayerOff L[NB_MAX_LAYERS];
+};
+
+static int egno_validate(const NbEgnoConfig* c) {
+  if (!c) { nb_set_error("null config"); return NB_ERR_INVALID; }
+  if (c->B < 1 || c->N < 2 || c->N > NB_MAX_NODES) { nb_set_error("unsupported B=%d N=%d (2 <= N <= %d)", c->B, c->N, NB_MAX_NODES); return NB_ERR_INVALID; }
+  if (c->n_layers < 1 || c->n_layers > NB_MAX_LAYERS) { nb_set_error("unsupported n_layers=%d", c->n_layers); return NB_ERR_INVALID; }
+  if (c->T < 1 || c->T > NB_MAX_T) { nb_set_error("unsupported num_timesteps=%d (<= %d)", c->T, NB_MAX_T); return NB_ERR_INVALID; }
+  if (c->use_time_conv && (c->num_modes < 1 || c->num_modes > c->T / 2 + 1)) { nb_set_error("num_modes=%d must be in [1, T/2+1] for T=%d", c->num_modes, c->T); return NB_ERR_INVALID; }
+  if (c->in_edge_nf < 0 || c->in_edge_nf > NB_MAX_EDGE_FEA) { nb_set_error("unsupported in_edge_nf=%d", c->in_edge_nf); return NB_ERR_INVALID; }
+  if (c->in_node_nf < 1 || c->time_emb_dim < 0 || c->time_emb_dim > 64 || (c->time_emb_dim & 1) || c->in_node_nf + c->time_emb_dim > 64) {
+    nb_set_error("unsupported in_node_nf=%d time_emb_dim=%d", c->in_node_nf, c->time_emb_dim);
+    return NB_ERR_INVALID;
+  }
+  if ((int64_t)c->T * c->B * c->N * (c->N - 1) > 2000000000LL) { nb_set_error("too many edges for 32-bit indexing"); return NB_ERR_INVALID; }
+  return NB_OK;
+}
+
+static void egno_layout(const NbEgnoConfig* c, EgnoLayout* lo) {
+  const int H = NB_H;
+  lo->F = c->in_node_nf + c->time_emb_dim;
+  lo->E = 1 + 2 * H + c->in_edge_nf;
+  int64_t o = 0;
+  // named_parameters() order of the reference: `layers` is registered before `embedding` (basic.py:193-197)
+  for (int l = 0; l < c->n_layers; ++l) {
+    EgnoLayerOff& L = lo->L[l];
+    L.e_w1 = o; o += (int64_t)H * lo->E;
+    L.e_b1 = o; o += H;
+    L.e_w2 = o; o += H * H;
+    L.e_b2 = o; o += H;
+    L.c_w1 = o; o += H * H;
+    L.c_b1 = o; o += H;
+    L.c_w2 = o; o += H;
+    L.c_b2 = o; o += 1;
+    L.v_w1 = o; o += H * H;
+    L.v_b1 = o; o += H;
+    L.v_w2 = o; o += H;
+    L.v_b2 = o; o += 1;
+    L.n_w1 = o; o += H * 2 * H;
+    L.n_b1 = o; o += H;
+    L.n_w2 = o; o += H * H;
+    L.n_b2 = o; o += H;
+  }
+  lo->emb_w = o; o += (int64_t)H * lo->F;
+  lo->emb_b = o; o += H;
+  if (c->use_time_conv) {
+    for (int l = 0; l < c->n_layers; ++l) { lo->L[l].tc = o; o += (int64_t)H * H * c->num_modes * 2; }
+    for (int l = 0; l < c->n_layers; ++l) { lo->L[l].tcx = o; o += (int64_t)2 * 2 * c->num_modes * 2; }
+  }
+  lo->total = o;
+}
+
+struct EgnoLayerBufs {
+  float *h0, *h1, *M, *U5, *UV, *x0, *v0, *x1, *v1, *Fsum;
+};
+static inline int64_t egno_layer_floats(int64_t Nn) { return Nn * (5 * NB_H + 5 * 3); }
+static EgnoLayerBufs egno_layer_bufs(float* base, int64_t Nn) {
+  EgnoLayerBufs b;
+  b.h0 = base; b.h1 = b.h0 + Nn * NB_H; b.M = b.h1 + Nn * NB_H; b.U5 = b.M + Nn * NB_H; b.UV = b.U5 + Nn * NB_H;
+  b.x0 = b.UV + Nn * NB_H; b.v0 = b.x0 + Nn * 3; b.x1 = b.v0 + Nn * 3; b.v1 = b.x1 + Nn * 3; b.Fsum = b.v1 + Nn * 3;
+  return b;
+}
+static inline int64_t align64(int64_t v) { return (v + 63) / 64 * 64; }
+
+extern "C" int64_t nb_egno_param_count(const NbEgnoConfig* cfg) {
+  if (egno_validate(cfg) != NB_OK) return -1;
+  EgnoLayout lo;
+  egno_layout(cfg, &lo);
+  return lo.total;
+}
+
+extern "C" int64_t nb_egno_saved_floats(const NbEgnoConfig* cfg) {
+  if (egno_validate(cfg) != NB_OK) return -1;
+  int64_t Nn = (int64_t)cfg->T * cfg->B * cfg->N;
+  return align64(egno_layer_floats(Nn)) * cfg->n_layers;
+}
+
+static int64_t egno_coef_floats(const NbEgnoConfig* c) {
+  int ncoef = c->use_time_conv ? 1 + 2 * (c->num_modes - 1) : 0;
+  return align64((int64_t)ncoef * c->B * c->N * NB_H);
+}
+
+extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int backward) {
+  if (egno_validate(cfg) != NB_OK) return -1;
+  int64_t Nn = (int64_t)cfg->T * cfg->B * cfg->N;
+  int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
+  if (!backward) return 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // last term: inference ping-pong
+  return 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
+         NB_PARTIAL_FLOATS;
+}
+
+struct EgnoCtx {
+  const NbEgnoConfig* c;
+  EgnoLayout lo;
+  NbTwiddle tw;
+  int64_t Nn0, Nn;
+  const float* params;
+  void* st;
+};
+
+static int egno_ctx_init(EgnoCtx* X, const NbEgnoConfig* cfg, const float* params, void* st) {
+  NB_TRY(egno_validate(cfg));
+  X->c = cfg;
+  egno_layout(cfg, &X->lo);
+  if (cfg->use_time_conv) NB_TRY(make_twiddle(cfg->T, cfg->num_modes, &X->tw));
+  X->Nn0 = (int64_t)cfg->B * cfg->N;
+  X->Nn = X->Nn0 * cfg->T;
+  X->params = params;
+  X->st = st;
+  return NB_OK;
+}
+
+// ---- temporal conv on h: mixing GEMMs coef -> ycoef (shared by forward and the backward's recompute)
+static int egno_tc_mix(const EgnoCtx& X, int l, const float* coef, float* ycoef) {
+  const int modes = X.c->num_modes;
+  const float* W = X.params + X.lo.L[l].tc;
+  const int64_t plane = X.Nn0 * NB_H;
+  const int64_t sk = (int64_t)NB_H * modes * 2, sn = (int64_t)modes * 2;  // B[k=i][n=o] = W[i][o][m][c]
+  for (int m = 0; m < modes; ++m) {
+    int ci = nb_coef_index(X.tw, m);
+    const float* Wr = W + m * 2;
+    const float* Wi = W + m * 2 + 1;
+    if (m == 0 || m == X.tw.nyq) {
+      NbGemmArgs a = gemm_args((int)X.Nn0);
+      a.nsrc = 1; a.src[0] = gsrc(coef + ci * plane, NB_H, 0, Wr, sk, sn);
+      a.out = ycoef + ci * plane;
+      NB_TRY(launch_gemm(a, X.st));
+    } else {
+      NbGemmArgs a = gemm_args((int)X.Nn0);  // P = C Wr + S Wi
+      a.nsrc = 2;
+      a.src[0] = gsrc(coef + ci * plane, NB_H, 0, Wr, sk, sn);
+      a.src[1] = gsrc(coef + (ci + 1) * plane, NB_H, 0, Wi, sk, sn);
+      a.out = ycoef + ci * plane;
+      NB_TRY(launch_gemm(a, X.st));
+      NbGemmArgs b = gemm_args((int)X.Nn0);  // Q = C Wi - S Wr
+      b.nsrc = 2;
+      b.src[0] = gsrc(coef + ci * plane, NB_H, 0, Wi, sk, sn);
+      b.src[1] = gsrc(coef + (ci + 1) * plane, NB_H, 0, Wr, sk, sn, -1.f);
+      b.out = ycoef + (ci + 1) * plane;
+      NB_TRY(launch_gemm(b, X.st));
+    }
+  }
+  return NB_OK;
+}
+
+static NbDftArgs dft_args(const EgnoCtx& X) {
+  NbDftArgs d;
+  memset(&d, 0, sizeof(d));
+  d.tw = X.tw;
+  d.Nn0 = (int)X.Nn0;
+  return d;
+}
+
+static int egno_pq(const EgnoCtx& X, int l, const float* h1, float* P, float* Q) {
+  const EgnoLayerOff& L = X.lo.L[l];
+  const int E = X.lo.E;
+  NbGemmArgs a = gemm_args((int)X.Nn);  // P = h W1[:, h_row]^T + b1   (cols 1..64, basic.py:98,170)
+  a.nsrc = 1; a.src[0] = gsrc(h1, NB_H, 0, X.params + L.e_w1 + 1, 1, E);
+  a.bias = X.params + L.e_b1; a.out = P;
+  NB_TRY(launch_gemm(a, X.st));
+  NbGemmArgs b = gemm_args((int)X.Nn);  // Q = h W1[:, h_col]^T         (cols 65..128)
+  b.nsrc = 1; b.src[0] = gsrc(h1, NB_H, 0, X.params + L.e_w1 + 1 + NB_H, 1, E);
+  b.out = Q;
+  return launch_gemm(b, X.st);
+}
+
+static NbEdgeW egno_edge_w(const EgnoCtx& X, int l) {
+  const EgnoLayerOff& L = X.lo.L[l];
+  NbEdgeW w;
+  w.W1 = X.params + L.e_w1; w.ldw1 = X.lo.E; w.col_rad = 0; w.col_ef = 1 + 2 * NB_H;
+  w.W2 = X.params + L.e_w2; w.b2 = X.params + L.e_b2; w.W3 = X.params + L.c_w1; w.b3 = X.params + L.c_b1;
+  w.w4 = X.params + L.c_w2; w.b4 = X.params + L.c_b2;
+  return w;
+}
+
+extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, const float* x, const float* nodes,
+                               const float* edge_fea, const float* v, const float* loc_mean,
+                               const int64_t* timesteps_out, float* x_out, float* v_out, float* h_out, float* saved,
+                               float* workspace, void* stream) {
+  EgnoCtx X;
+  NB_TRY(egno_ctx_init(&X, cfg, params, stream));
+  const int T = cfg->T, Ln = cfg->n_layers;
+  const int64_t Nn = X.Nn, Nn0 = X.Nn0;
+  const int64_t nh = align64(Nn * NB_H), cf = egno_coef_floats(cfg), lf = align64(egno_layer_floats(Nn));
+  float* P = workspace;
+  float* Q = P + nh;
+  float* coef = Q + nh;
+  float* ycoef = coef + cf;
+  float* infer = ycoef + cf;  // two layer-sets used when nothing is saved
+  auto bufs = [&](int l) { return egno_layer_bufs(saved ? saved + (int64_t)l * lf : infer + (int64_t)(l & 1) * lf, Nn); };
+
+  // ---- embedding (egno.py:50,63-76) + replication of x, v over T (egno.py:89-96)
+  EgnoLayerBufs b0 = bufs(0);
+  {
+    NbEmbedArgs e;
+    memset(&e, 0, sizeof(e));
+    e.T = T; e.Nn0 = (int)Nn0; e.B = cfg->B; e.F0 = cfg->in_node_nf; e.D = cfg->time_emb_dim;
+    e.nodes = nodes; e.tsteps = timesteps_out; e.W = params + X.lo.emb_w; e.bias = params + X.lo.emb_b; e.out = b0.h0;
+    int half = e.D / 2;
+    for (int k = 0; k < half; ++k) {
+      float sc = (float)(log(10000.0) / (double)(half - 1));  // layer_no.py:10-11 (fp32 arange * python scalar)
+      e.freq[k] = expf((float)k * -sc);
+    }
+    const size_t smem = ((size_t)X.lo.F * NB_H + 4 * X.lo.F) * sizeof(float);
+    NB_LAUNCH(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
+    NB_TRY(nb_check_launch("k_embed_fwd"));
+    NB_LAUNCH(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, x, b0.x0, (int)(Nn0 * 3), T);
+    NB_LAUNCH(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, v, b0.v0, (int)(Nn0 * 3), T);
+    NB_TRY(nb_check_launch("k_replicate3"));
+  }
+
+  const float* v_prev = b0.v0;
+  for (int l = 0; l < Ln; ++l) {
+    EgnoLayerBufs b = bufs(l);
+    const EgnoLayerOff& L = X.lo.L[l];
+    const float* v0 = v_prev;
+    float *h1 = b.h1, *x1 = b.x1, *v1 = b.v1;
+    if (cfg->use_time_conv) {
+      // h <- h + LeakyReLU(conv(h))      (layer_no.py:96-126)
+      NbDftArgs d = dft_args(X);
+      d.x = b.h0; d.coef = coef;
+      NB_LAUNCH(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+      NB_TRY(nb_check_launch("k_dft_fwd"));
+      NB_TRY(egno_tc_mix(X, l, coef, ycoef));
+      d.ycoef = ycoef; d.out = h1;
+      NB_LAUNCH(k_idft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+      NB_TRY(nb_check_launch("k_idft_fwd"));
+      // (x - mean, v) <- (x - mean, v) + conv(.)     (egno.py:103-108, layer_no.py:151-178)
+      NbTcxArgs t;
+      memset(&t, 0, sizeof(t));
+      t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
+      t.x1 = x1; t.v1 = v1;
+      NB_LAUNCH(k_tcx_fwd, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, t);
+      NB_TRY(nb_check_launch("k_tcx_fwd"));
+    } else {
+      h1 = b.h0; x1 = b.x0;
+      cudaMemcpyAsync(v1, v0, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    }
+    // ---- EGNN layer (basic.py:167-186)
+    NB_TRY(egno_pq(X, l, h1, P, Q));
+    NbEdgeFwdArgs ea;
+    ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
+    ea.w = egno_edge_w(X, l);
+    ea.x = x1; ea.P = P; ea.Q = Q; ea.ef = edge_fea; ea.M = b.M; ea.Fsum = b.Fsum;
+    NB_TRY(launch_edge_fwd(ea, stream));
+    float* h_next = (l + 1 < Ln) ? bufs(l + 1).h0 : h_out;
+    float* x_next = (l + 1 < Ln) ? bufs(l + 1).x0 : x_out;
+    {
+      NbGemmArgs a = gemm_args((int)Nn);  // U5 = [h, M] W5^T + b5      (basic.py:183-185)
+      a.nsrc = 2;
+      a.src[0] = gsrc(h1, NB_H, 0, params + L.n_w1, 1, 2 * NB_H);
+      a.src[1] = gsrc(b.M, NB_H, 0, params + L.n_w1 + NB_H, 1, 2 * NB_H);
+      a.bias = params + L.n_b1; a.out_pre = b.U5;
+      NB_TRY(launch_gemm(a, stream));
+      NbGemmArgs c2 = gemm_args((int)Nn);  // h' = SiLU(U5) W6^T + b6  (no residual)
+      c2.nsrc = 1; c2.src[0] = gsrc(b.U5, NB_H, 1, params + L.n_w2, 1, NB_H);
+      c2.bias = params + L.n_b2; c2.out = h_next;
+      NB_TRY(launch_gemm(c2, stream));
+      NbGemmArgs u = gemm_args((int)Nn);  // UV = h Wv1^T + bv1         (node_v_net, pre-update h)
+      u.nsrc = 1; u.src[0] = gsrc(h1, NB_H, 0, params + L.v_w1, 1, NB_H);
+      u.bias = params + L.v_b1; u.out_pre = b.UV;
+      NB_TRY(launch_gemm(u, stream));
+      NbXupdArgs xa;
+      memset(&xa, 0, sizeof(xa));
+      xa.rows = Nn; xa.N = cfg->N; xa.x = x1; xa.v = v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
+      xa.Fsum = b.Fsum; xa.x_out = x_next;
+      NB_LAUNCH(k_egno_xupd_fwd, (unsigned)imin(cdiv(Nn, 8), 8 * nb_num_sms()), 256, 0, stream, xa);
+      NB_TRY(nb_check_launch("k_egno_xupd_fwd"));
+    }
+    v_prev = v1;
+  }
+  cudaMemcpyAsync(v_out, v_prev, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return nb_check_launch("nb_egno_forward");
+}
+
+extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, const float* nodes, const float* edge_fea,
+                                const float* loc_mean, const int64_t* timesteps_out, const float* saved,
+                                const float* g_x_out, const float* g_v_out, const float* g_h_out, float* grad_params,
+                                float* g_x_in, float* g_v_in, float* workspace, void* stream) {
+  EgnoCtx X;
+  NB_TRY(egno_ctx_init(&X, cfg, params, stream));
+  if (!saved) { nb_set_error("nb_egno_backward needs the saved buffer of a forward call"); return NB_ERR_INVALID; }
+  const int T = cfg->T, Ln = cfg->n_layers, modes = cfg->num_modes;
+  const int64_t Nn = X.Nn, Nn0 = X.Nn0;
+  const int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
+  const int64_t lf = align64(egno_layer_floats(Nn));
+  float* w = workspace;
+  float* P = w; w += nh;
+  float* Q = w; w += nh;
+  float* coef = w; w += cf;
+  float* ycoef = w; w += cf;
+  float* gycoef = w; w += cf;
+  float* gcoef = w; w += cf;
+  float* ghA = w; w += nh;
+  float* ghB = w; w += nh;
+  float* GU5 = w; w += nh;
+  float* GUV = w; w += nh;
+  float* gM = w; w += nh;
+  float* gP = w; w += nh;
+  float* gQ = w; w += nh;
+  float* gxb[2]; gxb[0] = w; w += n3; gxb[1] = w; w += n3;
+  float* gvA = w; w += n3;
+  float* gvB = w; w += n3;
+  float* gFsum = w; w += n3;
+  float* partial = w;
+  cudaStream_t cst = (cudaStream_t)stream;
+
+  cudaMemsetAsync(grad_params, 0, X.lo.total * sizeof(float), cst);
+  // incoming gradients: gx must be writable (the edge backward accumulates into it)
+  int gxi = 0;
+  if (g_x_out) cudaMemcpyAsync(gxb[0], g_x_out, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+  else cudaMemsetAsync(gxb[0], 0, Nn * 3 * sizeof(float), cst);
+  const float* gv_in = g_v_out;
+  if (!gv_in) { cudaMemsetAsync(gvA, 0, Nn * 3 * sizeof(float), cst); gv_in = gvA; }
+  const float* gh_in = g_h_out;
+  if (!gh_in) { cudaMemsetAsync(ghB, 0, Nn * NB_H * sizeof(float), cst); gh_in = ghB; }
+
+  for (int l = Ln - 1; l >= 0; --l) {
+    const EgnoLayerOff& L = X.lo.L[l];
+    EgnoLayerBufs b = egno_layer_bufs(const_cast<float*>(saved) + (int64_t)l * lf, Nn);
+    const float* h1 = cfg->use_time_conv ? b.h1 : b.h0;
+    const float* x1 = cfg->use_time_conv ? b.x1 : b.x0;
+    const float* v0 = (l == 0) ? b.v0 : egno_layer_bufs(const_cast<float*>(saved) + (int64_t)(l - 1) * lf, Nn).v1;
+    float* gx = gxb[gxi];
+    // 1. x' = x + s v + clamp(mean f): gv1, gFsum, dL/dUV, and the 64->1 head of node_v_net
+    {
+      NbXupdArgs xa;
+      memset(&xa, 0, sizeof(xa));
+      xa.rows = Nn; xa.N = cfg->N; xa.v = b.v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
+      xa.Fsum = b.Fsum; xa.gx = gx; xa.gv = gv_in; xa.gv_out = gvB; xa.gFsum = gFsum; xa.GUV = GUV; xa.partial = partial;
+      int grid = imin(cdiv(Nn, 8), 4 * nb_num_sms());
+      NB_LAUNCH(k_egno_xupd_bwd, (unsigned)grid, 256, 0, stream, xa);
+      NB_TRY(nb_check_launch("k_egno_xupd_bwd"));
+      NbFinArgs f;
+      memset(&f, 0, sizeof(f));
+      f.partial = partial; f.nparts = grid; f.plen = 65; f.dst = grad_params; f.nseg = 2;
+      f.seg[0] = fseg(0, NB_H, NB_H, L.v_w2, 0, 1);
+      f.seg[1] = fseg(NB_H, 1, 1, L.v_b2, 0, 0);
+      NB_TRY(launch_finalize(f, stream));
+    }
+    // 2. node_net backward
+    {
+      NbGemmArgs a = gemm_args((int)Nn);  // GU5 = (gh W6) * SiLU'(U5)
+      a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + L.n_w2, NB_H, 1);
+      a.epi = NB_EPI_MUL_DSILU; a.U = b.U5; a.out = GU5;
+      NB_TRY(launch_gemm(a, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), partial, grad_params, L.n_w2, NB_H, 1,
+                      L.n_b2, 0, stream));
+      NbGemmArgs g1 = gemm_args((int)Nn);  // gh1 = GU5 W5[:, :64] + GUV Wv1
+      g1.nsrc = 2;
+      g1.src[0] = gsrc(GU5, NB_H, 0, params + L.n_w1, 2 * NB_H, 1);
+      g1.src[1] = gsrc(GUV, NB_H, 0, params + L.v_w1, NB_H, 1);
+      g1.out = ghA;
+      NB_TRY(launch_gemm(g1, stream));
+      NbGemmArgs g2 = gemm_args((int)Nn);  // gM = GU5 W5[:, 64:]
+      g2.nsrc = 1; g2.src[0] = gsrc(GU5, NB_H, 0, params + L.n_w1 + NB_H, 2 * NB_H, 1);
+      g2.out = gM;
+      NB_TRY(launch_gemm(g2, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, h1), wpair(nullptr, nullptr), partial, grad_params, L.n_w1, 2 * NB_H, 1,
+                      L.n_b1, 0, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), partial, grad_params, L.n_w1 + NB_H,
+                      2 * NB_H, 1, -1, 0, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GUV, h1), wpair(nullptr, nullptr), partial, grad_params, L.v_w1, NB_H, 1,
+                      L.v_b1, 0, stream));
+    }
+    // 3. edge tile backward (recompute)
+    NB_TRY(egno_pq(X, l, h1, P, Q));
+    {
+      NbEdgeBwdArgs ea;
+      memset(&ea, 0, sizeof(ea));
+      ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
+      ea.w = egno_edge_w(X, l);
+      ea.x = x1; ea.P = P; ea.Q = Q; ea.ef = edge_fea; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
+      EdgeGradDst d;
+      d.w1 = L.e_w1; d.W2 = L.e_w2; d.b2 = L.e_b2; d.W3 = L.c_w1; d.b3 = L.c_b1; d.w4 = L.c_w2; d.b4 = L.c_b2;
+      d.ldw1 = X.lo.E; d.col_rad = 0; d.col_ef = 1 + 2 * NB_H; d.b_unused = 0;
+      NB_TRY(launch_edge_bwd(ea, partial, grad_params, d, 0, stream));
+    }
+    // 4. pre-projection backward: gh1 += gP W1[:, h_row] + gQ W1[:, h_col]
+    {
+      NbGemmArgs a = gemm_args((int)Nn);
+      a.nsrc = 2;
+      a.src[0] = gsrc(gP, NB_H, 0, params + L.e_w1 + 1, X.lo.E, 1);
+      a.src[1] = gsrc(gQ, NB_H, 0, params + L.e_w1 + 1 + NB_H, X.lo.E, 1);
+      a.out = ghA; a.accumulate = 1;
+      NB_TRY(launch_gemm(a, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, h1), wpair(nullptr, nullptr), partial, grad_params, L.e_w1 + 1, X.lo.E, 1,
+                      L.e_b1, 0, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, h1), wpair(nullptr, nullptr), partial, grad_params, L.e_w1 + 1 + NB_H,
+                      X.lo.E, 1, -1, 0, stream));
+    }
+    // 5. temporal convolutions
+    if (cfg->use_time_conv) {
+      float* gx0 = gxb[gxi ^ 1];
+      {
+        NbTcxArgs t;
+        memset(&t, 0, sizeof(t));
+        t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
+        t.gx1 = gx; t.gv1 = gvB; t.gx0 = gx0; t.gv0 = gvA; t.partial = partial;
+        int grid = imin(cdiv(Nn0 * 3, 256), 2 * nb_num_sms());
+        NB_LAUNCH(k_tcx_bwd, (unsigned)grid, 256, 0, stream, t);
+        NB_TRY(nb_check_launch("k_tcx_bwd"));
+        NbFinArgs f;
+        memset(&f, 0, sizeof(f));
+        int nw = 2 * 2 * modes * 2;
+        f.partial = partial; f.nparts = grid; f.plen = nw; f.dst = grad_params; f.nseg = 1;
+        f.seg[0] = fseg(0, nw, nw, L.tcx, 0, 1);
+        NB_TRY(launch_finalize(f, stream));
+      }
+      gxi ^= 1;
+      gv_in = gvA;
+      {
+        NbDftArgs d = dft_args(X);
+        d.x = b.h0; d.coef = coef;
+        NB_LAUNCH(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_TRY(nb_check_launch("k_dft_fwd"));
+        NB_TRY(egno_tc_mix(X, l, coef, ycoef));
+        d.ycoef = ycoef; d.gout = ghA; d.gycoef = gycoef;
+        NB_LAUNCH(k_idft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_TRY(nb_check_launch("k_idft_bwd"));
+        const float* W = params + L.tc;
+        const int64_t plane = Nn0 * NB_H;
+        const int64_t tk = (int64_t)modes * 2, tn = (int64_t)NB_H * modes * 2;  // B[k=o][n=i] = W[i][o][m][c]
+        for (int m = 0; m < modes; ++m) {
+          int ci = nb_coef_index(X.tw, m);
+          const float *Wr = W + m * 2, *Wi = W + m * 2 + 1;
+          const float *C = coef + ci * plane, *S = coef + (ci + 1) * plane;
+          const float *gPm = gycoef + ci * plane, *gQm = gycoef + (ci + 1) * plane;
+          const int64_t wr_off = L.tc + m * 2, wi_off = L.tc + m * 2 + 1;
+          if (m == 0 || m == X.tw.nyq) {
+            NbGemmArgs a = gemm_args((int)Nn0);  // gC = gP Wr^T
+            a.nsrc = 1; a.src[0] = gsrc(gPm, NB_H, 0, Wr, tk, tn);
+            a.out = gcoef + ci * plane;
+            NB_TRY(launch_gemm(a, stream));
+            NB_TRY(wgrad_to((int)Nn0, 1, wpair(C, gPm), wpair(nullptr, nullptr), partial, grad_params, wr_off, tn, tk,
+                            -1, 0, stream));
+          } else {
+            NbGemmArgs a = gemm_args((int)Nn0);  // gC = gP Wr^T + gQ Wi^T
+            a.nsrc = 2;
+            a.src[0] = gsrc(gPm, NB_H, 0, Wr, tk, tn);
+            a.src[1] = gsrc(gQm, NB_H, 0, Wi, tk, tn);
+            a.out = gcoef + ci * plane;
+            NB_TRY(launch_gemm(a, stream));
+            NbGemmArgs s2 = gemm_args((int)Nn0);  // gS = gP Wi^T - gQ Wr^T
+            s2.nsrc = 2;
+            s2.src[0] = gsrc(gPm, NB_H, 0, Wi, tk, tn);
+            s2.src[1] = gsrc(gQm, NB_H, 0, Wr, tk, tn, -1.f);
+            s2.out = gcoef + (ci + 1) * plane;
+            NB_TRY(launch_gemm(s2, stream));
+            // dWr[i][o] = sum C_i gP_o - S_i gQ_o ; dWi[i][o] = sum S_i gP_o + C_i gQ_o
+            NB_TRY(wgrad_to((int)Nn0, 2, wpair(C, gPm), wpair(S, gQm, 0, -1.f), partial, grad_params, wr_off, tn, tk,
+                            -1, 0, stream));
+            NB_TRY(wgrad_to((int)Nn0, 2, wpair(S, gPm), wpair(C, gQm), partial, grad_params, wi_off, tn, tk, -1, 0,
+                            stream));
+          }
+        }
+        d.gcoef = gcoef; d.gx = ghB;
+        NB_LAUNCH(k_dft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_TRY(nb_check_launch("k_dft_bwd"));
+      }
+      gh_in = ghB;
+    } else {
+      gv_in = gvB;
+      // without the temporal conv gv1 must survive in gvB while the next layer writes its own gv1: swap roles
+      float* tmp = gvA; gvA = gvB; gvB = tmp;
+      gh_in = ghA;
+      float* t2 = ghA; ghA = ghB; ghB = t2;
+    }
+  }
+  // ---- embedding backward and the reduction of the T replicas of x, v
+  {
+    NbEmbedBwdArgs eb;
+    memset(&eb, 0, sizeof(eb));
+    NbEmbedArgs& e = eb.e;
+    e.T = T; e.Nn0 = (int)Nn0; e.B = cfg->B; e.F0 = cfg->in_node_nf; e.D = cfg->time_emb_dim;
+    e.nodes = nodes; e.tsteps = timesteps_out;
+    int half = e.D / 2;
+    for (int k = 0; k < half; ++k) {
+      float sc = (float)(log(10000.0) / (double)(half - 1));
+      e.freq[k] = expf((float)k * -sc);
+    }
+    eb.g = gh_in; eb.partial = partial;
+    const int F = X.lo.F;
+    int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
+    const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
+    NB_LAUNCH(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
+    NB_TRY(nb_check_launch("k_embed_bwd"));
+    NbFinArgs f;
+    memset(&f, 0, sizeof(f));
+    f.partial = partial; f.nparts = grid; f.plen = NB_H * F + NB_H; f.dst = grad_params; f.nseg = 2;
+    f.seg[0] = fseg(0, NB_H * F, NB_H * F, X.lo.emb_w, 0, 1);
+    f.seg[1] = fseg(NB_H * F, NB_H, NB_H, X.lo.emb_b, 0, 1);
+    NB_TRY(launch_finalize(f, stream));
+  }
+  if (g_x_in) NB_LAUNCH(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T);
+  if (g_v_in) NB_LAUNCH(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T);
+  return nb_check_launch("nb_egno_backward");
+}
+
+// ============================================================================= SEGNO
+struct SegnoLayout {
+  int E;
+  int64_t emb_w, emb_b, e_w1, e_b1, e_w2, e_b2, n_w1, n_b1, n_w2, n_b2, c_w1, c_b1, c_w2, c_b2, cv_w1, cv_b1, cv_w2,
+      cv_b2, total;
+};
+
+static int segno_validate(const NbSegnoConfig* c) {
+  if (!c) { nb_set_error("null config"); return NB_ERR_INVALID; }
+  if (c->B < 1 || c->N < 2 || c->N > NB_MAX_NODES) { nb_set_error("unsupported B=%d N=%d (2 <= N <= %d)", c->B, c->N, NB_MAX_NODES); return NB_ERR_INVALID; }
+  if (c->T < 1 || c->T > 4096) { nb_set_error("unsupported T=%d", c->T); return NB_ERR_INVALID; }
+  if (c->in_edge_nf < 0 || c->in_edge_nf > NB_MAX_EDGE_FEA) { nb_set_error("unsupported in_edge_nf=%d", c->in_edge_nf); return NB_ERR_INVALID; }
+  if (c->in_node_nf < 1 || c->in_node_nf > 64) { nb_set_error("unsupported in_node_nf=%d", c->in_node_nf); return NB_ERR_INVALID; }
+  if ((int64_t)c->B * c->N * (c->N - 1) > 2000000000LL) { nb_set_error("too many edges for 32-bit indexing"); return NB_ERR_INVALID; }
+  return NB_OK;
+}
+
+static void segno_layout(const NbSegnoConfig* c, SegnoLayout* lo) {
+  const int H = NB_H;
+  lo->E = 2 * H + 1 + c->in_edge_nf;
+  int64_t o = 0;
+  lo->emb_w = o; o += (int64_t)H * c->in_node_nf;
+  lo->emb_b = o; o += H;
+  lo->e_w1 = o; o += (int64_t)H * lo->E;
+  lo->e_b1 = o; o += H;
+  lo->e_w2 = o; o += H * H;
+  lo->e_b2 = o; o += H;
+  lo->n_w1 = o; o += H * 2 * H;
+  lo->n_b1 = o; o += H;
+  lo->n_w2 = o; o += H * H;
+  lo->n_b2 = o; o += H;
+  lo->c_w1 = o; o += H * H;
+  lo->c_b1 = o; o += H;
+  lo->c_w2 = o; o += H;
+  lo->c_b2 = o; o += 1;
+  lo->cv_w1 = o; o += H * H;
+  lo->cv_b1 = o; o += H;
+  lo->cv_w2 = o; o += H;
+  lo->cv_b2 = o; o += 1;
+  lo->total = o;
+}
+
+struct SegnoIterBufs {
+  float *h, *M, *U5, *x;
+};
+static inline int64_t segno_iter_floats(int64_t Nn) { return align64(Nn * (3 * NB_H + 3)); }
+static SegnoIterBufs segno_iter_bufs(float* base, int64_t Nn) {
+  SegnoIterBufs b;
+  b.h = base; b.M = b.h + Nn * NB_H; b.U5 = b.M + Nn * NB_H; b.x = b.U5 + Nn * NB_H;
+  return b;
+}
+
+extern "C" int64_t nb_segno_param_count(const NbSegnoConfig* cfg) {
+  if (segno_validate(cfg) != NB_OK) return -1;
+  SegnoLayout lo;
+  segno_layout(cfg, &lo);
+  return lo.total;
+}
+extern "C" int64_t nb_segno_saved_floats(const NbSegnoConfig* cfg) {
+  if (segno_validate(cfg) != NB_OK) return -1;
+  return segno_iter_floats((int64_t)cfg->B * cfg->N) * cfg->T;
+}
+extern "C" int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int backward) {
+  if (segno_validate(cfg) != NB_OK) return -1;
+  int64_t Nn = (int64_t)cfg->B * cfg->N;
+  int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3);
+  if (!backward) return 2 * nh /*P,Q*/ + 3 * n3 /*Fsum, v ping-pong*/ + 2 * segno_iter_floats(Nn);
+  return 2 * nh + 2 * nh /*gh*/ + 4 * nh /*GU5 gM gP gQ*/ + 4 * n3 + NB_PARTIAL_FLOATS;
+}
+
+struct SegnoCtx {
+  const NbSegnoConfig* c;
+  SegnoLayout lo;
+  int64_t Nn;
+  const float* params;
+  void* st;
+};
+
+static int segno_pq(const SegnoCtx& X, const float* h, float* P, float* Q) {
+  NbGemmArgs a = gemm_args((int)X.Nn);  // cols: h_row | h_col | radial | edge_attr  (gcl.py:78)
+  a.nsrc = 1; a.src[0] = gsrc(h, NB_H, 0, X.params + X.lo.e_w1, 1, X.lo.E);
+  a.bias = X.params + X.lo.e_b1; a.out = P;
+  NB_TRY(launch_gemm(a, X.st));
+  NbGemmArgs b = gemm_args((int)X.Nn);
+  b.nsrc = 1; b.src[0] = gsrc(h, NB_H, 0, X.params + X.lo.e_w1 + NB_H, 1, X.lo.E);
+  b.out = Q;
+  return launch_gemm(b, X.st);
+}
+
+static NbEdgeW segno_edge_w(const SegnoCtx& X) {
+  NbEdgeW w;
+  w.W1 = X.params + X.lo.e_w1; w.ldw1 = X.lo.E; w.col_rad = 2 * NB_H; w.col_ef = 2 * NB_H + 1;
+  w.W2 = X.params + X.lo.e_w2; w.b2 = X.params + X.lo.e_b2; w.W3 = X.params + X.lo.c_w1; w.b3 = X.params + X.lo.c_b1;
+  w.w4 = X.params + X.lo.c_w2; w.b4 = X.params + X.lo.c_b2;
+  return w;
+}
+
+static void segno_embed_args(const SegnoCtx& X, const float* his, NbEmbedArgs* e) {
+  memset(e, 0, sizeof(*e));
+  e->T = 1; e->Nn0 = (int)X.Nn; e->B = X.c->B; e->F0 = X.c->in_node_nf; e->D = 0;
+  e->nodes = his; e->tsteps = nullptr; e->W = X.params + X.lo.emb_w; e->bias = X.params + X.lo.emb_b;
+}
+
+extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, const float* his, const float* x,
+                                const float* v, const float* edge_attr, float* x_out, float* h_out, float* v_out,
+                                float* saved, float* workspace, void* stream) {
+  NB_TRY(segno_validate(cfg));
+  SegnoCtx X;
+  X.c = cfg; segno_layout(cfg, &X.lo); X.Nn = (int64_t)cfg->B * cfg->N; X.params = params; X.st = stream;
+  const int64_t Nn = X.Nn, nh = align64(Nn * NB_H), n3 = align64(Nn * 3), itf = segno_iter_floats(Nn);
+  const int T = cfg->T;
+  float* P = workspace;
+  float* Q = P + nh;
+  float* Fsum = Q + nh;
+  float* vb[2] = {Fsum + n3, Fsum + 2 * n3};
+  float* infer = Fsum + 3 * n3;
+  auto bufs = [&](int k) { return segno_iter_bufs(saved ? saved + (int64_t)k * itf : infer + (int64_t)(k & 1) * itf, Nn); };
+  cudaStream_t cst = (cudaStream_t)stream;
+
+  SegnoIterBufs b0 = bufs(0);
+  {
+    NbEmbedArgs e;
+    segno_embed_args(X, his, &e);
+    e.out = b0.h;
+    const size_t smem = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
+    NB_LAUNCH(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
+    NB_TRY(nb_check_launch("k_embed_fwd"));
+    cudaMemcpyAsync(b0.x, x, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+  }
+  const float* vcur = v;
+  for (int k = 0; k < T; ++k) {
+    SegnoIterBufs b = bufs(k);
+    float* h_next = (k + 1 < T) ? bufs(k + 1).h : h_out;
+    float* x_next = (k + 1 < T) ? bufs(k + 1).x : x_out;
+    float* v_next = (k + 1 < T) ? vb[k & 1] : v_out;
+    NB_TRY(segno_pq(X, b.h, P, Q));
+    NbEdgeFwdArgs ea;
+    ea.g = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
+    ea.w = segno_edge_w(X);
+    ea.x = b.x; ea.P = P; ea.Q = Q; ea.ef = edge_attr; ea.M = b.M; ea.Fsum = Fsum;
+    NB_TRY(launch_edge_fwd(ea, stream));
+    NbIntegArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.n3 = Nn * 3; ia.N = cfg->N; ia.inv_T = (float)(1.0 / (double)T); ia.cw = cfg->coords_weight;
+    ia.x = b.x; ia.v = vcur; ia.Fsum = Fsum; ia.x_out = x_next; ia.v_out = v_next;
+    NB_LAUNCH(k_segno_integ_fwd, (unsigned)ew_grid(Nn * 3), 256, 0, stream, ia);
+    NB_TRY(nb_check_launch("k_segno_integ_fwd"));
+    NbGemmArgs a = gemm_args((int)Nn);  // U5 = [h, M] W5^T + b5      (gcl.py:89-92)
+    a.nsrc = 2;
+    a.src[0] = gsrc(b.h, NB_H, 0, params + X.lo.n_w1, 1, 2 * NB_H);
+    a.src[1] = gsrc(b.M, NB_H, 0, params + X.lo.n_w1 + NB_H, 1, 2 * NB_H);
+    a.bias = params + X.lo.n_b1; a.out_pre = b.U5;
+    NB_TRY(launch_gemm(a, stream));
+    NbGemmArgs c2 = gemm_args((int)Nn);  // h' = h + SiLU(U5) W6^T + b6   (recurrent, gcl.py:93-94)
+    c2.nsrc = 1; c2.src[0] = gsrc(b.U5, NB_H, 1, params + X.lo.n_w2, 1, NB_H);
+    c2.bias = params + X.lo.n_b2; c2.out = h_next;
+    if (cfg->recurrent) c2.R = b.h;
+    NB_TRY(launch_gemm(c2, stream));
+    vcur = v_next;
+  }
+  return nb_check_launch("nb_segno_forward");
+}
+
+extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, const float* his,
+                                 const float* edge_attr, const float* saved, const float* g_x_out,
+                                 const float* g_h_out, const float* g_v_out, float* grad_params, float* g_x_in,
+                                 float* g_v_in, float* workspace, void* stream) {
+  NB_TRY(segno_validate(cfg));
+  if (!saved) { nb_set_error("nb_segno_backward needs the saved buffer of a forward call"); return NB_ERR_INVALID; }
+  SegnoCtx X;
+  X.c = cfg; segno_layout(cfg, &X.lo); X.Nn = (int64_t)cfg->B * cfg->N; X.params = params; X.st = stream;
+  const SegnoLayout& lo = X.lo;
+  const int64_t Nn = X.Nn, nh = align64(Nn * NB_H), n3 = align64(Nn * 3), itf = segno_iter_floats(Nn);
+  const int T = cfg->T;
+  float* w = workspace;
+  float* P = w; w += nh;
+  float* Q = w; w += nh;
+  float* ghb[2]; ghb[0] = w; w += nh; ghb[1] = w; w += nh;
+  float* GU5 = w; w += nh;
+  float* gM = w; w += nh;
+  float* gP = w; w += nh;
+  float* gQ = w; w += nh;
+  float* gx = w; w += n3;
+  float* gvb[2]; gvb[0] = w; w += n3; gvb[1] = w; w += n3;
+  float* gFsum = w; w += n3;
+  float* partial = w;
+  cudaStream_t cst = (cudaStream_t)stream;
+
+  cudaMemsetAsync(grad_params, 0, lo.total * sizeof(float), cst);
+  if (g_x_out) cudaMemcpyAsync(gx, g_x_out, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+  else cudaMemsetAsync(gx, 0, Nn * 3 * sizeof(float), cst);
+  const float* gv_in = g_v_out;
+  int gvi = 0;
+  const float* gh_in = g_h_out;
+  int ghi = 0;
+  if (!gh_in) { cudaMemsetAsync(ghb[1], 0, Nn * NB_H * sizeof(float), cst); gh_in = ghb[1]; }
+
+  for (int k = T - 1; k >= 0; --k) {
+    SegnoIterBufs b = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)k * itf, Nn);
+    float* gh_new = ghb[ghi];
+    // node_mlp backward
+    NbGemmArgs a = gemm_args((int)Nn);  // GU5 = (gh W6) * SiLU'(U5)
+    a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + lo.n_w2, NB_H, 1);
+    a.epi = NB_EPI_MUL_DSILU; a.U = b.U5; a.out = GU5;
+    NB_TRY(launch_gemm(a, stream));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), partial, grad_params, lo.n_w2, NB_H, 1,
+                    lo.n_b2, 1, stream));
+    NbGemmArgs g1 = gemm_args((int)Nn);  // gh = GU5 W5[:, :64] (+ gh: residual)
+    g1.nsrc = 1; g1.src[0] = gsrc(GU5, NB_H, 0, params + lo.n_w1, 2 * NB_H, 1);
+    if (cfg->recurrent) g1.R = gh_in;
+    g1.out = gh_new;
+    NB_TRY(launch_gemm(g1, stream));
+    NbGemmArgs g2 = gemm_args((int)Nn);  // gM = GU5 W5[:, 64:]
+    g2.nsrc = 1; g2.src[0] = gsrc(GU5, NB_H, 0, params + lo.n_w1 + NB_H, 2 * NB_H, 1);
+    g2.out = gM;
+    NB_TRY(launch_gemm(g2, stream));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.h), wpair(nullptr, nullptr), partial, grad_params, lo.n_w1, 2 * NB_H, 1,
+                    lo.n_b1, 1, stream));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), partial, grad_params, lo.n_w1 + NB_H, 2 * NB_H,
+                    1, -1, 1, stream));
+    // integrator backward
+    NbIntegArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.n3 = Nn * 3; ia.N = cfg->N; ia.inv_T = (float)(1.0 / (double)T); ia.cw = cfg->coords_weight;
+    ia.gx = gx; ia.gv = gv_in; ia.gx_out = gx; ia.gv_out = gvb[gvi]; ia.gFsum = gFsum;
+    NB_LAUNCH(k_segno_integ_bwd, (unsigned)ew_grid(Nn * 3), 256, 0, stream, ia);
+    NB_TRY(nb_check_launch("k_segno_integ_bwd"));
+    gv_in = gvb[gvi];
+    gvi ^= 1;
+    // edge tile backward
+    NB_TRY(segno_pq(X, b.h, P, Q));
+    NbEdgeBwdArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.g = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
+    ea.w = segno_edge_w(X);
+    ea.x = b.x; ea.P = P; ea.Q = Q; ea.ef = edge_attr; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
+    EdgeGradDst d;
+    d.w1 = lo.e_w1; d.W2 = lo.e_w2; d.b2 = lo.e_b2; d.W3 = lo.c_w1; d.b3 = lo.c_b1; d.w4 = lo.c_w2; d.b4 = lo.c_b2;
+    d.ldw1 = lo.E; d.col_rad = 2 * NB_H; d.col_ef = 2 * NB_H + 1; d.b_unused = 0;
+    NB_TRY(launch_edge_bwd(ea, partial, grad_params, d, 1, stream));
+    NbGemmArgs pa = gemm_args((int)Nn);  // gh += gP W1[:, h_row] + gQ W1[:, h_col]
+    pa.nsrc = 2;
+    pa.src[0] = gsrc(gP, NB_H, 0, params + lo.e_w1, lo.E, 1);
+    pa.src[1] = gsrc(gQ, NB_H, 0, params + lo.e_w1 + NB_H, lo.E, 1);
+    pa.out = gh_new; pa.accumulate = 1;
+    NB_TRY(launch_gemm(pa, stream));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, b.h), wpair(nullptr, nullptr), partial, grad_params, lo.e_w1, lo.E, 1, lo.e_b1,
+                    1, stream));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, b.h), wpair(nullptr, nullptr), partial, grad_params, lo.e_w1 + NB_H, lo.E, 1,
+                    -1, 1, stream));
+    gh_in = gh_new;
+    ghi ^= 1;
+  }
+  {
+    NbEmbedBwdArgs eb;
+    memset(&eb, 0, sizeof(eb));
+    segno_embed_args(X, his, &eb.e);
+    eb.g = gh_in; eb.partial = partial;
+    const int F = cfg->in_node_nf;
+    int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
+    const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
+    NB_LAUNCH(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
+    NB_TRY(nb_check_launch("k_embed_bwd"));
+    NbFinArgs f;
+    memset(&f, 0, sizeof(f));
+    f.partial = partial; f.nparts = grid; f.plen = NB_H * F + NB_H; f.dst = grad_params; f.nseg = 2;
+    f.seg[0] = fseg(0, NB_H * F, NB_H * F, lo.emb_w, 0, 1);
+    f.seg[1] = fseg(NB_H * F, NB_H, NB_H, lo.emb_b, 0, 1);
+    NB_TRY(launch_finalize(f, stream));
+  }
+  if (g_x_in) cudaMemcpyAsync(g_x_in, gx, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+  if (g_v_in) {
+    if (gv_in) cudaMemcpyAsync(g_v_in, gv_in, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+    else cudaMemsetAsync(g_v_in, 0, Nn * 3 * sizeof(float), cst);
+  }
+  return nb_check_launch("nb_segno_backward");
+}
+
+// ============================================================================= exported building blocks
+extern "C" int nb_check_canonical_edges(const int64_t* row, const int64_t* col, int64_t n_edges, int32_t B, int32_t N,
+                                        int32_t* flag_dev, void* stream) {
+  if (N < 2 || B < 1 || n_edges != (int64_t)B * N * (N - 1)) {
+    nb_set_error("edge_index has %lld edges, expected B*N*(N-1) = %lld", (long long)n_edges, (long long)B * N * (N - 1));
+    return NB_ERR_INVALID;
+  }
+  cudaMemsetAsync(flag_dev, 0, sizeof(int32_t), (cudaStream_t)stream);
+  NB_LAUNCH(k_check_edges, (unsigned)ew_grid(n_edges), 256, 0, stream, row, col, n_edges, (int)B, (int)N, (int*)flag_dev);
+  return nb_check_launch("k_check_edges");
+}
+
+extern "C" int nb_egcl_edge_forward(int32_t n_gt, int32_t B, int32_t N, int32_t n_edge_fea, int32_t clamp_per_edge,
+                                    const float* x, const float* P, const float* Q, const float* edge_fea,
+                                    const float* w1, int32_t ldw1, int32_t col_rad, int32_t col_ef, const float* W2,
+                                    const float* b2, const float* W3, const float* b3, const float* w4, const float* b4,
+                                    float* M, float* Fsum, void* stream) {
+  if (N < 2 || N > NB_MAX_NODES || n_edge_fea < 0 || n_edge_fea > NB_MAX_EDGE_FEA || n_gt < 1 || B < 1) {
+    nb_set_error("nb_egcl_edge_forward: unsupported shape");
+    return NB_ERR_INVALID;
+  }
+  NbEdgeFwdArgs a;
+  a.g = edge_geom(n_gt, B, N, n_edge_fea, clamp_per_edge);
+  a.w.W1 = w1; a.w.ldw1 = ldw1; a.w.col_rad = col_rad; a.w.col_ef = col_ef;
+  a.w.W2 = W2; a.w.b2 = b2; a.w.W3 = W3; a.w.b3 = b3; a.w.w4 = w4; a.w.b4 = b4;
+  a.x = x; a.P = P; a.Q = Q; a.ef = edge_fea; a.M = M; a.Fsum = Fsum;
+  return launch_edge_fwd(a, stream);
+}
+
+extern "C" int64_t nb_egcl_edge_backward_workspace_floats(int32_t n_gt, int32_t N) {
+  (void)n_gt; (void)N;
+  return NB_PARTIAL_FLOATS;
+}

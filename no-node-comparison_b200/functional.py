@@ -1,0 +1,233 @@
+"""Autograd wrappers over the C ABI (include/nbody_b200.h).
+
+One `torch.autograd.Function` per model: the whole EGNO / SEGNO forward is one C call that enqueues the
+kernel sequence on the current CUDA stream, and the whole backward is another.  PyTorch only owns the
+memory (inputs, outputs, the saved-for-backward buffer, scratch) and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._lib import check, load_library
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (this implementation has no CPU path); got {t.device}")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t.contiguous()
+
+
+class _ParamPack:
+    """Keeps a module's parameters as views of ONE flat fp32 buffer (the layout of the C ABI, which is
+    the order of named_parameters()).  The views survive optimizer steps and load_state_dict (both
+    in-place); `.to()` / `.cuda()` replace parameter storage, which is detected and re-flattened."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module = module
+        self.flat: Optional[torch.Tensor] = None
+        self.offsets: List[int] = []
+
+    def params(self) -> List[torch.nn.Parameter]:
+        return [p for _, p in self.module.named_parameters()]
+
+    def _views_ok(self, ps) -> bool:
+        f = self.flat
+        if f is None or len(ps) != len(self.offsets):
+            return False
+        base = f.data_ptr()
+        for p, off in zip(ps, self.offsets):
+            if p.data_ptr() != base + 4 * off or p.device != f.device or p.dtype != torch.float32:
+                return False
+        return True
+
+    def flat_params(self, expected: int, device: torch.device):
+        ps = self.params()
+        if not self._views_ok(ps) or self.flat.device != device:
+            for p in ps:
+                if p.dtype != torch.float32:
+                    raise ValueError("parameters must be float32")
+                if p.device != device:
+                    raise ValueError(f"parameters live on {p.device} but inputs on {device}; call model.to(device)")
+            with torch.no_grad():
+                flat = torch.cat([p.detach().reshape(-1) for p in ps]).contiguous()
+                offs, o = [], 0
+                for p in ps:
+                    offs.append(o)
+                    p.data = flat[o:o + p.numel()].view(p.shape)
+                    o += p.numel()
+            self.flat, self.offsets = flat, offs
+        if self.flat.numel() != expected:
+            raise RuntimeError(f"parameter count {self.flat.numel()} != C layout {expected}")
+        return self.flat, ps
+
+
+def _maybe_allreduce(grad_flat: torch.Tensor, group) -> None:
+    """Data parallel: ONE all-reduce of the flat gradient bucket (NCCL over NVLink), then the mean."""
+    if group is None:
+        return
+    import torch.distributed as dist
+
+    dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=group)
+    grad_flat.div_(dist.get_world_size(group))
+
+
+class EgnoFunction(torch.autograd.Function):
+    """x, v, h = EGNO.forward(...)   (reference: EGNO/model/egno.py:37-111)."""
+
+    @staticmethod
+    def forward(ctx, cfg_tuple, dp_group, flat, x, nodes, edge_fea, v, loc_mean, tsteps, *params):
+        lib = load_library()
+        cfg = _cabi.NbEgnoConfig(*cfg_tuple)
+        dev = x.device
+        Nn = cfg.T * cfg.B * cfg.N
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x.requires_grad or v.requires_grad)
+        x_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
+        v_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
+        h_out = torch.empty((Nn, 64), device=dev, dtype=torch.float32)
+        saved = torch.empty(lib.nb_egno_saved_floats(ctypes.byref(cfg)), device=dev, dtype=torch.float32) if need_grad else None
+        ws = torch.empty(lib.nb_egno_workspace_floats(ctypes.byref(cfg), 0), device=dev, dtype=torch.float32)
+        check(lib.nb_egno_forward(ctypes.byref(cfg), _ptr(flat), _ptr(x), _ptr(nodes), _ptr(edge_fea), _ptr(v),
+                                  _ptr(loc_mean), _ptr(tsteps), _ptr(x_out), _ptr(v_out), _ptr(h_out), _ptr(saved),
+                                  _ptr(ws), _stream_ptr(dev)), "nb_egno_forward")
+        ctx.cfg_tuple = cfg_tuple
+        ctx.dp_group = dp_group
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.save_for_backward(flat, nodes, edge_fea, loc_mean, tsteps, saved)
+        return x_out, v_out, h_out
+
+    @staticmethod
+    def backward(ctx, gx_out, gv_out, gh_out):
+        lib = load_library()
+        flat, nodes, edge_fea, loc_mean, tsteps, saved = ctx.saved_tensors
+        if saved is None:
+            raise RuntimeError("EGNO forward ran without autograd state; cannot run backward")
+        cfg = _cabi.NbEgnoConfig(*ctx.cfg_tuple)
+        dev = flat.device
+        n0 = cfg.B * cfg.N
+        gx_out = None if gx_out is None else gx_out.contiguous()
+        gv_out = None if gv_out is None else gv_out.contiguous()
+        gh_out = None if gh_out is None else gh_out.contiguous()
+        grad_flat = torch.empty_like(flat)
+        gx_in = torch.empty((n0, 3), device=dev, dtype=torch.float32)
+        gv_in = torch.empty((n0, 3), device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.nb_egno_workspace_floats(ctypes.byref(cfg), 1), device=dev, dtype=torch.float32)
+        check(lib.nb_egno_backward(ctypes.byref(cfg), _ptr(flat), _ptr(nodes), _ptr(edge_fea), _ptr(loc_mean),
+                                   _ptr(tsteps), _ptr(saved), _ptr(gx_out), _ptr(gv_out), _ptr(gh_out),
+                                   _ptr(grad_flat), _ptr(gx_in), _ptr(gv_in), _ptr(ws), _stream_ptr(dev)),
+              "nb_egno_backward")
+        _maybe_allreduce(grad_flat, ctx.dp_group)
+        grads, o = [], 0
+        for shp in ctx.param_shapes:
+            n = shp.numel()
+            grads.append(grad_flat[o:o + n].view(shp))
+            o += n
+        return (None, None, None, gx_in, None, None, gv_in, None, None, *grads)
+
+
+class SegnoFunction(torch.autograd.Function):
+    """x, h, v = SEGNO.forward_step(embedding(his), ...)   (reference: SEGNO/models/model.py:73,95-102)."""
+
+    @staticmethod
+    def forward(ctx, cfg_tuple, dp_group, flat, his, x, v, edge_attr, *params):
+        lib = load_library()
+        cfg = _cabi.NbSegnoConfig(*cfg_tuple)
+        dev = x.device
+        Nn = cfg.B * cfg.N
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x.requires_grad or v.requires_grad)
+        x_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
+        v_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
+        h_out = torch.empty((Nn, 64), device=dev, dtype=torch.float32)
+        saved = torch.empty(lib.nb_segno_saved_floats(ctypes.byref(cfg)), device=dev, dtype=torch.float32) if need_grad else None
+        ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 0), device=dev, dtype=torch.float32)
+        check(lib.nb_segno_forward(ctypes.byref(cfg), _ptr(flat), _ptr(his), _ptr(x), _ptr(v), _ptr(edge_attr),
+                                   _ptr(x_out), _ptr(h_out), _ptr(v_out), _ptr(saved), _ptr(ws), _stream_ptr(dev)),
+              "nb_segno_forward")
+        ctx.cfg_tuple = cfg_tuple
+        ctx.dp_group = dp_group
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.save_for_backward(flat, his, edge_attr, saved)
+        return x_out, h_out, v_out
+
+    @staticmethod
+    def backward(ctx, gx_out, gh_out, gv_out):
+        lib = load_library()
+        flat, his, edge_attr, saved = ctx.saved_tensors
+        if saved is None:
+            raise RuntimeError("SEGNO forward ran without autograd state; cannot run backward")
+        cfg = _cabi.NbSegnoConfig(*ctx.cfg_tuple)
+        dev = flat.device
+        Nn = cfg.B * cfg.N
+        gx_out = None if gx_out is None else gx_out.contiguous()
+        gv_out = None if gv_out is None else gv_out.contiguous()
+        gh_out = None if gh_out is None else gh_out.contiguous()
+        grad_flat = torch.empty_like(flat)
+        gx_in = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
+        gv_in = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 1), device=dev, dtype=torch.float32)
+        check(lib.nb_segno_backward(ctypes.byref(cfg), _ptr(flat), _ptr(his), _ptr(edge_attr), _ptr(saved),
+                                    _ptr(gx_out), _ptr(gh_out), _ptr(gv_out), _ptr(grad_flat), _ptr(gx_in),
+                                    _ptr(gv_in), _ptr(ws), _stream_ptr(dev)), "nb_segno_backward")
+        _maybe_allreduce(grad_flat, ctx.dp_group)
+        grads, o = [], 0
+        for shp in ctx.param_shapes:
+            n = shp.numel()
+            grads.append(grad_flat[o:o + n].view(shp))
+            o += n
+        return (None, None, None, None, gx_in, gv_in, None, *grads)
+
+
+class _EdgeCache:
+    """Validates `edge_index` against the canonical fully connected list once per distinct tensor
+    (key: storage address, length, version).  Non-canonical graphs raise: the kernels reduce each
+    receiver's N-1 contiguous edge rows and have no general scatter path."""
+
+    def __init__(self):
+        self._ok = {}
+
+    def validate(self, edge_index, B: int, N: int, device: torch.device) -> None:
+        row, col = edge_index[0], edge_index[1]
+        E = B * N * (N - 1)
+        if row.dim() != 1 or row.numel() != E or col.numel() != E:
+            raise ValueError(f"edge_index must hold B*N*(N-1) = {E} edges of a fully connected graph; got {row.numel()}")
+        key = (row.data_ptr(), col.data_ptr(), E, B, N, row._version, col._version, str(row.device))
+        if self._ok.get(key):
+            return
+        if row.dtype != torch.int64 or col.dtype != torch.int64:
+            raise ValueError("edge_index must be int64")
+        if row.is_cuda:
+            lib = load_library()
+            flag = torch.zeros(1, device=row.device, dtype=torch.int32)
+            check(lib.nb_check_canonical_edges(_ptr(row.contiguous()), _ptr(col.contiguous()), E, B, N, _ptr(flag),
+                                               _stream_ptr(row.device)), "nb_check_canonical_edges")
+            bad = int(flag.item())
+        else:  # index tensors kept on the host by the caller (SEGNO/train_nbody.py:76-78): check them there
+            e = torch.arange(E)
+            b, rem = e // (N * (N - 1)), e % (N * (N - 1))
+            i, jj = rem // (N - 1), rem % (N - 1)
+            j = jj + (jj >= i).long()
+            mism = (row != b * N + i) | (col != b * N + j)
+            bad = int(mism.nonzero()[0].item()) + 1 if bool(mism.any()) else 0
+        if bad:
+            raise ValueError(f"edge_index is not the canonical fully connected list (first mismatch at edge {bad - 1}); "
+                             "only `for i: for j != i` graphs offset by N*b are supported")
+        if len(self._ok) > 64:
+            self._ok.clear()
+        self._ok[key] = True
