@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the EGNO / SEGNO hot path on B200 (BASELINE.json metric: trajectories/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU implementation (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU (weak scaling: B per GPU fixed)
+
+A "step" is one training pass (forward + MSE loss + backward + Adam) of the 20-body EGNO (BASELINE.json
+configs[2]: N=20, num_timesteps=10, hidden 64, 4 layers) over one batch of B=256 synthetic trajectories
+(main.py:32 default batch) per GPU.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train trajectories/s (EGNO 20-body, fwd+bwd+Adam)"
+UNIT = "trajectories/s"
+
+# per-edge MACs of the reference formulas: phi_e = 131*64 + 64*64, phi_x = 64*64 + 64
+MAC_EDGE_REF = 131 * 64 + 64 * 64 + 64 * 64 + 64
+# MACs the fused edge kernel itself executes per edge (first layer's h-part runs per node, outside it)
+MAC_EDGE_KERNEL = 64 * 64 + 64 * 64 + 64 + 3 * 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="trajectories per GPU per step")
+    ap.add_argument("--n-balls", type=int, default=20)
+    ap.add_argument("--timesteps", type=int, default=10)
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=32, help="trajectories per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SEGNO / inference side numbers")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_arm(args, steps, warmup, sample):
+    """The reference's CPU implementation of the path: the oracle port (oracle/nbody_oracle.py, pinned to the
+    reference by golden vectors; /root/reference itself is not on the GPU box) with all host threads."""
+    from oracle import nbody_oracle as O
+    import no_node_comparison_b200 as nb
+    from no_node_comparison_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N, T, L = args.n_balls, args.timesteps, args.layers
+    torch.manual_seed(1)
+    holder = nb.EGNO(n_layers=L, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T,
+                     device="cpu")
+    p = {k: t.detach().clone().requires_grad_(True) for k, t in holder.state_dict().items()}
+    opt = torch.optim.Adam(list(p.values()), lr=1e-4, weight_decay=1e-8)
+    s = synth.sample_state("charged", sample, N, seed=0)
+    row, col = synth.canonical_edges(sample, N)
+    x, nodes, ea, v, lm = synth.egno_features(s["loc"], s["vel"], s["charges"], row, col)
+    t_out = torch.arange(1, T + 1)[None].repeat(sample, 1)
+    target = x.repeat(T, 1) + 0.05 * torch.randn(T * sample * N, 3, generator=torch.Generator().manual_seed(1))
+
+    def step():
+        opt.zero_grad()
+        xo, _, _ = O.egno_forward(p, x, nodes, row, col, ea, v, lm, t_out, n_layers=L, num_timesteps=T)
+        loss = ((xo - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": sample * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {sample} trajectories (N={N}, T={T}, L={L}) fwd+bwd+Adam, torch CPU fp32, "
+                      f"{cores} threads, {warmup} warm-up", "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 2))
+    cb = cpu_reference_arm(args, steps, warmup, args.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, per_step=args.cpu_sample, note="CPU reference arm: bounded sample per step"),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, per_step=None, note=None):
+    c = {"workload": f"EGNO charged N-body, {args.n_balls} particles, num_timesteps={args.timesteps}, hidden 64, "
+                     f"{args.layers} layers (BASELINE.json configs[2])",
+         "batch_per_gpu": per_step if per_step is not None else args.batch, "n_balls": args.n_balls,
+         "num_timesteps": args.timesteps, "n_layers": args.layers, "parallelism": f"dp{args.gpus}",
+         "cache": "per-step activation working set (~270 MB at B=256) exceeds the 126 MB L2; inputs rotate over "
+                  "8 distinct batches"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import no_node_comparison_b200 as nb
+    from no_node_comparison_b200 import synth
+    from no_node_comparison_b200.dataparallel import init_from_env, broadcast_parameters
+    import torch.distributed as dist
+    import ctypes
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    rank, local, world = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = nb.load_library()
+    N, T, L, B = args.n_balls, args.timesteps, args.layers, args.batch
+    K, W = args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(1)
+    model = nb.EGNO(n_layers=L, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T,
+                    device=dev)
+    if world > 1:
+        broadcast_parameters(model)
+        model.enable_data_parallel()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8)   # model_confs.yaml:15-17
+
+    # ---- synthetic data: NB distinct batches per rank, raw states in pinned host memory
+    NBATCH = 8
+    row, col = synth.canonical_edges(B, N)
+    row_d, col_d = row.to(dev), col.to(dev)
+    edges = [row_d, col_d]
+    t_out = torch.arange(1, T + 1, device=dev)[None].repeat(B, 1)
+    host, resident = [], []
+    for i in range(NBATCH):
+        s = synth.sample_state("charged", B, N, seed=1000 * rank + i)
+        tgt = (s["loc"].reshape(1, B * N, 3) + 0.05 * torch.randn(T, B * N, 3, generator=torch.Generator().manual_seed(i))
+               ).reshape(T * B * N, 3)
+        hb = {k: v.contiguous().pin_memory() for k, v in dict(loc=s["loc"], vel=s["vel"], charges=s["charges"], target=tgt).items()}
+        host.append(hb)
+        x, nodes, ea, v, lm = synth.egno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), row_d, col_d)
+        resident.append(dict(x=x, nodes=nodes, ea=ea, v=v, lm=lm, target=tgt.to(dev)))
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0].values())
+
+    def train_step(b):
+        opt.zero_grad(set_to_none=True)
+        xo, vo, ho = model(b["x"], b["nodes"], edges, b["ea"], v=b["v"], loc_mean=b["lm"], timesteps_out=t_out)
+        loss = ((xo - b["target"]) ** 2).mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def e2e_step(hb):
+        d = {k: t.to(dev, non_blocking=True) for k, t in hb.items()}                  # H2D from pinned memory
+        x, nodes, ea, v, lm = synth.egno_features(d["loc"], d["vel"], d["charges"], row_d, col_d)  # prepare_inputs
+        loss = train_step(dict(x=x, nodes=nodes, ea=ea, v=v, lm=lm, target=d["target"]))
+        return loss.item()                                                             # D2H read of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for i in range(W):
+        train_step(resident[i % NBATCH])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.nb_launch_count()
+    ms = timed(lambda i: train_step(resident[i % NBATCH]), K)
+    launches = lib.nb_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end: host buffers in, loss out, through the module API
+    for i in range(2):
+        e2e_step(host[i % NBATCH])
+    ms_e2e = timed(lambda i: e2e_step(host[i % NBATCH]), K)
+    e2e_value = world * B * K / (ms_e2e / 1e3)
+
+    # ---- per-kernel CUDA-event timing (separate pass so the events do not perturb `value`)
+    lib.nb_profile_enable(1)
+    ms_prof = timed(lambda i: train_step(resident[i % NBATCH]), K)
+    pm = (ctypes.c_double * 4)()
+    pc = (ctypes.c_longlong * 4)()
+    lib.nb_profile_read(pm, pc)
+    lib.nb_profile_enable(0)
+    cats = ["edge_fwd", "edge_bwd", "gemm64", "wgrad64"]
+    kern = {c: {"ms_total": pm[i], "launches": int(pc[i]), "ms_per_launch": (pm[i] / pc[i]) if pc[i] else None,
+                "share_of_step": pm[i] / ms_prof if ms_prof else None} for i, c in enumerate(cats)}
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        pk = json.load(open(peaks_path))
+        peak_tf, peak_src = float(pk["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        hbm = float(pk["hbm_gbs"])
+    else:
+        peak_tf, peak_src, hbm = 1400.0, "fallback (B200_PROFILING.md sustained bf16)", 6650.0
+    ne = T * B * N * (N - 1)
+    t_bwd = kern["edge_bwd"]["ms_per_launch"]
+    flop_kernel = 2 * 2 * MAC_EDGE_KERNEL * ne           # backward = 2 x forward; recompute is not credited
+    achieved = flop_kernel / (t_bwd * 1e-3) / 1e12 if t_bwd else None
+    roofline = {"kernel": "k_edge_bwd (fused E_GCL edge tile backward, fp32 SIMT in this round)", "bound": "tensor",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+                "peak_source": peak_src, "traffic": None,
+                "flop_per_launch": flop_kernel, "flop_per_launch_reference_formula": 2 * 2 * MAC_EDGE_REF * ne,
+                "note": "achieved counts the MACs the edge kernel owns (8448/edge fwd, x2 for bwd); the reference's dense "
+                        "131-wide first layer would count 16640/edge. fp32 FFMA peak of B200 is ~70 TFLOP/s; the tensor "
+                        "peak is the bf16 figure the tcgen05 port of these tiles is measured against.",
+                "hbm_peak_gbs": hbm}
+
+    extras = {}
+    if not args.no_extras:
+        # inference throughput (no_grad forward) of the same model
+        with torch.no_grad():
+            f = lambda i: model(resident[i % NBATCH]["x"], resident[i % NBATCH]["nodes"], edges, resident[i % NBATCH]["ea"],
+                                v=resident[i % NBATCH]["v"], loc_mean=resident[i % NBATCH]["lm"], timesteps_out=t_out)
+            for i in range(3):
+                f(i)
+            ms_inf = timed(f, K)
+        extras["egno_infer_traj_per_s"] = world * B * K / (ms_inf / 1e3)
+        # SEGNO, BASELINE.json configs[3] shape (N=20, T=10, B=256): train step and forward
+        torch.manual_seed(1)
+        seg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=dev, n_layers=8, recurrent=True)
+        if world > 1:
+            broadcast_parameters(seg)
+            seg.enable_data_parallel()
+        sopt = torch.optim.Adam(seg.parameters(), lr=5e-3, weight_decay=1e-12)
+        sb = []
+        for i in range(NBATCH):
+            s = synth.sample_state("gravity", B, N, seed=77 + 1000 * rank + i)
+            his, x, v, ea = synth.segno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), row_d, col_d)
+            sb.append(dict(his=his, x=x, v=v, ea=ea, target=x + 0.05 * torch.randn_like(x)))
+
+        def seg_step(i):
+            b = sb[i % NBATCH]
+            sopt.zero_grad(set_to_none=True)
+            xo, ho, vo = seg(b["his"], b["x"], edges, b["v"], b["ea"], T=T)
+            ((xo - b["target"]) ** 2).mean().backward()
+            sopt.step()
+
+        for i in range(3):
+            seg_step(i)
+        ms_seg = timed(seg_step, K)
+        extras["segno_train_traj_per_s"] = world * B * K / (ms_seg / 1e3)
+        with torch.no_grad():
+            g = lambda i: seg(sb[i % NBATCH]["his"], sb[i % NBATCH]["x"], edges, sb[i % NBATCH]["v"], sb[i % NBATCH]["ea"], T=T)
+            for i in range(3):
+                g(i)
+            ms_sinf = timed(g, K)
+        extras["segno_infer_traj_per_s"] = world * B * K / (ms_sinf / 1e3)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_arm(args, steps=8, warmup=1, sample=args.cpu_sample)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "kernels": kern, "extras": extras}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

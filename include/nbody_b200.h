@@ -147,6 +147,23 @@ int nb_egcl_edge_forward(int32_t n_gt, int32_t B, int32_t N, int32_t n_edge_fea,
  * Inputs gM[nodes,H], gFsum[nodes,3]; outputs gP, gQ [nodes,H] (overwritten), gx[nodes,3] (ACCUMULATED into),
  * and weight gradients written/accumulated into a slice laid out as the parameter buffer (see .cu). */
 int64_t nb_egcl_edge_backward_workspace_floats(int32_t n_gt, int32_t N);
+/* gw (output, overwritten): [gW2 64x64 | gW3 64x64 | gb2 64 | gb3 64 | gw4 64 | G1[64][1+n_edge_fea] | gb4 1] where
+ * G1[c][0] is the gradient of w_rad[c] and G1[c][1+f] that of w_ef[f][c]. */
+int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t n_edge_fea, int32_t clamp_per_edge,
+                          const float* x, const float* P, const float* Q, const float* edge_fea, const float* w1,
+                          int32_t ldw1, int32_t col_rad, int32_t col_ef, const float* W2, const float* b2,
+                          const float* W3, const float* b3, const float* w4, const float* b4, const float* gM,
+                          const float* gFsum, float* gP, float* gQ, float* gx, float* gw, float* workspace,
+                          void* stream);
+
+/* --- accounting --------------------------------------------------------------------------------- */
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long nb_launch_count(void);
+/* CUDA-event timing of the dominant kernels on their launch stream: categories
+ * 0 = edge tile forward, 1 = edge tile backward, 2 = gemm64, 3 = wgrad64.  enable(1) resets the counters;
+ * read() synchronises the recorded events and returns total milliseconds and launch counts per category. */
+int nb_profile_enable(int enable);
+int nb_profile_read(double* ms /*[4]*/, long long* counts /*[4]*/);
 
 #ifdef __cplusplus
 }

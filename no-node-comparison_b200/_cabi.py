@@ -33,6 +33,10 @@ EXPORTS = {
     "nb_check_canonical_edges": (C.c_int, [c_f, c_f, C.c_int64, C.c_int32, C.c_int32, c_f, c_f]),
     "nb_egcl_edge_forward": (C.c_int, [C.c_int32] * 5 + [c_f] * 5 + [C.c_int32] * 3 + [c_f] * 9),
     "nb_egcl_edge_backward_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "nb_egcl_edge_backward": (C.c_int, [C.c_int32] * 5 + [c_f] * 5 + [C.c_int32] * 3 + [c_f] * 14),
+    "nb_launch_count": (C.c_longlong, []),
+    "nb_profile_enable": (C.c_int, [C.c_int]),
+    "nb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
 }
 
 

@@ -10,6 +10,14 @@
 #include "nb_spectral.cuh"
 #include "nb_edge.cuh"
 
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+#define NB_LAUNCH_COUNTED(...) \
+  do {                         \
+    ++g_launches_ref();        \
+    NB_LAUNCH(__VA_ARGS__);    \
+  } while (0)
+static long long& g_launches_ref();
+
 // ============================================================================= errors / device info
 static thread_local char g_err[512] = "";
 
@@ -44,6 +52,66 @@ int nb_num_sms() {
 #endif
 }
 
+// ---- launch accounting and optional per-kernel CUDA-event timing (used by bench.py for the roofline)
+static long long g_launches = 0;
+static long long& g_launches_ref() { return g_launches; }
+#define NB_PROF_CATS 4  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64 */
+#define NB_PROF_MAX 8192
+#ifndef NB_EMU
+static int g_prof_on = 0;
+static cudaEvent_t g_prof_ev[NB_PROF_CATS][NB_PROF_MAX][2];
+static int g_prof_made[NB_PROF_CATS] = {0, 0, 0, 0};
+static int g_prof_n[NB_PROF_CATS] = {0, 0, 0, 0};
+static int prof_begin(int cat, void* st) {
+  if (!g_prof_on || g_prof_n[cat] >= NB_PROF_MAX) return -1;
+  int i = g_prof_n[cat];
+  if (i >= g_prof_made[cat]) {
+    cudaEventCreate(&g_prof_ev[cat][i][0]);
+    cudaEventCreate(&g_prof_ev[cat][i][1]);
+    g_prof_made[cat] = i + 1;
+  }
+  cudaEventRecord(g_prof_ev[cat][i][0], (cudaStream_t)st);
+  return i;
+}
+static void prof_end(int cat, int i, void* st) {
+  if (i < 0) return;
+  cudaEventRecord(g_prof_ev[cat][i][1], (cudaStream_t)st);
+  g_prof_n[cat] = i + 1;
+}
+#else
+static int prof_begin(int, void*) { return -1; }
+static void prof_end(int, int, void*) {}
+#endif
+
+extern "C" long long nb_launch_count(void) { return g_launches; }
+
+// enable != 0: start timing the dominant kernels with CUDA events on their launch stream (counters reset)
+extern "C" int nb_profile_enable(int enable) {
+#ifndef NB_EMU
+  g_prof_on = enable;
+  for (int c = 0; c < NB_PROF_CATS; ++c) g_prof_n[c] = 0;
+#else
+  (void)enable;
+#endif
+  return NB_OK;
+}
+
+// total milliseconds and launch counts per category since nb_profile_enable(1); synchronises the events
+extern "C" int nb_profile_read(double* ms, long long* counts) {
+  for (int c = 0; c < NB_PROF_CATS; ++c) { ms[c] = 0.0; counts[c] = 0; }
+#ifndef NB_EMU
+  for (int c = 0; c < NB_PROF_CATS; ++c) {
+    for (int i = 0; i < g_prof_n[c]; ++i) {
+      float t = 0.f;
+      cudaEventSynchronize(g_prof_ev[c][i][1]);
+      if (cudaEventElapsedTime(&t, g_prof_ev[c][i][0], g_prof_ev[c][i][1]) == cudaSuccess) ms[c] += t;
+    }
+    counts[c] = g_prof_n[c];
+  }
+#endif
+  return nb_check_launch("nb_profile_read");
+}
+
 extern "C" int nb_version(void) { return 1; }
 extern "C" const char* nb_last_error(void) { return g_err; }
 
@@ -66,7 +134,9 @@ static int launch_gemm(const NbGemmArgs& a, void* st) {
   if (a.rows <= 0) return NB_OK;
   const size_t smem = (NB_TILE * NB_LDA + NB_H * NB_H) * sizeof(float);
   NB_SET_SMEM(k_gemm64, smem);
-  NB_LAUNCH(k_gemm64, (unsigned)cdiv(a.rows, NB_TILE), NB_THREADS, smem, st, a);
+  int pi = prof_begin(2, st);
+  NB_LAUNCH_COUNTED(k_gemm64, (unsigned)cdiv(a.rows, NB_TILE), NB_THREADS, smem, st, a);
+  prof_end(2, pi, st);
   return nb_check_launch("k_gemm64");
 }
 
@@ -88,7 +158,7 @@ static int launch_finalize(NbFinArgs& f, void* st) {
   int total = 0;
   for (int s = 0; s < f.nseg; ++s) total += f.seg[s].count;
   f.total = total;
-  NB_LAUNCH(k_finalize, (unsigned)cdiv(total, 256), 256, 0, st, f);
+  NB_LAUNCH_COUNTED(k_finalize, (unsigned)cdiv(total, 256), 256, 0, st, f);
   return nb_check_launch("k_finalize");
 }
 
@@ -108,7 +178,9 @@ static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* 
   int grid = imin(cdiv(rows, NB_TILE), wgrad_grid_cap());
   const size_t smem = 2 * NB_TILE * NB_LDA * sizeof(float);
   NB_SET_SMEM(k_wgrad64, smem);
-  NB_LAUNCH(k_wgrad64, (unsigned)grid, NB_THREADS, smem, st, a);
+  int pi = prof_begin(3, st);
+  NB_LAUNCH_COUNTED(k_wgrad64, (unsigned)grid, NB_THREADS, smem, st, a);
+  prof_end(3, pi, st);
   NB_TRY(nb_check_launch("k_wgrad64"));
   NbFinArgs f;
   memset(&f, 0, sizeof(f));
@@ -144,7 +216,9 @@ static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
   const size_t smem = NB_EDGE_FWD_SMEM_FLOATS * sizeof(float);
   NB_SET_SMEM(k_edge_fwd, smem);
   int grid = imin(a.g.n_units, 3 * nb_num_sms());
-  NB_LAUNCH(k_edge_fwd, (unsigned)grid, NB_THREADS, smem, st, a);
+  int pi = prof_begin(0, st);
+  NB_LAUNCH_COUNTED(k_edge_fwd, (unsigned)grid, NB_THREADS, smem, st, a);
+  prof_end(0, pi, st);
   return nb_check_launch("k_edge_fwd");
 }
 
@@ -160,7 +234,9 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* partial, float* dst, const E
   NB_SET_SMEM(k_edge_bwd, smem);
   int grid = imin(a.g.n_units, edge_bwd_grid_cap());
   a.partial = partial;
-  NB_LAUNCH(k_edge_bwd, (unsigned)grid, NB_THREADS, smem, st, a);
+  int pi = prof_begin(1, st);
+  NB_LAUNCH_COUNTED(k_edge_bwd, (unsigned)grid, NB_THREADS, smem, st, a);
+  prof_end(1, pi, st);
   NB_TRY(nb_check_launch("k_edge_bwd"));
   NbFinArgs f;
   memset(&f, 0, sizeof(f));
@@ -410,10 +486,10 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       e.freq[k] = expf((float)k * -sc);
     }
     const size_t smem = ((size_t)X.lo.F * NB_H + 4 * X.lo.F) * sizeof(float);
-    NB_LAUNCH(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
+    NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
     NB_TRY(nb_check_launch("k_embed_fwd"));
-    NB_LAUNCH(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, x, b0.x0, (int)(Nn0 * 3), T);
-    NB_LAUNCH(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, v, b0.v0, (int)(Nn0 * 3), T);
+    NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, x, b0.x0, (int)(Nn0 * 3), T);
+    NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, v, b0.v0, (int)(Nn0 * 3), T);
     NB_TRY(nb_check_launch("k_replicate3"));
   }
 
@@ -427,18 +503,18 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       // h <- h + LeakyReLU(conv(h))      (layer_no.py:96-126)
       NbDftArgs d = dft_args(X);
       d.x = b.h0; d.coef = coef;
-      NB_LAUNCH(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+      NB_LAUNCH_COUNTED(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
       NB_TRY(nb_check_launch("k_dft_fwd"));
       NB_TRY(egno_tc_mix(X, l, coef, ycoef));
       d.ycoef = ycoef; d.out = h1;
-      NB_LAUNCH(k_idft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+      NB_LAUNCH_COUNTED(k_idft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
       NB_TRY(nb_check_launch("k_idft_fwd"));
       // (x - mean, v) <- (x - mean, v) + conv(.)     (egno.py:103-108, layer_no.py:151-178)
       NbTcxArgs t;
       memset(&t, 0, sizeof(t));
       t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
       t.x1 = x1; t.v1 = v1;
-      NB_LAUNCH(k_tcx_fwd, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, t);
+      NB_LAUNCH_COUNTED(k_tcx_fwd, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, t);
       NB_TRY(nb_check_launch("k_tcx_fwd"));
     } else {
       h1 = b.h0; x1 = b.x0;
@@ -472,7 +548,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       memset(&xa, 0, sizeof(xa));
       xa.rows = Nn; xa.N = cfg->N; xa.x = x1; xa.v = v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
       xa.Fsum = b.Fsum; xa.x_out = x_next;
-      NB_LAUNCH(k_egno_xupd_fwd, (unsigned)imin(cdiv(Nn, 8), 8 * nb_num_sms()), 256, 0, stream, xa);
+      NB_LAUNCH_COUNTED(k_egno_xupd_fwd, (unsigned)imin(cdiv(Nn, 8), 8 * nb_num_sms()), 256, 0, stream, xa);
       NB_TRY(nb_check_launch("k_egno_xupd_fwd"));
     }
     v_prev = v1;
@@ -537,7 +613,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       xa.rows = Nn; xa.N = cfg->N; xa.v = b.v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
       xa.Fsum = b.Fsum; xa.gx = gx; xa.gv = gv_in; xa.gv_out = gvB; xa.gFsum = gFsum; xa.GUV = GUV; xa.partial = partial;
       int grid = imin(cdiv(Nn, 8), 4 * nb_num_sms());
-      NB_LAUNCH(k_egno_xupd_bwd, (unsigned)grid, 256, 0, stream, xa);
+      NB_LAUNCH_COUNTED(k_egno_xupd_bwd, (unsigned)grid, 256, 0, stream, xa);
       NB_TRY(nb_check_launch("k_egno_xupd_bwd"));
       NbFinArgs f;
       memset(&f, 0, sizeof(f));
@@ -606,7 +682,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
         t.gx1 = gx; t.gv1 = gvB; t.gx0 = gx0; t.gv0 = gvA; t.partial = partial;
         int grid = imin(cdiv(Nn0 * 3, 256), 2 * nb_num_sms());
-        NB_LAUNCH(k_tcx_bwd, (unsigned)grid, 256, 0, stream, t);
+        NB_LAUNCH_COUNTED(k_tcx_bwd, (unsigned)grid, 256, 0, stream, t);
         NB_TRY(nb_check_launch("k_tcx_bwd"));
         NbFinArgs f;
         memset(&f, 0, sizeof(f));
@@ -620,11 +696,11 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       {
         NbDftArgs d = dft_args(X);
         d.x = b.h0; d.coef = coef;
-        NB_LAUNCH(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_LAUNCH_COUNTED(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
         NB_TRY(nb_check_launch("k_dft_fwd"));
         NB_TRY(egno_tc_mix(X, l, coef, ycoef));
         d.ycoef = ycoef; d.gout = ghA; d.gycoef = gycoef;
-        NB_LAUNCH(k_idft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_LAUNCH_COUNTED(k_idft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
         NB_TRY(nb_check_launch("k_idft_bwd"));
         const float* W = params + L.tc;
         const int64_t plane = Nn0 * NB_H;
@@ -663,7 +739,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
           }
         }
         d.gcoef = gcoef; d.gx = ghB;
-        NB_LAUNCH(k_dft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_LAUNCH_COUNTED(k_dft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
         NB_TRY(nb_check_launch("k_dft_bwd"));
       }
       gh_in = ghB;
@@ -691,7 +767,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     const int F = X.lo.F;
     int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
     const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
-    NB_LAUNCH(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
+    NB_LAUNCH_COUNTED(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
     NB_TRY(nb_check_launch("k_embed_bwd"));
     NbFinArgs f;
     memset(&f, 0, sizeof(f));
@@ -700,8 +776,8 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     f.seg[1] = fseg(NB_H * F, NB_H, NB_H, X.lo.emb_b, 0, 1);
     NB_TRY(launch_finalize(f, stream));
   }
-  if (g_x_in) NB_LAUNCH(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T);
-  if (g_v_in) NB_LAUNCH(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T);
+  if (g_x_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T);
+  if (g_v_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T);
   return nb_check_launch("nb_egno_backward");
 }
 
@@ -830,7 +906,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
     segno_embed_args(X, his, &e);
     e.out = b0.h;
     const size_t smem = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
-    NB_LAUNCH(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
+    NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
     NB_TRY(nb_check_launch("k_embed_fwd"));
     cudaMemcpyAsync(b0.x, x, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
   }
@@ -850,7 +926,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
     memset(&ia, 0, sizeof(ia));
     ia.n3 = Nn * 3; ia.N = cfg->N; ia.inv_T = (float)(1.0 / (double)T); ia.cw = cfg->coords_weight;
     ia.x = b.x; ia.v = vcur; ia.Fsum = Fsum; ia.x_out = x_next; ia.v_out = v_next;
-    NB_LAUNCH(k_segno_integ_fwd, (unsigned)ew_grid(Nn * 3), 256, 0, stream, ia);
+    NB_LAUNCH_COUNTED(k_segno_integ_fwd, (unsigned)ew_grid(Nn * 3), 256, 0, stream, ia);
     NB_TRY(nb_check_launch("k_segno_integ_fwd"));
     NbGemmArgs a = gemm_args((int)Nn);  // U5 = [h, M] W5^T + b5      (gcl.py:89-92)
     a.nsrc = 2;
@@ -930,7 +1006,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     memset(&ia, 0, sizeof(ia));
     ia.n3 = Nn * 3; ia.N = cfg->N; ia.inv_T = (float)(1.0 / (double)T); ia.cw = cfg->coords_weight;
     ia.gx = gx; ia.gv = gv_in; ia.gx_out = gx; ia.gv_out = gvb[gvi]; ia.gFsum = gFsum;
-    NB_LAUNCH(k_segno_integ_bwd, (unsigned)ew_grid(Nn * 3), 256, 0, stream, ia);
+    NB_LAUNCH_COUNTED(k_segno_integ_bwd, (unsigned)ew_grid(Nn * 3), 256, 0, stream, ia);
     NB_TRY(nb_check_launch("k_segno_integ_bwd"));
     gv_in = gvb[gvi];
     gvi ^= 1;
@@ -966,7 +1042,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     const int F = cfg->in_node_nf;
     int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
     const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
-    NB_LAUNCH(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
+    NB_LAUNCH_COUNTED(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
     NB_TRY(nb_check_launch("k_embed_bwd"));
     NbFinArgs f;
     memset(&f, 0, sizeof(f));
@@ -991,7 +1067,7 @@ extern "C" int nb_check_canonical_edges(const int64_t* row, const int64_t* col, 
     return NB_ERR_INVALID;
   }
   cudaMemsetAsync(flag_dev, 0, sizeof(int32_t), (cudaStream_t)stream);
-  NB_LAUNCH(k_check_edges, (unsigned)ew_grid(n_edges), 256, 0, stream, row, col, n_edges, (int)B, (int)N, (int*)flag_dev);
+  NB_LAUNCH_COUNTED(k_check_edges, (unsigned)ew_grid(n_edges), 256, 0, stream, row, col, n_edges, (int)B, (int)N, (int*)flag_dev);
   return nb_check_launch("k_check_edges");
 }
 
@@ -1015,4 +1091,29 @@ extern "C" int nb_egcl_edge_forward(int32_t n_gt, int32_t B, int32_t N, int32_t 
 extern "C" int64_t nb_egcl_edge_backward_workspace_floats(int32_t n_gt, int32_t N) {
   (void)n_gt; (void)N;
   return NB_PARTIAL_FLOATS;
+}
+
+extern "C" int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t n_edge_fea, int32_t clamp_per_edge,
+                                     const float* x, const float* P, const float* Q, const float* edge_fea,
+                                     const float* w1, int32_t ldw1, int32_t col_rad, int32_t col_ef, const float* W2,
+                                     const float* b2, const float* W3, const float* b3, const float* w4, const float* b4,
+                                     const float* gM, const float* gFsum, float* gP, float* gQ, float* gx,
+                                     float* gw, float* workspace, void* stream) {
+  if (N < 2 || N > NB_MAX_NODES || n_edge_fea < 0 || n_edge_fea > NB_MAX_EDGE_FEA || n_gt < 1 || B < 1) {
+    nb_set_error("nb_egcl_edge_backward: unsupported shape");
+    return NB_ERR_INVALID;
+  }
+  NbEdgeBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = edge_geom(n_gt, B, N, n_edge_fea, clamp_per_edge);
+  a.w.W1 = w1; a.w.ldw1 = ldw1; a.w.col_rad = col_rad; a.w.col_ef = col_ef;
+  a.w.W2 = W2; a.w.b2 = b2; a.w.W3 = W3; a.w.b3 = b3; a.w.w4 = w4; a.w.b4 = b4;
+  a.x = x; a.P = P; a.Q = Q; a.ef = edge_fea; a.gM = gM; a.gFsum = gFsum; a.gP = gP; a.gQ = gQ; a.gx = gx;
+  // gw layout: [gW2 64x64 | gW3 64x64 | gb2 | gb3 | gw4 | gw_rad | gw_ef[n_edge_fea][64] | gb4]
+  EdgeGradDst d;
+  d.w1 = 2 * NB_H * NB_H + 3 * NB_H;  // gw_rad at w1 + col_rad (0), gw_ef at w1 + col_ef + f + c*ldw1
+  d.W2 = 0; d.W3 = NB_H * NB_H; d.b2 = 2 * NB_H * NB_H; d.b3 = d.b2 + NB_H; d.w4 = d.b3 + NB_H;
+  d.ldw1 = 1 + n_edge_fea; d.col_rad = 0; d.col_ef = 1; d.b_unused = 0;
+  d.b4 = d.w1 + (int64_t)NB_H * d.ldw1;
+  return launch_edge_bwd(a, workspace, gw, d, 0, stream);
 }

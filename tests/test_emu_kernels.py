@@ -1,0 +1,124 @@
+"""Kernel logic on the CPU: the *same* csrc/*.cu sources compiled for the host CUDA emulator
+(tests/emu) must reproduce the reference's golden outputs and gradients, and the oracle on edge cases.
+This is test infrastructure — the product library is the nvcc build and has no CPU path."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nbody_oracle as O
+from tests import emu_harness as E
+from tests.helpers import load_case, egno_inputs_from_case, segno_inputs_from_case, rel_err
+
+TOL = 2e-5  # fp32 kernels vs fp32 reference: summation-order noise only
+
+
+def _check_grads(r, w, g, order):
+    off = 0
+    for k in order:
+        n = w[k].numel()
+        got = torch.tensor(r["grad_params"][off:off + n]).view_as(w[k])
+        assert rel_err(got, g[k]) < TOL, k
+        off += n
+    assert off == r["grad_params"].size
+
+
+@pytest.mark.parametrize("name", ["egno_n5_t8", "egno_n5_t6_m4", "egno_n7_t10_m5"])
+def test_egno_emulated_kernels_match_reference_golden(name):
+    d, w, g = load_case(name)
+    c = egno_inputs_from_case(d)
+    order = list(w.keys())
+    params = E.flat_params({k: v.numpy() for k, v in w.items()}, order)
+    cfg = dict(B=c["B"], N=c["n"], T=c["T"], n_layers=c["L"], num_modes=c["modes"], in_node_nf=2, in_edge_nf=2,
+               time_emb_dim=32, use_time_conv=1)
+    r = E.egno_run(cfg, params, c["x"].numpy(), c["nodes"].numpy(), c["edge_attr"].numpy(), c["v"].numpy(),
+                   c["loc_mean"].numpy(), c["t_out"].numpy(), d["Gx"], d["Gv"], d["Gh"])
+    for k in ("x_out", "v_out", "h_out", "gx_in", "gv_in"):
+        assert rel_err(torch.tensor(r[k]), torch.tensor(d[k])) < TOL, k
+    _check_grads(r, w, g, order)
+
+
+@pytest.mark.parametrize("name", ["segno_n5_t10", "segno_n20_t10_gravity"])
+def test_segno_emulated_kernels_match_reference_golden(name):
+    d, w, g = load_case(name)
+    c = segno_inputs_from_case(d)
+    order = list(w.keys())
+    params = E.flat_params({k: v.numpy() for k, v in w.items()}, order)
+    cfg = dict(B=c["B"], N=c["n"], T=c["T"], in_node_nf=1, in_edge_nf=2, recurrent=1, coords_weight=1.0)
+    r = E.segno_run(cfg, params, c["his"].numpy(), c["x"].numpy(), c["v"].numpy(), c["edge_attr"].numpy(), d["Gx"],
+                    d["Gh"], d["Gv"])
+    for k in ("x_out", "v_out", "h_out", "gx_in", "gv_in"):
+        assert rel_err(torch.tensor(r[k]), torch.tensor(d[k])) < TOL, k
+    _check_grads(r, w, g, order)
+
+
+@pytest.mark.parametrize("B,N,T", [(1, 2, 3), (7, 3, 2), (3, 12, 2)])
+def test_segno_emulated_edge_shapes_vs_oracle(B, N, T):
+    """Ragged packing (units of several graphs, partial last unit), N=2, and tiles straddling receivers."""
+    _, w, _ = load_case("segno_n5_t10")
+    order = list(w.keys())
+    gen = torch.Generator().manual_seed(B * 100 + N)
+    # amplify phi_x's last layer (xavier gain 1e-3 in the reference) so the coordinate path is exercised
+    w = {k: v.clone() for k, v in w.items()}
+    w["module.coord_mlp.2.weight"] *= 300.0
+    loc = torch.randn(B, N, 3, generator=gen)
+    vel = torch.randn(B, N, 3, generator=gen) * 0.5
+    q = torch.randint(0, 2, (B, N, 1), generator=gen).float() * 2 - 1
+    row, col = O.canonical_edges(B, N)
+    his, x, v, ea = O.segno_features(loc, vel, q, row, col)
+    Gx, Gv, Gh = torch.randn(B * N, 3, generator=gen), torch.randn(B * N, 3, generator=gen), torch.randn(B * N, 64, generator=gen) * 0.1
+    p = {k: t.clone().requires_grad_(True) for k, t in w.items()}
+    xr, vr = x.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    xo, ho, vo = O.segno_forward(p, his, xr, row, col, vr, ea, T)
+    ((xo * Gx).sum() + (vo * Gv).sum() + (ho * Gh).sum()).backward()
+    params = E.flat_params({k: t.numpy() for k, t in w.items()}, order)
+    cfg = dict(B=B, N=N, T=T, in_node_nf=1, in_edge_nf=2, recurrent=1, coords_weight=1.0)
+    r = E.segno_run(cfg, params, his.numpy(), x.numpy(), v.numpy(), ea.numpy(), Gx.numpy(), Gh.numpy(), Gv.numpy())
+    assert rel_err(torch.tensor(r["x_out"]), xo.detach()) < TOL
+    assert rel_err(torch.tensor(r["h_out"]), ho.detach()) < TOL
+    assert rel_err(torch.tensor(r["v_out"]), vo.detach()) < TOL
+    assert rel_err(torch.tensor(r["gx_in"]), xr.grad) < TOL
+    assert rel_err(torch.tensor(r["gv_in"]), vr.grad) < TOL
+    g = {k: (p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])) for k in order}
+    _check_grads(r, w, g, order)
+
+
+def test_segno_per_edge_clamp_is_reproduced():
+    """rij * c beyond +-100 must be clamped per edge BEFORE the mean (gcl.py:100), forward and backward."""
+    _, w, _ = load_case("segno_n5_t10")
+    order = list(w.keys())
+    w = {k: v.clone() for k, v in w.items()}
+    w["module.coord_mlp.2.weight"] *= 3.0e5          # push |rij * c| past 100 for many edges
+    B, N, T = 2, 5, 2
+    gen = torch.Generator().manual_seed(5)
+    loc = torch.randn(B, N, 3, generator=gen) * 2
+    vel = torch.randn(B, N, 3, generator=gen) * 0.5
+    q = torch.randint(0, 2, (B, N, 1), generator=gen).float() * 2 - 1
+    row, col = O.canonical_edges(B, N)
+    his, x, v, ea = O.segno_features(loc, vel, q, row, col)
+    p = {k: t.clone().requires_grad_(True) for k, t in w.items()}
+    xr = x.clone().requires_grad_(True)
+    xo, ho, vo = O.segno_forward(p, his, xr, row, col, v, ea, T)
+    Gx = torch.randn(B * N, 3, generator=gen)
+    (xo * Gx).sum().backward()
+    params = E.flat_params({k: t.numpy() for k, t in w.items()}, order)
+    cfg = dict(B=B, N=N, T=T, in_node_nf=1, in_edge_nf=2, recurrent=1, coords_weight=1.0)
+    z3, z64 = np.zeros((B * N, 3), np.float32), np.zeros((B * N, 64), np.float32)
+    r = E.segno_run(cfg, params, his.numpy(), x.numpy(), v.numpy(), ea.numpy(), Gx.numpy(), z64, z3)
+    assert float(xo.detach().abs().max()) > 5.0       # the clamp really was active
+    assert rel_err(torch.tensor(r["x_out"]), xo.detach()) < TOL
+    assert rel_err(torch.tensor(r["gx_in"]), xr.grad) < 1e-4
+
+
+def test_edge_index_check_kernel():
+    import ctypes
+    L = E.lib()
+    B, N = 3, 4
+    row, col = O.canonical_edges(B, N)
+    row, col = row.numpy().copy(), col.numpy().copy()
+    flag = np.zeros(1, np.int32)
+    E.check(L.nb_check_canonical_edges(E.ptr(row), E.ptr(col), row.size, B, N, E.ptr(flag), None))
+    assert flag[0] == 0
+    col[7], col[8] = col[8], col[7]
+    E.check(L.nb_check_canonical_edges(E.ptr(row), E.ptr(col), row.size, B, N, E.ptr(flag), None))
+    assert flag[0] in (8, 9)
+    assert L.nb_check_canonical_edges(E.ptr(row), E.ptr(col), row.size - 1, B, N, E.ptr(flag), None) < 0

@@ -1,0 +1,346 @@
+"""Parity of the CUDA path (through the drop-in modules -> C ABI -> sm_100a kernels) against the golden
+vectors of the reference and against the oracle; plus size-independent properties at BASELINE sizes.
+
+Tolerances (fp32 everywhere; BASELINE.json: predicted positions rel. err <= 1e-4):
+  outputs   : max|a-b| / max|b| <= 1e-4   (observed ~1e-6: only summation order differs)
+  gradients : <= 1e-3                       (observed ~1e-5)
+"""
+import math
+
+import pytest
+import torch
+
+import no_node_comparison_b200 as nb
+from no_node_comparison_b200 import synth
+from oracle import nbody_oracle as O
+from tests.helpers import (EGNO_CASES, SEGNO_CASES, load_case, rel_err, egno_inputs_from_case, segno_inputs_from_case)
+
+pytestmark = pytest.mark.gpu
+TOL_OUT = 1e-4
+TOL_GRAD = 1e-3
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no fallback exists)"
+    return torch.device("cuda:0")
+
+
+def make_egno(c, w=None, seed=1):
+    torch.manual_seed(seed)
+    m = nb.EGNO(n_layers=c["L"], in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=c["modes"],
+                num_timesteps=c["T"], device=dev())
+    if w is not None:
+        m.load_state_dict(w)
+    return m
+
+
+def run_egno(m, c, requires_grad=True):
+    d = dev()
+    x = c["x"].to(d).requires_grad_(requires_grad)
+    v = c["v"].to(d).requires_grad_(requires_grad)
+    out = m(x, c["nodes"].to(d), [c["row"].to(d), c["col"].to(d)], c["edge_attr"].to(d), v=v,
+            loc_mean=c["loc_mean"].to(d), timesteps_out=c["t_out"].to(d))
+    return x, v, out
+
+
+@pytest.mark.parametrize("name", EGNO_CASES)
+def test_egno_matches_reference_golden(name):
+    dd, w, g = load_case(name)
+    c = egno_inputs_from_case(dd)
+    m = make_egno(c, w)
+    x, v, (xo, vo, ho) = run_egno(m, c)
+    assert rel_err(xo.cpu(), torch.tensor(dd["x_out"])) < TOL_OUT
+    assert rel_err(vo.cpu(), torch.tensor(dd["v_out"])) < TOL_OUT
+    assert rel_err(ho.cpu(), torch.tensor(dd["h_out"])) < TOL_OUT
+    d = dev()
+    loss = (xo * torch.tensor(dd["Gx"], device=d)).sum() + (vo * torch.tensor(dd["Gv"], device=d)).sum() + \
+        (ho * torch.tensor(dd["Gh"], device=d)).sum()
+    loss.backward()
+    assert rel_err(x.grad.cpu(), torch.tensor(dd["gx_in"])) < TOL_GRAD
+    assert rel_err(v.grad.cpu(), torch.tensor(dd["gv_in"])) < TOL_GRAD
+    for k, p in m.named_parameters():
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g[k])
+        assert rel_err(got, g[k]) < TOL_GRAD, k
+
+
+@pytest.mark.parametrize("name", SEGNO_CASES)
+def test_segno_matches_reference_golden(name):
+    dd, w, g = load_case(name)
+    c = segno_inputs_from_case(dd)
+    d = dev()
+    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
+    m.load_state_dict(w)
+    x = c["x"].to(d).requires_grad_(True)
+    v = c["v"].to(d).requires_grad_(True)
+    # edge index left on the host, as SEGNO/train_nbody.py:76-78 does
+    xo, ho, vo = m(c["his"].to(d), x, [c["row"], c["col"]], v, c["edge_attr"].to(d), T=c["T"])
+    assert m.n_layers == c["T"] and m.module.n_layers == c["T"]          # model.py:96-97
+    assert rel_err(xo.cpu(), torch.tensor(dd["x_out"])) < TOL_OUT
+    assert rel_err(vo.cpu(), torch.tensor(dd["v_out"])) < TOL_OUT
+    assert rel_err(ho.cpu(), torch.tensor(dd["h_out"])) < TOL_OUT
+    loss = (xo * torch.tensor(dd["Gx"], device=d)).sum() + (vo * torch.tensor(dd["Gv"], device=d)).sum() + \
+        (ho * torch.tensor(dd["Gh"], device=d)).sum()
+    loss.backward()
+    assert rel_err(x.grad.cpu(), torch.tensor(dd["gx_in"])) < TOL_GRAD
+    assert rel_err(v.grad.cpu(), torch.tensor(dd["gv_in"])) < TOL_GRAD
+    for k, p in m.named_parameters():
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g[k])
+        assert rel_err(got, g[k]) < TOL_GRAD, k
+    assert m.module.coord_mlp_vel[0].weight.grad is None or float(m.module.coord_mlp_vel[0].weight.grad.abs().max()) == 0
+
+
+def _egno_case(B, N, T, L=2, modes=2, seed=0, kind="charged"):
+    s = synth.sample_state(kind, B, N, seed)
+    row, col = synth.canonical_edges(B, N)
+    x, nodes, ea, v, lm = synth.egno_features(s["loc"], s["vel"], s["charges"], row, col)
+    return dict(n=N, B=B, T=T, L=L, modes=modes, row=row, col=col, x=x, v=v, edge_attr=ea, nodes=nodes, loc_mean=lm,
+                t_out=torch.arange(1, T + 1)[None].repeat(B, 1))
+
+
+@pytest.mark.parametrize("B,N,T,L", [(8, 20, 10, 4), (1, 100, 3, 1), (5, 2, 4, 2), (3, 37, 5, 1), (13, 5, 8, 2)])
+def test_egno_vs_oracle_various_shapes(B, N, T, L):
+    c = _egno_case(B, N, T, L=L, seed=B + N)
+    m = make_egno(c)
+    w = {k: t.detach().cpu().clone() for k, t in m.state_dict().items()}
+    x, v, (xo, vo, ho) = run_egno(m, c)
+    gen = torch.Generator().manual_seed(3)
+    Gx, Gh = torch.randn(xo.shape, generator=gen), torch.randn(ho.shape, generator=gen) * 0.05
+    ((xo * Gx.to(dev())).sum() + (ho * Gh.to(dev())).sum()).backward()
+    p = {k: t.clone().requires_grad_(True) for k, t in w.items()}
+    xr = c["x"].clone().requires_grad_(True)
+    xo_r, vo_r, ho_r = O.egno_forward(p, xr, c["nodes"], c["row"], c["col"], c["edge_attr"], c["v"], c["loc_mean"],
+                                      c["t_out"], n_layers=L, num_timesteps=T)
+    ((xo_r * Gx).sum() + (ho_r * Gh).sum()).backward()
+    assert rel_err(xo.cpu(), xo_r.detach()) < TOL_OUT
+    assert rel_err(vo.cpu(), vo_r.detach()) < TOL_OUT
+    assert rel_err(ho.cpu(), ho_r.detach()) < TOL_OUT
+    assert rel_err(x.grad.cpu(), xr.grad) < TOL_GRAD
+    for k, q in m.named_parameters():
+        assert rel_err(q.grad.cpu(), p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])) < TOL_GRAD, k
+
+
+@pytest.mark.parametrize("B,N,T", [(16, 20, 10), (2, 100, 2), (9, 3, 5)])
+def test_segno_vs_oracle_various_shapes(B, N, T):
+    d = dev()
+    s = synth.sample_state("gravity", B, N, seed=B)
+    row, col = synth.canonical_edges(B, N)
+    his, x0, v0, ea = synth.segno_features(s["loc"], s["vel"], s["charges"], row, col)
+    torch.manual_seed(2)
+    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
+    with torch.no_grad():
+        m.module.coord_mlp[2].weight.mul_(200.0)     # make the coordinate path numerically visible
+    w = {k: t.detach().cpu().clone() for k, t in m.state_dict().items()}
+    x = x0.to(d).requires_grad_(True)
+    xo, ho, vo = m(his.to(d), x, torch.stack([row, col]).to(d), v0.to(d), ea.to(d), T=T)
+    gen = torch.Generator().manual_seed(4)
+    Gx, Gv = torch.randn(xo.shape, generator=gen), torch.randn(vo.shape, generator=gen)
+    ((xo * Gx.to(d)).sum() + (vo * Gv.to(d)).sum()).backward()
+    p = {k: t.clone().requires_grad_(True) for k, t in w.items()}
+    xr = x0.clone().requires_grad_(True)
+    xo_r, ho_r, vo_r = O.segno_forward(p, his, xr, row, col, v0, ea, T)
+    ((xo_r * Gx).sum() + (vo_r * Gv).sum()).backward()
+    assert rel_err(xo.cpu(), xo_r.detach()) < TOL_OUT
+    assert rel_err(vo.cpu(), vo_r.detach()) < TOL_OUT
+    assert rel_err(ho.cpu(), ho_r.detach()) < TOL_OUT
+    assert rel_err(x.grad.cpu(), xr.grad) < TOL_GRAD
+    for k, q in m.named_parameters():
+        ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
+        got = q.grad.cpu() if q.grad is not None else torch.zeros_like(ref)
+        assert rel_err(got, ref) < TOL_GRAD, k
+
+
+def _rotation(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+def test_egno_full_size_properties():
+    """BASELINE config 3 size (N=20, T=10, L=4, B=256): E(3) equivariance, batch independence,
+    data-parallel equivalence of gradients, bitwise determinism, no_grad == grad forward."""
+    d = dev()
+    B, N, T = 256, 20, 10
+    c = _egno_case(B, N, T, L=4, seed=11)
+    m = make_egno(c)
+    x, v, (xo, vo, ho) = run_egno(m, c)
+    loss = (xo ** 2).mean() + (ho ** 2).mean()
+    loss.backward()
+    g_full = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+    # determinism: same inputs -> bit-identical outputs and gradients (no atomics anywhere)
+    m.zero_grad()
+    x2, v2, (xo2, vo2, ho2) = run_egno(m, c)
+    ((xo2 ** 2).mean() + (ho2 ** 2).mean()).backward()
+    assert torch.equal(xo, xo2) and torch.equal(ho, ho2)
+    assert torch.equal(g_full, torch.cat([p.grad.reshape(-1) for p in m.parameters()]))
+    # inference path (nothing saved) gives the same numbers
+    with torch.no_grad():
+        _, _, (xo3, vo3, ho3) = run_egno(m, c, requires_grad=False)
+    assert torch.equal(xo, xo3) and torch.equal(vo, vo3) and torch.equal(ho, ho3)
+    # E(3): rotate + translate positions, rotate velocities -> outputs rotate/translate, h invariant
+    R, t = _rotation(1), torch.tensor([0.3, -1.2, 0.7])
+    s = synth.sample_state("charged", B, N, 11)
+    row, col = c["row"], c["col"]
+    xr, nodes_r, ea_r, vr, lm_r = synth.egno_features(s["loc"] @ R.T + t, s["vel"] @ R.T, s["charges"], row, col)
+    cr = dict(c, x=xr, v=vr, nodes=nodes_r, edge_attr=ea_r, loc_mean=lm_r)
+    with torch.no_grad():
+        _, _, (xo_r, vo_r, ho_r) = run_egno(m, cr, requires_grad=False)
+    Rd, td = R.to(d), t.to(d)
+    assert rel_err(xo_r, xo.detach() @ Rd.T + td) < 5e-5
+    assert rel_err(vo_r, vo.detach() @ Rd.T) < 5e-5
+    assert rel_err(ho_r, ho.detach()) < 5e-5
+    # batch independence + DP equivalence: two half batches reproduce outputs; mean of their grads == full grads
+    halves, g_halves = [], []
+    for lo in (0, B // 2):
+        sl = {k: s[k][lo:lo + B // 2] for k in s}
+        rr, cc = synth.canonical_edges(B // 2, N)
+        xh, nh, eh, vh, lmh = synth.egno_features(sl["loc"], sl["vel"], sl["charges"], rr, cc)
+        ch = dict(c, B=B // 2, row=rr, col=cc, x=xh, v=vh, nodes=nh, edge_attr=eh, loc_mean=lmh, t_out=c["t_out"][:B // 2])
+        m.zero_grad()
+        _, _, (xh_o, vh_o, hh_o) = run_egno(m, ch)
+        ((xh_o ** 2).mean() + (hh_o ** 2).mean()).backward()
+        halves.append(xh_o.detach().view(T, B // 2 * N, 3))
+        g_halves.append(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone())
+    xo_cat = torch.cat(halves, dim=1).reshape(-1, 3)
+    assert rel_err(xo_cat, xo.detach()) < 1e-6
+    assert rel_err(0.5 * (g_halves[0] + g_halves[1]), g_full) < 1e-4
+
+
+def test_segno_full_size_equivariance_and_rollout_energy():
+    """BASELINE config 4 size (gravity, N=20, T=10, B=256): E(3) equivariance and a short GPU-resident
+    rollout whose energies are finite and computed identically to the oracle's energy function."""
+    d = dev()
+    B, N, T = 256, 20, 10
+    s = synth.sample_state("gravity", B, N, seed=5)
+    row, col = synth.canonical_edges(B, N)
+    torch.manual_seed(1)
+    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
+    with torch.no_grad():
+        m.module.coord_mlp[2].weight.mul_(100.0)
+    edges = [row.to(d), col.to(d)]
+
+    def run(loc, vel):
+        his, x, v, ea = synth.segno_features(loc, vel, s["charges"], row, col)
+        with torch.no_grad():
+            return m(his.to(d), x.to(d), edges, v.to(d), ea.to(d), T=T)
+
+    xo, ho, vo = run(s["loc"], s["vel"])
+    R, t = _rotation(2), torch.tensor([1.0, 2.0, -0.5])
+    xo_r, ho_r, vo_r = run(s["loc"] @ R.T + t, s["vel"] @ R.T)
+    Rd, td = R.to(d), t.to(d)
+    assert rel_err(xo_r, xo @ Rd.T + td) < 5e-5
+    assert rel_err(vo_r, vo @ Rd.T) < 5e-5
+    assert rel_err(ho_r, ho) < 5e-5
+    # 3-call rollout (train_nbody.py:200-236): features recomputed from the prediction each call
+    loc, vel = s["loc"], s["vel"]
+    for _ in range(3):
+        xo, ho, vo = run(loc, vel)
+        loc, vel = xo.cpu().view(B, N, 3), vo.cpu().view(B, N, 3)
+        e = O.energy_gravity(loc, vel, s["charges"])
+        assert torch.isfinite(e).all()
+
+
+def test_training_steps_follow_the_oracle():
+    """Three Adam steps (lr from model_confs.yaml:16) on the CUDA path track the oracle's loss curve."""
+    d = dev()
+    c = _egno_case(16, 5, 8, L=4, seed=21)
+    target = torch.randn(8 * 16 * 5, 3, generator=torch.Generator().manual_seed(9)) * 0.1 + c["x"].repeat(8, 1)
+    m = make_egno(c)
+    w = {k: t.detach().cpu().clone() for k, t in m.state_dict().items()}
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        _, _, (xo, vo, ho) = run_egno(m, c, requires_grad=False)
+        loss = ((xo - target.to(d)) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    p = {k: t.clone().requires_grad_(True) for k, t in w.items()}
+    opt_r = torch.optim.Adam(list(p.values()), lr=1e-3)
+    ref_losses = []
+    for _ in range(3):
+        opt_r.zero_grad()
+        xo_r, _, _ = O.egno_forward(p, c["x"], c["nodes"], c["row"], c["col"], c["edge_attr"], c["v"], c["loc_mean"],
+                                    c["t_out"], n_layers=4, num_timesteps=8)
+        loss = ((xo_r - target) ** 2).mean()
+        loss.backward()
+        opt_r.step()
+        ref_losses.append(loss.item())
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 1e-4 * abs(b) + 1e-7, (losses, ref_losses)
+
+
+def test_non_canonical_edges_raise_on_device():
+    d = dev()
+    c = _egno_case(4, 5, 8, L=1)
+    m = make_egno(c)
+    col = c["col"].clone()
+    col[0], col[1] = c["col"][1], c["col"][0]
+    with pytest.raises(ValueError, match="canonical"):
+        m(c["x"].to(d), c["nodes"].to(d), [c["row"].to(d), col.to(d)], c["edge_attr"].to(d), v=c["v"].to(d),
+          loc_mean=c["loc_mean"].to(d), timesteps_out=c["t_out"].to(d))
+    with pytest.raises(ValueError):
+        m(c["x"].to(d), c["nodes"].to(d), [c["row"].to(d), c["col"].to(d)], c["edge_attr"].to(d), v=c["v"].to(d),
+          loc_mean=c["loc_mean"].to(d), timesteps_out=c["t_out"][:, :4].to(d))
+
+
+def test_edge_tile_building_block_vs_oracle():
+    """nb_egcl_edge_forward / _backward alone (C ABI, raw pointers) against a plain edge-list evaluation."""
+    import ctypes
+    d = dev()
+    lib = nb.load_library()
+    n_gt, B, N, nef = 12, 4, 20, 2
+    gen = torch.Generator().manual_seed(0)
+    nn_ = n_gt * N
+    x = torch.randn(nn_, 3, generator=gen)
+    P, Q = torch.randn(nn_, 64, generator=gen) * 0.5, torch.randn(nn_, 64, generator=gen) * 0.5
+    ef = torch.randn(B * N * (N - 1), nef, generator=gen)
+    w1 = torch.randn(64, 1 + nef, generator=gen) * 0.3
+    W2, W3 = torch.randn(64, 64, generator=gen) * 0.15, torch.randn(64, 64, generator=gen) * 0.15
+    b2, b3, w4, b4 = [torch.randn(n, generator=gen) * 0.1 for n in (64, 64, 64, 1)]
+    gM, gF = torch.randn(nn_, 64, generator=gen), torch.randn(nn_, 3, generator=gen)
+    row, col = O.canonical_edges(n_gt, N)
+    eidx = (torch.arange(n_gt).repeat_interleave(N * (N - 1)) % B) * (N * (N - 1)) + torch.arange(N * (N - 1)).repeat(n_gt)
+    leaves = [t.clone().requires_grad_(True) for t in (x, P, Q, w1, W2, b2, W3, b3, w4, b4)]
+    xr, Pr, Qr, w1r, W2r, b2r, W3r, b3r, w4r, b4r = leaves
+    rij = xr[row] - xr[col]
+    r2 = (rij ** 2).sum(1, keepdim=True)
+    z1 = O.silu(Pr[row] + Qr[col] + r2 * w1r[:, 0] + ef[eidx] @ w1r[:, 1:].t())
+    mm = O.silu(z1 @ W2r.t() + b2r)
+    cc = O.silu(mm @ W3r.t() + b3r) @ w4r[:, None] + b4r
+    M_ref = O.segment_sum(mm, row, nn_)
+    F_ref = O.segment_sum(rij * cc, row, nn_)
+    ((M_ref * gM).sum() + (F_ref * gF).sum()).backward()
+    dv = lambda t: t.detach().to(d).contiguous()
+    X, Pd, Qd, EF, W1, W2d, B2, W3d, B3, W4, B4, GM, GF = map(dv, (x, P, Q, ef, w1, W2, b2, W3, b3, w4, b4, gM, gF))
+    M = torch.empty(nn_, 64, device=d)
+    F = torch.empty(nn_, 3, device=d)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.nb_egcl_edge_forward(n_gt, B, N, nef, 0, ptr(X), ptr(Pd), ptr(Qd), ptr(EF), ptr(W1), 1 + nef, 0, 1,
+                                  ptr(W2d), ptr(B2), ptr(W3d), ptr(B3), ptr(W4), ptr(B4), ptr(M), ptr(F), st)
+    assert rc == 0, lib.nb_last_error()
+    assert rel_err(M.cpu(), M_ref.detach()) < 1e-5
+    assert rel_err(F.cpu(), F_ref.detach()) < 1e-5
+    gP, gQ = torch.empty(nn_, 64, device=d), torch.empty(nn_, 64, device=d)
+    gx = torch.zeros(nn_, 3, device=d)
+    gw = torch.empty(2 * 4096 + 3 * 64 + 64 * (1 + nef) + 1, device=d)
+    ws = torch.empty(lib.nb_egcl_edge_backward_workspace_floats(n_gt, N), device=d)
+    rc = lib.nb_egcl_edge_backward(n_gt, B, N, nef, 0, ptr(X), ptr(Pd), ptr(Qd), ptr(EF), ptr(W1), 1 + nef, 0, 1,
+                                   ptr(W2d), ptr(B2), ptr(W3d), ptr(B3), ptr(W4), ptr(B4), ptr(GM), ptr(GF), ptr(gP),
+                                   ptr(gQ), ptr(gx), ptr(gw), ptr(ws), st)
+    assert rc == 0, lib.nb_last_error()
+    assert rel_err(gP.cpu(), Pr.grad) < 1e-5
+    assert rel_err(gQ.cpu(), Qr.grad) < 1e-5
+    assert rel_err(gx.cpu(), xr.grad) < 1e-5
+    gwc = gw.cpu()
+    assert rel_err(gwc[:4096].view(64, 64), W2r.grad) < 1e-5
+    assert rel_err(gwc[4096:8192].view(64, 64), W3r.grad) < 1e-5
+    o = 8192
+    assert rel_err(gwc[o:o + 64], b2r.grad) < 1e-5
+    assert rel_err(gwc[o + 64:o + 128], b3r.grad) < 1e-5
+    assert rel_err(gwc[o + 128:o + 192], w4r.grad) < 1e-5
+    assert rel_err(gwc[o + 192:o + 192 + 64 * (1 + nef)].view(64, 1 + nef), w1r.grad) < 1e-5
+    assert rel_err(gwc[-1:], b4r.grad) < 1e-5
