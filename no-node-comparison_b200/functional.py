@@ -98,7 +98,7 @@ class EgnoFunction(torch.autograd.Function):
         cfg = _cabi.NbEgnoConfig(*cfg_tuple)
         dev = x.device
         Nn = cfg.T * cfg.B * cfg.N
-        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x.requires_grad or v.requires_grad)
+        need_grad = any(ctx.needs_input_grad)   # False under torch.no_grad(): nothing is kept for backward
         x_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         v_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         h_out = torch.empty((Nn, 64), device=dev, dtype=torch.float32)
@@ -151,7 +151,7 @@ class SegnoFunction(torch.autograd.Function):
         cfg = _cabi.NbSegnoConfig(*cfg_tuple)
         dev = x.device
         Nn = cfg.B * cfg.N
-        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x.requires_grad or v.requires_grad)
+        need_grad = any(ctx.needs_input_grad)   # False under torch.no_grad(): nothing is kept for backward
         x_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         v_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         h_out = torch.empty((Nn, 64), device=dev, dtype=torch.float32)
