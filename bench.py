@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=32, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the SEGNO / inference side numbers")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (for profiler runs)")
     return ap.parse_args()
 
 
@@ -254,6 +255,14 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms / 1e3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                              "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end: host buffers in, loss out, through the module API
     for i in range(2):
         e2e_step(host[i % NBATCH])
@@ -284,7 +293,10 @@ def run_ours(args):
     achieved = flop_kernel / (t_bwd * 1e-3) / 1e12 if t_bwd else None
     roofline = {"kernel": "k_edge_bwd (fused E_GCL edge tile backward, fp32 SIMT in this round)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_edge_bwd_r01_raw.csv);
+                # valid for the default workload only
+                "traffic": 43.8e6 if (N, T, B) == (20, 10, 256) else None,
                 "flop_per_launch": flop_kernel, "flop_per_launch_reference_formula": 2 * 2 * MAC_EDGE_REF * ne,
                 "note": "achieved counts the MACs the edge kernel owns (8448/edge fwd, x2 for bwd); the reference's dense "
                         "131-wide first layer would count 16640/edge. fp32 FFMA peak of B200 is ~70 TFLOP/s; the tensor "
