@@ -1,0 +1,218 @@
+// nb_tc.cuh — tcgen05 / TMEM / mbarrier building blocks (sm_100a inline PTX) for the 64-wide MLP tiles.
+//
+// Numerics: operands are split into two bf16 pieces, x = b1 + b2 (+ O(2^-18 x)), and every product is evaluated as
+// b1*c1 + b2*c1 + b1*c2 with fp32 accumulation in TMEM ("fp32-accumulated split-BF16"): three
+// kind::f16 MMAs per logical fp32 MMA, ~1e-5 relative error per product, at 1.5x the tensor time of one TF32 pass
+// and half the shared-memory bytes of a TF32 hi/lo split.
+//
+// One physical tile layout serves every operand role.  A tile is [rows][64] bf16, 128 bytes per row, with the
+// canonical 128-byte swizzle (16-byte chunk index XOR (row & 7)); tile bases are 1024-byte aligned.
+//   * K-major operand   (K = the 64 columns):  k-step s (16 elements) starts at byte 32*s of each row;
+//                                              SBO = 1024 B between 8-row groups.
+//   * MN-major operand  (MN = the 64 columns, K = rows): k-step s covers rows 16 s .. 16 s + 15, start = 2048 * s;
+//                                              SBO = 1024 B between 8-row K groups; one 128-byte MN block (LBO unused).
+// For 16-bit types these two canonical layouts (cute::UMMA::Layout_K_SW128_Atom / Layout_MN_SW128_Atom) coincide
+// physically, which is what lets the backward reuse one copy of m, z1, g and W for recompute, dgrad and wgrad.
+#pragma once
+#ifndef NB_EMU
+#include <cuda_bf16.h>
+#include "nb_common.cuh"
+
+#define NB_TC_ROW_BYTES 128            // 64 bf16
+#define NB_TC_TILE_BYTES(rows) ((rows) * NB_TC_ROW_BYTES)
+
+__device__ __forceinline__ uint32_t nb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ----------------------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void nb_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void nb_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void nb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t a = nb_smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------- TMEM
+__device__ __forceinline__ void nb_tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(nb_smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void nb_tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void nb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void nb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void nb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive fp32 columns: thread l of warp w reads TMEM lane 32*(w%4)+l
+__device__ __forceinline__ void nb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------- descriptors
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t nb_make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major view of a [rows][64] bf16 tile, k-step s (16 columns)
+__device__ __forceinline__ uint64_t nb_desc_kmajor(uint32_t tile_addr, int s) {
+  return nb_make_desc(tile_addr + 32 * s, 16, 1024);
+}
+// MN-major view (MN = the 64 columns, K = rows), k-step s (rows 16 s ..)
+__device__ __forceinline__ uint64_t nb_desc_mnmajor(uint32_t tile_addr, int s) {
+  return nb_make_desc(tile_addr + 2048 * s, 8192, 1024);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32
+__host__ __device__ constexpr uint32_t nb_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) /*c=f32*/ | (1u << 7) /*a=bf16*/ | (1u << 10) /*b=bf16*/ | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem], issued by ONE thread
+__device__ __forceinline__ void nb_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void nb_mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(nb_smem_u32(bar)) : "memory");
+}
+
+// ----------------------------------------------------------------------------- split-bf16 tile stores
+// byte offset of the 16-byte chunk j (8 bf16, columns 8j..8j+7) of row r inside a swizzled tile
+__device__ __forceinline__ uint32_t nb_tc_chunk_off(int r, int j) { return (uint32_t)r * NB_TC_ROW_BYTES + (uint32_t)((j ^ (r & 7)) << 4); }
+
+// split 8 consecutive fp32 values into their bf16 pieces and store chunk j of row r into the hi / lo tiles
+__device__ __forceinline__ void nb_tc_store8(unsigned char* hi, unsigned char* lo, int r, int j, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b1 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    float2 f1 = __bfloat1622float2(b1);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i] - f1.x, v[2 * i + 1] - f1.y);
+    h[i] = *reinterpret_cast<uint32_t*>(&b1);
+    l[i] = *reinterpret_cast<uint32_t*>(&b2);
+  }
+  uint32_t off = nb_tc_chunk_off(r, j);
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Issue the three split passes of one logical 64-deep (K-major A) or rows-deep (MN-major) product.
+//   a_mn / b_mn: operand views;  ksteps: 4 for K = 64 columns, rows/16 for K = rows.
+__device__ __forceinline__ void nb_tc_issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int a_mn, uint32_t b_hi,
+                                             uint32_t b_lo, int b_mn, int ksteps, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    uint32_t a = pass == 1 ? a_lo : a_hi;
+    uint32_t b = pass == 2 ? b_lo : b_hi;
+    for (int s = 0; s < ksteps; ++s) {
+      uint64_t ad = a_mn ? nb_desc_mnmajor(a, s) : nb_desc_kmajor(a, s);
+      uint64_t bd = b_mn ? nb_desc_mnmajor(b, s) : nb_desc_kmajor(b, s);
+      nb_mma_bf16(tmem_d, ad, bd, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+
+// ============================================================================= self test
+// mode 0: D[128x64] = A[128x64] * W^T      (A K-major, B = W[o][k] K-major)        forward form
+// mode 1: D[128x64] = A[128x64] * W        (A K-major, B = W[o][k] MN-major)       data-gradient form
+// mode 2: D[ 64x64] = A^T * G              (A = A[r][c] MN-major (M = c), B = G[r][c] MN-major (N = c), K = 128 rows)
+// out: raw dump of the 128 TMEM lanes x 64 columns
+__global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ W,
+                                                     float* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)tsm + 1023) & ~(uintptr_t)1023);
+  unsigned char* a_hi = base;
+  unsigned char* a_lo = a_hi + NB_TC_TILE_BYTES(128);
+  unsigned char* b_hi = a_lo + NB_TC_TILE_BYTES(128);
+  unsigned char* b_lo = b_hi + NB_TC_TILE_BYTES(128);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    nb_mbar_init(&bar, 1);
+    nb_mbar_fence_init();
+  }
+  if (warp == 0) nb_tmem_alloc(&tmem_base, 64);
+  // operand tiles: this thread owns row `tid`
+  {
+    const float* ar = A + (size_t)tid * 64;
+    for (int j = 0; j < 8; ++j) nb_tc_store8(a_hi, a_lo, tid, j, ar + 8 * j);
+    const int brows = (mode == 2) ? 128 : 64;
+    if (tid < brows) {
+      const float* wr = W + (size_t)tid * 64;
+      for (int j = 0; j < 8; ++j) nb_tc_store8(b_hi, b_lo, tid, j, wr + 8 * j);
+    }
+  }
+  nb_fence_async_smem();
+  nb_tc_fence_before();
+  __syncthreads();
+  nb_tc_fence_after();
+  const uint32_t tm = tmem_base;
+  if (tid == 0) {
+    if (mode == 0)
+      nb_tc_issue3(tm, nb_smem_u32(a_hi), nb_smem_u32(a_lo), 0, nb_smem_u32(b_hi), nb_smem_u32(b_lo), 0, 4,
+                   nb_idesc_bf16(128, 64, 0, 0), false);
+    else if (mode == 1)
+      nb_tc_issue3(tm, nb_smem_u32(a_hi), nb_smem_u32(a_lo), 0, nb_smem_u32(b_hi), nb_smem_u32(b_lo), 1, 4,
+                   nb_idesc_bf16(128, 64, 0, 1), false);
+    else
+      nb_tc_issue3(tm, nb_smem_u32(a_hi), nb_smem_u32(a_lo), 1, nb_smem_u32(b_hi), nb_smem_u32(b_lo), 1, 8,
+                   nb_idesc_bf16(64, 64, 1, 1), false);
+    nb_mma_commit(&bar);
+  }
+  nb_mbar_wait(&bar, 0);
+  nb_tc_fence_after();
+  float v[32];
+  const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+  nb_tmem_ld32(lane_addr, v);
+  for (int i = 0; i < 32; ++i) out[(size_t)tid * 64 + i] = v[i];
+  nb_tmem_ld32(lane_addr + 32, v);
+  for (int i = 0; i < 32; ++i) out[(size_t)tid * 64 + 32 + i] = v[i];
+  nb_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nb_tmem_dealloc(tm, 64);
+}
+#endif  // NB_EMU

@@ -9,6 +9,7 @@
 #include "nb_node.cuh"
 #include "nb_spectral.cuh"
 #include "nb_edge.cuh"
+#include "nb_tc.cuh"
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 #define NB_LAUNCH_COUNTED(...) \
@@ -1116,4 +1117,19 @@ extern "C" int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t
   d.ldw1 = 1 + n_edge_fea; d.col_rad = 0; d.col_ef = 1; d.b_unused = 0;
   d.b4 = d.w1 + (int64_t)NB_H * d.ldw1;
   return launch_edge_bwd(a, workspace, gw, d, 0, stream);
+}
+
+// tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.
+extern "C" int nb_tc_selftest(int32_t mode, const float* A, const float* W, float* out, void* stream) {
+#ifdef NB_EMU
+  (void)mode; (void)A; (void)W; (void)out; (void)stream;
+  nb_set_error("tcgen05 is not available in the host emulator");
+  return NB_ERR_INVALID;
+#else
+  if (mode < 0 || mode > 2) { nb_set_error("mode must be 0..2"); return NB_ERR_INVALID; }
+  const size_t smem = 4 * NB_TC_TILE_BYTES(128) + 1024;
+  NB_SET_SMEM(k_tc_selftest, smem);
+  NB_LAUNCH_COUNTED(k_tc_selftest, 1, 128, smem, stream, (int)mode, A, W, out);
+  return nb_check_launch("k_tc_selftest");
+#endif
 }

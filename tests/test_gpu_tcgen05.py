@@ -1,0 +1,52 @@
+"""tcgen05 building blocks on the device: the three MMA forms used by the edge tiles (forward, data-gradient,
+weight-gradient) with split-bf16 operands and fp32 accumulation in TMEM, against an fp64 matmul."""
+import ctypes
+
+import pytest
+import torch
+
+import no_node_comparison_b200 as nb
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(mode, A, W):
+    lib = nb.load_library()
+    d = torch.device("cuda:0")
+    Ad, Wd = A.to(d).contiguous(), W.to(d).contiguous()
+    out = torch.zeros(128, 64, device=d)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.nb_tc_selftest(mode, P(Ad), P(Wd), P(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.nb_last_error()
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def _relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
+
+
+def test_tcgen05_forward_form():
+    g = torch.Generator().manual_seed(0)
+    A, W = torch.randn(128, 64, generator=g), torch.randn(64, 64, generator=g)
+    out = _run(0, A, W)
+    ref = A.double() @ W.double().t()
+    assert _relerr(out, ref) < 3e-5, _relerr(out, ref)
+
+
+def test_tcgen05_dgrad_form():
+    g = torch.Generator().manual_seed(1)
+    A, W = torch.randn(128, 64, generator=g), torch.randn(64, 64, generator=g)
+    out = _run(1, A, W)
+    ref = A.double() @ W.double()
+    assert _relerr(out, ref) < 3e-5, _relerr(out, ref)
+
+
+def test_tcgen05_wgrad_form_and_m64_lane_layout():
+    g = torch.Generator().manual_seed(2)
+    A, G = torch.randn(128, 64, generator=g), torch.randn(128, 64, generator=g)
+    out = _run(2, A, G)
+    ref = A.double().t() @ G.double()          # [64, 64]
+    # M = 64 accumulators live in TMEM lanes (i % 16) + 32 * (i // 16)   (cute tmem_frg, M_MMA == 64)
+    lanes = torch.tensor([(i % 16) + 32 * (i // 16) for i in range(64)])
+    assert _relerr(out[lanes], ref) < 3e-5, _relerr(out[lanes], ref)
