@@ -165,6 +165,11 @@ long long nb_launch_count(void);
 int nb_profile_enable(int enable);
 int nb_profile_read(double* ms /*[4]*/, long long* counts /*[4]*/);
 
+/* Edge-tile implementation: 1 = tcgen05 tensor-core tiles (default, product path), 0 = fp32 SIMT tiles (kept as an
+ * independent cross-check and for the host emulator of the test suite).  Both are CUDA kernels of this library. */
+int nb_set_edge_impl(int impl);
+int nb_get_edge_impl(void);
+
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]
  * and dumps the raw 128 TMEM lanes x 64 columns into out[128*64]. */

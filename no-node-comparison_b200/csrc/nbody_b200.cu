@@ -10,6 +10,7 @@
 #include "nb_spectral.cuh"
 #include "nb_edge.cuh"
 #include "nb_tc.cuh"
+#include "nb_edge_tc.cuh"
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 #define NB_LAUNCH_COUNTED(...) \
@@ -213,7 +214,35 @@ static NbEdgeGeom edge_geom(int n_gt, int B, int N, int nef, int clamp_edge) {
   return g;
 }
 
+// 1 = tcgen05 edge tiles (product path on sm_100a), 0 = fp32 SIMT tiles (cross-check; the only variant the host
+// emulator can run)
+#ifdef NB_EMU
+static int g_edge_impl = 0;
+#else
+static int g_edge_impl = 1;
+#endif
+extern "C" int nb_set_edge_impl(int impl) {
+#ifdef NB_EMU
+  if (impl != 0) { nb_set_error("the host emulator only runs the SIMT edge tiles"); return NB_ERR_INVALID; }
+#endif
+  if (impl != 0 && impl != 1) { nb_set_error("edge impl must be 0 (SIMT) or 1 (tcgen05)"); return NB_ERR_INVALID; }
+  g_edge_impl = impl;
+  return NB_OK;
+}
+extern "C" int nb_get_edge_impl(void) { return g_edge_impl; }
+
 static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
+#ifndef NB_EMU
+  if (g_edge_impl == 1) {
+    const size_t smem_tc = NB_EDGE_FWD_TC_SMEM;
+    NB_SET_SMEM(k_edge_fwd_tc, smem_tc);
+    int grid_tc = imin(a.g.n_units, 3 * nb_num_sms());
+    int pi_tc = prof_begin(0, st);
+    NB_LAUNCH_COUNTED(k_edge_fwd_tc, (unsigned)grid_tc, NB_THREADS, smem_tc, st, a);
+    prof_end(0, pi_tc, st);
+    return nb_check_launch("k_edge_fwd_tc");
+  }
+#endif
   const size_t smem = NB_EDGE_FWD_SMEM_FLOATS * sizeof(float);
   NB_SET_SMEM(k_edge_fwd, smem);
   int grid = imin(a.g.n_units, 3 * nb_num_sms());

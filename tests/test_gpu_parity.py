@@ -286,11 +286,22 @@ def test_non_canonical_edges_raise_on_device():
           loc_mean=c["loc_mean"].to(d), timesteps_out=c["t_out"][:, :4].to(d))
 
 
-def test_edge_tile_building_block_vs_oracle():
-    """nb_egcl_edge_forward / _backward alone (C ABI, raw pointers) against a plain edge-list evaluation."""
+@pytest.mark.parametrize("impl", [1, 0])
+def test_edge_tile_building_block_vs_oracle(impl):
+    """nb_egcl_edge_forward / _backward alone (C ABI, raw pointers) against a plain edge-list evaluation, for the
+    tcgen05 tiles (impl 1, split-bf16 operands: ~1e-5) and the fp32 SIMT tiles (impl 0: ~1e-6)."""
     import ctypes
     d = dev()
     lib = nb.load_library()
+    assert lib.nb_set_edge_impl(impl) == 0
+    try:
+        _edge_tile_check(lib, d, 5e-5 if impl == 1 else 1e-5)
+    finally:
+        lib.nb_set_edge_impl(1)
+
+
+def _edge_tile_check(lib, d, tol):
+    import ctypes
     n_gt, B, N, nef = 12, 4, 20, 2
     gen = torch.Generator().manual_seed(0)
     nn_ = n_gt * N
@@ -322,8 +333,8 @@ def test_edge_tile_building_block_vs_oracle():
     rc = lib.nb_egcl_edge_forward(n_gt, B, N, nef, 0, ptr(X), ptr(Pd), ptr(Qd), ptr(EF), ptr(W1), 1 + nef, 0, 1,
                                   ptr(W2d), ptr(B2), ptr(W3d), ptr(B3), ptr(W4), ptr(B4), ptr(M), ptr(F), st)
     assert rc == 0, lib.nb_last_error()
-    assert rel_err(M.cpu(), M_ref.detach()) < 1e-5
-    assert rel_err(F.cpu(), F_ref.detach()) < 1e-5
+    assert rel_err(M.cpu(), M_ref.detach()) < tol
+    assert rel_err(F.cpu(), F_ref.detach()) < tol
     gP, gQ = torch.empty(nn_, 64, device=d), torch.empty(nn_, 64, device=d)
     gx = torch.zeros(nn_, 3, device=d)
     gw = torch.empty(2 * 4096 + 3 * 64 + 64 * (1 + nef) + 1, device=d)
@@ -332,15 +343,15 @@ def test_edge_tile_building_block_vs_oracle():
                                    ptr(W2d), ptr(B2), ptr(W3d), ptr(B3), ptr(W4), ptr(B4), ptr(GM), ptr(GF), ptr(gP),
                                    ptr(gQ), ptr(gx), ptr(gw), ptr(ws), st)
     assert rc == 0, lib.nb_last_error()
-    assert rel_err(gP.cpu(), Pr.grad) < 1e-5
-    assert rel_err(gQ.cpu(), Qr.grad) < 1e-5
-    assert rel_err(gx.cpu(), xr.grad) < 1e-5
+    assert rel_err(gP.cpu(), Pr.grad) < tol
+    assert rel_err(gQ.cpu(), Qr.grad) < tol
+    assert rel_err(gx.cpu(), xr.grad) < tol
     gwc = gw.cpu()
-    assert rel_err(gwc[:4096].view(64, 64), W2r.grad) < 1e-5
-    assert rel_err(gwc[4096:8192].view(64, 64), W3r.grad) < 1e-5
+    assert rel_err(gwc[:4096].view(64, 64), W2r.grad) < tol
+    assert rel_err(gwc[4096:8192].view(64, 64), W3r.grad) < tol
     o = 8192
-    assert rel_err(gwc[o:o + 64], b2r.grad) < 1e-5
-    assert rel_err(gwc[o + 64:o + 128], b3r.grad) < 1e-5
-    assert rel_err(gwc[o + 128:o + 192], w4r.grad) < 1e-5
-    assert rel_err(gwc[o + 192:o + 192 + 64 * (1 + nef)].view(64, 1 + nef), w1r.grad) < 1e-5
-    assert rel_err(gwc[-1:], b4r.grad) < 1e-5
+    assert rel_err(gwc[o:o + 64], b2r.grad) < tol
+    assert rel_err(gwc[o + 64:o + 128], b3r.grad) < tol
+    assert rel_err(gwc[o + 128:o + 192], w4r.grad) < tol
+    assert rel_err(gwc[o + 192:o + 192 + 64 * (1 + nef)].view(64, 1 + nef), w1r.grad) < tol
+    assert rel_err(gwc[-1:], b4r.grad) < tol
