@@ -75,6 +75,24 @@ __device__ __forceinline__ void nb_tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// store 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void nb_tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- descriptors
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B)
@@ -94,6 +112,16 @@ __device__ __forceinline__ uint64_t nb_desc_kmajor(uint32_t tile_addr, int s) {
 // MN-major view (MN = the 64 columns, K = rows), k-step s (rows 16 s ..)
 __device__ __forceinline__ uint64_t nb_desc_mnmajor(uint32_t tile_addr, int s) {
   return nb_make_desc(tile_addr + 2048 * s, 8192, 1024);
+}
+// dense [rows][8] bf16 tile (16 bytes per row, no swizzle) as an MN-major operand with MN = 8, K = rows:
+// canonical INTERLEAVE layout ((8,1),(8,k)) : 8x8 core matrices of 128 contiguous bytes, K groups LBO = 128 B apart.
+__device__ __forceinline__ uint64_t nb_desc_mn8_noswizzle(uint32_t tile_addr, int s) {
+  uint64_t d = 0;
+  d |= (uint64_t)(((tile_addr + 256 * s) >> 4) & 0x3FFF);
+  d |= (uint64_t)((128 >> 4) & 0x3FFF) << 16;   // LBO: stride between 8-row K groups
+  d |= (uint64_t)((128 >> 4) & 0x3FFF) << 32;   // SBO: stride between MN blocks (single block: unused)
+  d |= (uint64_t)1 << 46;
+  return d;                                      // layout_type 0 = SWIZZLE_NONE
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32
 __host__ __device__ constexpr uint32_t nb_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
@@ -158,6 +186,7 @@ __device__ __forceinline__ void nb_tc_issue3(uint32_t tmem_d, uint32_t a_hi, uin
 // ============================================================================= self test
 // mode 0: D[128x64] = A[128x64] * W^T      (A K-major, B = W[o][k] K-major)        forward form
 // mode 1: D[128x64] = A[128x64] * W        (A K-major, B = W[o][k] MN-major)       data-gradient form
+// mode 3: D[ 64x 8] = A^T * ones[128x8]  (column sums; dense no-swizzle B operand)
 // mode 2: D[ 64x64] = A^T * G              (A = A[r][c] MN-major (M = c), B = G[r][c] MN-major (N = c), K = 128 rows)
 // out: raw dump of the 128 TMEM lanes x 64 columns
 __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ W,
@@ -181,7 +210,10 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
     const float* ar = A + (size_t)tid * 64;
     for (int j = 0; j < 8; ++j) nb_tc_store8(a_hi, a_lo, tid, j, ar + 8 * j);
     const int brows = (mode == 2) ? 128 : 64;
-    if (tid < brows) {
+    if (mode == 3) {  // ones[128][8] bf16
+      uint32_t one2 = 0x3F803F80u;
+      *reinterpret_cast<uint4*>(b_hi + tid * 16) = make_uint4(one2, one2, one2, one2);
+    } else if (tid < brows) {
       const float* wr = W + (size_t)tid * 64;
       for (int j = 0; j < 8; ++j) nb_tc_store8(b_hi, b_lo, tid, j, wr + 8 * j);
     }
@@ -198,9 +230,18 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
     else if (mode == 1)
       nb_tc_issue3(tm, nb_smem_u32(a_hi), nb_smem_u32(a_lo), 0, nb_smem_u32(b_hi), nb_smem_u32(b_lo), 1, 4,
                    nb_idesc_bf16(128, 64, 0, 1), false);
-    else
+    else if (mode == 2)
       nb_tc_issue3(tm, nb_smem_u32(a_hi), nb_smem_u32(a_lo), 1, nb_smem_u32(b_hi), nb_smem_u32(b_lo), 1, 8,
                    nb_idesc_bf16(64, 64, 1, 1), false);
+    else {  // mode 3: column sums  D[64 x 8] = A^T * ones[128 x 8]  (ones tile: dense, no swizzle, exact in bf16)
+      uint32_t acc = 0;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int s = 0; s < 8; ++s) {
+          nb_mma_bf16(tm, nb_desc_mnmajor(nb_smem_u32(pass ? a_lo : a_hi), s), nb_desc_mn8_noswizzle(nb_smem_u32(b_hi), s),
+                      nb_idesc_bf16(64, 8, 1, 1), acc);
+          acc = 1;
+        }
+    }
     nb_mma_commit(&bar);
   }
   nb_mbar_wait(&bar, 0);

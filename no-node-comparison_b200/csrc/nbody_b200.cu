@@ -260,14 +260,28 @@ struct EdgeGradDst {
 
 static int launch_edge_bwd(NbEdgeBwdArgs& a, float* partial, float* dst, const EdgeGradDst& d, int accumulate,
                            void* st) {
-  const size_t smem = NB_EDGE_BWD_SMEM_FLOATS(a.g.G * a.g.N) * sizeof(float);
-  NB_SET_SMEM(k_edge_bwd, smem);
   int grid = imin(a.g.n_units, edge_bwd_grid_cap());
   a.partial = partial;
-  int pi = prof_begin(1, st);
-  NB_LAUNCH_COUNTED(k_edge_bwd, (unsigned)grid, NB_THREADS, smem, st, a);
-  prof_end(1, pi, st);
-  NB_TRY(nb_check_launch("k_edge_bwd"));
+  bool done = false;
+#ifndef NB_EMU
+  if (g_edge_impl == 1) {
+    const size_t smem_tc = NB_EDGE_BWD_TC_SMEM(a.g.G * a.g.N);
+    NB_SET_SMEM(k_edge_bwd_tc, smem_tc);
+    int pi_tc = prof_begin(1, st);
+    NB_LAUNCH_COUNTED(k_edge_bwd_tc, (unsigned)grid, NB_THREADS, smem_tc, st, a);
+    prof_end(1, pi_tc, st);
+    NB_TRY(nb_check_launch("k_edge_bwd_tc"));
+    done = true;
+  }
+#endif
+  if (!done) {
+    const size_t smem = NB_EDGE_BWD_SMEM_FLOATS(a.g.G * a.g.N) * sizeof(float);
+    NB_SET_SMEM(k_edge_bwd, smem);
+    int pi = prof_begin(1, st);
+    NB_LAUNCH_COUNTED(k_edge_bwd, (unsigned)grid, NB_THREADS, smem, st, a);
+    prof_end(1, pi, st);
+    NB_TRY(nb_check_launch("k_edge_bwd"));
+  }
   NbFinArgs f;
   memset(&f, 0, sizeof(f));
   f.partial = partial; f.nparts = grid; f.plen = NB_EB_PLEN; f.dst = dst; f.accumulate = accumulate;
@@ -1155,7 +1169,7 @@ extern "C" int nb_tc_selftest(int32_t mode, const float* A, const float* W, floa
   nb_set_error("tcgen05 is not available in the host emulator");
   return NB_ERR_INVALID;
 #else
-  if (mode < 0 || mode > 2) { nb_set_error("mode must be 0..2"); return NB_ERR_INVALID; }
+  if (mode < 0 || mode > 3) { nb_set_error("mode must be 0..3"); return NB_ERR_INVALID; }
   const size_t smem = 4 * NB_TC_TILE_BYTES(128) + 1024;
   NB_SET_SMEM(k_tc_selftest, smem);
   NB_LAUNCH_COUNTED(k_tc_selftest, 1, 128, smem, stream, (int)mode, A, W, out);

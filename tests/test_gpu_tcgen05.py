@@ -50,3 +50,13 @@ def test_tcgen05_wgrad_form_and_m64_lane_layout():
     # M = 64 accumulators live in TMEM lanes (i % 16) + 32 * (i // 16)   (cute tmem_frg, M_MMA == 64)
     lanes = torch.tensor([(i % 16) + 32 * (i // 16) for i in range(64)])
     assert _relerr(out[lanes], ref) < 3e-5, _relerr(out[lanes], ref)
+
+
+def test_tcgen05_column_sum_form_noswizzle_operand():
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(128, 64, generator=g)
+    out = _run(3, A, torch.zeros(64, 64))
+    ref = A.double().sum(0)                    # [64]
+    lanes = torch.tensor([(i % 16) + 32 * (i // 16) for i in range(64)])
+    for col in range(8):
+        assert _relerr(out[lanes, col], ref) < 3e-5, (col, _relerr(out[lanes, col], ref))
