@@ -19,12 +19,23 @@
 
 // ----------------------------------------------------------------------------- activations
 // SiLU and its derivative from one sigmoid evaluation (ex2.approx + rcp.approx: ~2 ulp).
+#ifndef NB_EMU
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) with the two MUFU approximations issued directly (no range fix-up code:
+// ex2 saturates to 0 / +inf and rcp(+inf) = 0, which are the correct limits)
+__device__ __forceinline__ float nb_sigmoid(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return r;
+}
+#else
 __device__ __forceinline__ float nb_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#endif
 __device__ __forceinline__ float nb_silu(float x) { return x * nb_sigmoid(x); }
 __device__ __forceinline__ void nb_silu_grad(float x, float& y, float& dy) {
   float s = nb_sigmoid(x);
   y = x * s;
-  dy = s * (1.0f + x * (1.0f - s));
+  dy = fmaf(y, 1.0f - s, s);  // s (1 + x (1 - s))
 }
 __device__ __forceinline__ float nb_dsilu(float x) {
   float s = nb_sigmoid(x);

@@ -113,7 +113,8 @@ __device__ __forceinline__ float2 nb_tc_load_pair(const unsigned char* hi, const
 
 __global__ void __launch_bounds__(NB_THREADS) k_edge_fwd_tc(NbEdgeFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
-  unsigned char* base = (unsigned char*)(((uintptr_t)nb_smraw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared state space: LDS/STS, not LD/ST)
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
   unsigned char* W2h = base + NB_EFT_W;
   unsigned char* W2l = W2h + NB_TC_TILE_BYTES(64);
   unsigned char* W3h = W2l + NB_TC_TILE_BYTES(64);
@@ -299,7 +300,8 @@ __device__ __forceinline__ float nb_scratch_get(const float* S, int r, int c) {
 
 __global__ void __launch_bounds__(NB_THREADS, 1) k_edge_bwd_tc(NbEdgeBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
-  unsigned char* base = (unsigned char*)(((uintptr_t)nb_smraw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared state space: LDS/STS, not LD/ST)
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
   unsigned char* W2h = base + NB_EBT_W;
   unsigned char* W2l = W2h + NB_TC_TILE_BYTES(64);
   unsigned char* W3h = W2l + NB_TC_TILE_BYTES(64);
