@@ -34,7 +34,16 @@ struct NbGemmArgs {
   int ldp;
 };
 
-__global__ void __launch_bounds__(NB_THREADS) k_gemm64(NbGemmArgs a) {
+#define NB_MAX_GEMM_JOBS 4
+struct NbGemmBatch {
+  int njobs;
+  NbGemmArgs job[NB_MAX_GEMM_JOBS];
+};
+
+// blockIdx.y selects the job; blockIdx.x the 128-row tile (CTAs past a job's last tile exit)
+__global__ void __launch_bounds__(NB_THREADS) k_gemm64(NbGemmBatch batch) {
+  const NbGemmArgs& a = batch.job[blockIdx.y];
+  if ((int)blockIdx.x * NB_TILE >= a.rows) return;
   NB_DYN_SMEM(sm);
   float* As = sm;                     // [128][68]
   float* Bs = sm + NB_TILE * NB_LDA;  // [64][64]
@@ -132,7 +141,15 @@ struct NbWgradArgs {
   float* partial;  // [gridDim.x][NB_WGRAD_PLEN]
 };
 
-__global__ void __launch_bounds__(NB_THREADS) k_wgrad64(NbWgradArgs a) {
+#define NB_MAX_WGRAD_JOBS 12
+struct NbWgradBatch {
+  int njobs;
+  NbWgradArgs job[NB_MAX_WGRAD_JOBS];
+};
+
+// blockIdx.y selects the job; each job owns gridDim.x partial slices
+__global__ void __launch_bounds__(NB_THREADS) k_wgrad64(NbWgradBatch batch) {
+  const NbWgradArgs& a = batch.job[blockIdx.y];
   NB_DYN_SMEM(sm);
   float* Gs = sm;                     // [128][68]
   float* As = sm + NB_TILE * NB_LDA;  // [128][68]
@@ -182,8 +199,12 @@ __global__ void __launch_bounds__(NB_THREADS) k_wgrad64(NbWgradArgs a) {
 }
 
 // ============================================================================= finalize
-// dst[seg.dst_off + o*so + k*si] (=|+=) scale * sum_p partial[p][e],  e = seg.start + o*inner + k
+// dst[seg.dst_off + o*so + k*si] (=|+=) sum_p partial[p][e],  e = seg.start + o*inner + k
+// One launch finalises a batch of reductions (blockIdx.y = job).  A block handles 32 consecutive elements: lane =
+// element (coalesced 128-byte reads of each partial slice), warp w sums the slices p = w, w+8, ...; the 8 warp sums
+// meet in shared memory in a fixed order (deterministic).
 #define NB_MAX_SEG 8
+#define NB_MAX_FIN_JOBS 16
 struct NbFinSeg {
   int start, count, inner;
   int64_t dst_off, so, si;
@@ -195,25 +216,43 @@ struct NbFinArgs {
   float* dst;
   int accumulate;
 };
+struct NbFinBatch {
+  int njobs;
+  NbFinArgs job[NB_MAX_FIN_JOBS];
+};
 
-__global__ void __launch_bounds__(256) k_finalize(NbFinArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.total) return;
-  // locate the segment of flat element idx (segments listed back to back in `total` space)
+__global__ void __launch_bounds__(256) k_finalize(NbFinBatch batch) {
+  __shared__ float red[8][33];
+  const NbFinArgs& a = batch.job[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;
+  if (blockIdx.x * 32 >= a.total) return;
+  // locate the segment of flat element idx (segments are listed back to back in `total` space)
   int s = 0, base = 0;
-  while (s < a.nseg - 1 && idx >= base + a.seg[s].count) {
-    base += a.seg[s].count;
-    ++s;
+  const bool act = idx < a.total;
+  if (act) {
+    while (s < a.nseg - 1 && idx >= base + a.seg[s].count) {
+      base += a.seg[s].count;
+      ++s;
+    }
   }
-  const NbFinSeg sg = a.seg[s];
-  int l = idx - base;
-  int e = sg.start + l;
+  const int l = idx - base;
+  const int e = a.seg[s].start + l;
   float sum = 0.f;
-  for (int p = 0; p < a.nparts; ++p) sum += a.partial[(int64_t)p * a.plen + e];
-  int o = l / sg.inner, k = l - o * sg.inner;
-  float* d = a.dst + sg.dst_off + (int64_t)o * sg.so + (int64_t)k * sg.si;
-  if (a.accumulate) sum += *d;
-  *d = sum;
+  if (act)
+    for (int p = warp; p < a.nparts; p += 8) sum += a.partial[(int64_t)p * a.plen + e];
+  red[warp][lane] = sum;
+  __syncthreads();
+  if (warp == 0 && act) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    const NbFinSeg sg = a.seg[s];
+    int o = l / sg.inner, k = l - o * sg.inner;
+    float* d = a.dst + sg.dst_off + (int64_t)o * sg.so + (int64_t)k * sg.si;
+    if (a.accumulate) t += *d;
+    *d = t;
+  }
 }
 
 // ============================================================================= embedding

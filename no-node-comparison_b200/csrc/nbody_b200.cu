@@ -127,20 +127,35 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int imin(int64_t a, int64_t b) { return (int)(a < b ? a : b); }
 
 // partial-sum scratch shared by all reducing kernels (floats)
-#define NB_PARTIAL_FLOATS ((int64_t)320 * NB_EB_PLEN)
-static inline int wgrad_grid_cap() { return imin(2 * nb_num_sms(), 640); }
+#define NB_PARTIAL_FLOATS ((int64_t)8 * 1024 * 1024)
+static inline int wgrad_grid_cap() { return imin(nb_num_sms(), 160); }
 static inline int edge_bwd_grid_cap() { return imin(nb_num_sms(), 320); }
 
 // ============================================================================= launch helpers
-static int launch_gemm(const NbGemmArgs& a, void* st) {
-  if (a.rows <= 0) return NB_OK;
-  const size_t smem = (NB_TILE * NB_LDA + NB_H * NB_H) * sizeof(float);
-  NB_SET_SMEM(k_gemm64, smem);
-  int pi = prof_begin(2, st);
-  NB_LAUNCH_COUNTED(k_gemm64, (unsigned)cdiv(a.rows, NB_TILE), NB_THREADS, smem, st, a);
-  prof_end(2, pi, st);
-  return nb_check_launch("k_gemm64");
+static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st) {
+  int i = 0;
+  while (i < n) {
+    NbGemmBatch b;
+    memset(&b, 0, sizeof(b));
+    int maxrows = 0;
+    while (i < n && b.njobs < NB_MAX_GEMM_JOBS) {
+      if (jobs[i].rows > 0) {
+        b.job[b.njobs++] = jobs[i];
+        if (jobs[i].rows > maxrows) maxrows = jobs[i].rows;
+      }
+      ++i;
+    }
+    if (b.njobs == 0) continue;
+    const size_t smem = (NB_TILE * NB_LDA + NB_H * NB_H) * sizeof(float);
+    NB_SET_SMEM(k_gemm64, smem);
+    int pi = prof_begin(2, st);
+    NB_LAUNCH_COUNTED(k_gemm64, dim3((unsigned)cdiv(maxrows, NB_TILE), (unsigned)b.njobs), NB_THREADS, smem, st, b);
+    prof_end(2, pi, st);
+    NB_TRY(nb_check_launch("k_gemm64"));
+  }
+  return NB_OK;
 }
+static int launch_gemm(const NbGemmArgs& a, void* st) { return launch_gemm_batch(&a, 1, st); }
 
 static NbGemmSrc gsrc(const float* A, int lda, int a_silu, const float* W, int64_t sk, int64_t sn, float scale = 1.f) {
   NbGemmSrc s;
@@ -156,41 +171,123 @@ static NbGemmArgs gemm_args(int rows) {
   return a;
 }
 
-static int launch_finalize(NbFinArgs& f, void* st) {
-  int total = 0;
-  for (int s = 0; s < f.nseg; ++s) total += f.seg[s].count;
-  f.total = total;
-  NB_LAUNCH_COUNTED(k_finalize, (unsigned)cdiv(total, 256), 256, 0, st, f);
-  return nb_check_launch("k_finalize");
-}
-
 static NbFinSeg fseg(int start, int count, int inner, int64_t dst_off, int64_t so, int64_t si) {
   NbFinSeg s;
   s.start = start; s.count = count; s.inner = inner; s.dst_off = dst_off; s.so = so; s.si = si;
   return s;
 }
 
-// dst[w_off + o*so + k*si] (+)= sum_rows sum_p scale_p G_p[r][o] A_p[r][k];  dst[b_off + o] (+)= colsum(G_0) if b_off >= 0
-static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* partial, float* dst, int64_t w_off,
-                    int64_t so, int64_t si, int64_t b_off, int accumulate, void* st) {
-  if (rows <= 0) return NB_OK;
-  NbWgradArgs a;
-  memset(&a, 0, sizeof(a));
-  a.rows = rows; a.npair = npair; a.pair[0] = p0; a.pair[1] = p1; a.colsum = b_off >= 0; a.partial = partial;
-  int grid = imin(cdiv(rows, NB_TILE), wgrad_grid_cap());
+// ---- deferred reductions: weight-gradient GEMMs and partial-sum finalisations are queued and launched in batches
+// (one k_wgrad64 + one k_finalize launch per layer / iteration instead of one pair per parameter tensor).
+// Jobs of one batch must target disjoint destination elements; q_flush() separates dependent batches.
+struct WgradFin {
+  int64_t w_off, so, si, b_off;
+  float* dst;
+  int accumulate;
+};
+struct LaunchQueue {
+  float* pbase;
+  int64_t pcap, pused;
+  NbWgradBatch wb;
+  WgradFin wfin[NB_MAX_WGRAD_JOBS];
+  NbFinBatch fb;
+};
+static thread_local LaunchQueue g_q;
+
+static void q_begin(float* partial_base, int64_t cap) {
+  g_q.pbase = partial_base;
+  g_q.pcap = cap;
+  g_q.pused = 0;
+  g_q.wb.njobs = 0;
+  g_q.fb.njobs = 0;
+}
+static int q_flush(void* st);
+static int q_flush_fin(void* st, bool release_scratch = true) {
+  if (g_q.fb.njobs == 0) {
+    if (release_scratch) g_q.pused = 0;
+    return NB_OK;
+  }
+  int maxtotal = 0;
+  for (int j = 0; j < g_q.fb.njobs; ++j)
+    if (g_q.fb.job[j].total > maxtotal) maxtotal = g_q.fb.job[j].total;
+  NB_LAUNCH_COUNTED(k_finalize, dim3((unsigned)cdiv(maxtotal, 32), (unsigned)g_q.fb.njobs), 256, 0, st, g_q.fb);
+  g_q.fb.njobs = 0;
+  // stream order: the finalisation has consumed every partial slice whose reduction was queued; the caller keeps
+  // the scratch when a slice has been handed out but its reduction is not queued yet
+  if (release_scratch) g_q.pused = 0;
+  return nb_check_launch("k_finalize");
+}
+// partial-sum scratch for a kernel launched now and finalised at the next flush
+static float* q_alloc(int64_t nfloats, void* st) {
+  nfloats = (nfloats + 63) / 64 * 64;
+  if (g_q.pused + nfloats > g_q.pcap) {
+    if (q_flush(st) != NB_OK || nfloats > g_q.pcap) return nullptr;
+  }
+  float* p = g_q.pbase + g_q.pused;
+  g_q.pused += nfloats;
+  return p;
+}
+static int launch_finalize(NbFinArgs& f, void* st) {
+  int total = 0;
+  for (int s = 0; s < f.nseg; ++s) total += f.seg[s].count;
+  f.total = total;
+  if (g_q.fb.njobs == NB_MAX_FIN_JOBS) NB_TRY(q_flush_fin(st, false));
+  g_q.fb.job[g_q.fb.njobs++] = f;
+  return NB_OK;
+}
+static int q_flush_wgrad(void* st) {
+  NbWgradBatch& wb = g_q.wb;
+  if (wb.njobs == 0) return NB_OK;
+  int maxrows = 0;
+  for (int j = 0; j < wb.njobs; ++j)
+    if (wb.job[j].rows > maxrows) maxrows = wb.job[j].rows;
+  const int grid = imin(cdiv(maxrows, NB_TILE), wgrad_grid_cap());
+  const int64_t need = (int64_t)wb.njobs * grid * NB_WGRAD_PLEN;
+  if (g_q.pused + need > g_q.pcap) NB_TRY(q_flush_fin(st));
+  if (need > g_q.pcap) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+  for (int j = 0; j < wb.njobs; ++j) {
+    wb.job[j].partial = g_q.pbase + g_q.pused;
+    g_q.pused += (int64_t)grid * NB_WGRAD_PLEN;
+  }
   const size_t smem = 2 * NB_TILE * NB_LDA * sizeof(float);
   NB_SET_SMEM(k_wgrad64, smem);
   int pi = prof_begin(3, st);
-  NB_LAUNCH_COUNTED(k_wgrad64, (unsigned)grid, NB_THREADS, smem, st, a);
+  NB_LAUNCH_COUNTED(k_wgrad64, dim3((unsigned)grid, (unsigned)wb.njobs), NB_THREADS, smem, st, wb);
   prof_end(3, pi, st);
   NB_TRY(nb_check_launch("k_wgrad64"));
-  NbFinArgs f;
-  memset(&f, 0, sizeof(f));
-  f.partial = partial; f.nparts = grid; f.plen = NB_WGRAD_PLEN; f.dst = dst; f.accumulate = accumulate;
-  f.nseg = 0;
-  f.seg[f.nseg++] = fseg(0, NB_H * NB_H, NB_H, w_off, so, si);
-  if (b_off >= 0) f.seg[f.nseg++] = fseg(NB_H * NB_H, NB_H, NB_H, b_off, 0, 1);
-  return launch_finalize(f, st);
+  const int n = wb.njobs;
+  wb.njobs = 0;
+  for (int j = 0; j < n; ++j) {
+    NbFinArgs f;
+    memset(&f, 0, sizeof(f));
+    const WgradFin& wf = g_q.wfin[j];
+    f.partial = wb.job[j].partial; f.nparts = grid; f.plen = NB_WGRAD_PLEN; f.dst = wf.dst; f.accumulate = wf.accumulate;
+    f.nseg = 0;
+    f.seg[f.nseg++] = fseg(0, NB_H * NB_H, NB_H, wf.w_off, wf.so, wf.si);
+    if (wf.b_off >= 0) f.seg[f.nseg++] = fseg(NB_H * NB_H, NB_H, NB_H, wf.b_off, 0, 1);
+    NB_TRY(launch_finalize(f, st));
+  }
+  return NB_OK;
+}
+static int q_flush(void* st) {
+  NB_TRY(q_flush_wgrad(st));
+  return q_flush_fin(st);
+}
+
+// dst[w_off + o*so + k*si] (+)= sum_rows sum_p scale_p G_p[r][o] A_p[r][k];  dst[b_off + o] (+)= colsum(G_0) if b_off >= 0
+// (queued; executed at the next q_flush)
+static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* dst, int64_t w_off, int64_t so,
+                    int64_t si, int64_t b_off, int accumulate, void* st) {
+  if (rows <= 0) return NB_OK;
+  if (g_q.wb.njobs == NB_MAX_WGRAD_JOBS) NB_TRY(q_flush_wgrad(st));
+  NbWgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows; a.npair = npair; a.pair[0] = p0; a.pair[1] = p1; a.colsum = b_off >= 0;
+  WgradFin wf;
+  wf.w_off = w_off; wf.so = so; wf.si = si; wf.b_off = b_off; wf.dst = dst; wf.accumulate = accumulate;
+  g_q.wfin[g_q.wb.njobs] = wf;
+  g_q.wb.job[g_q.wb.njobs++] = a;
+  return NB_OK;
 }
 
 static NbWgradPair wpair(const float* G, const float* A, int a_silu = 0, float scale = 1.f) {
@@ -258,9 +355,10 @@ struct EdgeGradDst {
   int ldw1, col_rad, col_ef;
 };
 
-static int launch_edge_bwd(NbEdgeBwdArgs& a, float* partial, float* dst, const EdgeGradDst& d, int accumulate,
-                           void* st) {
+static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, int accumulate, void* st) {
   int grid = imin(a.g.n_units, edge_bwd_grid_cap());
+  float* partial = q_alloc((int64_t)grid * NB_EB_PLEN, st);
+  if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
   a.partial = partial;
   bool done = false;
 #ifndef NB_EMU
@@ -444,6 +542,8 @@ static int egno_tc_mix(const EgnoCtx& X, int l, const float* coef, float* ycoef)
   const float* W = X.params + X.lo.L[l].tc;
   const int64_t plane = X.Nn0 * NB_H;
   const int64_t sk = (int64_t)NB_H * modes * 2, sn = (int64_t)modes * 2;  // B[k=i][n=o] = W[i][o][m][c]
+  NbGemmArgs jobs[2 * NB_MAX_T];
+  int nj = 0;
   for (int m = 0; m < modes; ++m) {
     int ci = nb_coef_index(X.tw, m);
     const float* Wr = W + m * 2;
@@ -452,23 +552,23 @@ static int egno_tc_mix(const EgnoCtx& X, int l, const float* coef, float* ycoef)
       NbGemmArgs a = gemm_args((int)X.Nn0);
       a.nsrc = 1; a.src[0] = gsrc(coef + ci * plane, NB_H, 0, Wr, sk, sn);
       a.out = ycoef + ci * plane;
-      NB_TRY(launch_gemm(a, X.st));
+      jobs[nj++] = a;
     } else {
       NbGemmArgs a = gemm_args((int)X.Nn0);  // P = C Wr + S Wi
       a.nsrc = 2;
       a.src[0] = gsrc(coef + ci * plane, NB_H, 0, Wr, sk, sn);
       a.src[1] = gsrc(coef + (ci + 1) * plane, NB_H, 0, Wi, sk, sn);
       a.out = ycoef + ci * plane;
-      NB_TRY(launch_gemm(a, X.st));
+      jobs[nj++] = a;
       NbGemmArgs b = gemm_args((int)X.Nn0);  // Q = C Wi - S Wr
       b.nsrc = 2;
       b.src[0] = gsrc(coef + ci * plane, NB_H, 0, Wi, sk, sn);
       b.src[1] = gsrc(coef + (ci + 1) * plane, NB_H, 0, Wr, sk, sn, -1.f);
       b.out = ycoef + (ci + 1) * plane;
-      NB_TRY(launch_gemm(b, X.st));
+      jobs[nj++] = b;
     }
   }
-  return NB_OK;
+  return launch_gemm_batch(jobs, nj, X.st);
 }
 
 static NbDftArgs dft_args(const EgnoCtx& X) {
@@ -485,11 +585,11 @@ static int egno_pq(const EgnoCtx& X, int l, const float* h1, float* P, float* Q)
   NbGemmArgs a = gemm_args((int)X.Nn);  // P = h W1[:, h_row]^T + b1   (cols 1..64, basic.py:98,170)
   a.nsrc = 1; a.src[0] = gsrc(h1, NB_H, 0, X.params + L.e_w1 + 1, 1, E);
   a.bias = X.params + L.e_b1; a.out = P;
-  NB_TRY(launch_gemm(a, X.st));
   NbGemmArgs b = gemm_args((int)X.Nn);  // Q = h W1[:, h_col]^T         (cols 65..128)
   b.nsrc = 1; b.src[0] = gsrc(h1, NB_H, 0, X.params + L.e_w1 + 1 + NB_H, 1, E);
   b.out = Q;
-  return launch_gemm(b, X.st);
+  NbGemmArgs ab[2] = {a, b};
+  return launch_gemm_batch(ab, 2, X.st);
 }
 
 static NbEdgeW egno_edge_w(const EgnoCtx& X, int l) {
@@ -579,15 +679,15 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       a.src[0] = gsrc(h1, NB_H, 0, params + L.n_w1, 1, 2 * NB_H);
       a.src[1] = gsrc(b.M, NB_H, 0, params + L.n_w1 + NB_H, 1, 2 * NB_H);
       a.bias = params + L.n_b1; a.out_pre = b.U5;
-      NB_TRY(launch_gemm(a, stream));
+      NbGemmArgs u = gemm_args((int)Nn);  // UV = h Wv1^T + bv1         (node_v_net, pre-update h)
+      u.nsrc = 1; u.src[0] = gsrc(h1, NB_H, 0, params + L.v_w1, 1, NB_H);
+      u.bias = params + L.v_b1; u.out_pre = b.UV;
+      NbGemmArgs au[2] = {a, u};
+      NB_TRY(launch_gemm_batch(au, 2, stream));
       NbGemmArgs c2 = gemm_args((int)Nn);  // h' = SiLU(U5) W6^T + b6  (no residual)
       c2.nsrc = 1; c2.src[0] = gsrc(b.U5, NB_H, 1, params + L.n_w2, 1, NB_H);
       c2.bias = params + L.n_b2; c2.out = h_next;
       NB_TRY(launch_gemm(c2, stream));
-      NbGemmArgs u = gemm_args((int)Nn);  // UV = h Wv1^T + bv1         (node_v_net, pre-update h)
-      u.nsrc = 1; u.src[0] = gsrc(h1, NB_H, 0, params + L.v_w1, 1, NB_H);
-      u.bias = params + L.v_b1; u.out_pre = b.UV;
-      NB_TRY(launch_gemm(u, stream));
       NbXupdArgs xa;
       memset(&xa, 0, sizeof(xa));
       xa.rows = Nn; xa.N = cfg->N; xa.x = x1; xa.v = v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
@@ -630,7 +730,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   float* gvA = w; w += n3;
   float* gvB = w; w += n3;
   float* gFsum = w; w += n3;
-  float* partial = w;
+  q_begin(w, NB_PARTIAL_FLOATS);
   cudaStream_t cst = (cudaStream_t)stream;
 
   cudaMemsetAsync(grad_params, 0, X.lo.total * sizeof(float), cst);
@@ -655,8 +755,11 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       NbXupdArgs xa;
       memset(&xa, 0, sizeof(xa));
       xa.rows = Nn; xa.N = cfg->N; xa.v = b.v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
-      xa.Fsum = b.Fsum; xa.gx = gx; xa.gv = gv_in; xa.gv_out = gvB; xa.gFsum = gFsum; xa.GUV = GUV; xa.partial = partial;
+      xa.Fsum = b.Fsum; xa.gx = gx; xa.gv = gv_in; xa.gv_out = gvB; xa.gFsum = gFsum; xa.GUV = GUV;
       int grid = imin(cdiv(Nn, 8), 4 * nb_num_sms());
+      float* partial = q_alloc((int64_t)grid * 65, stream);
+      if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+      xa.partial = partial;
       NB_LAUNCH_COUNTED(k_egno_xupd_bwd, (unsigned)grid, 256, 0, stream, xa);
       NB_TRY(nb_check_launch("k_egno_xupd_bwd"));
       NbFinArgs f;
@@ -672,23 +775,23 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + L.n_w2, NB_H, 1);
       a.epi = NB_EPI_MUL_DSILU; a.U = b.U5; a.out = GU5;
       NB_TRY(launch_gemm(a, stream));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), partial, grad_params, L.n_w2, NB_H, 1,
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), grad_params, L.n_w2, NB_H, 1,
                       L.n_b2, 0, stream));
       NbGemmArgs g1 = gemm_args((int)Nn);  // gh1 = GU5 W5[:, :64] + GUV Wv1
       g1.nsrc = 2;
       g1.src[0] = gsrc(GU5, NB_H, 0, params + L.n_w1, 2 * NB_H, 1);
       g1.src[1] = gsrc(GUV, NB_H, 0, params + L.v_w1, NB_H, 1);
       g1.out = ghA;
-      NB_TRY(launch_gemm(g1, stream));
       NbGemmArgs g2 = gemm_args((int)Nn);  // gM = GU5 W5[:, 64:]
       g2.nsrc = 1; g2.src[0] = gsrc(GU5, NB_H, 0, params + L.n_w1 + NB_H, 2 * NB_H, 1);
       g2.out = gM;
-      NB_TRY(launch_gemm(g2, stream));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, h1), wpair(nullptr, nullptr), partial, grad_params, L.n_w1, 2 * NB_H, 1,
+      NbGemmArgs g12[2] = {g1, g2};
+      NB_TRY(launch_gemm_batch(g12, 2, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, h1), wpair(nullptr, nullptr), grad_params, L.n_w1, 2 * NB_H, 1,
                       L.n_b1, 0, stream));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), partial, grad_params, L.n_w1 + NB_H,
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), grad_params, L.n_w1 + NB_H,
                       2 * NB_H, 1, -1, 0, stream));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(GUV, h1), wpair(nullptr, nullptr), partial, grad_params, L.v_w1, NB_H, 1,
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GUV, h1), wpair(nullptr, nullptr), grad_params, L.v_w1, NB_H, 1,
                       L.v_b1, 0, stream));
     }
     // 3. edge tile backward (recompute)
@@ -702,7 +805,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       EdgeGradDst d;
       d.w1 = L.e_w1; d.W2 = L.e_w2; d.b2 = L.e_b2; d.W3 = L.c_w1; d.b3 = L.c_b1; d.w4 = L.c_w2; d.b4 = L.c_b2;
       d.ldw1 = X.lo.E; d.col_rad = 0; d.col_ef = 1 + 2 * NB_H; d.b_unused = 0;
-      NB_TRY(launch_edge_bwd(ea, partial, grad_params, d, 0, stream));
+      NB_TRY(launch_edge_bwd(ea, grad_params, d, 0, stream));
     }
     // 4. pre-projection backward: gh1 += gP W1[:, h_row] + gQ W1[:, h_col]
     {
@@ -712,9 +815,9 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       a.src[1] = gsrc(gQ, NB_H, 0, params + L.e_w1 + 1 + NB_H, X.lo.E, 1);
       a.out = ghA; a.accumulate = 1;
       NB_TRY(launch_gemm(a, stream));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, h1), wpair(nullptr, nullptr), partial, grad_params, L.e_w1 + 1, X.lo.E, 1,
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, h1), wpair(nullptr, nullptr), grad_params, L.e_w1 + 1, X.lo.E, 1,
                       L.e_b1, 0, stream));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, h1), wpair(nullptr, nullptr), partial, grad_params, L.e_w1 + 1 + NB_H,
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, h1), wpair(nullptr, nullptr), grad_params, L.e_w1 + 1 + NB_H,
                       X.lo.E, 1, -1, 0, stream));
     }
     // 5. temporal convolutions
@@ -724,8 +827,11 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         NbTcxArgs t;
         memset(&t, 0, sizeof(t));
         t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
-        t.gx1 = gx; t.gv1 = gvB; t.gx0 = gx0; t.gv0 = gvA; t.partial = partial;
+        t.gx1 = gx; t.gv1 = gvB; t.gx0 = gx0; t.gv0 = gvA;
         int grid = imin(cdiv(Nn0 * 3, 256), 2 * nb_num_sms());
+        float* partial = q_alloc((int64_t)grid * 2 * 2 * modes * 2, stream);
+        if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+        t.partial = partial;
         NB_LAUNCH_COUNTED(k_tcx_bwd, (unsigned)grid, 256, 0, stream, t);
         NB_TRY(nb_check_launch("k_tcx_bwd"));
         NbFinArgs f;
@@ -749,6 +855,8 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         const float* W = params + L.tc;
         const int64_t plane = Nn0 * NB_H;
         const int64_t tk = (int64_t)modes * 2, tn = (int64_t)NB_H * modes * 2;  // B[k=o][n=i] = W[i][o][m][c]
+        NbGemmArgs gj[2 * NB_MAX_T];
+        int ngj = 0;
         for (int m = 0; m < modes; ++m) {
           int ci = nb_coef_index(X.tw, m);
           const float *Wr = W + m * 2, *Wi = W + m * 2 + 1;
@@ -759,8 +867,8 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
             NbGemmArgs a = gemm_args((int)Nn0);  // gC = gP Wr^T
             a.nsrc = 1; a.src[0] = gsrc(gPm, NB_H, 0, Wr, tk, tn);
             a.out = gcoef + ci * plane;
-            NB_TRY(launch_gemm(a, stream));
-            NB_TRY(wgrad_to((int)Nn0, 1, wpair(C, gPm), wpair(nullptr, nullptr), partial, grad_params, wr_off, tn, tk,
+            gj[ngj++] = a;
+            NB_TRY(wgrad_to((int)Nn0, 1, wpair(C, gPm), wpair(nullptr, nullptr), grad_params, wr_off, tn, tk,
                             -1, 0, stream));
           } else {
             NbGemmArgs a = gemm_args((int)Nn0);  // gC = gP Wr^T + gQ Wi^T
@@ -768,26 +876,30 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
             a.src[0] = gsrc(gPm, NB_H, 0, Wr, tk, tn);
             a.src[1] = gsrc(gQm, NB_H, 0, Wi, tk, tn);
             a.out = gcoef + ci * plane;
-            NB_TRY(launch_gemm(a, stream));
+            gj[ngj++] = a;
             NbGemmArgs s2 = gemm_args((int)Nn0);  // gS = gP Wi^T - gQ Wr^T
             s2.nsrc = 2;
             s2.src[0] = gsrc(gPm, NB_H, 0, Wi, tk, tn);
             s2.src[1] = gsrc(gQm, NB_H, 0, Wr, tk, tn, -1.f);
             s2.out = gcoef + (ci + 1) * plane;
-            NB_TRY(launch_gemm(s2, stream));
+            gj[ngj++] = s2;
             // dWr[i][o] = sum C_i gP_o - S_i gQ_o ; dWi[i][o] = sum S_i gP_o + C_i gQ_o
-            NB_TRY(wgrad_to((int)Nn0, 2, wpair(C, gPm), wpair(S, gQm, 0, -1.f), partial, grad_params, wr_off, tn, tk,
+            NB_TRY(wgrad_to((int)Nn0, 2, wpair(C, gPm), wpair(S, gQm, 0, -1.f), grad_params, wr_off, tn, tk,
                             -1, 0, stream));
-            NB_TRY(wgrad_to((int)Nn0, 2, wpair(S, gPm), wpair(C, gQm), partial, grad_params, wi_off, tn, tk, -1, 0,
+            NB_TRY(wgrad_to((int)Nn0, 2, wpair(S, gPm), wpair(C, gQm), grad_params, wi_off, tn, tk, -1, 0,
                             stream));
           }
         }
+        NB_TRY(launch_gemm_batch(gj, ngj, stream));
+        // queued weight-gradient jobs read gh_in / GU5 / gP / coefficients: run them before ghB is overwritten
+        NB_TRY(q_flush(stream));
         d.gcoef = gcoef; d.gx = ghB;
         NB_LAUNCH_COUNTED(k_dft_bwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
         NB_TRY(nb_check_launch("k_dft_bwd"));
       }
       gh_in = ghB;
     } else {
+      NB_TRY(q_flush(stream));
       gv_in = gvB;
       // without the temporal conv gv1 must survive in gvB while the next layer writes its own gv1: swap roles
       float* tmp = gvA; gvA = gvB; gvB = tmp;
@@ -807,9 +919,12 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       float sc = (float)(log(10000.0) / (double)(half - 1));
       e.freq[k] = expf((float)k * -sc);
     }
-    eb.g = gh_in; eb.partial = partial;
+    eb.g = gh_in;
     const int F = X.lo.F;
     int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
+    float* partial = q_alloc((int64_t)grid * (NB_H * F + NB_H), stream);
+    if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+    eb.partial = partial;
     const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
     NB_LAUNCH_COUNTED(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
     NB_TRY(nb_check_launch("k_embed_bwd"));
@@ -819,6 +934,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     f.seg[0] = fseg(0, NB_H * F, NB_H * F, X.lo.emb_w, 0, 1);
     f.seg[1] = fseg(NB_H * F, NB_H, NB_H, X.lo.emb_b, 0, 1);
     NB_TRY(launch_finalize(f, stream));
+    NB_TRY(q_flush(stream));
   }
   if (g_x_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T);
   if (g_v_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T);
@@ -907,11 +1023,11 @@ static int segno_pq(const SegnoCtx& X, const float* h, float* P, float* Q) {
   NbGemmArgs a = gemm_args((int)X.Nn);  // cols: h_row | h_col | radial | edge_attr  (gcl.py:78)
   a.nsrc = 1; a.src[0] = gsrc(h, NB_H, 0, X.params + X.lo.e_w1, 1, X.lo.E);
   a.bias = X.params + X.lo.e_b1; a.out = P;
-  NB_TRY(launch_gemm(a, X.st));
   NbGemmArgs b = gemm_args((int)X.Nn);
   b.nsrc = 1; b.src[0] = gsrc(h, NB_H, 0, X.params + X.lo.e_w1 + NB_H, 1, X.lo.E);
   b.out = Q;
-  return launch_gemm(b, X.st);
+  NbGemmArgs ab[2] = {a, b};
+  return launch_gemm_batch(ab, 2, X.st);
 }
 
 static NbEdgeW segno_edge_w(const SegnoCtx& X) {
@@ -1010,7 +1126,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   float* gx = w; w += n3;
   float* gvb[2]; gvb[0] = w; w += n3; gvb[1] = w; w += n3;
   float* gFsum = w; w += n3;
-  float* partial = w;
+  q_begin(w, NB_PARTIAL_FLOATS);
   cudaStream_t cst = (cudaStream_t)stream;
 
   cudaMemsetAsync(grad_params, 0, lo.total * sizeof(float), cst);
@@ -1030,20 +1146,20 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + lo.n_w2, NB_H, 1);
     a.epi = NB_EPI_MUL_DSILU; a.U = b.U5; a.out = GU5;
     NB_TRY(launch_gemm(a, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), partial, grad_params, lo.n_w2, NB_H, 1,
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1,
                     lo.n_b2, 1, stream));
     NbGemmArgs g1 = gemm_args((int)Nn);  // gh = GU5 W5[:, :64] (+ gh: residual)
     g1.nsrc = 1; g1.src[0] = gsrc(GU5, NB_H, 0, params + lo.n_w1, 2 * NB_H, 1);
     if (cfg->recurrent) g1.R = gh_in;
     g1.out = gh_new;
-    NB_TRY(launch_gemm(g1, stream));
     NbGemmArgs g2 = gemm_args((int)Nn);  // gM = GU5 W5[:, 64:]
     g2.nsrc = 1; g2.src[0] = gsrc(GU5, NB_H, 0, params + lo.n_w1 + NB_H, 2 * NB_H, 1);
     g2.out = gM;
-    NB_TRY(launch_gemm(g2, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.h), wpair(nullptr, nullptr), partial, grad_params, lo.n_w1, 2 * NB_H, 1,
+    NbGemmArgs g12[2] = {g1, g2};
+    NB_TRY(launch_gemm_batch(g12, 2, stream));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.h), wpair(nullptr, nullptr), grad_params, lo.n_w1, 2 * NB_H, 1,
                     lo.n_b1, 1, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), partial, grad_params, lo.n_w1 + NB_H, 2 * NB_H,
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), grad_params, lo.n_w1 + NB_H, 2 * NB_H,
                     1, -1, 1, stream));
     // integrator backward
     NbIntegArgs ia;
@@ -1064,17 +1180,18 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     EdgeGradDst d;
     d.w1 = lo.e_w1; d.W2 = lo.e_w2; d.b2 = lo.e_b2; d.W3 = lo.c_w1; d.b3 = lo.c_b1; d.w4 = lo.c_w2; d.b4 = lo.c_b2;
     d.ldw1 = lo.E; d.col_rad = 2 * NB_H; d.col_ef = 2 * NB_H + 1; d.b_unused = 0;
-    NB_TRY(launch_edge_bwd(ea, partial, grad_params, d, 1, stream));
+    NB_TRY(launch_edge_bwd(ea, grad_params, d, 1, stream));
     NbGemmArgs pa = gemm_args((int)Nn);  // gh += gP W1[:, h_row] + gQ W1[:, h_col]
     pa.nsrc = 2;
     pa.src[0] = gsrc(gP, NB_H, 0, params + lo.e_w1, lo.E, 1);
     pa.src[1] = gsrc(gQ, NB_H, 0, params + lo.e_w1 + NB_H, lo.E, 1);
     pa.out = gh_new; pa.accumulate = 1;
     NB_TRY(launch_gemm(pa, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, b.h), wpair(nullptr, nullptr), partial, grad_params, lo.e_w1, lo.E, 1, lo.e_b1,
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, b.h), wpair(nullptr, nullptr), grad_params, lo.e_w1, lo.E, 1, lo.e_b1,
                     1, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, b.h), wpair(nullptr, nullptr), partial, grad_params, lo.e_w1 + NB_H, lo.E, 1,
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, b.h), wpair(nullptr, nullptr), grad_params, lo.e_w1 + NB_H, lo.E, 1,
                     -1, 1, stream));
+    NB_TRY(q_flush(stream));  // the shared weights accumulate across iterations: one reduction batch per iteration
     gh_in = gh_new;
     ghi ^= 1;
   }
@@ -1082,9 +1199,12 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     NbEmbedBwdArgs eb;
     memset(&eb, 0, sizeof(eb));
     segno_embed_args(X, his, &eb.e);
-    eb.g = gh_in; eb.partial = partial;
+    eb.g = gh_in;
     const int F = cfg->in_node_nf;
     int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
+    float* partial = q_alloc((int64_t)grid * (NB_H * F + NB_H), stream);
+    if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+    eb.partial = partial;
     const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
     NB_LAUNCH_COUNTED(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
     NB_TRY(nb_check_launch("k_embed_bwd"));
@@ -1094,6 +1214,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     f.seg[0] = fseg(0, NB_H * F, NB_H * F, lo.emb_w, 0, 1);
     f.seg[1] = fseg(NB_H * F, NB_H, NB_H, lo.emb_b, 0, 1);
     NB_TRY(launch_finalize(f, stream));
+    NB_TRY(q_flush(stream));
   }
   if (g_x_in) cudaMemcpyAsync(g_x_in, gx, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
   if (g_v_in) {
@@ -1159,7 +1280,9 @@ extern "C" int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t
   d.W2 = 0; d.W3 = NB_H * NB_H; d.b2 = 2 * NB_H * NB_H; d.b3 = d.b2 + NB_H; d.w4 = d.b3 + NB_H;
   d.ldw1 = 1 + n_edge_fea; d.col_rad = 0; d.col_ef = 1; d.b_unused = 0;
   d.b4 = d.w1 + (int64_t)NB_H * d.ldw1;
-  return launch_edge_bwd(a, workspace, gw, d, 0, stream);
+  q_begin(workspace, NB_PARTIAL_FLOATS);
+  NB_TRY(launch_edge_bwd(a, gw, d, 0, stream));
+  return q_flush(stream);
 }
 
 // tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.
