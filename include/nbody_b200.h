@@ -165,8 +165,10 @@ long long nb_launch_count(void);
 int nb_profile_enable(int enable);
 int nb_profile_read(double* ms /*[4]*/, long long* counts /*[4]*/);
 
-/* Edge-tile implementation: 1 = tcgen05 tensor-core tiles (default, product path), 0 = fp32 SIMT tiles (kept as an
- * independent cross-check and for the host emulator of the test suite).  Both are CUDA kernels of this library. */
+/* Edge-tile implementation: 2 = tcgen05 tensor-core tiles whose node gathers and receiver / sender reductions are
+ * one-hot MMAs (default, product path; graphs with more than 27 nodes run variant 1), 1 = tcgen05 tiles with
+ * CUDA-core gathers / reductions, 0 = fp32 SIMT tiles (kept as an independent cross-check and for the host emulator
+ * of the test suite).  All are CUDA kernels of this library. */
 int nb_set_edge_impl(int impl);
 int nb_get_edge_impl(void);
 

@@ -1,0 +1,443 @@
+// nb_edge_sel.cuh — fused E_GCL edge tiles with ALL gathers and scatters on the tensor cores.
+//
+// Same math and unit / tile decomposition as nb_edge.cuh / nb_edge_tc.cuh.  What changes is how per-node data reaches
+// the edge rows and how per-edge data is reduced back onto nodes: both go through a one-hot *selector* tile
+//
+//     Sel[row][col]   (128 edge rows x 64 columns, bf16, exact 0/1 entries plus a few split scalars)
+//       col li          (0 <= li < GN)         1 iff the row's receiver is local node li
+//       col GN + lj                            1 iff the row's sender   is local node lj
+//       cols 54..63                            r2_hi, r2_lo, e0_hi, e0_lo, ... e3_hi, e3_lo   (split-bf16 scalars)
+//
+// and a per-unit node tile  NT[k][0:64]  (rows: P of the unit's nodes | Q of the unit's nodes | w_rad, w_ef rows):
+//
+//     pre1      = Sel  . NT                      P_i + Q_j + w_rad r2 + W_ef e        (gather  = MMA, A K-major)
+//     gm       += Sel  . gM_unit                 broadcast of dL/dM_i onto the rows   (gather  = MMA)
+//     M_i, ...  = Sel^T . m                      receiver / sender sums               (scatter = MMA, A MN-major)
+//     gP|gQ|gw  = Sel^T . g1 ,  gx = Sel^T . rG
+//
+// One-hot products are exact, so the only rounding is the 2-piece bf16 split of the gathered / reduced operand
+// (2^-17 relative), the same as every other operand of these kernels.  The unit-level accumulators live in TMEM
+// across the tiles of a unit and are read out once per unit: no per-edge global gather, no shared-memory reduction
+// loops, no atomics; bitwise deterministic.
+//
+// Valid for G*N <= 27 (2 G N + 10 selector columns <= 64): N <= 27, which covers the 5- and 20-body configurations;
+// larger graphs use the kernels of nb_edge_tc.cuh.
+#pragma once
+#ifndef NB_EMU
+#include "nb_edge.cuh"
+#include "nb_tc.cuh"
+#include "nb_edge_tc.cuh"
+
+#define NB_SEL_MAX_GN 27
+#define NB_SEL_XC0 54  // first scalar column of the selector / first weight row of the node tile
+
+// ----------------------------------------------------------------------------- cheap descriptor arithmetic
+// 64-bit shared-memory descriptors as (lo, hi) halves: hi is a per-layout constant, lo = address field + LBO field;
+// advancing a k-step is one 32-bit add on lo.
+#define NB_DESC_HI_SW128 (((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29))
+#define NB_DESC_HI_NOSW (((128u >> 4) & 0x3FFFu) | (1u << 14))
+__device__ __forceinline__ uint32_t nb_desc_lo_k(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | ((16u >> 4) << 16); }      // K-major SW128
+__device__ __forceinline__ uint32_t nb_desc_lo_mn(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | ((8192u >> 4) << 16); }  // MN-major SW128
+__device__ __forceinline__ uint32_t nb_desc_lo_n8(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | ((128u >> 4) << 16); }   // dense [rows][8]
+#define NB_KSTEP_K 2u     // 32 bytes  >> 4
+#define NB_KSTEP_MN 128u  // 2048 bytes >> 4
+#define NB_KSTEP_N8 16u   // 256 bytes >> 4
+
+__device__ __forceinline__ void nb_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// the three split passes of a 64-deep product, A K-major [128][64], B = weight tile (K-major: W^T product, MN-major: W product)
+__device__ __forceinline__ void nb_issue_w3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo,
+                                            bool w_mn, uint32_t idesc, uint32_t acc0) {
+  const uint32_t bstep = w_mn ? NB_KSTEP_MN : NB_KSTEP_K;
+  uint32_t acc = acc0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = nb_desc_lo_k(pass == 1 ? a_lo : a_hi);
+    const uint32_t b = w_mn ? nb_desc_lo_mn(pass == 2 ? w_lo : w_hi) : nb_desc_lo_k(pass == 2 ? w_lo : w_hi);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      nb_mma2(tmem_d, a + NB_KSTEP_K * s, NB_DESC_HI_SW128, b + bstep * s, NB_DESC_HI_SW128, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+
+// gather: D[128 x 64] (+)= Sel[128 x 16 ksteps] . (Nh + Nl),  Sel K-major, node tile MN-major (K = node-tile rows)
+__device__ __forceinline__ void nb_issue_gather(uint32_t tmem_d, uint32_t sel, uint32_t n_hi, uint32_t n_lo, int ksteps,
+                                                uint32_t idesc, uint32_t acc0) {
+  uint32_t acc = acc0;
+  const uint32_t a = nb_desc_lo_k(sel);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t b = nb_desc_lo_mn(pass ? n_lo : n_hi);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      if (s < ksteps) {
+        nb_mma2(tmem_d, a + NB_KSTEP_K * s, NB_DESC_HI_SW128, b + NB_KSTEP_MN * s, NB_DESC_HI_SW128, idesc, acc);
+        acc = 1u;
+      }
+  }
+}
+
+// scatter: D[64 x 64] (+)= Sel^T . (Vh + Vl),  Sel MN-major (M = selector columns, K = 128 rows), V MN-major [128][64]
+__device__ __forceinline__ void nb_issue_scatter(uint32_t tmem_d, uint32_t sel, uint32_t v_hi, uint32_t v_lo,
+                                                 uint32_t idesc, uint32_t acc0) {
+  uint32_t acc = acc0;
+  const uint32_t a = nb_desc_lo_mn(sel);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t b = nb_desc_lo_mn(pass ? v_lo : v_hi);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      nb_mma2(tmem_d, a + NB_KSTEP_MN * s, NB_DESC_HI_SW128, b + NB_KSTEP_MN * s, NB_DESC_HI_SW128, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+// scatter of a dense [128][8] tile: D[64 x 8] (+)= Sel^T . (Vh + Vl)
+__device__ __forceinline__ void nb_issue_scatter8(uint32_t tmem_d, uint32_t sel, uint32_t v_hi, uint32_t v_lo,
+                                                  uint32_t idesc, uint32_t acc0) {
+  uint32_t acc = acc0;
+  const uint32_t a = nb_desc_lo_mn(sel);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t b = nb_desc_lo_n8(pass ? v_lo : v_hi);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      nb_mma2(tmem_d, a + NB_KSTEP_MN * s, NB_DESC_HI_SW128, b + NB_KSTEP_N8 * s, NB_DESC_HI_NOSW, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+
+// 16 / 8 / 4 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void nb_tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------- row bookkeeping
+// rowinfo[r] for unit-local row r:  li | lj << 8 | lg << 16   (built once per CTA; every unit has the same structure)
+__device__ __forceinline__ void nb_sel_build_rowinfo(uint32_t* rowinfo, const NbEdgeGeom& g, int tid, int nthreads) {
+  const int R = g.G * g.EPG;
+  for (int r = tid; r < R; r += nthreads) {
+    int lg = r / g.EPG, rem = r - lg * g.EPG;
+    int i = rem / (g.N - 1), jj = rem - i * (g.N - 1);
+    int j = jj + (jj >= i ? 1 : 0);
+    rowinfo[r] = (uint32_t)(lg * g.N + i) | ((uint32_t)(lg * g.N + j) << 8) | ((uint32_t)lg << 16);
+  }
+}
+
+__device__ __forceinline__ uint32_t nb_pack_split(float v) {  // (hi, lo) bf16 pieces of v in one 32-bit word
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+}
+
+// this thread's half (hf) of selector row `row`: 4 chunks of 16 bytes, then the two one-hot entries
+__device__ __forceinline__ void nb_sel_write_row(unsigned char* Sel, int row, int hf, bool valid, int li, int cj,
+                                                 float r2, const float (&e)[NB_MAX_EF]) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  unsigned char* rp = Sel + row * NB_TC_ROW_BYTES;
+  const int sw = row & 7;
+  if (hf == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(rp + ((c ^ sw) << 4)) = z;
+  } else {
+    *reinterpret_cast<uint4*>(rp + ((4 ^ sw) << 4)) = z;
+    *reinterpret_cast<uint4*>(rp + ((5 ^ sw) << 4)) = z;
+    uint4 c6 = z, c7 = z;
+    if (valid) {
+      c6.w = nb_pack_split(r2);  // columns 54, 55
+      c7.x = nb_pack_split(e[0]);
+      c7.y = nb_pack_split(e[1]);
+      c7.z = nb_pack_split(e[2]);
+      c7.w = nb_pack_split(e[3]);
+    }
+    *reinterpret_cast<uint4*>(rp + ((6 ^ sw) << 4)) = c6;
+    *reinterpret_cast<uint4*>(rp + ((7 ^ sw) << 4)) = c7;
+  }
+  if (valid) {  // same thread, after its own zero fill: program order
+    if ((li >> 5) == hf) *reinterpret_cast<unsigned short*>(rp + (((li >> 3) ^ sw) << 4) + (li & 7) * 2) = 0x3F80;
+    if ((cj >> 5) == hf) *reinterpret_cast<unsigned short*>(rp + (((cj >> 3) ^ sw) << 4) + (cj & 7) * 2) = 0x3F80;
+  }
+}
+
+// rows [0, GN) and [GN, 2 GN) of the node tile <- P, Q of the unit's nodes (split bf16)
+__device__ __forceinline__ void nb_sel_stage_nodes(unsigned char* Nh, unsigned char* Nl, const float* __restrict__ P,
+                                                   const float* __restrict__ Q, int64_t node0, int nnode, int GN, int tid,
+                                                   int nthreads) {
+  for (int idx = tid; idx < nnode * 16; idx += nthreads) {
+    int n = idx >> 4, which = (idx >> 3) & 1, j = idx & 7;
+    const float* src = (which ? Q : P) + (node0 + n) * NB_H + 8 * j;
+    float4 a = nb_ld4(src), b = nb_ld4(src + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    nb_tc_store8(Nh, Nl, which ? GN + n : n, j, v);
+  }
+}
+
+// TMEM lane of accumulator row i for M = 64 MMAs; thread (warp quarter q, lane < 16) owns row 16 q + lane
+// ----------------------------------------------------------------------------- forward
+// shared memory (bytes after 1024-alignment)
+#define NB_SF_W 0                                   // W2 hi/lo, W3 hi/lo       4 x 8 KB
+#define NB_SF_T (4 * NB_TC_TILE_BYTES(64))          // activation tile hi/lo    2 x 16 KB
+#define NB_SF_SEL (NB_SF_T + 2 * NB_TC_TILE_BYTES(128))   // selector          16 KB
+#define NB_SF_NT (NB_SF_SEL + NB_TC_TILE_BYTES(128))      // node tile hi/lo   2 x 8 KB
+#define NB_SF_F (NB_SF_NT + 2 * NB_TC_TILE_BYTES(64))     // force tile hi/lo  2 x 2 KB  ([128][8] bf16)
+#define NB_SF_FL (NB_SF_F + 2 * NB_TILE * 16)
+#define NB_SF_NFLOAT (3 * NB_H + 2 * NB_TILE + 32 * 3)
+#define NB_EDGE_FWD_SEL_SMEM(RU) (NB_SF_FL + NB_SF_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
+#define NB_SF_TMEM_COLS 256  // [0,64) pre-activations | [64,128) M accumulators | [128,136) Fsum accumulators
+
+__global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char nb_smraw[];
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
+  unsigned char* W2h = base + NB_SF_W;
+  unsigned char* W2l = W2h + NB_TC_TILE_BYTES(64);
+  unsigned char* W3h = W2l + NB_TC_TILE_BYTES(64);
+  unsigned char* W3l = W3h + NB_TC_TILE_BYTES(64);
+  unsigned char* Th = base + NB_SF_T;
+  unsigned char* Tl = Th + NB_TC_TILE_BYTES(128);
+  unsigned char* Sel = base + NB_SF_SEL;
+  unsigned char* Nh = base + NB_SF_NT;
+  unsigned char* Nl = Nh + NB_TC_TILE_BYTES(64);
+  unsigned char* Fh = base + NB_SF_F;
+  unsigned char* Fl = Fh + NB_TILE * 16;
+  float* fl = reinterpret_cast<float*>(base + NB_SF_FL);
+  float* vb2 = fl;
+  float* vb3 = vb2 + NB_H;
+  float* vw4 = vb3 + NB_H;
+  float* cpart = vw4 + NB_H;         // [2][128]
+  float* xs = cpart + 2 * NB_TILE;   // [GN][3] positions of the unit's nodes
+  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(xs + 32 * 3);
+  const NbEdgeGeom g = a.g;
+  const int RU = g.G * g.EPG, GN = g.G * g.N;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int row = 32 * q + lane;
+  const int cb = 32 * hf;
+
+  nb_tc_stage_weight(W2h, W2l, a.w.W2, tid);
+  nb_tc_stage_weight(W3h, W3l, a.w.W3, tid);
+  for (int idx = tid; idx < 2 * NB_TC_TILE_BYTES(64) / 16; idx += NB_THREADS)
+    reinterpret_cast<uint4*>(Nh)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  nb_sel_build_rowinfo(rowinfo, g, tid, NB_THREADS);
+  if (tid < NB_H) {
+    vb2[tid] = __ldg(a.w.b2 + tid);
+    vb3[tid] = __ldg(a.w.b3 + tid);
+    vw4[tid] = __ldg(a.w.w4 + tid);
+  }
+  if (tid == 0) {
+    nb_mbar_init(bar, 1);
+    nb_mbar_fence_init();
+  }
+  if (warp == 0) nb_tmem_alloc(tmem_slot, NB_SF_TMEM_COLS);
+  __syncthreads();
+  // weight rows of the node tile: 54,55 <- w_rad ; 56 + 2f, 57 + 2f <- w_ef[f]
+  for (int idx = tid; idx < 10 * 8; idx += NB_THREADS) {
+    int k = idx >> 3, j = idx & 7;
+    int f = (k >> 1) - 1;  // -1: radial
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int c = 8 * j + i;
+      v[i] = f < 0 ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_rad)
+                   : (f < g.nef ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_ef + f) : 0.f);
+    }
+    nb_tc_store8(Nh, Nl, NB_SEL_XC0 + k, j, v);
+  }
+  nb_fence_async_smem();
+  nb_tc_fence_before();
+  __syncthreads();
+  nb_tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t tm_mine = tm + ((uint32_t)(32 * q) << 16) + (uint32_t)cb;
+  const uint32_t idesc_fwd = nb_idesc_bf16(128, 64, 0, 0);  // A K-major, B K-major (W^T)
+  const uint32_t idesc_gat = nb_idesc_bf16(128, 64, 0, 1);  // A K-major, B MN-major
+  const uint32_t idesc_sc = nb_idesc_bf16(64, 64, 1, 1);    // Sel^T . tile
+  const uint32_t idesc_sc8 = nb_idesc_bf16(64, 8, 1, 1);
+  const uint32_t sTh = nb_smem_u32(Th), sTl = nb_smem_u32(Tl), sSel = nb_smem_u32(Sel), sNh = nb_smem_u32(Nh),
+                 sNl = nb_smem_u32(Nl), sFh = nb_smem_u32(Fh), sFl = nb_smem_u32(Fl), sW2h = nb_smem_u32(W2h),
+                 sW2l = nb_smem_u32(W2l), sW3h = nb_smem_u32(W3h), sW3l = nb_smem_u32(W3l);
+  const float b4 = __ldg(a.w.b4);
+  uint32_t phase = 0;
+
+  for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+    const int gt0 = u * g.G;
+    const int ngt = min(g.G, g.NGT - gt0);
+    const int R = ngt * g.EPG;
+    const int nnode = ngt * g.N;
+    const int64_t node0 = (int64_t)gt0 * g.N;
+    // every MMA of the previous unit has completed (its read-out waited for the last commit)
+    nb_sel_stage_nodes(Nh, Nl, a.P, a.Q, node0, nnode, GN, tid, NB_THREADS);
+    for (int idx = tid; idx < nnode * 3; idx += NB_THREADS) xs[idx] = __ldg(a.x + node0 * 3 + idx);
+    __syncthreads();
+
+    for (int r0 = 0; r0 < R; r0 += NB_TILE) {
+      const int nv = min(NB_TILE, R - r0);
+      const bool valid = row < nv;
+      // ---- geometry + selector row
+      float dx = 0.f, dy = 0.f, dz = 0.f, r2 = 0.f;
+      float e[NB_MAX_EF];
+#pragma unroll
+      for (int f = 0; f < NB_MAX_EF; ++f) e[f] = 0.f;
+      int li = 0, lj = 0;
+      if (valid) {
+        const uint32_t ri = rowinfo[r0 + row];
+        li = ri & 0xff;
+        lj = (ri >> 8) & 0xff;
+        const int lg = ri >> 16;
+        dx = xs[li * 3 + 0] - xs[lj * 3 + 0];
+        dy = xs[li * 3 + 1] - xs[lj * 3 + 1];
+        dz = xs[li * 3 + 2] - xs[lj * 3 + 2];
+        r2 = dx * dx + dy * dy + dz * dz;
+        const int64_t eoff = ((int64_t)((gt0 + lg) % g.B) * g.EPG + (r0 + row - lg * g.EPG)) * g.nef;
+#pragma unroll
+        for (int f = 0; f < NB_MAX_EF; ++f)
+          if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
+      }
+      // the scatter MMAs of the previous tile read Sel / T / F: they were issued before, and therefore complete
+      // before, the MMA whose commit this CTA waited for last  -> Sel may be rewritten only after that wait; the
+      // last wait of a tile (stage 3) precedes the scatter issue, so wait for the scatters here.
+      if (r0 > 0) {
+        nb_mbar_wait(bar, phase);
+        phase ^= 1;
+        nb_tc_fence_after();
+      }
+      nb_sel_write_row(Sel, row, hf, valid, li, GN + lj, r2, e);
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_gat, 0u);
+        nb_mma_commit(bar);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- z1 = SiLU(pre1) -> tile
+      {
+        float v[32];
+        nb_tmem_ld32(tm_mine, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Th, Tl, row, 4 * hf + jj, v + 8 * jj);
+      }
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_w3(tm, sTh, sTl, sW2h, sW2l, false, idesc_fwd, 0u);
+        nb_mma_commit(bar);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- m = SiLU(pre2 + b2) -> tile
+      {
+        float v[32];
+        nb_tmem_ld32(tm_mine, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i] + vb2[cb + i]);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Th, Tl, row, 4 * hf + jj, v + 8 * jj);
+      }
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_w3(tm, sTh, sTl, sW3h, sW3l, false, idesc_fwd, 0u);
+        nb_mma_commit(bar);
+        // M_i += Sel^T m  (runs underneath the phi_x epilogue)
+        nb_issue_scatter(tm + 64, sSel, sTh, sTl, idesc_sc, r0 > 0 ? 1u : 0u);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- c = w4 . SiLU(pre3 + b3) + b4 ; F = rij c -> force tile
+      {
+        float v[32];
+        nb_tmem_ld32(tm_mine, v);
+        float cp = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cp = fmaf(vw4[cb + i], nb_silu(v[i] + vb3[cb + i]), cp);
+        cpart[hf * NB_TILE + row] = cp;
+      }
+      nb_tc_fence_before();
+      __syncthreads();
+      if (hf == 0) {
+        float c = cpart[row] + cpart[NB_TILE + row] + b4;
+        float fx = dx * c, fy = dy * c, fz = dz * c;  // 0 for padded rows
+        if (g.clamp_edge) {
+          fx = fminf(fmaxf(fx, -100.f), 100.f);
+          fy = fminf(fmaxf(fy, -100.f), 100.f);
+          fz = fminf(fmaxf(fz, -100.f), 100.f);
+        }
+        const uint32_t px = nb_pack_split(fx), py = nb_pack_split(fy), pz = nb_pack_split(fz);
+        *reinterpret_cast<uint4*>(Fh + row * 16) = make_uint4((px & 0xffffu) | (py << 16), pz & 0xffffu, 0u, 0u);
+        *reinterpret_cast<uint4*>(Fl + row * 16) = make_uint4((px >> 16) | (py & 0xffff0000u), pz >> 16, 0u, 0u);
+      }
+      nb_fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_scatter8(tm + 128, sSel, sFh, sFl, idesc_sc8, r0 > 0 ? 1u : 0u);
+        nb_mma_commit(bar);  // waited for at the top of the next tile / at the unit read-out
+      }
+    }
+    // ---- unit read-out: M_i and Fsum_i of the unit's nodes (accumulator row i <-> TMEM lane (i % 16) + 32 (i / 16))
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    {
+      const int nl = 16 * q + lane;
+      float v[32];
+      nb_tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + 64 + (uint32_t)cb, v);
+      if (lane < 16 && nl < nnode) {
+        float* dst = a.M + (node0 + nl) * NB_H + cb;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+      }
+      float f4[4];
+      nb_tmem_ld4(tm + ((uint32_t)(32 * q) << 16) + 128, f4);
+      if (hf == 0 && lane < 16 && nl < nnode) {
+        float* dst = a.Fsum + (node0 + nl) * 3;
+        dst[0] = f4[0];
+        dst[1] = f4[1];
+        dst[2] = f4[2];
+      }
+    }
+    nb_tc_fence_before();
+    __syncthreads();
+  }
+  nb_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nb_tmem_dealloc(tm, NB_SF_TMEM_COLS);
+}
+#endif  // NB_EMU

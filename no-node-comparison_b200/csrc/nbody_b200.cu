@@ -11,6 +11,7 @@
 #include "nb_edge.cuh"
 #include "nb_tc.cuh"
 #include "nb_edge_tc.cuh"
+#include "nb_edge_sel.cuh"
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 #define NB_LAUNCH_COUNTED(...) \
@@ -311,26 +312,49 @@ static NbEdgeGeom edge_geom(int n_gt, int B, int N, int nef, int clamp_edge) {
   return g;
 }
 
-// 1 = tcgen05 edge tiles (product path on sm_100a), 0 = fp32 SIMT tiles (cross-check; the only variant the host
-// emulator can run)
+// 2 = tcgen05 edge tiles with tensor-core gathers / scatters (nb_edge_sel.cuh; product path on sm_100a for N <= 27,
+//     larger graphs run variant 1), 1 = tcgen05 edge tiles with CUDA-core gathers / reductions (nb_edge_tc.cuh),
+// 0 = fp32 SIMT tiles (cross-check; the only variant the host emulator can run)
 #ifdef NB_EMU
 static int g_edge_impl = 0;
 #else
-static int g_edge_impl = 1;
+static int g_edge_impl = 2;
 #endif
 extern "C" int nb_set_edge_impl(int impl) {
 #ifdef NB_EMU
   if (impl != 0) { nb_set_error("the host emulator only runs the SIMT edge tiles"); return NB_ERR_INVALID; }
 #endif
-  if (impl != 0 && impl != 1) { nb_set_error("edge impl must be 0 (SIMT) or 1 (tcgen05)"); return NB_ERR_INVALID; }
+  if (impl < 0 || impl > 2) { nb_set_error("edge impl must be 0 (SIMT), 1 (tcgen05) or 2 (tcgen05 + selector MMAs)"); return NB_ERR_INVALID; }
   g_edge_impl = impl;
   return NB_OK;
 }
 extern "C" int nb_get_edge_impl(void) { return g_edge_impl; }
 
+#ifndef NB_EMU
+// unit geometry of the selector kernels: G graph-instances with G*N <= 27 nodes and (for G > 1) at most 128 rows
+static bool sel_geom(NbEdgeGeom& g) {
+  if (g.N > NB_SEL_MAX_GN) return false;
+  int G = NB_TILE / g.EPG;
+  if (G > NB_SEL_MAX_GN / g.N) G = NB_SEL_MAX_GN / g.N;
+  if (G < 1) G = 1;
+  g.G = G;
+  g.n_units = (int)cdiv(g.NGT, G);
+  return true;
+}
+#endif
+
 static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
 #ifndef NB_EMU
-  if (g_edge_impl == 1) {
+  if (g_edge_impl == 2 && sel_geom(a.g)) {
+    const size_t smem_sel = NB_EDGE_FWD_SEL_SMEM(a.g.G * a.g.EPG);
+    NB_SET_SMEM(k_edge_fwd_sel, smem_sel);
+    int grid_sel = imin(a.g.n_units, 2 * nb_num_sms());
+    int pi_sel = prof_begin(0, st);
+    NB_LAUNCH_COUNTED(k_edge_fwd_sel, (unsigned)grid_sel, NB_THREADS, smem_sel, st, a);
+    prof_end(0, pi_sel, st);
+    return nb_check_launch("k_edge_fwd_sel");
+  }
+  if (g_edge_impl >= 1) {
     const size_t smem_tc = NB_EDGE_FWD_TC_SMEM;
     NB_SET_SMEM(k_edge_fwd_tc, smem_tc);
     int grid_tc = imin(a.g.n_units, 3 * nb_num_sms());
@@ -362,7 +386,7 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
   a.partial = partial;
   bool done = false;
 #ifndef NB_EMU
-  if (g_edge_impl == 1) {
+  if (g_edge_impl >= 1) {
     const size_t smem_tc = NB_EDGE_BWD_TC_SMEM(a.g.G * a.g.N);
     NB_SET_SMEM(k_edge_bwd_tc, smem_tc);
     int pi_tc = prof_begin(1, st);

@@ -286,18 +286,19 @@ def test_non_canonical_edges_raise_on_device():
           loc_mean=c["loc_mean"].to(d), timesteps_out=c["t_out"][:, :4].to(d))
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [2, 1, 0])
 def test_edge_tile_building_block_vs_oracle(impl):
     """nb_egcl_edge_forward / _backward alone (C ABI, raw pointers) against a plain edge-list evaluation, for the
-    tcgen05 tiles (impl 1, split-bf16 operands: ~1e-5) and the fp32 SIMT tiles (impl 0: ~1e-6)."""
+    tcgen05 tiles with tensor-core gathers / scatters (impl 2, the default), the tcgen05 tiles with CUDA-core
+    gathers (impl 1; split-bf16 operands: ~1e-5) and the fp32 SIMT tiles (impl 0: ~1e-6)."""
     import ctypes
     d = dev()
     lib = nb.load_library()
     assert lib.nb_set_edge_impl(impl) == 0
     try:
-        _edge_tile_check(lib, d, 5e-5 if impl == 1 else 1e-5)
+        _edge_tile_check(lib, d, 5e-5 if impl >= 1 else 1e-5)
     finally:
-        lib.nb_set_edge_impl(1)
+        lib.nb_set_edge_impl(2)
 
 
 def _edge_tile_check(lib, d, tol):
