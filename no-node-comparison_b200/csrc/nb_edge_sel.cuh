@@ -440,4 +440,519 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
   __syncthreads();
   if (warp == 0) nb_tmem_dealloc(tm, NB_SF_TMEM_COLS);
 }
+
+// ----------------------------------------------------------------------------- backward
+// 512 threads: thread (warp w, lane l) owns row 32 (w & 3) + l and the 16 columns of quarter (w >> 2).
+//   T0  selector row                                   -> gather  pre1            (MMA, waited)
+//   S1  z1, SiLU'(pre1) parked in TMEM                 -> MMA 1   pre2
+//   S2  m,  SiLU'(pre2) parked in TMEM                 -> MMA 2   pre3
+//   S3  phi_x head, g3                                 -> dgrad 3 + gM broadcast  | side: dW3, db3
+//   S4  g2 = (gm + gM_i) SiLU'(pre2)                   -> dgrad 2                 | side: dW2, db2
+//   S5  g1 = gz1 SiLU'(pre1), dL/drij                  ->                           side: gP|gQ|gw += Sel^T g1, gx += Sel^T rG
+// The critical-path MMAs are issued by thread 0 (mbarrier `bar`), the side MMAs by thread 32 (`bar2`); the side MMAs
+// run underneath the next stage's CUDA-core work.
+//
+// TMEM columns: [0,64) pre1 -> SiLU'(pre1) | [64,128) pre2 -> SiLU'(pre2) | [128,192) pre3 -> gm -> gz1 |
+//               [192,256) dW3 | [256,320) dW2 | [320,328) db3 | [328,336) db2 | [336,400) node sums | [400,408) x sums
+#define NB_SB_THREADS 512
+#define NB_SB_W 0
+#define NB_SB_TZ (4 * NB_TC_TILE_BYTES(64))
+#define NB_SB_TM (NB_SB_TZ + 2 * NB_TC_TILE_BYTES(128))
+#define NB_SB_TG (NB_SB_TM + 2 * NB_TC_TILE_BYTES(128))
+#define NB_SB_SEL (NB_SB_TG + 2 * NB_TC_TILE_BYTES(128))
+#define NB_SB_NT (NB_SB_SEL + NB_TC_TILE_BYTES(128))
+#define NB_SB_GM (NB_SB_NT + 2 * NB_TC_TILE_BYTES(64))
+#define NB_SB_ONES (NB_SB_GM + 2 * NB_TC_TILE_BYTES(64))
+#define NB_SB_RG (NB_SB_ONES + NB_TILE * 16)
+#define NB_SB_FL (NB_SB_RG + 2 * NB_TILE * 16)
+#define NB_SB_NFLOAT (4 * NB_H + 4 * NB_TILE + 2 * 32 * 3 + 10 * NB_H + NB_H * 4)
+#define NB_EDGE_BWD_SEL_SMEM(RU) (NB_SB_FL + NB_SB_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
+#define NB_SB_TMEM_COLS 512
+
+__device__ __forceinline__ void nb_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void nb_tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// dW (+)= G^T A  (both MN-major, K = 128 rows, three split passes) and db (+)= G^T 1
+__device__ __forceinline__ void nb_issue_wgrad(uint32_t tmem_w, uint32_t tmem_b, uint32_t g_hi, uint32_t g_lo, uint32_t a_hi,
+                                               uint32_t a_lo, uint32_t ones, uint32_t idesc_wg, uint32_t idesc_bs,
+                                               uint32_t acc0) {
+  uint32_t acc = acc0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t ga = nb_desc_lo_mn(pass == 1 ? g_lo : g_hi);
+    const uint32_t ab = nb_desc_lo_mn(pass == 2 ? a_lo : a_hi);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      nb_mma2(tmem_w, ga + NB_KSTEP_MN * s, NB_DESC_HI_SW128, ab + NB_KSTEP_MN * s, NB_DESC_HI_SW128, idesc_wg, acc);
+      acc = 1u;
+    }
+  }
+  acc = acc0;
+  const uint32_t ob = nb_desc_lo_n8(ones);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t ga = nb_desc_lo_mn(pass ? g_lo : g_hi);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      nb_mma2(tmem_b, ga + NB_KSTEP_MN * s, NB_DESC_HI_SW128, ob + NB_KSTEP_N8 * s, NB_DESC_HI_NOSW, idesc_bs, acc);
+      acc = 1u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs a) {
+  extern __shared__ __align__(1024) unsigned char nb_smraw[];
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
+  unsigned char* W2h = base + NB_SB_W;
+  unsigned char* W2l = W2h + NB_TC_TILE_BYTES(64);
+  unsigned char* W3h = W2l + NB_TC_TILE_BYTES(64);
+  unsigned char* W3l = W3h + NB_TC_TILE_BYTES(64);
+  unsigned char* Tzh = base + NB_SB_TZ;
+  unsigned char* Tzl = Tzh + NB_TC_TILE_BYTES(128);
+  unsigned char* Tmh = base + NB_SB_TM;
+  unsigned char* Tml = Tmh + NB_TC_TILE_BYTES(128);
+  unsigned char* Tgh = base + NB_SB_TG;
+  unsigned char* Tgl = Tgh + NB_TC_TILE_BYTES(128);
+  unsigned char* Sel = base + NB_SB_SEL;
+  unsigned char* Nh = base + NB_SB_NT;
+  unsigned char* Nl = Nh + NB_TC_TILE_BYTES(64);
+  unsigned char* GMh = base + NB_SB_GM;
+  unsigned char* GMl = GMh + NB_TC_TILE_BYTES(64);
+  unsigned char* ones = base + NB_SB_ONES;
+  unsigned char* RGh = base + NB_SB_RG;
+  unsigned char* RGl = RGh + NB_TILE * 16;
+  float* scratch = reinterpret_cast<float*>(Tzh);  // fp32 [128][64] view, CTA epilogue only
+  float* fl = reinterpret_cast<float*>(base + NB_SB_FL);
+  float* vb2 = fl;
+  float* vb3 = vb2 + NB_H;
+  float* vw4 = vb3 + NB_H;
+  float* vwr = vw4 + NB_H;
+  float* cpart = vwr + NB_H;          // [4][128]
+  float* xs = cpart + 4 * NB_TILE;    // [GN][3]
+  float* gfs = xs + 32 * 3;           // [GN][3] dL/dFsum of the unit's nodes
+  float* gwacc = gfs + 32 * 3;        // [10][64]: rows 0,1 w_rad (hi, lo piece) ; 2 + 2f, 3 + 2f w_ef[f]
+  float* gxst = gwacc + 10 * NB_H;    // [64][4]
+  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(gxst + NB_H * 4);
+  const NbEdgeGeom g = a.g;
+  const int RU = g.G * g.EPG, GN = g.G * g.N;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
+  uint64_t* bar2 = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar2 + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cq = warp >> 2;
+  const int row = 32 * q + lane;
+  const int cb = 16 * cq;
+
+  for (int idx = tid; idx < 64 * 8; idx += NB_SB_THREADS) {
+    int o = idx >> 3, j = idx & 7;
+    float v2[8], v3[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v2[i] = __ldg(a.w.W2 + o * NB_H + 8 * j + i);
+      v3[i] = __ldg(a.w.W3 + o * NB_H + 8 * j + i);
+    }
+    nb_tc_store8(W2h, W2l, o, j, v2);
+    nb_tc_store8(W3h, W3l, o, j, v3);
+  }
+  for (int idx = tid; idx < 4 * NB_TC_TILE_BYTES(64) / 16; idx += NB_SB_THREADS)  // node tile + gM tile (contiguous)
+    reinterpret_cast<uint4*>(Nh)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  nb_sel_build_rowinfo(rowinfo, g, tid, NB_SB_THREADS);
+  if (tid < NB_TILE) {
+    uint32_t one2 = 0x3F803F80u;  // bf16 (1.0, 1.0)
+    *reinterpret_cast<uint4*>(ones + tid * 16) = make_uint4(one2, one2, one2, one2);
+  }
+  if (tid < NB_H) {
+    vb2[tid] = __ldg(a.w.b2 + tid);
+    vb3[tid] = __ldg(a.w.b3 + tid);
+    vw4[tid] = __ldg(a.w.w4 + tid);
+    vwr[tid] = __ldg(a.w.W1 + (int64_t)tid * a.w.ldw1 + a.w.col_rad);
+  }
+  for (int idx = tid; idx < 10 * NB_H; idx += NB_SB_THREADS) gwacc[idx] = 0.f;
+  if (tid == 0) {
+    nb_mbar_init(bar, 1);
+    nb_mbar_init(bar2, 1);
+    nb_mbar_fence_init();
+  }
+  if (warp == 0) nb_tmem_alloc(tmem_slot, NB_SB_TMEM_COLS);
+  __syncthreads();
+  for (int idx = tid; idx < 10 * 8; idx += NB_SB_THREADS) {
+    int k = idx >> 3, j = idx & 7;
+    int f = (k >> 1) - 1;  // -1: radial
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int c = 8 * j + i;
+      v[i] = f < 0 ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_rad)
+                   : (f < g.nef ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_ef + f) : 0.f);
+    }
+    nb_tc_store8(Nh, Nl, NB_SEL_XC0 + k, j, v);
+  }
+  nb_fence_async_smem();
+  nb_tc_fence_before();
+  __syncthreads();
+  nb_tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+  const uint32_t t1 = tm + lane_base + 0 + (uint32_t)cb;    // pre1 / SiLU'(pre1)
+  const uint32_t t2 = tm + lane_base + 64 + (uint32_t)cb;   // pre2 / SiLU'(pre2)
+  const uint32_t t3 = tm + lane_base + 128 + (uint32_t)cb;  // pre3 / gm / gz1
+  const uint32_t idesc_fwd = nb_idesc_bf16(128, 64, 0, 0);
+  const uint32_t idesc_dg = nb_idesc_bf16(128, 64, 0, 1);   // also the gathers
+  const uint32_t idesc_wg = nb_idesc_bf16(64, 64, 1, 1);    // also the 64-wide scatters
+  const uint32_t idesc_bs = nb_idesc_bf16(64, 8, 1, 1);
+  const uint32_t sTzh = nb_smem_u32(Tzh), sTzl = nb_smem_u32(Tzl), sTmh = nb_smem_u32(Tmh), sTml = nb_smem_u32(Tml),
+                 sTgh = nb_smem_u32(Tgh), sTgl = nb_smem_u32(Tgl), sSel = nb_smem_u32(Sel), sNh = nb_smem_u32(Nh),
+                 sNl = nb_smem_u32(Nl), sGMh = nb_smem_u32(GMh), sGMl = nb_smem_u32(GMl), sOnes = nb_smem_u32(ones),
+                 sRGh = nb_smem_u32(RGh), sRGl = nb_smem_u32(RGl), sW2h = nb_smem_u32(W2h), sW2l = nb_smem_u32(W2l),
+                 sW3h = nb_smem_u32(W3h), sW3l = nb_smem_u32(W3l);
+  const float b4 = __ldg(a.w.b4);
+  const int ks_recv = (GN + 15) >> 4;
+  uint32_t phase = 0, phase2 = 0;
+  uint32_t wacc = 0;
+
+  float gw4acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gw4acc[i] = 0.f;
+  float gb4acc = 0.f;
+
+  for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
+    const int gt0 = u * g.G;
+    const int ngt = min(g.G, g.NGT - gt0);
+    const int R = ngt * g.EPG;
+    const int nnode = ngt * g.N;
+    const int64_t node0 = (int64_t)gt0 * g.N;
+    // every MMA of the previous unit has completed (the read-out waited for the last side commit)
+    nb_sel_stage_nodes(Nh, Nl, a.P, a.Q, node0, nnode, GN, tid, NB_SB_THREADS);
+    for (int idx = tid; idx < nnode * 8; idx += NB_SB_THREADS) {
+      int n = idx >> 3, j = idx & 7;
+      const float* src = a.gM + (node0 + n) * NB_H + 8 * j;
+      float4 p0 = nb_ld4(src), p1 = nb_ld4(src + 4);
+      float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      nb_tc_store8(GMh, GMl, n, j, v);
+    }
+    for (int idx = tid; idx < nnode * 3; idx += NB_SB_THREADS) {
+      xs[idx] = __ldg(a.x + node0 * 3 + idx);
+      gfs[idx] = __ldg(a.gFsum + node0 * 3 + idx);
+    }
+    __syncthreads();
+
+    for (int r0 = 0; r0 < R; r0 += NB_TILE) {
+      const int nv = min(NB_TILE, R - r0);
+      const bool valid = row < nv;
+      // ---- T0: geometry + selector row
+      float dx = 0.f, dy = 0.f, dz = 0.f, r2 = 0.f, gfx = 0.f, gfy = 0.f, gfz = 0.f;
+      float e[NB_MAX_EF];
+#pragma unroll
+      for (int f = 0; f < NB_MAX_EF; ++f) e[f] = 0.f;
+      int li = 0, lj = 0;
+      if (valid) {
+        const uint32_t ri = rowinfo[r0 + row];
+        li = ri & 0xff;
+        lj = (ri >> 8) & 0xff;
+        const int lg = ri >> 16;
+        dx = xs[li * 3 + 0] - xs[lj * 3 + 0];
+        dy = xs[li * 3 + 1] - xs[lj * 3 + 1];
+        dz = xs[li * 3 + 2] - xs[lj * 3 + 2];
+        r2 = dx * dx + dy * dy + dz * dz;
+        gfx = gfs[li * 3 + 0];
+        gfy = gfs[li * 3 + 1];
+        gfz = gfs[li * 3 + 2];
+        if (cq == 1) {
+          const int64_t eoff = ((int64_t)((gt0 + lg) % g.B) * g.EPG + (r0 + row - lg * g.EPG)) * g.nef;
+#pragma unroll
+          for (int f = 0; f < NB_MAX_EF; ++f)
+            if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
+        }
+      }
+      if (r0 > 0) {  // the side MMAs of the previous tile (dW2, scatters) have consumed Sel, Tz, Tm, Tg, rG
+        nb_mbar_wait(bar2, phase2);
+        phase2 ^= 1;
+        nb_tc_fence_after();
+      }
+      if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, GN + lj, r2, e);
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_dg, 0u);
+        nb_mma_commit(bar);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- S1: z1 -> tile, SiLU'(pre1) -> TMEM
+      {
+        float v[16], d[16];
+        nb_tmem_ld16(t1, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nb_silu_grad(v[i], v[i], d[i]);
+        nb_tmem_st16(t1, d);
+        nb_tc_store8(Tzh, Tzl, row, 2 * cq, v);
+        nb_tc_store8(Tzh, Tzl, row, 2 * cq + 1, v + 8);
+      }
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_w3(tm + 64, sTzh, sTzl, sW2h, sW2l, false, idesc_fwd, 0u);
+        nb_mma_commit(bar);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- S2: m -> tile, SiLU'(pre2) -> TMEM
+      {
+        float v[16], d[16];
+        nb_tmem_ld16(t2, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nb_silu_grad(v[i] + vb2[cb + i], v[i], d[i]);
+        nb_tmem_st16(t2, d);
+        nb_tc_store8(Tmh, Tml, row, 2 * cq, v);
+        nb_tc_store8(Tmh, Tml, row, 2 * cq + 1, v + 8);
+      }
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_w3(tm + 128, sTmh, sTml, sW3h, sW3l, false, idesc_fwd, 0u);
+        nb_mma_commit(bar);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- S3: phi_x head, g3 = dL/dpre3
+      float rgx, rgy, rgz;
+      {
+        float v[16], d[16];
+        nb_tmem_ld16(t3, v);
+        float cp = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          nb_silu_grad(v[i] + vb3[cb + i], v[i], d[i]);  // v = z3
+          cp = fmaf(vw4[cb + i], v[i], cp);
+        }
+        cpart[cq * NB_TILE + row] = cp;
+        nb_tc_fence_before();
+        __syncthreads();
+        const float cval = (cpart[row] + cpart[NB_TILE + row]) + (cpart[2 * NB_TILE + row] + cpart[3 * NB_TILE + row]) + b4;
+        if (g.clamp_edge) {  // clamp(rij * c) passes gradient only inside [-100, 100]
+          float fx = dx * cval, fy = dy * cval, fz = dz * cval;
+          if (!(fx >= -100.f && fx <= 100.f)) gfx = 0.f;
+          if (!(fy >= -100.f && fy <= 100.f)) gfy = 0.f;
+          if (!(fz >= -100.f && fz <= 100.f)) gfz = 0.f;
+        }
+        const float gc = dx * gfx + dy * gfy + dz * gfz;  // 0 for padded rows
+        rgx = cval * gfx;
+        rgy = cval * gfy;
+        rgz = cval * gfz;
+        if (cq == 0) gb4acc += gc;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          gw4acc[i] = fmaf(gc, v[i], gw4acc[i]);
+          v[i] = gc * vw4[cb + i] * d[i];  // g3
+        }
+        nb_tc_store8(Tgh, Tgl, row, 2 * cq, v);
+        nb_tc_store8(Tgh, Tgl, row, 2 * cq + 1, v + 8);
+      }
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_w3(tm + 128, sTgh, sTgl, sW3h, sW3l, true, idesc_dg, 0u);          // gm = g3 W3
+        nb_issue_gather(tm + 128, sSel, sGMh, sGMl, ks_recv, idesc_dg, 1u);          //    + gM_i
+        nb_mma_commit(bar);
+      } else if (tid == 32) {
+        nb_tc_fence_after();
+        nb_issue_wgrad(tm + 192, tm + 320, sTgh, sTgl, sTmh, sTml, sOnes, idesc_wg, idesc_bs, wacc);  // dW3, db3
+        nb_mma_commit(bar2);
+      }
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- S4: g2 = (gm + gM_i) * SiLU'(pre2)    (padded rows: gm = 0 and the gathered gM = 0)
+      {
+        float v[16], d[16];
+        nb_tmem_ld16(t3, v);
+        nb_tmem_ld16(t2, d);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= d[i];
+        nb_mbar_wait(bar2, phase2);  // dW3 / db3 have consumed the g3 and m tiles
+        phase2 ^= 1;
+        nb_tc_store8(Tgh, Tgl, row, 2 * cq, v);
+        nb_tc_store8(Tgh, Tgl, row, 2 * cq + 1, v + 8);
+      }
+      nb_fence_async_smem();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        nb_tc_fence_after();
+        nb_issue_w3(tm + 128, sTgh, sTgl, sW2h, sW2l, true, idesc_dg, 0u);  // gz1 = g2 W2
+        nb_mma_commit(bar);
+      } else if (tid == 32) {
+        nb_tc_fence_after();
+        nb_issue_wgrad(tm + 256, tm + 328, sTgh, sTgl, sTzh, sTzl, sOnes, idesc_wg, idesc_bs, wacc);  // dW2, db2
+      }
+      wacc = 1;
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
+      nb_tc_fence_after();
+      // ---- S5: g1 = gz1 * SiLU'(pre1) -> the (free) m tile ; dL/drij -> rG tile
+      {
+        float v[16], d[16];
+        nb_tmem_ld16(t3, v);
+        nb_tmem_ld16(t1, d);
+        float gr2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] *= d[i];
+          gr2 = fmaf(vwr[cb + i], v[i], gr2);  // dL/dr2 = w_rad . g1
+        }
+        cpart[cq * NB_TILE + row] = gr2;
+        nb_tc_store8(Tmh, Tml, row, 2 * cq, v);
+        nb_tc_store8(Tmh, Tml, row, 2 * cq + 1, v + 8);
+      }
+      nb_tc_fence_before();
+      __syncthreads();
+      if (cq == 0) {
+        const float gr2 = 2.f * ((cpart[row] + cpart[NB_TILE + row]) + (cpart[2 * NB_TILE + row] + cpart[3 * NB_TILE + row]));
+        const uint32_t px = nb_pack_split(fmaf(dx, gr2, rgx)), py = nb_pack_split(fmaf(dy, gr2, rgy)),
+                       pz = nb_pack_split(fmaf(dz, gr2, rgz));
+        *reinterpret_cast<uint4*>(RGh + row * 16) = make_uint4((px & 0xffffu) | (py << 16), pz & 0xffffu, 0u, 0u);
+        *reinterpret_cast<uint4*>(RGl + row * 16) = make_uint4((px >> 16) | (py & 0xffff0000u), pz >> 16, 0u, 0u);
+      }
+      nb_fence_async_smem();
+      __syncthreads();
+      if (tid == 32) {
+        nb_tc_fence_after();
+        const uint32_t uacc = r0 > 0 ? 1u : 0u;
+        nb_issue_scatter(tm + 336, sSel, sTmh, sTml, idesc_wg, uacc);    // gP | gQ | gw partials += Sel^T g1
+        nb_issue_scatter8(tm + 400, sSel, sRGh, sRGl, idesc_bs, uacc);   // x sums += Sel^T rG
+        nb_mma_commit(bar2);  // also covers dW2 / db2; waited for at the top of the next tile / at the read-out
+      }
+    }
+    // ---- unit read-out (accumulator row i <-> TMEM lane (i % 16) + 32 (i / 16): thread (q, lane < 16) owns row 16 q + lane)
+    nb_mbar_wait(bar2, phase2);
+    phase2 ^= 1;
+    nb_tc_fence_after();
+    {
+      const int i = 16 * q + lane;
+      float v[16];
+      nb_tmem_ld16(tm + lane_base + 336 + (uint32_t)cb, v);
+      if (lane < 16) {
+        if (i < nnode) {
+          float* dst = a.gP + (node0 + i) * NB_H + cb;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        } else if (i >= GN && i < GN + nnode) {
+          float* dst = a.gQ + (node0 + i - GN) * NB_H + cb;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        } else if (i >= NB_SEL_XC0) {
+          float* dst = gwacc + (i - NB_SEL_XC0) * NB_H + cb;  // exclusive owner of these 16 accumulators
+#pragma unroll
+          for (int k = 0; k < 16; ++k) dst[k] += v[k];
+        }
+      }
+      float f4[4];
+      nb_tmem_ld4(tm + lane_base + 400, f4);
+      if (cq == 0 && lane < 16) {
+        gxst[i * 4 + 0] = f4[0];
+        gxst[i * 4 + 1] = f4[1];
+        gxst[i * 4 + 2] = f4[2];
+      }
+    }
+    nb_tc_fence_before();
+    __syncthreads();
+    for (int idx = tid; idx < nnode * 3; idx += NB_SB_THREADS) {
+      int n = idx / 3, dd = idx - 3 * n;
+      a.gx[node0 * 3 + idx] += gxst[n * 4 + dd] - gxst[(GN + n) * 4 + dd];
+    }
+    __syncthreads();
+  }
+
+  // ---- CTA epilogue: weight-gradient accumulators (TMEM), register / shared accumulators -> this CTA's partial slice
+  float* out = a.partial + (int64_t)blockIdx.x * NB_EB_PLEN;
+  nb_tc_fence_after();
+  {
+    float v[16];
+    const int o = 16 * q + lane;
+    nb_tmem_ld16(tm + lane_base + 192 + (uint32_t)cb, v);  // dW3[o][cb..]
+    if (lane < 16 && wacc) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nb_st4(out + NB_EB_GW3 + o * NB_H + cb + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    }
+    nb_tmem_ld16(tm + lane_base + 256 + (uint32_t)cb, v);  // dW2[o][cb..]
+    if (lane < 16 && wacc) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nb_st4(out + NB_EB_GW2 + o * NB_H + cb + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    }
+    nb_tmem_ld16(tm + lane_base + 320, v);  // db3 in column 0, db2 in column 8
+    if (lane < 16 && cq == 0 && wacc) {
+      out[NB_EB_GB3 + o] = v[0];
+      out[NB_EB_GB2 + o] = v[8];
+    }
+  }
+  if (!wacc) {  // a CTA that processed no tile contributes zeros
+    for (int idx = tid; idx < 2 * NB_H * NB_H + 2 * NB_H; idx += NB_SB_THREADS) out[idx] = 0.f;
+  }
+  // dw4: sum of the per-row accumulators over the 128 rows (through an fp32 scratch over the z1 tile); db4 likewise
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    nb_st4(nb_scratch_chunk(scratch, row, (cb >> 2) + k),
+           make_float4(gw4acc[4 * k], gw4acc[4 * k + 1], gw4acc[4 * k + 2], gw4acc[4 * k + 3]));
+  if (cq == 0) cpart[row] = gb4acc;
+  __syncthreads();
+  {
+    const int rc = tid & 63, rpart = tid >> 6;  // column, part (0..7): 16 rows each
+    float sacc = 0.f;
+    for (int r = rpart * 16; r < rpart * 16 + 16; ++r) sacc += nb_scratch_get(scratch, r, rc);
+    float* red = reinterpret_cast<float*>(Tmh);  // [8][64]
+    red[rpart * NB_H + rc] = sacc;
+    __syncthreads();
+    if (tid < NB_H) {
+      float t = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) t += red[p * NB_H + tid];
+      out[NB_EB_GW4 + tid] = t;
+      out[NB_EB_GWR + tid] = gwacc[tid] + gwacc[NB_H + tid];
+#pragma unroll
+      for (int f = 0; f < NB_MAX_EF; ++f) out[NB_EB_GWE + f * NB_H + tid] = gwacc[(2 + 2 * f) * NB_H + tid] + gwacc[(3 + 2 * f) * NB_H + tid];
+      float t4 = 0.f;
+      if (tid == 0)
+        for (int r = 0; r < NB_TILE; ++r) t4 += cpart[r];
+      out[NB_EB_GB4 + tid] = t4;
+    }
+  }
+  nb_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nb_tmem_dealloc(tm, NB_SB_TMEM_COLS);
+}
 #endif  // NB_EMU

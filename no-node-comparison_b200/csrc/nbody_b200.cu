@@ -380,13 +380,25 @@ struct EdgeGradDst {
 };
 
 static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, int accumulate, void* st) {
-  int grid = imin(a.g.n_units, edge_bwd_grid_cap());
+  bool use_sel = false;
+#ifndef NB_EMU
+  use_sel = g_edge_impl == 2 && sel_geom(a.g);
+#endif
+  int grid = imin(a.g.n_units, use_sel ? nb_num_sms() : edge_bwd_grid_cap());
   float* partial = q_alloc((int64_t)grid * NB_EB_PLEN, st);
   if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
   a.partial = partial;
   bool done = false;
 #ifndef NB_EMU
-  if (g_edge_impl >= 1) {
+  if (use_sel) {
+    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.G * a.g.EPG);
+    NB_SET_SMEM(k_edge_bwd_sel, smem_sel);
+    int pi_sel = prof_begin(1, st);
+    NB_LAUNCH_COUNTED(k_edge_bwd_sel, (unsigned)grid, NB_SB_THREADS, smem_sel, st, a);
+    prof_end(1, pi_sel, st);
+    NB_TRY(nb_check_launch("k_edge_bwd_sel"));
+    done = true;
+  } else if (g_edge_impl >= 1) {
     const size_t smem_tc = NB_EDGE_BWD_TC_SMEM(a.g.G * a.g.N);
     NB_SET_SMEM(k_edge_bwd_tc, smem_tc);
     int pi_tc = prof_begin(1, st);
