@@ -171,6 +171,10 @@ int nb_profile_read(double* ms /*[4]*/, long long* counts /*[4]*/);
  * of the test suite).  All are CUDA kernels of this library. */
 int nb_set_edge_impl(int impl);
 int nb_get_edge_impl(void);
+/* Node-level 64-wide GEMMs and weight-gradient reductions: 1 = tcgen05 kernels (default, product path), 0 = fp32 SIMT
+ * kernels (cross-check; the variant the host emulator runs). */
+int nb_set_node_impl(int impl);
+int nb_get_node_impl(void);
 
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]

@@ -38,6 +38,8 @@ EXPORTS = {
     "nb_profile_enable": (C.c_int, [C.c_int]),
     "nb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "nb_set_edge_impl": (C.c_int, [C.c_int]),
+    "nb_set_node_impl": (C.c_int, [C.c_int]),
+    "nb_get_node_impl": (C.c_int, []),
     "nb_get_edge_impl": (C.c_int, []),
     "nb_tc_selftest": (C.c_int, [C.c_int32, c_f, c_f, c_f, c_f]),
 }

@@ -12,6 +12,7 @@
 #include "nb_tc.cuh"
 #include "nb_edge_tc.cuh"
 #include "nb_edge_sel.cuh"
+#include "nb_node_tc.cuh"
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 #define NB_LAUNCH_COUNTED(...) \
@@ -132,8 +133,28 @@ static inline int imin(int64_t a, int64_t b) { return (int)(a < b ? a : b); }
 static inline int wgrad_grid_cap() { return imin(nb_num_sms(), 160); }
 static inline int edge_bwd_grid_cap() { return imin(nb_num_sms(), 320); }
 
+// node-level GEMMs / weight-gradient reductions: 1 = tcgen05 kernels (nb_node_tc.cuh, product path), 0 = fp32 SIMT
+#ifdef NB_EMU
+static int g_node_impl = 0;
+#else
+static int g_node_impl = 1;
+#endif
+extern "C" int nb_set_node_impl(int impl) {
+#ifdef NB_EMU
+  if (impl != 0) { nb_set_error("the host emulator only runs the SIMT node kernels"); return NB_ERR_INVALID; }
+#endif
+  if (impl != 0 && impl != 1) { nb_set_error("node impl must be 0 (SIMT) or 1 (tcgen05)"); return NB_ERR_INVALID; }
+  g_node_impl = impl;
+  return NB_OK;
+}
+extern "C" int nb_get_node_impl(void) { return g_node_impl; }
+
 // ============================================================================= launch helpers
-static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st) {
+// exact_fp32: run the fp32 SIMT kernel even when the tcgen05 node kernels are selected.  Used for the spectral mode
+// mixing, whose result feeds LeakyReLU: split-bf16 rounding (1e-5) would flip the kink for ~1e-5 of the elements and
+// move the weight gradients by O(1/rows) per flip; fp32 keeps the forward mask and its backward recompute identical
+// to the reference's.  These GEMMs have T times fewer rows than every other node GEMM.
+static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st, bool exact_fp32 = false) {
   int i = 0;
   while (i < n) {
     NbGemmBatch b;
@@ -147,6 +168,17 @@ static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st) {
       ++i;
     }
     if (b.njobs == 0) continue;
+#ifndef NB_EMU
+    if (g_node_impl == 1 && !exact_fp32) {
+      const size_t smem_tc = NB_GEMM_TC_SMEM;
+      NB_SET_SMEM(k_gemm64_tc, smem_tc);
+      int pi_tc = prof_begin(2, st);
+      NB_LAUNCH_COUNTED(k_gemm64_tc, dim3((unsigned)cdiv(maxrows, NB_TILE), (unsigned)b.njobs), NB_THREADS, smem_tc, st, b);
+      prof_end(2, pi_tc, st);
+      NB_TRY(nb_check_launch("k_gemm64_tc"));
+      continue;
+    }
+#endif
     const size_t smem = (NB_TILE * NB_LDA + NB_H * NB_H) * sizeof(float);
     NB_SET_SMEM(k_gemm64, smem);
     int pi = prof_begin(2, st);
@@ -242,7 +274,15 @@ static int q_flush_wgrad(void* st) {
   int maxrows = 0;
   for (int j = 0; j < wb.njobs; ++j)
     if (wb.job[j].rows > maxrows) maxrows = wb.job[j].rows;
-  const int grid = imin(cdiv(maxrows, NB_TILE), wgrad_grid_cap());
+  int grid = imin(cdiv(maxrows, NB_TILE), wgrad_grid_cap());
+#ifndef NB_EMU
+  if (g_node_impl == 1) {  // 3 co-resident CTAs per SM over all jobs of the batch
+    int per_job = 3 * nb_num_sms() / wb.njobs;
+    if (per_job < 16) per_job = 16;
+    if (per_job > nb_num_sms()) per_job = nb_num_sms();
+    grid = imin(cdiv(maxrows, NB_TILE), per_job);
+  }
+#endif
   const int64_t need = (int64_t)wb.njobs * grid * NB_WGRAD_PLEN;
   if (g_q.pused + need > g_q.pcap) NB_TRY(q_flush_fin(st));
   if (need > g_q.pcap) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
@@ -250,12 +290,26 @@ static int q_flush_wgrad(void* st) {
     wb.job[j].partial = g_q.pbase + g_q.pused;
     g_q.pused += (int64_t)grid * NB_WGRAD_PLEN;
   }
-  const size_t smem = 2 * NB_TILE * NB_LDA * sizeof(float);
-  NB_SET_SMEM(k_wgrad64, smem);
-  int pi = prof_begin(3, st);
-  NB_LAUNCH_COUNTED(k_wgrad64, dim3((unsigned)grid, (unsigned)wb.njobs), NB_THREADS, smem, st, wb);
-  prof_end(3, pi, st);
-  NB_TRY(nb_check_launch("k_wgrad64"));
+  bool wdone = false;
+#ifndef NB_EMU
+  if (g_node_impl == 1) {
+    const size_t smem_tc = NB_WT_SMEM;
+    NB_SET_SMEM(k_wgrad64_tc, smem_tc);
+    int pi_tc = prof_begin(3, st);
+    NB_LAUNCH_COUNTED(k_wgrad64_tc, dim3((unsigned)grid, (unsigned)wb.njobs), NB_THREADS, smem_tc, st, wb);
+    prof_end(3, pi_tc, st);
+    NB_TRY(nb_check_launch("k_wgrad64_tc"));
+    wdone = true;
+  }
+#endif
+  if (!wdone) {
+    const size_t smem = 2 * NB_TILE * NB_LDA * sizeof(float);
+    NB_SET_SMEM(k_wgrad64, smem);
+    int pi = prof_begin(3, st);
+    NB_LAUNCH_COUNTED(k_wgrad64, dim3((unsigned)grid, (unsigned)wb.njobs), NB_THREADS, smem, st, wb);
+    prof_end(3, pi, st);
+    NB_TRY(nb_check_launch("k_wgrad64"));
+  }
   const int n = wb.njobs;
   wb.njobs = 0;
   for (int j = 0; j < n; ++j) {
@@ -604,7 +658,7 @@ static int egno_tc_mix(const EgnoCtx& X, int l, const float* coef, float* ycoef)
       jobs[nj++] = b;
     }
   }
-  return launch_gemm_batch(jobs, nj, X.st);
+  return launch_gemm_batch(jobs, nj, X.st, /*exact_fp32=*/true);
 }
 
 static NbDftArgs dft_args(const EgnoCtx& X) {
