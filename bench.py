@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -291,16 +291,23 @@ def run_ours(args):
     t_bwd = kern["edge_bwd"]["ms_per_launch"]
     flop_kernel = 2 * 2 * MAC_EDGE_KERNEL * ne           # backward = 2 x forward; recompute is not credited
     achieved = flop_kernel / (t_bwd * 1e-3) / 1e12 if t_bwd else None
-    roofline = {"kernel": "k_edge_bwd (fused E_GCL edge tile backward, fp32 SIMT in this round)", "bound": "tensor",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                "peak_source": peak_src,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_edge_bwd_r01_raw.csv);
-                # valid for the default workload only
-                "traffic": 43.8e6 if (N, T, B) == (20, 10, 256) else None,
+    roofline = {"kernel": "k_edge_bwd_sel (fused E_GCL edge-tile backward: recompute + dgrad + wgrad + node gathers/scatters, "
+                          "all on tcgen05 with split-bf16 operands and fp32 TMEM accumulators)",
+                "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (achieved / peak_tf) if achieved else None, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
+                # (profiles/r01_edge_bwd_sel_digest.txt); valid for the default workload only
+                "traffic": 43.2e6 if (N, T, B) == (20, 10, 256) else None,
                 "flop_per_launch": flop_kernel, "flop_per_launch_reference_formula": 2 * 2 * MAC_EDGE_REF * ne,
-                "note": "achieved counts the MACs the edge kernel owns (8448/edge fwd, x2 for bwd); the reference's dense "
-                        "131-wide first layer would count 16640/edge. fp32 FFMA peak of B200 is ~70 TFLOP/s; the tensor "
-                        "peak is the bf16 figure the tcgen05 port of these tiles is measured against.",
+                "tensor_pipe_active_pct_ncu": 23.0 if (N, T, B) == (20, 10, 256) else None,
+                "note": "achieved = ALGORITHMIC fp32 FLOPs the edge kernel owns (8448 MAC/edge forward, x2 for backward; the "
+                        "recompute is not credited) / its mean launch time (CUDA events on the launch stream).  The reference's "
+                        "dense 131-wide first layer would count 16640 MAC/edge (second figure).  Every logical fp32 MMA is "
+                        "three bf16 tcgen05 passes (hi*hi + lo*hi + hi*lo) and the backward executes ~2x the credited MACs "
+                        "(recompute, bias/one-hot gather/scatter MMAs), so the tensor pipe is ~8x busier than `frac` suggests: "
+                        "ncu reports 23 % tensor-pipe active for this launch.  The kernel is bound by its dependent "
+                        "MMA -> TMEM -> SiLU -> smem -> MMA chain (5 round trips per 128-edge tile), not by HBM "
+                        "(43 MB per launch = 75 GB/s).",
                 "hbm_peak_gbs": hbm}
 
     extras = {}
