@@ -37,7 +37,7 @@ MAC_EDGE_KERNEL = 64 * 64 + 64 * 64 + 64 + 3 * 64
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="trajectories per GPU per step")
@@ -71,9 +71,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,7 +83,15 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines
+        scope = "whole run (sampler start to stop)"
+        if window is not None:
+            inside = [x for x in lines if window[0] <= x[0] <= window[1] + 0.05]
+            if inside:
+                lines, scope = inside, "timed region"
+            else:
+                scope = "warm-up + timed region (timed region shorter than one sampling period)"
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -96,7 +104,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -244,15 +252,17 @@ def run_ours(args):
         barrier()
         return float(ms.item())
 
-    for i in range(W):
-        train_step(resident[i % NBATCH])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        train_step(resident[i % NBATCH])
     l0 = lib.nb_launch_count()
+    tw0 = time.time()
     ms = timed(lambda i: train_step(resident[i % NBATCH]), K)
+    tw1 = time.time()
     launches = lib.nb_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(window=(tw0, tw1)) if rank == 0 else None
     value = world * B * K / (ms / 1e3)
 
     if args.quick:
