@@ -266,9 +266,16 @@ def run_ours(args):
     value = world * B * K / (ms / 1e3)
 
     if args.quick:
+        lib.nb_profile_enable(1)
+        ms_q = timed(lambda i: train_step(resident[i % NBATCH]), K)
+        qm, qc = (ctypes.c_double * 4)(), (ctypes.c_longlong * 4)()
+        lib.nb_profile_read(qm, qc)
+        lib.nb_profile_enable(0)
+        per = {c: round(1e3 * qm[i] / max(qc[i], 1), 1) for i, c in enumerate(["edge_fwd", "edge_bwd", "gemm64", "wgrad64"])}
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                              "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True}))
+                              "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True,
+                              "us_per_launch": per, "ms_in_kernels_per_step": round(sum(qm) / K, 3)}))
         if world > 1:
             dist.destroy_process_group()
         return

@@ -8,23 +8,25 @@
 #include "nb_edge_sel.cuh"
 
 // ============================================================================= gemm64 on tensor cores
-// One CTA per (128-row tile, job).  Shared memory: per source an A tile [128][64] and a B tile [64][64], hi + lo.
-#define NB_GT_A(s) ((s) * 2 * NB_TC_TILE_BYTES(128))
-#define NB_GT_B(s) (4 * NB_TC_TILE_BYTES(128) + (s) * 2 * NB_TC_TILE_BYTES(64))
-#define NB_GEMM_TC_SMEM (4 * NB_TC_TILE_BYTES(128) + 4 * NB_TC_TILE_BYTES(64) + 64 + 1024)
+// Persistent CTAs: blockIdx.y = job, blockIdx.x strides over the job's 128-row tiles.  The B operands (weights) are
+// split and staged once per CTA; per tile the A rows are loaded (coalesced, 32 bytes per thread), split into their
+// bf16 pieces and multiplied with three MMA passes per source into one TMEM accumulator.
+// Shared memory: per source an A tile [128][64] and a B tile [64][64], hi + lo (48 KB per source).
+#define NB_GT_A(s) ((s) * (2 * NB_TC_TILE_BYTES(128) + 2 * NB_TC_TILE_BYTES(64)))
+#define NB_GT_B(s) (NB_GT_A(s) + 2 * NB_TC_TILE_BYTES(128))
+#define NB_GEMM_TC_SMEM(nsrc) ((nsrc) * (2 * NB_TC_TILE_BYTES(128) + 2 * NB_TC_TILE_BYTES(64)) + 64 + 1024)
 
-__global__ void __launch_bounds__(NB_THREADS, 2) k_gemm64_tc(NbGemmBatch batch) {
+__global__ void __launch_bounds__(NB_THREADS, 3) k_gemm64_tc(NbGemmBatch batch, int nsrc_max) {
   const NbGemmArgs& a = batch.job[blockIdx.y];
-  if ((int)blockIdx.x * NB_TILE >= a.rows) return;
+  const int ntiles = (a.rows + NB_TILE - 1) / NB_TILE;
+  if ((int)blockIdx.x >= ntiles) return;
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 4 * NB_TC_TILE_BYTES(128) + 4 * NB_TC_TILE_BYTES(64));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + NB_GT_A(nsrc_max));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, hf = warp >> 2;
   const int row = 32 * q + lane, cb = 32 * hf;
-  const int r0 = blockIdx.x * NB_TILE;
-  const int nv = min(NB_TILE, a.rows - r0);
 
   if (tid == 0) {
     nb_mbar_init(bar, 1);
@@ -33,8 +35,6 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_gemm64_tc(NbGemmBatch batch) 
   if (warp == 0) nb_tmem_alloc(tmem_slot, 64);
   for (int s = 0; s < a.nsrc; ++s) {
     const NbGemmSrc src = a.src[s];
-    unsigned char* Ah = base + NB_GT_A(s);
-    unsigned char* Al = Ah + NB_TC_TILE_BYTES(128);
     unsigned char* Bh = base + NB_GT_B(s);
     unsigned char* Bl = Bh + NB_TC_TILE_BYTES(64);
     // B operand, K-major: tile row n (output column), tile column k:  W[k * sk + n * sn] * scale
@@ -48,89 +48,112 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_gemm64_tc(NbGemmBatch batch) 
       for (int i = 0; i < 8; ++i) v[i] = __ldg(w + (int64_t)i * src.sk) * src.scale;
       nb_tc_store8(Bh, Bl, n, j, v);
     }
-    // A operand, K-major: 8 threads per row, 32 contiguous bytes each
-    for (int idx = tid; idx < NB_TILE * 8; idx += NB_THREADS) {
-      const int r = idx >> 3, j = idx & 7;
-      float v[8];
-      if (r < nv) {
-        const float* p = src.A + (int64_t)(r0 + r) * src.lda + 8 * j;
-        float4 x0 = nb_ld4(p), x1 = nb_ld4(p + 4);
-        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-        if (src.a_silu) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = nb_silu(v[i]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      }
-      nb_tc_store8(Ah, Al, r, j, v);
-    }
   }
-  nb_fence_async_smem();
   nb_tc_fence_before();
   __syncthreads();
   nb_tc_fence_after();
   const uint32_t tm = *tmem_slot;
-  if (tid == 0) {
-    const uint32_t idesc = nb_idesc_bf16(128, 64, 0, 0);
+  const uint32_t idesc = nb_idesc_bf16(128, 64, 0, 0);
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * NB_TILE;
+    const int nv = min(NB_TILE, a.rows - r0);
     for (int s = 0; s < a.nsrc; ++s) {
-      const uint32_t sa = nb_smem_u32(base + NB_GT_A(s)), sb = nb_smem_u32(base + NB_GT_B(s));
-      nb_issue_w3(tm, sa, sa + NB_TC_TILE_BYTES(128), sb, sb + NB_TC_TILE_BYTES(64), false, idesc, s > 0 ? 1u : 0u);
+      const NbGemmSrc src = a.src[s];
+      unsigned char* Ah = base + NB_GT_A(s);
+      unsigned char* Al = Ah + NB_TC_TILE_BYTES(128);
+      // A operand, K-major: 8 threads per row, 32 contiguous bytes each; all four loads of a thread are in flight together
+      float4 x0[4], x1[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = tid + it * NB_THREADS;
+        const int r = idx >> 3, j = idx & 7;
+        if (r < nv) {
+          const float* p = src.A + (int64_t)(r0 + r) * src.lda + 8 * j;
+          x0[it] = nb_ld4(p);
+          x1[it] = nb_ld4(p + 4);
+        } else {
+          x0[it] = x1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = tid + it * NB_THREADS;
+        const int r = idx >> 3, j = idx & 7;
+        float v[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
+        if (src.a_silu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = nb_silu(v[i]);
+        }
+        nb_tc_store8(Ah, Al, r, j, v);
+      }
     }
-    nb_mma_commit(bar);
-  }
-  nb_mbar_wait(bar, 0);
-  nb_tc_fence_after();
-  {
-    float v[32];
-    nb_tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + (uint32_t)cb, v);
-    if (row < nv) {
-      const int64_t gr = r0 + row;
-      if (a.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + cb + i);
+    nb_fence_async_smem();
+    nb_tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      nb_tc_fence_after();
+      for (int s = 0; s < a.nsrc; ++s) {
+        const uint32_t sa = nb_smem_u32(base + NB_GT_A(s)), sb = nb_smem_u32(base + NB_GT_B(s));
+        nb_issue_w3(tm, sa, sa + NB_TC_TILE_BYTES(128), sb, sb + NB_TC_TILE_BYTES(64), false, idesc, s > 0 ? 1u : 0u);
       }
-      if (a.out_pre) {
-        float* o = a.out_pre + gr * a.ldp + cb;
+      nb_mma_commit(bar);
+    }
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    {
+      float v[32];
+      nb_tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + (uint32_t)cb, v);
+      if (row < nv) {
+        const int64_t gr = r0 + row;
+        if (a.bias) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) nb_st4(o + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
-      }
-      if (a.epi == NB_EPI_SILU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
-      } else if (a.epi == NB_EPI_MUL_DSILU) {
-        const float* up = a.U + gr * a.ldu + cb;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 u = nb_ld4(up + 4 * k);
-          v[4 * k + 0] *= nb_dsilu(u.x);
-          v[4 * k + 1] *= nb_dsilu(u.y);
-          v[4 * k + 2] *= nb_dsilu(u.z);
-          v[4 * k + 3] *= nb_dsilu(u.w);
+          for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + cb + i);  // parameter offsets are not 16-byte aligned
         }
-      }
-      if (a.R) {
-        const float* rp = a.R + gr * a.ldr + cb;
+        if (a.out_pre) {
+          float* o = a.out_pre + gr * a.ldp + cb;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 t = nb_ld4(rp + 4 * k);
-          v[4 * k + 0] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+          for (int k = 0; k < 8; ++k) nb_st4(o + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
         }
-      }
-      if (a.out) {
-        float* o = a.out + gr * a.ldo + cb;
-        if (a.accumulate) {
+        if (a.epi == NB_EPI_SILU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
+        } else if (a.epi == NB_EPI_MUL_DSILU) {
+          const float* up = a.U + gr * a.ldu + cb;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            float4 t = nb_ld4(o + 4 * k);
+            float4 u = nb_ld4(up + 4 * k);
+            v[4 * k + 0] *= nb_dsilu(u.x);
+            v[4 * k + 1] *= nb_dsilu(u.y);
+            v[4 * k + 2] *= nb_dsilu(u.z);
+            v[4 * k + 3] *= nb_dsilu(u.w);
+          }
+        }
+        if (a.R) {
+          const float* rp = a.R + gr * a.ldr + cb;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 t = nb_ld4(rp + 4 * k);
             v[4 * k + 0] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
           }
         }
+        if (a.out) {
+          float* o = a.out + gr * a.ldo + cb;
+          if (a.accumulate) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) nb_st4(o + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+            for (int k = 0; k < 8; ++k) {
+              float4 t = nb_ld4(o + 4 * k);
+              v[4 * k + 0] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) nb_st4(o + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        }
       }
     }
+    nb_tc_fence_before();  // the next tile's MMA overwrites the accumulator this thread has just read
   }
   nb_tc_fence_before();
   __syncthreads();

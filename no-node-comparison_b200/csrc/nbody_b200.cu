@@ -170,10 +170,17 @@ static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st, bool exact
     if (b.njobs == 0) continue;
 #ifndef NB_EMU
     if (g_node_impl == 1 && !exact_fp32) {
-      const size_t smem_tc = NB_GEMM_TC_SMEM;
-      NB_SET_SMEM(k_gemm64_tc, smem_tc);
+      int nsrc_max = 1;
+      for (int j = 0; j < b.njobs; ++j)
+        if (b.job[j].nsrc > nsrc_max) nsrc_max = b.job[j].nsrc;
+      const size_t smem_tc = NB_GEMM_TC_SMEM(nsrc_max);
+      NB_SET_SMEM(k_gemm64_tc, NB_GEMM_TC_SMEM(2));
+      // persistent CTAs: about three co-resident CTAs per SM over the jobs of the batch
+      int per_job = 3 * nb_num_sms() / b.njobs;
+      if (per_job < 1) per_job = 1;
+      const int gx = imin(cdiv(maxrows, NB_TILE), per_job);
       int pi_tc = prof_begin(2, st);
-      NB_LAUNCH_COUNTED(k_gemm64_tc, dim3((unsigned)cdiv(maxrows, NB_TILE), (unsigned)b.njobs), NB_THREADS, smem_tc, st, b);
+      NB_LAUNCH_COUNTED(k_gemm64_tc, dim3((unsigned)gx, (unsigned)b.njobs), NB_THREADS, smem_tc, st, b, nsrc_max);
       prof_end(2, pi_tc, st);
       NB_TRY(nb_check_launch("k_gemm64_tc"));
       continue;
