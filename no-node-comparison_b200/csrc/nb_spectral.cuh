@@ -339,3 +339,216 @@ __global__ void __launch_bounds__(256) k_tcx_bwd(NbTcxArgs a) {
     a.partial[(int64_t)blockIdx.x * nw + threadIdx.x] = s;
   }
 }
+
+// ----------------------------------------------------------------------------- fused temporal convolution (modes <= 2)
+// One kernel for  out = x + LeakyReLU(irfft(mix(rfft(x))))  and one for its backward, for the configured case
+// num_modes <= 2 (model_confs.yaml:1-13): coefficient planes C0 | C1 | S1.  A CTA processes groups of 16
+// node-trajectories; thread (r = tid / 16, c4 = tid % 16) owns row r and channels 4 c4 .. 4 c4 + 3 in BOTH the DFT and
+// the 64x64 mode-mixing GEMM (fp32 FFMA: the result feeds LeakyReLU, see launch_gemm_batch), so the mixed
+// coefficients come out in the registers of the thread that holds x[t] — x and out cross HBM exactly once.
+//   forward : 2 x T x 256 B per node-trajectory;  backward: reads x, gout, writes gx (+ coef, gycoef planes for the
+//   weight-gradient reduction).
+#define NB_TCV_ROWS 16
+#define NB_TCV_LDA 68
+struct NbTconvArgs {
+  NbTwiddle tw;
+  int Nn0;
+  const float* x;      // [T][Nn0][64]
+  const float* W;      // [64][64][modes][2]  (i, o, m, re/im)
+  float* out;          // [T][Nn0][64]                 forward
+  const float* gout;   // [T][Nn0][64]                 backward
+  float* gx;           // [T][Nn0][64]
+  float* coef;         // [ncoef][Nn0][64]  C0 | C1 | S1   (backward: written for the weight-gradient jobs)
+  float* gycoef;       // [ncoef][Nn0][64]  gP0 | gP1 | gQ1
+};
+#define NB_TCONV_FWD_SMEM ((3 * NB_H * NB_H + 3 * NB_TCV_ROWS * NB_TCV_LDA) * sizeof(float))
+#define NB_TCONV_BWD_SMEM ((3 * NB_H * NB_H + 3 * NB_H * 68 + 3 * NB_TCV_ROWS * NB_TCV_LDA) * sizeof(float))
+
+// De-interleave W[i][o][m][re/im] (modes <= 2) into the k-major planes B0 = Re W_0, B1 = Re W_1, B2 = Im W_1
+// (Bq[i][o], row stride 64) and, when Tq != nullptr, their transposes Tq[o][i] (row stride NB_TCV_LDT).
+// One coalesced pass: 8-byte loads (the parameter offset is only guaranteed to be 8-byte aligned).
+#define NB_TCV_LDT 68
+__device__ __forceinline__ void nb_tconv_stage_w(float* B0, float* B1, float* B2, float* T0, float* T1, float* T2,
+                                                 const float* __restrict__ W, int modes, int tid) {
+  for (int idx = tid; idx < NB_H * NB_H; idx += 256) {
+    const int i = idx >> 6, o = idx & 63;
+    const float2 w0 = __ldg(reinterpret_cast<const float2*>(W + (int64_t)idx * modes * 2));
+    float2 w1 = make_float2(0.f, 0.f);
+    if (modes > 1) w1 = __ldg(reinterpret_cast<const float2*>(W + (int64_t)idx * modes * 2 + 2));
+    B0[idx] = w0.x;
+    B1[idx] = w1.x;
+    B2[idx] = w1.y;
+    if (T0) {
+      T0[o * NB_TCV_LDT + i] = w0.x;
+      T1[o * NB_TCV_LDT + i] = w1.x;
+      T2[o * NB_TCV_LDT + i] = w1.y;
+    }
+  }
+}
+
+// acc_p (+)= sum_k A_p[row][k] * B_q[k][4 tx ..]  for the three coefficient planes:
+//   out0 = A0 B0 ; out1 = A1 B1 + A2 B2 ; out2 = A1 B2 - A2 B1
+__device__ __forceinline__ void nb_tconv_mix(const float* As, const float* B0, const float* B1, const float* B2, int ldb,
+                                             int r, int c4, bool has1, bool pair1, float4& o0, float4& o1, float4& o2) {
+  o0 = o1 = o2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* a0 = As + r * NB_TCV_LDA;
+  const float* a1 = a0 + NB_TCV_ROWS * NB_TCV_LDA;
+  const float* a2 = a1 + NB_TCV_ROWS * NB_TCV_LDA;
+#pragma unroll 2
+  for (int k0 = 0; k0 < NB_H; k0 += 4) {
+    const float4 v0 = nb_ld4(a0 + k0);
+    const float4 v1 = has1 ? nb_ld4(a1 + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v2 = pair1 ? nb_ld4(a2 + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float x0[4] = {v0.x, v0.y, v0.z, v0.w}, x1[4] = {v1.x, v1.y, v1.z, v1.w}, x2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = k0 + kk;
+      o0 = nb_f4_fma(x0[kk], nb_ld4(B0 + k * ldb + c4 * 4), o0);
+      if (has1) {
+        const float4 b1 = nb_ld4(B1 + k * ldb + c4 * 4);
+        o1 = nb_f4_fma(x1[kk], b1, o1);
+        if (pair1) {
+          const float4 b2 = nb_ld4(B2 + k * ldb + c4 * 4);
+          o1 = nb_f4_fma(x2[kk], b2, o1);
+          o2 = nb_f4_fma(x1[kk], b2, o2);
+          o2 = nb_f4_fma(-x2[kk], b1, o2);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tconv_fwd(NbTconvArgs a) {
+  NB_DYN_SMEM(sm);
+  float* B0 = sm;                    // W[.][.][0][re]
+  float* B1 = B0 + NB_H * NB_H;      // W[.][.][1][re]
+  float* B2 = B1 + NB_H * NB_H;      // W[.][.][1][im]
+  float* As = B2 + NB_H * NB_H;      // [3][16][68]
+  const int tid = threadIdx.x, r = tid >> 4, c4 = tid & 15;
+  const NbTwiddle& tw = a.tw;
+  const bool has1 = tw.modes > 1, pair1 = has1 && tw.nyq != 1;
+  nb_tconv_stage_w(B0, B1, B2, nullptr, nullptr, nullptr, a.W, tw.modes, tid);
+  const int64_t plane = (int64_t)a.Nn0 * NB_H;
+  const float invT = 1.0f / (float)tw.T;
+  const int ngroups = (a.Nn0 + NB_TCV_ROWS - 1) / NB_TCV_ROWS;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int row = grp * NB_TCV_ROWS + r;
+    const bool act = row < a.Nn0;
+    const int64_t off = (int64_t)row * NB_H + c4 * 4;
+    float4 xs[NB_MAX_T];
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) xs[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0;
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) {
+        C0 = nb_f4_fma(tw.c[0][t], xs[t], C0);
+        if (has1) C1 = nb_f4_fma(tw.c[1][t], xs[t], C1);
+        if (pair1) S1 = nb_f4_fma(tw.s[1][t], xs[t], S1);
+      }
+    __syncthreads();  // previous group's GEMM has finished reading As (also orders the weight staging)
+    nb_st4(As + r * NB_TCV_LDA + c4 * 4, C0);
+    nb_st4(As + (NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, C1);
+    nb_st4(As + (2 * NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, S1);
+    __syncthreads();
+    float4 P0, P1, Q1;
+    nb_tconv_mix(As, B0, B1, B2, NB_H, r, c4, has1, pair1, P0, P1, Q1);
+    if (act) {
+      const float s1 = pair1 ? 2.f * invT : invT;
+#pragma unroll
+      for (int t = 0; t < NB_MAX_T; ++t)
+        if (t < tw.T) {
+          float4 y = make_float4(P0.x * invT, P0.y * invT, P0.z * invT, P0.w * invT);
+          if (has1) y = nb_f4_fma(s1 * tw.c[1][t], P1, y);
+          if (pair1) y = nb_f4_fma(-s1 * tw.s[1][t], Q1, y);
+          nb_st4(a.out + t * plane + off, make_float4(xs[t].x + nb_leaky(y.x), xs[t].y + nb_leaky(y.y),
+                                                      xs[t].z + nb_leaky(y.z), xs[t].w + nb_leaky(y.w)));
+        }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tconv_bwd(NbTconvArgs a) {
+  NB_DYN_SMEM(sm);
+  float* B0 = sm;
+  float* B1 = B0 + NB_H * NB_H;
+  float* B2 = B1 + NB_H * NB_H;
+  float* T0 = B2 + NB_H * NB_H;      // transposed copies for the data gradient, row stride NB_TCV_LDT
+  float* T1 = T0 + NB_H * NB_TCV_LDT;
+  float* T2 = T1 + NB_H * NB_TCV_LDT;
+  float* As = T2 + NB_H * NB_TCV_LDT;  // [3][16][68]
+  const int tid = threadIdx.x, r = tid >> 4, c4 = tid & 15;
+  const NbTwiddle& tw = a.tw;
+  const bool has1 = tw.modes > 1, pair1 = has1 && tw.nyq != 1;
+  nb_tconv_stage_w(B0, B1, B2, T0, T1, T2, a.W, tw.modes, tid);
+  const int64_t plane = (int64_t)a.Nn0 * NB_H;
+  const float invT = 1.0f / (float)tw.T;
+  const float s1 = pair1 ? 2.f * invT : invT;
+  const int ngroups = (a.Nn0 + NB_TCV_ROWS - 1) / NB_TCV_ROWS;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int row = grp * NB_TCV_ROWS + r;
+    const bool act = row < a.Nn0;
+    const int64_t off = (int64_t)row * NB_H + c4 * 4;
+    // ---- recompute: coefficients of x, mixed coefficients, y
+    float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0;
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) {
+        const float4 xv = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        C0 = nb_f4_fma(tw.c[0][t], xv, C0);
+        if (has1) C1 = nb_f4_fma(tw.c[1][t], xv, C1);
+        if (pair1) S1 = nb_f4_fma(tw.s[1][t], xv, S1);
+      }
+    if (act) {
+      nb_st4(a.coef + off, C0);
+      if (has1) nb_st4(a.coef + plane + off, C1);
+      if (pair1) nb_st4(a.coef + 2 * plane + off, S1);
+    }
+    __syncthreads();
+    nb_st4(As + r * NB_TCV_LDA + c4 * 4, C0);
+    nb_st4(As + (NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, C1);
+    nb_st4(As + (2 * NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, S1);
+    __syncthreads();
+    float4 P0, P1, Q1;
+    nb_tconv_mix(As, B0, B1, B2, NB_H, r, c4, has1, pair1, P0, P1, Q1);
+    // ---- gy = gout * LeakyReLU'(y) ; adjoint of the inverse DFT -> gP0, gP1, gQ1
+    float4 gP0 = make_float4(0.f, 0.f, 0.f, 0.f), gP1 = gP0, gQ1 = gP0;
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) {
+        float4 y = make_float4(P0.x * invT, P0.y * invT, P0.z * invT, P0.w * invT);
+        if (has1) y = nb_f4_fma(s1 * tw.c[1][t], P1, y);
+        if (pair1) y = nb_f4_fma(-s1 * tw.s[1][t], Q1, y);
+        const float4 g = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 gy = make_float4(g.x * nb_dleaky(y.x), g.y * nb_dleaky(y.y), g.z * nb_dleaky(y.z), g.w * nb_dleaky(y.w));
+        gP0 = nb_f4_fma(invT * tw.c[0][t], gy, gP0);
+        if (has1) gP1 = nb_f4_fma(s1 * tw.c[1][t], gy, gP1);
+        if (pair1) gQ1 = nb_f4_fma(-s1 * tw.s[1][t], gy, gQ1);
+      }
+    if (act) {
+      nb_st4(a.gycoef + off, gP0);
+      if (has1) nb_st4(a.gycoef + plane + off, gP1);
+      if (pair1) nb_st4(a.gycoef + 2 * plane + off, gQ1);
+    }
+    __syncthreads();  // the forward mix has finished reading As
+    nb_st4(As + r * NB_TCV_LDA + c4 * 4, gP0);
+    nb_st4(As + (NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, gP1);
+    nb_st4(As + (2 * NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, gQ1);
+    __syncthreads();
+    // gC0 = gP0 Wr0^T ; gC1 = gP1 Wr1^T + gQ1 Wi1^T ; gS1 = gP1 Wi1^T - gQ1 Wr1^T   (same pattern as the forward mix)
+    float4 gC0, gC1, gS1;
+    nb_tconv_mix(As, T0, T1, T2, NB_TCV_LDT, r, c4, has1, pair1, gC0, gC1, gS1);
+    if (act) {
+#pragma unroll
+      for (int t = 0; t < NB_MAX_T; ++t)
+        if (t < tw.T) {
+          float4 g = nb_ld4(a.gout + t * plane + off);  // residual path
+          g = nb_f4_fma(tw.c[0][t], gC0, g);
+          if (has1) g = nb_f4_fma(tw.c[1][t], gC1, g);
+          if (pair1) g = nb_f4_fma(tw.s[1][t], gS1, g);
+          nb_st4(a.gx + t * plane + off, g);
+        }
+    }
+  }
+}

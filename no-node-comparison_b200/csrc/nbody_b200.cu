@@ -59,13 +59,13 @@ int nb_num_sms() {
 // ---- launch accounting and optional per-kernel CUDA-event timing (used by bench.py for the roofline)
 static long long g_launches = 0;
 static long long& g_launches_ref() { return g_launches; }
-#define NB_PROF_CATS 4  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64 */
+#define NB_PROF_CATS 5  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64, 4 temporal conv */
 #define NB_PROF_MAX 8192
 #ifndef NB_EMU
 static int g_prof_on = 0;
 static cudaEvent_t g_prof_ev[NB_PROF_CATS][NB_PROF_MAX][2];
-static int g_prof_made[NB_PROF_CATS] = {0, 0, 0, 0};
-static int g_prof_n[NB_PROF_CATS] = {0, 0, 0, 0};
+static int g_prof_made[NB_PROF_CATS] = {0, 0, 0, 0, 0};
+static int g_prof_n[NB_PROF_CATS] = {0, 0, 0, 0, 0};
 static int prof_begin(int cat, void* st) {
   if (!g_prof_on || g_prof_n[cat] >= NB_PROF_MAX) return -1;
   int i = g_prof_n[cat];
@@ -676,6 +676,20 @@ static NbDftArgs dft_args(const EgnoCtx& X) {
   return d;
 }
 
+// fused temporal convolution kernels (k_tconv_fwd / k_tconv_bwd) serve num_modes <= 2, the configured case
+static inline bool egno_tconv_fused(const EgnoCtx& X) { return X.c->num_modes <= 2; }
+static NbTconvArgs tconv_args(const EgnoCtx& X, int l) {
+  NbTconvArgs t;
+  memset(&t, 0, sizeof(t));
+  t.tw = X.tw;
+  t.Nn0 = (int)X.Nn0;
+  t.W = X.params + X.lo.L[l].tc;
+  return t;
+}
+static inline int tconv_grid(const EgnoCtx& X, int per_sm) {
+  return imin(cdiv(X.Nn0, NB_TCV_ROWS), (int64_t)per_sm * nb_num_sms());
+}
+
 static int egno_pq(const EgnoCtx& X, int l, const float* h1, float* P, float* Q) {
   const EgnoLayerOff& L = X.lo.L[l];
   const int E = X.lo.E;
@@ -742,14 +756,24 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
     float *h1 = b.h1, *x1 = b.x1, *v1 = b.v1;
     if (cfg->use_time_conv) {
       // h <- h + LeakyReLU(conv(h))      (layer_no.py:96-126)
-      NbDftArgs d = dft_args(X);
-      d.x = b.h0; d.coef = coef;
-      NB_LAUNCH_COUNTED(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
-      NB_TRY(nb_check_launch("k_dft_fwd"));
-      NB_TRY(egno_tc_mix(X, l, coef, ycoef));
-      d.ycoef = ycoef; d.out = h1;
-      NB_LAUNCH_COUNTED(k_idft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
-      NB_TRY(nb_check_launch("k_idft_fwd"));
+      if (egno_tconv_fused(X)) {
+        NbTconvArgs tc = tconv_args(X, l);
+        tc.x = b.h0; tc.out = h1;
+        NB_SET_SMEM(k_tconv_fwd, NB_TCONV_FWD_SMEM);
+        int pi = prof_begin(4, stream);
+        NB_LAUNCH_COUNTED(k_tconv_fwd, (unsigned)tconv_grid(X, 3), 256, NB_TCONV_FWD_SMEM, stream, tc);
+        prof_end(4, pi, stream);
+        NB_TRY(nb_check_launch("k_tconv_fwd"));
+      } else {
+        NbDftArgs d = dft_args(X);
+        d.x = b.h0; d.coef = coef;
+        NB_LAUNCH_COUNTED(k_dft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_TRY(nb_check_launch("k_dft_fwd"));
+        NB_TRY(egno_tc_mix(X, l, coef, ycoef));
+        d.ycoef = ycoef; d.out = h1;
+        NB_LAUNCH_COUNTED(k_idft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
+        NB_TRY(nb_check_launch("k_idft_fwd"));
+      }
       // (x - mean, v) <- (x - mean, v) + conv(.)     (egno.py:103-108, layer_no.py:151-178)
       NbTcxArgs t;
       memset(&t, 0, sizeof(t));
@@ -940,6 +964,33 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       }
       gxi ^= 1;
       gv_in = gvA;
+      if (egno_tconv_fused(X)) {
+        // queued weight-gradient jobs read gh_in (= ghB of the layer above), GU5, gP, ...: run them before ghB is
+        // overwritten.  The spectral weight gradients of THIS layer are queued after the kernel that produces their
+        // operands (coef, gycoef) and run with the next flush, before those planes are overwritten again.
+        NB_TRY(q_flush(stream));
+        NbTconvArgs tc = tconv_args(X, l);
+        tc.x = b.h0; tc.gout = ghA; tc.gx = ghB; tc.coef = coef; tc.gycoef = gycoef;
+        NB_SET_SMEM(k_tconv_bwd, NB_TCONV_BWD_SMEM);
+        int pi = prof_begin(4, stream);
+        NB_LAUNCH_COUNTED(k_tconv_bwd, (unsigned)tconv_grid(X, 2), 256, NB_TCONV_BWD_SMEM, stream, tc);
+        prof_end(4, pi, stream);
+        NB_TRY(nb_check_launch("k_tconv_bwd"));
+        const int64_t plane = Nn0 * NB_H;
+        const int64_t tk = (int64_t)modes * 2, tn = (int64_t)NB_H * modes * 2;
+        for (int m = 0; m < modes; ++m) {
+          int ci = nb_coef_index(X.tw, m);
+          const float *C = coef + ci * plane, *S = coef + (ci + 1) * plane;
+          const float *gPm = gycoef + ci * plane, *gQm = gycoef + (ci + 1) * plane;
+          const int64_t wr_off = L.tc + m * 2, wi_off = L.tc + m * 2 + 1;
+          if (m == 0 || m == X.tw.nyq) {
+            NB_TRY(wgrad_to((int)Nn0, 1, wpair(C, gPm), wpair(nullptr, nullptr), grad_params, wr_off, tn, tk, -1, 0, stream));
+          } else {
+            NB_TRY(wgrad_to((int)Nn0, 2, wpair(C, gPm), wpair(S, gQm, 0, -1.f), grad_params, wr_off, tn, tk, -1, 0, stream));
+            NB_TRY(wgrad_to((int)Nn0, 2, wpair(S, gPm), wpair(C, gQm), grad_params, wi_off, tn, tk, -1, 0, stream));
+          }
+        }
+      } else
       {
         NbDftArgs d = dft_args(X);
         d.x = b.h0; d.coef = coef;

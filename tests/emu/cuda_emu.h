@@ -166,6 +166,7 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __ldg(const float* p) { return *p; }
 static inline float4 __ldg(const float4* p) { return *p; }
+static inline float2 __ldg(const float2* p) { return *p; }
 static inline int64_t __ldg(const int64_t* p) { return *p; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
