@@ -177,6 +177,10 @@ int nb_get_edge_impl(void);
  * kernels (cross-check; the variant the host emulator runs). */
 int nb_set_node_impl(int impl);
 int nb_get_node_impl(void);
+/* SEGNO forward: 1 = all T integration sub-steps fused into one kernel, node state resident in shared memory (default;
+ * needs edge impl 2, node impl 1 and N <= 27), 0 = one kernel sequence per sub-step. */
+int nb_set_segno_fused(int on);
+int nb_get_segno_fused(void);
 
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]

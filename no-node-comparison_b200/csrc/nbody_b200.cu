@@ -13,6 +13,7 @@
 #include "nb_edge_tc.cuh"
 #include "nb_edge_sel.cuh"
 #include "nb_node_tc.cuh"
+#include "nb_segno_fused.cuh"
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 #define NB_LAUNCH_COUNTED(...) \
@@ -148,6 +149,22 @@ extern "C" int nb_set_node_impl(int impl) {
   return NB_OK;
 }
 extern "C" int nb_get_node_impl(void) { return g_node_impl; }
+
+// SEGNO forward: 1 = all T sub-steps in one kernel with the node state resident in shared memory (nb_segno_fused.cuh;
+// needs the tcgen05 variants and N <= 27), 0 = one kernel sequence per sub-step
+#ifdef NB_EMU
+static int g_segno_fused = 0;
+#else
+static int g_segno_fused = 1;
+#endif
+extern "C" int nb_set_segno_fused(int on) {
+#ifdef NB_EMU
+  if (on) { nb_set_error("the host emulator runs SEGNO one sub-step at a time"); return NB_ERR_INVALID; }
+#endif
+  g_segno_fused = on ? 1 : 0;
+  return NB_OK;
+}
+extern "C" int nb_get_segno_fused(void) { return g_segno_fused; }
 
 // ============================================================================= launch helpers
 // exact_fp32: run the fp32 SIMT kernel even when the tcgen05 node kernels are selected.  Used for the spectral mode
@@ -1208,6 +1225,35 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
   auto bufs = [&](int k) { return segno_iter_bufs(saved ? saved + (int64_t)k * itf : infer + (int64_t)(k & 1) * itf, Nn); };
   cudaStream_t cst = (cudaStream_t)stream;
 
+#ifndef NB_EMU
+  {
+    NbEdgeGeom fg = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
+    if (g_segno_fused && g_edge_impl == 2 && g_node_impl == 1 && sel_geom(fg)) {
+      // embedding into scratch (the fused kernel writes h_k of every sub-step into `saved` itself)
+      NbEmbedArgs e;
+      segno_embed_args(X, his, &e);
+      e.out = P;
+      const size_t esm = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
+      NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, esm, stream, e);
+      NB_TRY(nb_check_launch("k_embed_fwd"));
+      NbSegnoFusedArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.g = fg; fa.T = T; fa.recurrent = cfg->recurrent; fa.inv_T = (float)(1.0 / (double)T); fa.cw = cfg->coords_weight;
+      fa.W1 = params + X.lo.e_w1; fa.b1 = params + X.lo.e_b1; fa.ldw1 = X.lo.E; fa.col_rad = 2 * NB_H; fa.col_ef = 2 * NB_H + 1;
+      fa.W2 = params + X.lo.e_w2; fa.b2 = params + X.lo.e_b2; fa.W3 = params + X.lo.c_w1; fa.b3 = params + X.lo.c_b1;
+      fa.w4 = params + X.lo.c_w2; fa.b4 = params + X.lo.c_b2;
+      fa.W5 = params + X.lo.n_w1; fa.b5 = params + X.lo.n_b1; fa.W6 = params + X.lo.n_w2; fa.b6 = params + X.lo.n_b2;
+      fa.h_in = P; fa.x_in = x; fa.v_in = v; fa.ef = edge_attr;
+      fa.h_out = h_out; fa.x_out = x_out; fa.v_out = v_out; fa.saved = saved; fa.iter_stride = itf;
+      const size_t fsm = NB_SEGNO_FUSED_SMEM(fg.G * fg.EPG);
+      NB_SET_SMEM(k_segno_fused_fwd, fsm);
+      int pi = prof_begin(0, stream);
+      NB_LAUNCH_COUNTED(k_segno_fused_fwd, (unsigned)imin(fg.n_units, nb_num_sms()), NB_THREADS, fsm, stream, fa);
+      prof_end(0, pi, stream);
+      return nb_check_launch("k_segno_fused_fwd");
+    }
+  }
+#endif
   SegnoIterBufs b0 = bufs(0);
   {
     NbEmbedArgs e;

@@ -382,3 +382,32 @@ def test_kernel_variants_agree_on_golden_case(edge_impl, node_impl):
         lib.nb_set_edge_impl(2)
         lib.nb_set_node_impl(1)
     assert lib.nb_get_edge_impl() == 2 and lib.nb_get_node_impl() == 1
+
+
+def test_segno_fused_forward_matches_stepwise_kernels():
+    """The fused T-sub-step SEGNO forward (node state resident in shared memory, nb_segno_fused.cuh) against the
+    one-kernel-sequence-per-sub-step path, at BASELINE.json configs[3] shape: outputs, and gradients through the
+    backward that consumes the state each of them saved."""
+    lib = nb.load_library()
+    d = dev()
+    B, N, T = 64, 20, 10
+    s = synth.sample_state("gravity", B, N, seed=5)
+    row, col = synth.canonical_edges(B, N)
+    his, x, v, ea = synth.segno_features(s["loc"], s["vel"], s["charges"], row, col)
+    torch.manual_seed(3)
+    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
+    out = {}
+    for fused in (1, 0):
+        assert lib.nb_set_segno_fused(fused) == 0
+        try:
+            m.zero_grad(set_to_none=True)
+            xg = x.to(d).requires_grad_(True)
+            xo, ho, vo = m(his.to(d), xg, [row, col], v.to(d), ea.to(d), T=T)
+            (xo.square().sum() + 0.1 * ho.sum() + vo.square().sum()).backward()
+            out[fused] = [xo.detach().cpu(), ho.detach().cpu(), vo.detach().cpu(), xg.grad.cpu()] + \
+                [p.grad.cpu().clone() for p in m.parameters() if p.grad is not None]
+        finally:
+            lib.nb_set_segno_fused(1)
+    assert lib.nb_get_segno_fused() == 1
+    for a, b in zip(out[1], out[0]):
+        assert rel_err(a, b) < 2e-5
