@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the SEGNO / inference side numbers")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (for profiler runs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA "
+                                                            "graph per training step")
     return ap.parse_args()
 
 
@@ -169,7 +171,7 @@ def workload_config(args, per_step=None, note=None):
     c = {"workload": f"EGNO charged N-body, {args.n_balls} particles, num_timesteps={args.timesteps}, hidden 64, "
                      f"{args.layers} layers (BASELINE.json configs[2])",
          "batch_per_gpu": per_step if per_step is not None else args.batch, "n_balls": args.n_balls,
-         "num_timesteps": args.timesteps, "n_layers": args.layers, "parallelism": f"dp{args.gpus}",
+         "num_timesteps": args.timesteps, "n_layers": args.layers, "parallelism": f"dp{args.gpus}", "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per step)",
          "cache": "per-step activation working set (~270 MB at B=256) exceeds the 126 MB L2; inputs rotate over "
                   "8 distinct batches"}
     if note:
@@ -200,7 +202,8 @@ def run_ours(args):
     if world > 1:
         broadcast_parameters(model)
         model.enable_data_parallel()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8)   # model_confs.yaml:15-17
+    use_graph = not args.no_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8, capturable=use_graph)  # model_confs.yaml:15-17
 
     # ---- synthetic data: NB distinct batches per rank, raw states in pinned host memory
     NBATCH = 8
@@ -219,19 +222,39 @@ def run_ours(args):
         resident.append(dict(x=x, nodes=nodes, ea=ea, v=v, lm=lm, target=tgt.to(dev)))
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0].values())
 
-    def train_step(b):
-        opt.zero_grad(set_to_none=True)
-        xo, vo, ho = model(b["x"], b["nodes"], edges, b["ea"], v=b["v"], loc_mean=b["lm"], timesteps_out=t_out)
-        loss = ((xo - b["target"]) ** 2).mean()
-        loss.backward()
-        opt.step()
-        return loss
+    def loss_fn(x, nodes, ea, v, lm, target):
+        xo, vo, ho = model(x, nodes, edges, ea, v=v, loc_mean=lm, timesteps_out=t_out)
+        return ((xo - target) ** 2).mean()
 
-    def e2e_step(hb):
-        d = {k: t.to(dev, non_blocking=True) for k, t in hb.items()}                  # H2D from pinned memory
-        x, nodes, ea, v, lm = synth.egno_features(d["loc"], d["vel"], d["charges"], row_d, col_d)  # prepare_inputs
-        loss = train_step(dict(x=x, nodes=nodes, ea=ea, v=v, lm=lm, target=d["target"]))
-        return loss.item()                                                             # D2H read of the step's loss
+    def loss_from_raw(loc, vel, charges, target):
+        x, nodes, ea, v, lm = synth.egno_features(loc, vel, charges, row_d, col_d)    # prepare_inputs on the device
+        return loss_fn(x, nodes, ea, v, lm, target)
+
+    if use_graph:
+        # one CUDA graph per step shape: forward + loss + backward (+ all-reduce) + Adam replayed as a single launch
+        g_res = nb.GraphedStep(loss_fn, {k: resident[0][k] for k in ("x", "nodes", "ea", "v", "lm", "target")}, opt)
+        g_raw = nb.GraphedStep(loss_from_raw, {k: host[0][k].to(dev) for k in ("loc", "vel", "charges", "target")}, opt)
+
+        def train_step(b):
+            return g_res(**{k: b[k] for k in ("x", "nodes", "ea", "v", "lm", "target")})
+
+        def e2e_step(hb):
+            return g_raw(**hb).item()      # H2D from pinned memory into the graph's input buffers; D2H read of the loss
+    else:
+        def train_step(b):
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(b["x"], b["nodes"], b["ea"], b["v"], b["lm"], b["target"])
+            loss.backward()
+            opt.step()
+            return loss
+
+        def e2e_step(hb):
+            d = {k: t.to(dev, non_blocking=True) for k, t in hb.items()}              # H2D from pinned memory
+            loss = loss_from_raw(d["loc"], d["vel"], d["charges"], d["target"])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss.item()                                                         # D2H read of the step's loss
 
     def barrier():
         if world > 1:
@@ -262,6 +285,8 @@ def run_ours(args):
     ms = timed(lambda i: train_step(resident[i % NBATCH]), K)
     tw1 = time.time()
     launches = lib.nb_launch_count() - l0
+    if use_graph:   # replays do not pass through the library's host-side counter: kernels per captured step x K
+        launches = g_res.launches_per_replay * K
     clocks = sampler.stop(window=(tw0, tw1)) if rank == 0 else None
     value = world * B * K / (ms / 1e3)
 

@@ -11,5 +11,6 @@ from .egno import EGNO  # noqa: F401
 from .segno import SEGNO  # noqa: F401
 from .build import build_library  # noqa: F401
 from ._lib import load_library, library_path  # noqa: F401
+from .graph import GraphedStep  # noqa: F401
 
-__all__ = ["EGNO", "SEGNO", "build_library", "load_library", "library_path"]
+__all__ = ["EGNO", "SEGNO", "GraphedStep", "build_library", "load_library", "library_path"]

@@ -411,3 +411,38 @@ def test_segno_fused_forward_matches_stepwise_kernels():
     assert lib.nb_get_segno_fused() == 1
     for a, b in zip(out[1], out[0]):
         assert rel_err(a, b) < 2e-5
+
+
+def test_cuda_graph_training_step_matches_eager():
+    """GraphedStep (forward + loss + backward + Adam captured in one CUDA graph) follows the eager step bit for bit:
+    the C ABI is enqueue-only and allocation-free, so capture must not change any result."""
+    d = dev()
+    c = _egno_case(16, 20, 10, L=2, seed=9)
+    tgt = (c["x"].repeat(10, 1) + 0.05 * torch.randn(10 * 16 * 20, 3, generator=torch.Generator().manual_seed(2))).to(d)
+    ins = dict(x=c["x"].to(d), nodes=c["nodes"].to(d), ea=c["edge_attr"].to(d), v=c["v"].to(d), lm=c["loc_mean"].to(d))
+    edges = [c["row"].to(d), c["col"].to(d)]
+    t_out = c["t_out"].to(d)
+    losses = {}
+    for mode in ("eager", "graph"):
+        m = make_egno(c, seed=4)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+
+        def fn(x, nodes, ea, v, lm):
+            xo, _, _ = m(x, nodes, edges, ea, v=v, loc_mean=lm, timesteps_out=t_out)
+            return ((xo - tgt) ** 2).mean()
+
+        out = []
+        if mode == "graph":
+            step = nb.GraphedStep(fn, ins, opt, warmup=3)     # 3 eager steps (lazy optimizer state), then capture
+            assert step.launches_per_replay > 10
+            for _ in range(4):
+                out.append(float(step(**ins)))
+        else:
+            for _ in range(7):
+                opt.zero_grad(set_to_none=True)
+                loss = fn(**ins)
+                loss.backward()
+                opt.step()
+                out.append(float(loss.detach()))
+        losses[mode] = out
+    assert losses["graph"] == losses["eager"][3:], losses
