@@ -180,6 +180,18 @@ def workload_config(args, per_step=None, note=None):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def finish(world, dist):
+    """End of a rank: every rank reaches the barrier, then leaves without tearing NCCL down — destroying the process
+    group while captured CUDA graphs still hold its collectives can block forever, and the process is exiting anyway."""
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_ours(args):
     import no_node_comparison_b200 as nb
     from no_node_comparison_b200 import synth
@@ -230,6 +242,13 @@ def run_ours(args):
         x, nodes, ea, v, lm = synth.egno_features(loc, vel, charges, row_d, col_d)    # prepare_inputs on the device
         return loss_fn(x, nodes, ea, v, lm, target)
 
+    def eager_step(b):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(b["x"], b["nodes"], b["ea"], b["v"], b["lm"], b["target"])
+        loss.backward()
+        opt.step()
+        return loss
+
     if use_graph:
         # one CUDA graph per step shape: forward + loss + backward (+ all-reduce) + Adam replayed as a single launch
         g_res = nb.GraphedStep(loss_fn, {k: resident[0][k] for k in ("x", "nodes", "ea", "v", "lm", "target")}, opt)
@@ -241,12 +260,7 @@ def run_ours(args):
         def e2e_step(hb):
             return g_raw(**hb).item()      # H2D from pinned memory into the graph's input buffers; D2H read of the loss
     else:
-        def train_step(b):
-            opt.zero_grad(set_to_none=True)
-            loss = loss_fn(b["x"], b["nodes"], b["ea"], b["v"], b["lm"], b["target"])
-            loss.backward()
-            opt.step()
-            return loss
+        train_step = eager_step
 
         def e2e_step(hb):
             d = {k: t.to(dev, non_blocking=True) for k, t in hb.items()}              # H2D from pinned memory
@@ -292,7 +306,7 @@ def run_ours(args):
 
     if args.quick:
         lib.nb_profile_enable(1)
-        ms_q = timed(lambda i: train_step(resident[i % NBATCH]), K)
+        ms_q = timed(lambda i: eager_step(resident[i % NBATCH]), K)
         qm, qc = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
         lib.nb_profile_read(qm, qc)
         lib.nb_profile_enable(0)
@@ -301,8 +315,7 @@ def run_ours(args):
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                               "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True,
                               "us_per_launch": per, "ms_in_kernels_per_step": round(sum(qm[:5]) / K, 3)}))
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world, dist)
         return
 
     # ---- end to end: host buffers in, loss out, through the module API
@@ -312,8 +325,9 @@ def run_ours(args):
     e2e_value = world * B * K / (ms_e2e / 1e3)
 
     # ---- per-kernel CUDA-event timing (separate pass so the events do not perturb `value`)
+    # (eager launches: the per-kernel events are recorded by the library's host-side launch code, which a graph replay skips)
     lib.nb_profile_enable(1)
-    ms_prof = timed(lambda i: train_step(resident[i % NBATCH]), K)
+    ms_prof = timed(lambda i: eager_step(resident[i % NBATCH]), K)
     pm = (ctypes.c_double * 8)()
     pc = (ctypes.c_longlong * 8)()
     lib.nb_profile_read(pm, pc)
@@ -406,10 +420,8 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernels": kern, "extras": extras}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    finish(world, dist)
 
 
 def main():
