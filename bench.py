@@ -366,6 +366,19 @@ def run_ours(args):
                         "(43 MB per launch = 75 GB/s).",
                 "hbm_peak_gbs": hbm}
 
+    # HBM-bound side of the path: the fused temporal convolution (forward reads h and writes h once; the backward reads h
+    # and dL/dh_out, writes dL/dh_in and the 2 x 3 coefficient planes the weight-gradient reduction consumes)
+    nn0 = B * N
+    tconv_bytes_fwd = 2 * T * nn0 * 64 * 4
+    tconv_bytes_bwd = 3 * T * nn0 * 64 * 4 + 2 * 3 * nn0 * 64 * 4
+    t_tc = kern["tconv"]["ms_per_launch"]
+    tc_ach = 0.5 * (tconv_bytes_fwd + tconv_bytes_bwd) / (t_tc * 1e-3) / 1e9 if t_tc else None
+    roofline_hbm = {"kernel": "k_tconv_fwd / k_tconv_bwd (fused DFT + fp32 mode mixing + inverse DFT + LeakyReLU/residual)",
+                    "bound": "hbm", "achieved": tc_ach, "peak": hbm, "unit": "GB/s", "frac": (tc_ach / hbm) if tc_ach else None,
+                    "bytes_per_launch_fwd": tconv_bytes_fwd, "bytes_per_launch_bwd": tconv_bytes_bwd,
+                    "note": "mean over the forward and backward launches of a step (CUDA events); algorithmic bytes = "
+                            "2*T*64*4 B per node-trajectory forward, (3*T + 6)*64*4 B backward"}
+
     extras = {}
     if not args.no_extras:
         # inference throughput (no_grad forward) of the same model
@@ -418,7 +431,8 @@ def run_ours(args):
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "cpu_baseline": cpu_baseline,
                 "kernels": kern, "extras": extras}
         print(json.dumps(line), flush=True)
     finish(world, dist)

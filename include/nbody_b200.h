@@ -182,6 +182,19 @@ int nb_get_node_impl(void);
 int nb_set_segno_fused(int on);
 int nb_get_segno_fused(void);
 
+/* --- caller-side helpers that keep training / rollout loops on the device -----------------
+ * nb_nbody_features: the featurisation of one frame — EGNO prepare_inputs (EGNO/main_simulation_simple_no.py:326-338)
+ * and SEGNO's (SEGNO/train_nbody.py:119-123, :228-233) — for the canonical fully connected edge order:
+ *   nodes[B*N][1 + with_charge] = |v| (, charge);  loc_mean[B*N][3] = per-trajectory mean position (nullable);
+ *   edge_attr[B*N*(N-1)][2] = (edge_attr_o or q_i q_j, |x_i - x_j|^2).
+ * nb_nbody_energy: conserved energy per frame and trajectory, energy[F][B] — kind 0 charged
+ * (utils.py:126-144: K + 1/2 sum_{i!=j} q_i q_j / r_ij), kind 1 gravity (utils.py:175-195: 1/2 sum m v^2 -
+ * G sum_{i<j} m_i m_j / r_ij); loc / vel are [F][B*N][3], charges (or masses) [B*N]. */
+int nb_nbody_features(int32_t B, int32_t N, int32_t with_charge, const float* loc, const float* vel, const float* charges,
+                      const float* edge_attr_o, float* nodes, float* loc_mean, float* edge_attr, void* stream);
+int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, float G, const float* loc, const float* vel,
+                    const float* charges, float* energy, void* stream);
+
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]
  * and dumps the raw 128 TMEM lanes x 64 columns into out[128*64]. */

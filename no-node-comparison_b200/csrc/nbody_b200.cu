@@ -8,6 +8,7 @@
 #include "nb_common.cuh"
 #include "nb_node.cuh"
 #include "nb_spectral.cuh"
+#include "nb_rollout.cuh"
 #include "nb_edge.cuh"
 #include "nb_tc.cuh"
 #include "nb_edge_tc.cuh"
@@ -1477,6 +1478,36 @@ extern "C" int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t
   q_begin(workspace, NB_PARTIAL_FLOATS);
   NB_TRY(launch_edge_bwd(a, gw, d, 0, stream));
   return q_flush(stream);
+}
+
+// ============================================================================= caller-side device helpers
+extern "C" int nb_nbody_features(int32_t B, int32_t N, int32_t with_charge, const float* loc, const float* vel,
+                                 const float* charges, const float* edge_attr_o, float* nodes, float* loc_mean,
+                                 float* edge_attr, void* stream) {
+  if (B < 1 || N < 2 || N > 1024 || !loc || !vel || !charges || !nodes || !edge_attr) {
+    nb_set_error("nb_nbody_features: unsupported shape or null pointer (B=%d, N=%d)", B, N);
+    return NB_ERR_INVALID;
+  }
+  NbFeatArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.with_charge = with_charge ? 1 : 0; a.loc = loc; a.vel = vel; a.charges = charges;
+  a.edge_attr_o = edge_attr_o; a.nodes = nodes; a.loc_mean = loc_mean; a.edge_attr = edge_attr;
+  NB_LAUNCH_COUNTED(k_nbody_features, (unsigned)imin(B, 8 * nb_num_sms()), 128, (size_t)N * 4 * sizeof(float), stream, a);
+  return nb_check_launch("k_nbody_features");
+}
+
+extern "C" int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, float G, const float* loc, const float* vel,
+                               const float* charges, float* energy, void* stream) {
+  if ((kind != 0 && kind != 1) || F < 1 || B < 1 || N < 1 || N > 1024 || !loc || !vel || !charges || !energy) {
+    nb_set_error("nb_nbody_energy: unsupported arguments (kind=%d, F=%d, B=%d, N=%d)", kind, F, B, N);
+    return NB_ERR_INVALID;
+  }
+  NbEnergyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.F = F; a.B = B; a.N = N; a.kind = kind; a.G = G; a.loc = loc; a.vel = vel; a.charges = charges; a.out = energy;
+  NB_LAUNCH_COUNTED(k_nbody_energy, (unsigned)imin((int64_t)F * B, 16 * nb_num_sms()), 128,
+                    ((size_t)N * 4 + 128) * sizeof(float), stream, a);
+  return nb_check_launch("k_nbody_energy");
 }
 
 // tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.

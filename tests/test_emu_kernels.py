@@ -122,3 +122,38 @@ def test_edge_index_check_kernel():
     E.check(L.nb_check_canonical_edges(E.ptr(row), E.ptr(col), row.size, B, N, E.ptr(flag), None))
     assert flag[0] in (8, 9)
     assert L.nb_check_canonical_edges(E.ptr(row), E.ptr(col), row.size - 1, B, N, E.ptr(flag), None) < 0
+
+
+
+@pytest.mark.parametrize("B,N", [(3, 5), (2, 20), (1, 2)])
+def test_featurisation_and_energy_kernels_vs_oracle(B, N):
+    """nb_nbody_features / nb_nbody_energy (the device-side prepare_inputs and conserved-energy evaluation) against
+    the oracle's restatements of main_simulation_simple_no.py:326-338 and utils.py:126-144, :175-195."""
+    import ctypes
+    L = E.lib()
+    g = torch.Generator().manual_seed(B * 100 + N)
+    loc, vel = torch.randn(B, N, 3, generator=g), torch.randn(B, N, 3, generator=g)
+    q = torch.randint(0, 2, (B, N, 1), generator=g).float() * 2 - 1
+    row, col = O.canonical_edges(B, N)
+    x, v, ea_r, nodes_r, lm_r = O.egno_features(loc, vel, q, row, col)
+    bn, n_edges = B * N, B * N * (N - 1)
+    nodes, mean, ea = np.zeros((bn, 2), np.float32), np.zeros((bn, 3), np.float32), np.zeros((n_edges, 2), np.float32)
+    E.check(L.nb_nbody_features(B, N, 1, E.ptr(E.f32(x)), E.ptr(E.f32(v)), E.ptr(E.f32(q.reshape(-1))), None, E.ptr(nodes),
+                                E.ptr(mean), E.ptr(ea), None))
+    np.testing.assert_allclose(nodes, nodes_r.numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(mean, lm_r.numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ea, ea_r.numpy(), rtol=1e-6, atol=1e-6)
+    his = np.zeros((bn, 1), np.float32)
+    E.check(L.nb_nbody_features(B, N, 0, E.ptr(E.f32(x)), E.ptr(E.f32(v)), E.ptr(E.f32(q.reshape(-1))), None, E.ptr(his),
+                                None, E.ptr(ea), None))
+    np.testing.assert_allclose(his[:, 0], nodes_r[:, 0].numpy(), rtol=1e-6)
+    # energies over F = 2 frames
+    F = 2
+    locs = torch.stack([loc, loc + 0.1 * torch.randn(B, N, 3, generator=g)]).reshape(F, bn, 3)
+    vels = torch.stack([vel, 0.5 * vel]).reshape(F, bn, 3)
+    for kind, fn, ch in ((0, O.energy_charged, q), (1, O.energy_gravity, 1.0 + 0.1 * torch.rand(B, N, 1, generator=g))):
+        out = np.zeros((F, B), np.float32)
+        E.check(L.nb_nbody_energy(kind, F, B, N, ctypes.c_float(1.0), E.ptr(E.f32(locs)), E.ptr(E.f32(vels)),
+                                  E.ptr(E.f32(ch.reshape(-1))), E.ptr(out), None))
+        ref = torch.stack([fn(locs[f].reshape(B, N, 3), vels[f].reshape(B, N, 3), ch) for f in range(F)]).numpy()
+        np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-5)

@@ -446,3 +446,50 @@ def test_cuda_graph_training_step_matches_eager():
                 out.append(float(loss.detach()))
         losses[mode] = out
     assert losses["graph"] == losses["eager"][3:], losses
+
+
+def test_device_resident_rollouts_match_a_stepwise_loop_with_oracle_features_and_energies():
+    """egno_rollout / segno_rollout (featurisation + energy kernels, no host synchronisation inside) against the
+    reference's rollout structure written out with the oracle's featurisation and energy functions
+    (main_simulation_simple_no.py:342-384, train_nbody.py:200-236, utils.py:126-144,175-195)."""
+    d = dev()
+    B, N, T, L = 6, 5, 4, 3
+    # ---- EGNO, charged
+    s = synth.sample_state("charged", B, N, seed=11)
+    row, col = synth.canonical_edges(B, N)
+    edges = [row.to(d), col.to(d)]
+    torch.manual_seed(2)
+    m = nb.EGNO(n_layers=2, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T, device=d)
+    loc0, vel0, q = s["loc"].reshape(-1, 3).to(d), s["vel"].reshape(-1, 3).to(d), s["charges"].reshape(-1, 1).to(d)
+    preds, e_last, e_all = nb.egno_rollout(m, loc0, vel0, q, edges, N, traj_len=L, dataset="charged")
+    assert preds.shape == (L * T, B * N, 3) and e_last.shape == (L, B) and e_all.shape == (L * T, B)
+    t_out = torch.arange(1, T + 1, device=d)[None].repeat(B, 1)
+    loc, vel, ref_p, ref_e = loc0, vel0, [], []
+    with torch.no_grad():
+        for _ in range(L):
+            x, nodes, ea, v, lm = synth.egno_features(loc.view(B, N, 3), vel.view(B, N, 3), q.view(B, N, 1), edges[0], edges[1])
+            xo, vo, _ = m(x, nodes, edges, ea, v=v, loc_mean=lm, timesteps_out=t_out)
+            xo, vo = xo.view(T, B * N, 3), vo.view(T, B * N, 3)
+            ref_p.append(xo)
+            for t in range(T):
+                ref_e.append(O.energy_charged(xo[t].view(B, N, 3).cpu(), vo[t].view(B, N, 3).cpu(), q.view(B, N, 1).cpu()))
+            loc, vel = xo[T - 1], vo[T - 1]
+    assert rel_err(preds.cpu(), torch.cat(ref_p).cpu()) < 1e-5
+    assert rel_err(e_all.cpu(), torch.stack(ref_e)) < 1e-4
+    assert torch.equal(e_last, e_all.view(L, T, B)[:, T - 1])
+    # ---- SEGNO, gravity
+    s = synth.sample_state("gravity", B, N, seed=12)
+    torch.manual_seed(3)
+    sg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
+    loc0, vel0, mass = s["loc"].reshape(-1, 3).to(d), s["vel"].reshape(-1, 3).to(d), s["charges"].reshape(-1, 1).to(d)
+    preds, en = nb.segno_rollout(sg, loc0, vel0, mass, edges, N, traj_len=L, num_steps=T, dataset="gravity")
+    loc, vel, ref_p, ref_e = loc0, vel0, [], []
+    with torch.no_grad():
+        for _ in range(L):
+            his, x, v, ea = synth.segno_features(loc.view(B, N, 3), vel.view(B, N, 3), mass.view(B, N, 1), edges[0], edges[1])
+            xo, _, vo = sg(his, x, edges, v, ea, T=T)
+            ref_p.append(xo)
+            ref_e.append(O.energy_gravity(xo.view(B, N, 3).cpu(), vo.view(B, N, 3).cpu(), mass.view(B, N, 1).cpu()))
+            loc, vel = xo, vo
+    assert rel_err(preds.cpu(), torch.stack(ref_p).cpu()) < 1e-5
+    assert rel_err(en.cpu(), torch.stack(ref_e)) < 1e-4
