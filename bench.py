@@ -239,7 +239,9 @@ def run_ours(args):
         return ((xo - target) ** 2).mean()
 
     def loss_from_raw(loc, vel, charges, target):
-        x, nodes, ea, v, lm = synth.egno_features(loc, vel, charges, row_d, col_d)    # prepare_inputs on the device
+        # prepare_inputs on the device: one featurisation kernel (nb_nbody_features)
+        x, v = loc.reshape(-1, 3), vel.reshape(-1, 3)
+        nodes, lm, ea = nb.prepare_inputs(x, v, charges, N, with_charge=True)
         return loss_fn(x, nodes, ea, v, lm, target)
 
     def eager_step(b):
@@ -419,6 +421,23 @@ def run_ours(args):
                 g(i)
             ms_sinf = timed(g, K)
         extras["segno_infer_traj_per_s"] = world * B * K / (ms_sinf / 1e3)
+        # long-horizon rollouts kept on the device (featurisation + model + energies; BASELINE.json configs[3]:
+        # traj_len = 20 calls, main.py:42), one host read at the end
+        TL = 20
+        s0 = synth.sample_state("gravity", B, N, seed=4242 + rank)
+        l0_, v0_, m0_ = (s0[k].reshape(B * N, -1).to(dev) for k in ("loc", "vel", "charges"))
+        ro = lambda i: nb.segno_rollout(seg, l0_, v0_, m0_, edges, N, traj_len=TL, num_steps=T, dataset="gravity")[1].sum().item()
+        ro(0)
+        ms_ro = timed(ro, 3)
+        extras["segno_rollout_traj_per_s"] = world * B * 3 / (ms_ro / 1e3)
+        extras["segno_rollout_note"] = f"{TL} autoregressive calls x {T} sub-steps + energy of every frame per trajectory"
+        c0 = synth.sample_state("charged", B, N, seed=777 + rank)
+        cl, cv, cq = (c0[k].reshape(B * N, -1).to(dev) for k in ("loc", "vel", "charges"))
+        er = lambda i: nb.egno_rollout(model, cl, cv, cq, edges, N, traj_len=TL, dataset="charged")[2].sum().item()
+        er(0)
+        ms_er = timed(er, 3)
+        extras["egno_rollout_traj_per_s"] = world * B * 3 / (ms_er / 1e3)
+        extras["egno_rollout_note"] = f"{TL} autoregressive calls x {T} frames + energy of every frame per trajectory"
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
