@@ -31,6 +31,7 @@ struct NbEdgeW {
 struct NbEdgeGeom {
   int N, EPG, NGT, B, G, n_units, nef;
   int clamp_edge;  // SEGNO: clamp(rij*c, +-100) per edge before the mean (gcl.py:100)
+  int blk, nI, nJ, IB, JB;  // selector kernels, N > 27: a graph is walked in (IB receivers x JB senders) blocks, one tile each
 };
 
 struct NbEdgeFwdArgs {

@@ -20,8 +20,12 @@
 // across the tiles of a unit and are read out once per unit: no per-edge global gather, no shared-memory reduction
 // loops, no atomics; bitwise deterministic.
 //
-// Valid for G*N <= 27 (2 G N + 10 selector columns <= 64): N <= 27, which covers the 5- and 20-body configurations;
-// larger graphs use the kernels of nb_edge_tc.cuh.
+// Units.  N <= 27: a unit is G whole graph-instances (G*N <= 27 nodes: 2 G N + 10 selector columns <= 64), walked in
+// the canonical edge order, accumulators read out once per unit.  N > 27: a graph-instance is walked in blocks of
+// (IB receivers) x (JB senders) = one tile of IB*JB <= 128 rows each (selector columns: IB receivers | JB senders |
+// scalars, IB + JB <= 54; the host picks the pair that minimises the number of tiles, e.g. 5 x 25 for N = 100); the
+// read-out of a tile adds onto global memory (M_i / gP_i over the sender blocks, gQ_j over the receiver blocks); all
+// blocks of a graph-instance belong to one CTA, in a fixed order, so there are still no atomics and no races.
 #pragma once
 #ifndef NB_EMU
 #include "nb_edge.cuh"
@@ -30,6 +34,64 @@
 
 #define NB_SEL_MAX_GN 27
 #define NB_SEL_XC0 54  // first scalar column of the selector / first weight row of the node tile
+
+// one unit of work of a selector kernel (see "Units" above)
+struct NbSelUnit {
+  int R;               // edge rows (blocked mode: 128, validity per row)
+  int gt0;             // first graph-instance
+  int recv0, nrecv;    // global node index of receiver slot 0, slots in use
+  int send0, nsend;    // same for the senders
+  int RC;              // selector column / node-tile row of sender slot 0
+  int I0, J0;          // blocked mode: first receiver / sender index inside the graph
+  bool racc, sacc;     // read-out adds onto the receiver / sender outputs already in global memory
+};
+__device__ __forceinline__ NbSelUnit nb_sel_unit(const NbEdgeGeom& g, int uo, int sub) {
+  NbSelUnit U;
+  if (!g.blk) {
+    U.gt0 = uo * g.G;
+    const int ngt = min(g.G, g.NGT - U.gt0);
+    U.R = ngt * g.EPG;
+    U.recv0 = U.send0 = U.gt0 * g.N;
+    U.nrecv = U.nsend = ngt * g.N;
+    U.RC = g.G * g.N;
+    U.I0 = U.J0 = 0;
+    U.racc = U.sacc = false;
+  } else {
+    const int ib = sub / g.nJ, jb = sub - ib * g.nJ;
+    U.gt0 = uo;
+    U.R = NB_TILE;
+    U.I0 = ib * g.IB;
+    U.J0 = jb * g.JB;
+    U.recv0 = uo * g.N + U.I0;
+    U.nrecv = min(g.IB, g.N - U.I0);
+    U.send0 = uo * g.N + U.J0;
+    U.nsend = min(g.JB, g.N - U.J0);
+    U.RC = g.IB;
+    U.racc = jb > 0;
+    U.sacc = ib > 0;
+  }
+  return U;
+}
+// row r of the unit -> receiver / sender slots, graph-instance, edge index inside the graph; false for padding rows
+__device__ __forceinline__ bool nb_sel_row(const NbEdgeGeom& g, const NbSelUnit& U, const uint32_t* rowinfo, int r, int& li,
+                                           int& lj, int& gt, int& rem) {
+  if (!g.blk) {
+    if (r >= U.R) return false;
+    const uint32_t ri = rowinfo[r];
+    li = ri & 0xff;
+    lj = (ri >> 8) & 0xff;
+    const int lg = ri >> 16;
+    gt = U.gt0 + lg;
+    rem = r - lg * g.EPG;
+    return true;
+  }
+  li = r / g.JB;
+  lj = r - li * g.JB;
+  const int i = U.I0 + li, j = U.J0 + lj;
+  gt = U.gt0;
+  rem = i * (g.N - 1) + (j < i ? j : j - 1);
+  return li < U.nrecv && lj < U.nsend && i != j;
+}
 
 // ----------------------------------------------------------------------------- cheap descriptor arithmetic
 // 64-bit shared-memory descriptors as (lo, hi) halves: hi is a per-layout constant, lo = address field + LBO field;
@@ -138,7 +200,7 @@ __device__ __forceinline__ void nb_tmem_ld4(uint32_t taddr, float (&v)[4]) {
 // ----------------------------------------------------------------------------- row bookkeeping
 // rowinfo[r] for unit-local row r:  li | lj << 8 | lg << 16   (built once per CTA; every unit has the same structure)
 __device__ __forceinline__ void nb_sel_build_rowinfo(uint32_t* rowinfo, const NbEdgeGeom& g, int tid, int nthreads) {
-  const int R = g.G * g.EPG;
+  const int R = g.blk ? 0 : g.G * g.EPG;
   for (int r = tid; r < R; r += nthreads) {
     int lg = r / g.EPG, rem = r - lg * g.EPG;
     int i = rem / (g.N - 1), jj = rem - i * (g.N - 1);
@@ -194,6 +256,19 @@ __device__ __forceinline__ void nb_sel_stage_nodes(unsigned char* Nh, unsigned c
     nb_tc_store8(Nh, Nl, which ? GN + n : n, j, v);
   }
 }
+// general unit: rows [0, nrecv) <- P of the receiver list, rows [RC, RC + nsend) <- Q of the sender list
+__device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned char* Nl, const float* __restrict__ P,
+                                                  const float* __restrict__ Q, const NbSelUnit& U, int tid, int nthreads) {
+  const int total = (U.nrecv + U.nsend) * 8;
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int n = idx >> 3, j = idx & 7;
+    const bool snd = n >= U.nrecv;
+    const float* src = snd ? Q + (int64_t)(U.send0 + n - U.nrecv) * NB_H + 8 * j : P + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
+    float4 a = nb_ld4(src), b = nb_ld4(src + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    nb_tc_store8(Nh, Nl, snd ? U.RC + n - U.nrecv : n, j, v);
+  }
+}
 
 // TMEM lane of accumulator row i for M = 64 MMAs; thread (warp quarter q, lane < 16) owns row 16 q + lane
 // ----------------------------------------------------------------------------- forward
@@ -204,7 +279,7 @@ __device__ __forceinline__ void nb_sel_stage_nodes(unsigned char* Nh, unsigned c
 #define NB_SF_NT (NB_SF_SEL + NB_TC_TILE_BYTES(128))      // node tile hi/lo   2 x 8 KB
 #define NB_SF_F (NB_SF_NT + 2 * NB_TC_TILE_BYTES(64))     // force tile hi/lo  2 x 2 KB  ([128][8] bf16)
 #define NB_SF_FL (NB_SF_F + 2 * NB_TILE * 16)
-#define NB_SF_NFLOAT (3 * NB_H + 2 * NB_TILE + 32 * 3)
+#define NB_SF_NFLOAT (3 * NB_H + 2 * NB_TILE + 2 * 32 * 3)
 #define NB_EDGE_FWD_SEL_SMEM(RU) (NB_SF_FL + NB_SF_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
 #define NB_SF_TMEM_COLS 256  // [0,64) pre-activations | [64,128) M accumulators | [128,136) Fsum accumulators
 
@@ -227,10 +302,11 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
   float* vb3 = vb2 + NB_H;
   float* vw4 = vb3 + NB_H;
   float* cpart = vw4 + NB_H;         // [2][128]
-  float* xs = cpart + 2 * NB_TILE;   // [GN][3] positions of the unit's nodes
-  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(xs + 32 * 3);
+  float* xs = cpart + 2 * NB_TILE;   // [32][3] positions of the unit's receivers
+  float* xq = xs + 32 * 3;           // [32][3] positions of the unit's senders
+  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(xq + 32 * 3);
   const NbEdgeGeom g = a.g;
-  const int RU = g.G * g.EPG, GN = g.G * g.N;
+  const int RU = g.blk ? 0 : g.G * g.EPG;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -284,36 +360,31 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
   const float b4 = __ldg(a.w.b4);
   uint32_t phase = 0;
 
-  for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
-    const int gt0 = u * g.G;
-    const int ngt = min(g.G, g.NGT - gt0);
-    const int R = ngt * g.EPG;
-    const int nnode = ngt * g.N;
-    const int64_t node0 = (int64_t)gt0 * g.N;
+  const int n_outer = g.blk ? g.NGT : g.n_units, n_sub = g.blk ? g.nI * g.nJ : 1;
+  for (int uo = blockIdx.x; uo < n_outer; uo += gridDim.x)
+  for (int sub = 0; sub < n_sub; ++sub) {
+    const NbSelUnit U = nb_sel_unit(g, uo, sub);
+    const int R = U.R;
     // every MMA of the previous unit has completed (its read-out waited for the last commit)
-    nb_sel_stage_nodes(Nh, Nl, a.P, a.Q, node0, nnode, GN, tid, NB_THREADS);
-    for (int idx = tid; idx < nnode * 3; idx += NB_THREADS) xs[idx] = __ldg(a.x + node0 * 3 + idx);
+    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_THREADS);
+    for (int idx = tid; idx < U.nrecv * 3; idx += NB_THREADS) xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
+    for (int idx = tid; idx < U.nsend * 3; idx += NB_THREADS) xq[idx] = __ldg(a.x + (int64_t)U.send0 * 3 + idx);
     __syncthreads();
 
     for (int r0 = 0; r0 < R; r0 += NB_TILE) {
-      const int nv = min(NB_TILE, R - r0);
-      const bool valid = row < nv;
       // ---- geometry + selector row
       float dx = 0.f, dy = 0.f, dz = 0.f, r2 = 0.f;
       float e[NB_MAX_EF];
 #pragma unroll
       for (int f = 0; f < NB_MAX_EF; ++f) e[f] = 0.f;
-      int li = 0, lj = 0;
+      int li = 0, lj = 0, gt = 0, rem = 0;
+      const bool valid = nb_sel_row(g, U, rowinfo, r0 + row, li, lj, gt, rem);
       if (valid) {
-        const uint32_t ri = rowinfo[r0 + row];
-        li = ri & 0xff;
-        lj = (ri >> 8) & 0xff;
-        const int lg = ri >> 16;
-        dx = xs[li * 3 + 0] - xs[lj * 3 + 0];
-        dy = xs[li * 3 + 1] - xs[lj * 3 + 1];
-        dz = xs[li * 3 + 2] - xs[lj * 3 + 2];
+        dx = xs[li * 3 + 0] - xq[lj * 3 + 0];
+        dy = xs[li * 3 + 1] - xq[lj * 3 + 1];
+        dz = xs[li * 3 + 2] - xq[lj * 3 + 2];
         r2 = dx * dx + dy * dy + dz * dz;
-        const int64_t eoff = ((int64_t)((gt0 + lg) % g.B) * g.EPG + (r0 + row - lg * g.EPG)) * g.nef;
+        const int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
 #pragma unroll
         for (int f = 0; f < NB_MAX_EF; ++f)
           if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
@@ -326,7 +397,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         phase ^= 1;
         nb_tc_fence_after();
       }
-      nb_sel_write_row(Sel, row, hf, valid, li, GN + lj, r2, e);
+      nb_sel_write_row(Sel, row, hf, valid, li, U.RC + lj, r2, e);
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
@@ -419,18 +490,25 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
       const int nl = 16 * q + lane;
       float v[32];
       nb_tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + 64 + (uint32_t)cb, v);
-      if (lane < 16 && nl < nnode) {
-        float* dst = a.M + (node0 + nl) * NB_H + cb;
+      if (lane < 16 && nl < U.nrecv) {
+        float* dst = a.M + (int64_t)(U.recv0 + nl) * NB_H + cb;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        for (int k = 0; k < 8; ++k) {
+          float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          if (U.racc) {
+            const float4 old = nb_ld4(dst + 4 * k);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          nb_st4(dst + 4 * k, o);
+        }
       }
       float f4[4];
       nb_tmem_ld4(tm + ((uint32_t)(32 * q) << 16) + 128, f4);
-      if (hf == 0 && lane < 16 && nl < nnode) {
-        float* dst = a.Fsum + (node0 + nl) * 3;
-        dst[0] = f4[0];
-        dst[1] = f4[1];
-        dst[2] = f4[2];
+      if (hf == 0 && lane < 16 && nl < U.nrecv) {
+        float* dst = a.Fsum + (int64_t)(U.recv0 + nl) * 3;
+        dst[0] = U.racc ? dst[0] + f4[0] : f4[0];
+        dst[1] = U.racc ? dst[1] + f4[1] : f4[1];
+        dst[2] = U.racc ? dst[2] + f4[2] : f4[2];
       }
     }
     nb_tc_fence_before();
@@ -465,7 +543,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 #define NB_SB_ONES (NB_SB_GM + 2 * NB_TC_TILE_BYTES(64))
 #define NB_SB_RG (NB_SB_ONES + NB_TILE * 16)
 #define NB_SB_FL (NB_SB_RG + 2 * NB_TILE * 16)
-#define NB_SB_NFLOAT (4 * NB_H + 4 * NB_TILE + 2 * 32 * 3 + 10 * NB_H + NB_H * 4)
+#define NB_SB_NFLOAT (4 * NB_H + 4 * NB_TILE + 3 * 32 * 3 + 10 * NB_H + NB_H * 4)
 #define NB_EDGE_BWD_SEL_SMEM(RU) (NB_SB_FL + NB_SB_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
 #define NB_SB_TMEM_COLS 512
 
@@ -550,13 +628,14 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   float* vw4 = vb3 + NB_H;
   float* vwr = vw4 + NB_H;
   float* cpart = vwr + NB_H;          // [4][128]
-  float* xs = cpart + 4 * NB_TILE;    // [GN][3]
-  float* gfs = xs + 32 * 3;           // [GN][3] dL/dFsum of the unit's nodes
+  float* xs = cpart + 4 * NB_TILE;    // [32][3] positions of the unit's receivers
+  float* xq = xs + 32 * 3;            // [32][3] positions of the unit's senders
+  float* gfs = xq + 32 * 3;           // [32][3] dL/dFsum of the unit's receivers
   float* gwacc = gfs + 32 * 3;        // [10][64]: rows 0,1 w_rad (hi, lo piece) ; 2 + 2f, 3 + 2f w_ef[f]
   float* gxst = gwacc + 10 * NB_H;    // [64][4]
   uint32_t* rowinfo = reinterpret_cast<uint32_t*>(gxst + NB_H * 4);
   const NbEdgeGeom g = a.g;
-  const int RU = g.G * g.EPG, GN = g.G * g.N;
+  const int RU = g.blk ? 0 : g.G * g.EPG;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
   uint64_t* bar2 = bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar2 + 1);
@@ -629,7 +708,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
                  sRGh = nb_smem_u32(RGh), sRGl = nb_smem_u32(RGl), sW2h = nb_smem_u32(W2h), sW2l = nb_smem_u32(W2l),
                  sW3h = nb_smem_u32(W3h), sW3l = nb_smem_u32(W3l);
   const float b4 = __ldg(a.w.b4);
-  const int ks_recv = (GN + 15) >> 4;
+  const int ks_recv = ((g.blk ? g.IB : g.G * g.N) + 15) >> 4;  // k-steps holding the receiver columns
   uint32_t phase = 0, phase2 = 0;
   uint32_t wacc = 0;
 
@@ -638,50 +717,45 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   for (int i = 0; i < 16; ++i) gw4acc[i] = 0.f;
   float gb4acc = 0.f;
 
-  for (int u = blockIdx.x; u < g.n_units; u += gridDim.x) {
-    const int gt0 = u * g.G;
-    const int ngt = min(g.G, g.NGT - gt0);
-    const int R = ngt * g.EPG;
-    const int nnode = ngt * g.N;
-    const int64_t node0 = (int64_t)gt0 * g.N;
+  const int n_outer = g.blk ? g.NGT : g.n_units, n_sub = g.blk ? g.nI * g.nJ : 1;
+  for (int uo = blockIdx.x; uo < n_outer; uo += gridDim.x)
+  for (int sub = 0; sub < n_sub; ++sub) {
+    const NbSelUnit U = nb_sel_unit(g, uo, sub);
+    const int R = U.R;
     // every MMA of the previous unit has completed (the read-out waited for the last side commit)
-    nb_sel_stage_nodes(Nh, Nl, a.P, a.Q, node0, nnode, GN, tid, NB_SB_THREADS);
-    for (int idx = tid; idx < nnode * 8; idx += NB_SB_THREADS) {
+    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_SB_THREADS);
+    for (int idx = tid; idx < U.nrecv * 8; idx += NB_SB_THREADS) {
       int n = idx >> 3, j = idx & 7;
-      const float* src = a.gM + (node0 + n) * NB_H + 8 * j;
+      const float* src = a.gM + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
       float4 p0 = nb_ld4(src), p1 = nb_ld4(src + 4);
       float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
       nb_tc_store8(GMh, GMl, n, j, v);
     }
-    for (int idx = tid; idx < nnode * 3; idx += NB_SB_THREADS) {
-      xs[idx] = __ldg(a.x + node0 * 3 + idx);
-      gfs[idx] = __ldg(a.gFsum + node0 * 3 + idx);
+    for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
+      xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
+      gfs[idx] = __ldg(a.gFsum + (int64_t)U.recv0 * 3 + idx);
     }
+    for (int idx = tid; idx < U.nsend * 3; idx += NB_SB_THREADS) xq[idx] = __ldg(a.x + (int64_t)U.send0 * 3 + idx);
     __syncthreads();
 
     for (int r0 = 0; r0 < R; r0 += NB_TILE) {
-      const int nv = min(NB_TILE, R - r0);
-      const bool valid = row < nv;
       // ---- T0: geometry + selector row
       float dx = 0.f, dy = 0.f, dz = 0.f, r2 = 0.f, gfx = 0.f, gfy = 0.f, gfz = 0.f;
       float e[NB_MAX_EF];
 #pragma unroll
       for (int f = 0; f < NB_MAX_EF; ++f) e[f] = 0.f;
-      int li = 0, lj = 0;
+      int li = 0, lj = 0, gt = 0, rem = 0;
+      const bool valid = nb_sel_row(g, U, rowinfo, r0 + row, li, lj, gt, rem);
       if (valid) {
-        const uint32_t ri = rowinfo[r0 + row];
-        li = ri & 0xff;
-        lj = (ri >> 8) & 0xff;
-        const int lg = ri >> 16;
-        dx = xs[li * 3 + 0] - xs[lj * 3 + 0];
-        dy = xs[li * 3 + 1] - xs[lj * 3 + 1];
-        dz = xs[li * 3 + 2] - xs[lj * 3 + 2];
+        dx = xs[li * 3 + 0] - xq[lj * 3 + 0];
+        dy = xs[li * 3 + 1] - xq[lj * 3 + 1];
+        dz = xs[li * 3 + 2] - xq[lj * 3 + 2];
         r2 = dx * dx + dy * dy + dz * dz;
         gfx = gfs[li * 3 + 0];
         gfy = gfs[li * 3 + 1];
         gfz = gfs[li * 3 + 2];
         if (cq == 1) {
-          const int64_t eoff = ((int64_t)((gt0 + lg) % g.B) * g.EPG + (r0 + row - lg * g.EPG)) * g.nef;
+          const int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
 #pragma unroll
           for (int f = 0; f < NB_MAX_EF; ++f)
             if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
@@ -692,7 +766,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         phase2 ^= 1;
         nb_tc_fence_after();
       }
-      if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, GN + lj, r2, e);
+      if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, U.RC + lj, r2, e);
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
@@ -866,14 +940,19 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       float v[16];
       nb_tmem_ld16(tm + lane_base + 336 + (uint32_t)cb, v);
       if (lane < 16) {
-        if (i < nnode) {
-          float* dst = a.gP + (node0 + i) * NB_H + cb;
+        const bool is_recv = i < U.nrecv, is_send = i >= U.RC && i < U.RC + U.nsend;
+        if (is_recv || is_send) {
+          float* dst = is_recv ? a.gP + (int64_t)(U.recv0 + i) * NB_H + cb : a.gQ + (int64_t)(U.send0 + i - U.RC) * NB_H + cb;
+          const bool acc = is_recv ? U.racc : U.sacc;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
-        } else if (i >= GN && i < GN + nnode) {
-          float* dst = a.gQ + (node0 + i - GN) * NB_H + cb;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+          for (int k = 0; k < 4; ++k) {
+            float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            if (acc) {
+              const float4 old = nb_ld4(dst + 4 * k);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            nb_st4(dst + 4 * k, o);
+          }
         } else if (i >= NB_SEL_XC0) {
           float* dst = gwacc + (i - NB_SEL_XC0) * NB_H + cb;  // exclusive owner of these 16 accumulators
 #pragma unroll
@@ -890,9 +969,15 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     }
     nb_tc_fence_before();
     __syncthreads();
-    for (int idx = tid; idx < nnode * 3; idx += NB_SB_THREADS) {
+    // dL/dx: + receiver sums, then - sender sums (two passes: in blocked mode the two node lists may overlap)
+    for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
       int n = idx / 3, dd = idx - 3 * n;
-      a.gx[node0 * 3 + idx] += gxst[n * 4 + dd] - gxst[(GN + n) * 4 + dd];
+      a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < U.nsend * 3; idx += NB_SB_THREADS) {
+      int n = idx / 3, dd = idx - 3 * n;
+      a.gx[(int64_t)U.send0 * 3 + idx] -= gxst[(U.RC + n) * 4 + dd];
     }
     __syncthreads();
   }

@@ -382,6 +382,7 @@ static int ew_grid(int64_t n) { return imin(cdiv(n, 256), 8 * nb_num_sms()); }
 static NbEdgeGeom edge_geom(int n_gt, int B, int N, int nef, int clamp_edge) {
   NbEdgeGeom g;
   g.N = N; g.EPG = N * (N - 1); g.NGT = n_gt; g.B = B; g.nef = nef; g.clamp_edge = clamp_edge;
+  g.blk = 0; g.nI = g.nJ = g.IB = g.JB = 0;
   int G = NB_TILE / g.EPG;            // pack small graphs so a tile is (nearly) full
   if (G < 1) G = 1;
   if (G * N > 128) G = 128 / N;
@@ -412,7 +413,27 @@ extern "C" int nb_get_edge_impl(void) { return g_edge_impl; }
 #ifndef NB_EMU
 // unit geometry of the selector kernels: G graph-instances with G*N <= 27 nodes and (for G > 1) at most 128 rows
 static bool sel_geom(NbEdgeGeom& g) {
-  if (g.N > NB_SEL_MAX_GN) return false;
+  if (g.N > NB_SEL_MAX_GN) {  // blocked walk: (8 receivers) x (16 senders) per tile, one CTA per graph-instance
+    if (g.N > 255) return false;
+    g.blk = 1;
+    // receivers x senders per tile: IB * JB <= 128 rows, IB + JB <= 54 selector columns, IB <= 32 (position slots);
+    // fewest tiles per graph wins
+    int best = 1 << 30;
+    for (int ib = 1; ib <= 32; ++ib) {
+      int jb = NB_TILE / ib;
+      if (jb > 32) jb = 32;
+      if (jb > g.N) jb = g.N;
+      if (ib + jb > NB_SEL_XC0 || jb < 1) continue;
+      const int tiles = (int)(cdiv(g.N, ib) * cdiv(g.N, jb));
+      if (tiles < best) { best = tiles; g.IB = ib; g.JB = jb; }
+    }
+    g.nI = (int)cdiv(g.N, g.IB);
+    g.nJ = (int)cdiv(g.N, g.JB);
+    g.G = 1;
+    g.n_units = g.NGT;
+    return true;
+  }
+  g.blk = 0; g.nI = g.nJ = g.IB = g.JB = 0;
   int G = NB_TILE / g.EPG;
   if (G > NB_SEL_MAX_GN / g.N) G = NB_SEL_MAX_GN / g.N;
   if (G < 1) G = 1;
@@ -425,7 +446,7 @@ static bool sel_geom(NbEdgeGeom& g) {
 static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
 #ifndef NB_EMU
   if (g_edge_impl == 2 && sel_geom(a.g)) {
-    const size_t smem_sel = NB_EDGE_FWD_SEL_SMEM(a.g.G * a.g.EPG);
+    const size_t smem_sel = NB_EDGE_FWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG);
     NB_SET_SMEM(k_edge_fwd_sel, smem_sel);
     int grid_sel = imin(a.g.n_units, 2 * nb_num_sms());
     int pi_sel = prof_begin(0, st);
@@ -470,7 +491,7 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
   bool done = false;
 #ifndef NB_EMU
   if (use_sel) {
-    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.G * a.g.EPG);
+    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG);
     NB_SET_SMEM(k_edge_bwd_sel, smem_sel);
     int pi_sel = prof_begin(1, st);
     NB_LAUNCH_COUNTED(k_edge_bwd_sel, (unsigned)grid, NB_SB_THREADS, smem_sel, st, a);
@@ -1229,7 +1250,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
 #ifndef NB_EMU
   {
     NbEdgeGeom fg = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
-    if (g_segno_fused && g_edge_impl == 2 && g_node_impl == 1 && sel_geom(fg)) {
+    if (g_segno_fused && g_edge_impl == 2 && g_node_impl == 1 && sel_geom(fg) && !fg.blk) {
       // embedding into scratch (the fused kernel writes h_k of every sub-step into `saved` itself)
       NbEmbedArgs e;
       segno_embed_args(X, his, &e);
