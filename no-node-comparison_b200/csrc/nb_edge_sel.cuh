@@ -45,9 +45,10 @@ struct NbSelUnit {
   int I0, J0;          // blocked mode: first receiver / sender index inside the graph
   bool racc, sacc;     // read-out adds onto the receiver / sender outputs already in global memory
 };
+template <bool BLK>
 __device__ __forceinline__ NbSelUnit nb_sel_unit(const NbEdgeGeom& g, int uo, int sub) {
   NbSelUnit U;
-  if (!g.blk) {
+  if (!BLK) {
     U.gt0 = uo * g.G;
     const int ngt = min(g.G, g.NGT - U.gt0);
     U.R = ngt * g.EPG;
@@ -73,9 +74,10 @@ __device__ __forceinline__ NbSelUnit nb_sel_unit(const NbEdgeGeom& g, int uo, in
   return U;
 }
 // row r of the unit -> receiver / sender slots, graph-instance, edge index inside the graph; false for padding rows
+template <bool BLK>
 __device__ __forceinline__ bool nb_sel_row(const NbEdgeGeom& g, const NbSelUnit& U, const uint32_t* rowinfo, int r, int& li,
                                            int& lj, int& gt, int& rem) {
-  if (!g.blk) {
+  if (!BLK) {
     if (r >= U.R) return false;
     const uint32_t ri = rowinfo[r];
     li = ri & 0xff;
@@ -283,6 +285,7 @@ __device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned ch
 #define NB_EDGE_FWD_SEL_SMEM(RU) (NB_SF_FL + NB_SF_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
 #define NB_SF_TMEM_COLS 256  // [0,64) pre-activations | [64,128) M accumulators | [128,136) Fsum accumulators
 
+template <bool BLK>
 __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
   float* xq = xs + 32 * 3;           // [32][3] positions of the unit's senders
   uint32_t* rowinfo = reinterpret_cast<uint32_t*>(xq + 32 * 3);
   const NbEdgeGeom g = a.g;
-  const int RU = g.blk ? 0 : g.G * g.EPG;
+  const int RU = BLK ? 0 : g.G * g.EPG;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -360,15 +363,21 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
   const float b4 = __ldg(a.w.b4);
   uint32_t phase = 0;
 
-  const int n_outer = g.blk ? g.NGT : g.n_units, n_sub = g.blk ? g.nI * g.nJ : 1;
+  const int n_outer = BLK ? g.NGT : g.n_units, n_sub = BLK ? g.nI * g.nJ : 1;
   for (int uo = blockIdx.x; uo < n_outer; uo += gridDim.x)
   for (int sub = 0; sub < n_sub; ++sub) {
-    const NbSelUnit U = nb_sel_unit(g, uo, sub);
+    const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
     // every MMA of the previous unit has completed (its read-out waited for the last commit)
     nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_THREADS);
-    for (int idx = tid; idx < U.nrecv * 3; idx += NB_THREADS) xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
-    for (int idx = tid; idx < U.nsend * 3; idx += NB_THREADS) xq[idx] = __ldg(a.x + (int64_t)U.send0 * 3 + idx);
+    {  // positions of the receiver and (blocked mode: distinct) sender lists, one pass
+      const int n3r = U.nrecv * 3, n3 = n3r + (BLK ? U.nsend * 3 : 0);
+      for (int idx = tid; idx < n3; idx += NB_THREADS) {
+        if (idx < n3r) xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
+        else xq[idx - n3r] = __ldg(a.x + (int64_t)U.send0 * 3 + (idx - n3r));
+      }
+    }
+    const float* xsnd = BLK ? xq : xs;  // whole-graph units: senders = receivers
     __syncthreads();
 
     for (int r0 = 0; r0 < R; r0 += NB_TILE) {
@@ -378,11 +387,11 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 #pragma unroll
       for (int f = 0; f < NB_MAX_EF; ++f) e[f] = 0.f;
       int li = 0, lj = 0, gt = 0, rem = 0;
-      const bool valid = nb_sel_row(g, U, rowinfo, r0 + row, li, lj, gt, rem);
+      const bool valid = nb_sel_row<BLK>(g, U, rowinfo, r0 + row, li, lj, gt, rem);
       if (valid) {
-        dx = xs[li * 3 + 0] - xq[lj * 3 + 0];
-        dy = xs[li * 3 + 1] - xq[lj * 3 + 1];
-        dz = xs[li * 3 + 2] - xq[lj * 3 + 2];
+        dx = xs[li * 3 + 0] - xsnd[lj * 3 + 0];
+        dy = xs[li * 3 + 1] - xsnd[lj * 3 + 1];
+        dz = xs[li * 3 + 2] - xsnd[lj * 3 + 2];
         r2 = dx * dx + dy * dy + dz * dz;
         const int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
 #pragma unroll
@@ -600,6 +609,7 @@ __device__ __forceinline__ void nb_issue_wgrad(uint32_t tmem_w, uint32_t tmem_b,
   }
 }
 
+template <bool BLK>
 __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs a) {
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
@@ -635,7 +645,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   float* gxst = gwacc + 10 * NB_H;    // [64][4]
   uint32_t* rowinfo = reinterpret_cast<uint32_t*>(gxst + NB_H * 4);
   const NbEdgeGeom g = a.g;
-  const int RU = g.blk ? 0 : g.G * g.EPG;
+  const int RU = BLK ? 0 : g.G * g.EPG;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
   uint64_t* bar2 = bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar2 + 1);
@@ -708,7 +718,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
                  sRGh = nb_smem_u32(RGh), sRGl = nb_smem_u32(RGl), sW2h = nb_smem_u32(W2h), sW2l = nb_smem_u32(W2l),
                  sW3h = nb_smem_u32(W3h), sW3l = nb_smem_u32(W3l);
   const float b4 = __ldg(a.w.b4);
-  const int ks_recv = ((g.blk ? g.IB : g.G * g.N) + 15) >> 4;  // k-steps holding the receiver columns
+  const int ks_recv = ((BLK ? g.IB : g.G * g.N) + 15) >> 4;  // k-steps holding the receiver columns
   uint32_t phase = 0, phase2 = 0;
   uint32_t wacc = 0;
 
@@ -717,10 +727,10 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   for (int i = 0; i < 16; ++i) gw4acc[i] = 0.f;
   float gb4acc = 0.f;
 
-  const int n_outer = g.blk ? g.NGT : g.n_units, n_sub = g.blk ? g.nI * g.nJ : 1;
+  const int n_outer = BLK ? g.NGT : g.n_units, n_sub = BLK ? g.nI * g.nJ : 1;
   for (int uo = blockIdx.x; uo < n_outer; uo += gridDim.x)
   for (int sub = 0; sub < n_sub; ++sub) {
-    const NbSelUnit U = nb_sel_unit(g, uo, sub);
+    const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
     // every MMA of the previous unit has completed (the read-out waited for the last side commit)
     nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_SB_THREADS);
@@ -731,11 +741,18 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
       nb_tc_store8(GMh, GMl, n, j, v);
     }
-    for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
-      xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
-      gfs[idx] = __ldg(a.gFsum + (int64_t)U.recv0 * 3 + idx);
+    {
+      const int n3r = U.nrecv * 3, n3 = n3r + (BLK ? U.nsend * 3 : 0);
+      for (int idx = tid; idx < n3; idx += NB_SB_THREADS) {
+        if (idx < n3r) {
+          xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
+          gfs[idx] = __ldg(a.gFsum + (int64_t)U.recv0 * 3 + idx);
+        } else {
+          xq[idx - n3r] = __ldg(a.x + (int64_t)U.send0 * 3 + (idx - n3r));
+        }
+      }
     }
-    for (int idx = tid; idx < U.nsend * 3; idx += NB_SB_THREADS) xq[idx] = __ldg(a.x + (int64_t)U.send0 * 3 + idx);
+    const float* xsnd = BLK ? xq : xs;  // whole-graph units: senders = receivers
     __syncthreads();
 
     for (int r0 = 0; r0 < R; r0 += NB_TILE) {
@@ -745,11 +762,11 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
 #pragma unroll
       for (int f = 0; f < NB_MAX_EF; ++f) e[f] = 0.f;
       int li = 0, lj = 0, gt = 0, rem = 0;
-      const bool valid = nb_sel_row(g, U, rowinfo, r0 + row, li, lj, gt, rem);
+      const bool valid = nb_sel_row<BLK>(g, U, rowinfo, r0 + row, li, lj, gt, rem);
       if (valid) {
-        dx = xs[li * 3 + 0] - xq[lj * 3 + 0];
-        dy = xs[li * 3 + 1] - xq[lj * 3 + 1];
-        dz = xs[li * 3 + 2] - xq[lj * 3 + 2];
+        dx = xs[li * 3 + 0] - xsnd[lj * 3 + 0];
+        dy = xs[li * 3 + 1] - xsnd[lj * 3 + 1];
+        dz = xs[li * 3 + 2] - xsnd[lj * 3 + 2];
         r2 = dx * dx + dy * dy + dz * dz;
         gfx = gfs[li * 3 + 0];
         gfy = gfs[li * 3 + 1];
@@ -969,15 +986,22 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     }
     nb_tc_fence_before();
     __syncthreads();
-    // dL/dx: + receiver sums, then - sender sums (two passes: in blocked mode the two node lists may overlap)
-    for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
-      int n = idx / 3, dd = idx - 3 * n;
-      a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < U.nsend * 3; idx += NB_SB_THREADS) {
-      int n = idx / 3, dd = idx - 3 * n;
-      a.gx[(int64_t)U.send0 * 3 + idx] -= gxst[(U.RC + n) * 4 + dd];
+    // dL/dx: + receiver sums - sender sums
+    if (!BLK) {  // one node list
+      for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
+        int n = idx / 3, dd = idx - 3 * n;
+        a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd] - gxst[(U.RC + n) * 4 + dd];
+      }
+    } else {       // two lists that may overlap: two passes
+      for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
+        int n = idx / 3, dd = idx - 3 * n;
+        a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < U.nsend * 3; idx += NB_SB_THREADS) {
+        int n = idx / 3, dd = idx - 3 * n;
+        a.gx[(int64_t)U.send0 * 3 + idx] -= gxst[(U.RC + n) * 4 + dd];
+      }
     }
     __syncthreads();
   }

@@ -239,8 +239,19 @@ __global__ void __launch_bounds__(256) k_finalize(NbFinBatch batch) {
   const int l = idx - base;
   const int e = a.seg[s].start + l;
   float sum = 0.f;
-  if (act)
-    for (int p = warp; p < a.nparts; p += 8) sum += a.partial[(int64_t)p * a.plen + e];
+  if (act) {
+    // 4 independent partial sums per warp keep 4 loads in flight; combined in a fixed order (deterministic)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = warp;
+    for (; p + 24 < a.nparts; p += 32) {
+      s0 += a.partial[(int64_t)p * a.plen + e];
+      s1 += a.partial[(int64_t)(p + 8) * a.plen + e];
+      s2 += a.partial[(int64_t)(p + 16) * a.plen + e];
+      s3 += a.partial[(int64_t)(p + 24) * a.plen + e];
+    }
+    for (; p < a.nparts; p += 8) s0 += a.partial[(int64_t)p * a.plen + e];
+    sum = (s0 + s1) + (s2 + s3);
+  }
   red[warp][lane] = sum;
   __syncthreads();
   if (warp == 0 && act) {
@@ -266,14 +277,23 @@ struct NbEmbedArgs {
   const float* bias;     // [64]
   float* out;            // [T*Nn0][64]
   float freq[32];        // D/2 frequencies
+  float* table;          // [T][B][D] sinusoidal embedding of timesteps[b][t] (k_time_table), read by the kernels below
 };
+
+// table[t][b][j] = sin(ts * freq[j]) (j < D/2) | cos(ts * freq[j - D/2]),  ts = timesteps[b][t]   (layer_no.py:8-17)
+__global__ void __launch_bounds__(256) k_time_table(NbEmbedArgs a) {
+  const int total = a.T * a.B * a.D, half = a.D >> 1;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int j = idx % a.D, tb = idx / a.D, b = tb % a.B, t = tb / a.B;
+    const float ts = (float)__ldg(a.tsteps + (int64_t)b * a.T + t);
+    const float arg = ts * a.freq[j < half ? j : j - half];
+    a.table[idx] = j < half ? sinf(arg) : cosf(arg);
+  }
+}
 
 __device__ __forceinline__ float nb_embed_feature(const NbEmbedArgs& a, int t, int k, int f) {
   if (f < a.F0) return __ldg(a.nodes + (int64_t)k * a.F0 + f);
-  int j = f - a.F0, half = a.D >> 1;
-  float ts = (float)__ldg(a.tsteps + (int64_t)(k % a.B) * a.T + t);
-  float arg = ts * a.freq[j < half ? j : j - half];
-  return j < half ? sinf(arg) : cosf(arg);
+  return __ldg(a.table + ((int64_t)t * a.B + (k % a.B)) * a.D + (f - a.F0));   // the `k mod B` broadcast of egno.py:66
 }
 
 __global__ void __launch_bounds__(256) k_embed_fwd(NbEmbedArgs a) {
@@ -389,10 +409,11 @@ struct NbXupdArgs {
 
 __global__ void __launch_bounds__(256) k_egno_xupd_fwd(NbXupdArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float w0 = __ldg(a.w2 + lane), w1 = __ldg(a.w2 + lane + 32), b2 = __ldg(a.b2);
+  const float w0 = __ldg(a.w2 + 2 * lane), w1 = __ldg(a.w2 + 2 * lane + 1), b2 = __ldg(a.b2);
   const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < a.rows; row += (int64_t)gridDim.x * 8) {
-    float s = w0 * nb_silu(a.UV[row * NB_H + lane]) + w1 * nb_silu(a.UV[row * NB_H + lane + 32]);
+    const float2 uv = *reinterpret_cast<const float2*>(a.UV + row * NB_H + 2 * lane);  // one 256-byte row per warp load
+    float s = w0 * nb_silu(uv.x) + w1 * nb_silu(uv.y);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
     s += b2;
@@ -407,13 +428,14 @@ __global__ void __launch_bounds__(256) k_egno_xupd_fwd(NbXupdArgs a) {
 __global__ void __launch_bounds__(256) k_egno_xupd_bwd(NbXupdArgs a) {
   __shared__ float red[8][65];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float w0 = __ldg(a.w2 + lane), w1 = __ldg(a.w2 + lane + 32), b2 = __ldg(a.b2);
+  const float w0 = __ldg(a.w2 + 2 * lane), w1 = __ldg(a.w2 + 2 * lane + 1), b2 = __ldg(a.b2);
   const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
   float gw0 = 0.f, gw1 = 0.f, gb = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < a.rows; row += (int64_t)gridDim.x * 8) {
     float z0, d0, z1, d1;
-    nb_silu_grad(a.UV[row * NB_H + lane], z0, d0);
-    nb_silu_grad(a.UV[row * NB_H + lane + 32], z1, d1);
+    const float2 uv = *reinterpret_cast<const float2*>(a.UV + row * NB_H + 2 * lane);  // lane owns columns 2l, 2l+1
+    nb_silu_grad(uv.x, z0, d0);
+    nb_silu_grad(uv.y, z1, d1);
     float s = w0 * z0 + w1 * z1;
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
@@ -430,14 +452,13 @@ __global__ void __launch_bounds__(256) k_egno_xupd_bwd(NbXupdArgs a) {
       float f = a.Fsum[row * 3 + lane] / cnt;
       a.gFsum[row * 3 + lane] = (f >= -100.f && f <= 100.f) ? gxl / cnt : 0.f;
     }
-    a.GUV[row * NB_H + lane] = gs * w0 * d0;
-    a.GUV[row * NB_H + lane + 32] = gs * w1 * d1;
+    *reinterpret_cast<float2*>(a.GUV + row * NB_H + 2 * lane) = make_float2(gs * w0 * d0, gs * w1 * d1);
     gw0 = fmaf(gs, z0, gw0);
     gw1 = fmaf(gs, z1, gw1);
     gb += gs;
   }
-  red[warp][lane] = gw0;
-  red[warp][lane + 32] = gw1;
+  red[warp][2 * lane] = gw0;
+  red[warp][2 * lane + 1] = gw1;
   if (lane == 0) red[warp][64] = gb;
   __syncthreads();
   if (threadIdx.x < 65) {

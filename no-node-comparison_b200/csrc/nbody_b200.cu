@@ -447,10 +447,15 @@ static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
 #ifndef NB_EMU
   if (g_edge_impl == 2 && sel_geom(a.g)) {
     const size_t smem_sel = NB_EDGE_FWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG);
-    NB_SET_SMEM(k_edge_fwd_sel, smem_sel);
     int grid_sel = imin(a.g.n_units, 2 * nb_num_sms());
     int pi_sel = prof_begin(0, st);
-    NB_LAUNCH_COUNTED(k_edge_fwd_sel, (unsigned)grid_sel, NB_THREADS, smem_sel, st, a);
+    if (a.g.blk) {
+      NB_SET_SMEM(k_edge_fwd_sel<true>, smem_sel);
+      NB_LAUNCH_COUNTED(k_edge_fwd_sel<true>, (unsigned)grid_sel, NB_THREADS, smem_sel, st, a);
+    } else {
+      NB_SET_SMEM(k_edge_fwd_sel<false>, smem_sel);
+      NB_LAUNCH_COUNTED(k_edge_fwd_sel<false>, (unsigned)grid_sel, NB_THREADS, smem_sel, st, a);
+    }
     prof_end(0, pi_sel, st);
     return nb_check_launch("k_edge_fwd_sel");
   }
@@ -492,9 +497,14 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
 #ifndef NB_EMU
   if (use_sel) {
     const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG);
-    NB_SET_SMEM(k_edge_bwd_sel, smem_sel);
     int pi_sel = prof_begin(1, st);
-    NB_LAUNCH_COUNTED(k_edge_bwd_sel, (unsigned)grid, NB_SB_THREADS, smem_sel, st, a);
+    if (a.g.blk) {
+      NB_SET_SMEM(k_edge_bwd_sel<true>, smem_sel);
+      NB_LAUNCH_COUNTED(k_edge_bwd_sel<true>, (unsigned)grid, NB_SB_THREADS, smem_sel, st, a);
+    } else {
+      NB_SET_SMEM(k_edge_bwd_sel<false>, smem_sel);
+      NB_LAUNCH_COUNTED(k_edge_bwd_sel<false>, (unsigned)grid, NB_SB_THREADS, smem_sel, st, a);
+    }
     prof_end(1, pi_sel, st);
     NB_TRY(nb_check_launch("k_edge_bwd_sel"));
     done = true;
@@ -637,6 +647,15 @@ extern "C" int64_t nb_egno_saved_floats(const NbEgnoConfig* cfg) {
   return align64(egno_layer_floats(Nn)) * cfg->n_layers;
 }
 
+static inline int64_t egno_table_floats(const NbEgnoConfig* c) { return align64((int64_t)c->T * c->B * (c->time_emb_dim > 0 ? c->time_emb_dim : 1)); }
+// sinusoidal time-embedding table shared by the embedding forward / backward kernels (first region of the workspace)
+static int egno_time_table(const NbEgnoConfig* cfg, NbEmbedArgs& e, float* table, void* stream) {
+  e.table = table;
+  if (cfg->time_emb_dim <= 0) return NB_OK;
+  NB_LAUNCH_COUNTED(k_time_table, (unsigned)imin(cdiv((int64_t)e.T * e.B * e.D, 256), 4 * nb_num_sms()), 256, 0, stream, e);
+  return nb_check_launch("k_time_table");
+}
+
 static int64_t egno_coef_floats(const NbEgnoConfig* c) {
   int ncoef = c->use_time_conv ? 1 + 2 * (c->num_modes - 1) : 0;
   return align64((int64_t)ncoef * c->B * c->N * NB_H);
@@ -646,8 +665,9 @@ extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int backwar
   if (egno_validate(cfg) != NB_OK) return -1;
   int64_t Nn = (int64_t)cfg->T * cfg->B * cfg->N;
   int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
-  if (!backward) return 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // last term: inference ping-pong
-  return 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
+  const int64_t tab = egno_table_floats(cfg);
+  if (!backward) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // last term: inference ping-pong
+  return tab + 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
          NB_PARTIAL_FLOATS;
 }
 
@@ -760,7 +780,8 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
   const int T = cfg->T, Ln = cfg->n_layers;
   const int64_t Nn = X.Nn, Nn0 = X.Nn0;
   const int64_t nh = align64(Nn * NB_H), cf = egno_coef_floats(cfg), lf = align64(egno_layer_floats(Nn));
-  float* P = workspace;
+  float* ttab = workspace;
+  float* P = ttab + egno_table_floats(cfg);
   float* Q = P + nh;
   float* coef = Q + nh;
   float* ycoef = coef + cf;
@@ -779,6 +800,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       float sc = (float)(log(10000.0) / (double)(half - 1));  // layer_no.py:10-11 (fp32 arange * python scalar)
       e.freq[k] = expf((float)k * -sc);
     }
+    NB_TRY(egno_time_table(cfg, e, ttab, stream));
     const size_t smem = ((size_t)X.lo.F * NB_H + 4 * X.lo.F) * sizeof(float);
     NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
     NB_TRY(nb_check_launch("k_embed_fwd"));
@@ -873,6 +895,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   const int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
   const int64_t lf = align64(egno_layer_floats(Nn));
   float* w = workspace;
+  float* ttab = w; w += egno_table_floats(cfg);
   float* P = w; w += nh;
   float* Q = w; w += nh;
   float* coef = w; w += cf;
@@ -1107,6 +1130,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       e.freq[k] = expf((float)k * -sc);
     }
     eb.g = gh_in;
+    NB_TRY(egno_time_table(cfg, e, ttab, stream));
     const int F = X.lo.F;
     int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
     float* partial = q_alloc((int64_t)grid * (NB_H * F + NB_H), stream);
