@@ -438,6 +438,9 @@ def run_ours(args):
         ms_er = timed(er, 3)
         extras["egno_rollout_traj_per_s"] = world * B * 3 / (ms_er / 1e3)
         extras["egno_rollout_note"] = f"{TL} autoregressive calls x {T} frames + energy of every frame per trajectory"
+        # the two 5-body configurations (BASELINE.json configs[0], configs[1]): launch-bound, so one CUDA graph per step
+        if world == 1:
+            extras.update(small_configs(nb, synth, dev, K))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -455,6 +458,59 @@ def run_ours(args):
                 "kernels": kern, "extras": extras}
         print(json.dumps(line), flush=True)
     finish(world, dist)
+
+
+def small_configs(nb, synth, dev, K):
+    """Training throughput of the 5-body configurations: EGNO N=5, T=8, L=4, B=100 and SEGNO N=5, T=10, B=100."""
+    out = {}
+    B, N = 100, 5
+    row, col = synth.canonical_edges(B, N)
+    edges = [row.to(dev), col.to(dev)]
+
+    def run(step, n):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return B * n / (e0.elapsed_time(e1) / 1e3)
+
+    T = 8
+    torch.manual_seed(1)
+    m = nb.EGNO(n_layers=4, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T, device=dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, weight_decay=1e-8, capturable=True)
+    s = synth.sample_state("charged", B, N, seed=5)
+    x, nodes, ea, v, lm = synth.egno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), edges[0], edges[1])
+    tgt = x.repeat(T, 1) + 0.05 * torch.randn(T * B * N, 3, device=dev)
+    t_out = torch.arange(1, T + 1, device=dev)[None].repeat(B, 1)
+
+    def f1(x, nodes, ea, v, lm, tgt):
+        xo, _, _ = m(x, nodes, edges, ea, v=v, loc_mean=lm, timesteps_out=t_out)
+        return ((xo - tgt) ** 2).mean()
+
+    ins = dict(x=x, nodes=nodes, ea=ea, v=v, lm=lm, tgt=tgt)
+    g1 = nb.GraphedStep(f1, ins, opt)
+    out["egno_n5_t8_b100_train_traj_per_s"] = run(lambda: g1(**ins), 4 * K)
+    T2 = 10
+    torch.manual_seed(1)
+    sg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=dev, n_layers=8, recurrent=True)
+    sopt = torch.optim.Adam(sg.parameters(), lr=5e-3, weight_decay=1e-12, capturable=True)
+    his, x2, v2, ea2 = synth.segno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), edges[0], edges[1])
+    tgt2 = x2 + 0.05 * torch.randn_like(x2)
+
+    def f2(his, x, v, ea, tgt):
+        xo, _, _ = sg(his, x, edges, v, ea, T=T2)
+        return ((xo - tgt) ** 2).mean()
+
+    ins2 = dict(his=his, x=x2, v=v2, ea=ea2, tgt=tgt2)
+    g2 = nb.GraphedStep(f2, ins2, sopt)
+    out["segno_n5_t10_b100_train_traj_per_s"] = run(lambda: g2(**ins2), 4 * K)
+    out["small_configs_note"] = "BASELINE.json configs[0] / [1] (B=100): launch-bound; whole step replayed as one CUDA graph"
+    return out
 
 
 def main():

@@ -111,17 +111,18 @@ __device__ __forceinline__ void nb_tile_wgrad(const float* __restrict__ Gs, cons
 }
 
 // Stage a 64x64 operand into shared memory as Bs[k][n] = src[k * sk + n * sn] * scale.
+// kmax: number of valid k (rows of the operand); rows k >= kmax are zero (operands narrower than 64)
 __device__ __forceinline__ void nb_stage_b(float* __restrict__ Bs, const float* __restrict__ src, int64_t sk,
-                                           int64_t sn, float scale, int tid) {
+                                           int64_t sn, float scale, int tid, int kmax = NB_H) {
   if (sn == 1) {  // rows of src are contiguous in n: coalesced reads, conflict-free writes
     for (int idx = tid; idx < NB_H * NB_H; idx += NB_THREADS) {
       int k = idx >> 6, n = idx & 63;
-      Bs[idx] = __ldg(src + (int64_t)k * sk + n) * scale;
+      Bs[idx] = k < kmax ? __ldg(src + (int64_t)k * sk + n) * scale : 0.f;
     }
   } else {        // read along k (contiguous when sk == 1), transposing on the way in
     for (int idx = tid; idx < NB_H * NB_H; idx += NB_THREADS) {
       int n = idx >> 6, k = idx & 63;
-      Bs[k * NB_H + n] = __ldg(src + (int64_t)k * sk + (int64_t)n * sn) * scale;
+      Bs[k * NB_H + n] = k < kmax ? __ldg(src + (int64_t)k * sk + (int64_t)n * sn) * scale : 0.f;
     }
   }
 }

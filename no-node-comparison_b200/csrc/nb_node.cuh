@@ -15,6 +15,7 @@ struct NbGemmSrc {
   const float* W;
   int64_t sk, sn;
   float scale;
+  int kmax;    // valid k of this source (<= 64; operand rows beyond it are taken as zero)
 };
 enum { NB_EPI_NONE = 0, NB_EPI_SILU = 1, NB_EPI_MUL_DSILU = 2 };
 struct NbGemmArgs {
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_gemm64(NbGemmBatch batch) {
 
   for (int s = 0; s < a.nsrc; ++s) {
     if (s > 0) __syncthreads();
-    nb_stage_b(Bs, a.src[s].W, a.src[s].sk, a.src[s].sn, a.src[s].scale, tid);
+    nb_stage_b(Bs, a.src[s].W, a.src[s].sk, a.src[s].sn, a.src[s].scale, tid, a.src[s].kmax);
     const float* A = a.src[s].A;
     const int lda = a.src[s].lda;
     const int asilu = a.src[s].a_silu;
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_wgrad64(NbWgradBatch batch) {
 struct NbFinSeg {
   int start, count, inner;
   int64_t dst_off, so, si;
+  int klimit;  // > 0: only k < klimit is written (results narrower than the 64-wide accumulator rows)
 };
 struct NbFinArgs {
   const float* partial;
@@ -260,9 +262,11 @@ __global__ void __launch_bounds__(256) k_finalize(NbFinBatch batch) {
     for (int w = 1; w < 8; ++w) t += red[w][lane];
     const NbFinSeg sg = a.seg[s];
     int o = l / sg.inner, k = l - o * sg.inner;
-    float* d = a.dst + sg.dst_off + (int64_t)o * sg.so + (int64_t)k * sg.si;
-    if (a.accumulate) t += *d;
-    *d = t;
+    if (sg.klimit <= 0 || k < sg.klimit) {
+      float* d = a.dst + sg.dst_off + (int64_t)o * sg.so + (int64_t)k * sg.si;
+      if (a.accumulate) t += *d;
+      *d = t;
+    }
   }
 }
 
@@ -294,6 +298,22 @@ __global__ void __launch_bounds__(256) k_time_table(NbEmbedArgs a) {
 __device__ __forceinline__ float nb_embed_feature(const NbEmbedArgs& a, int t, int k, int f) {
   if (f < a.F0) return __ldg(a.nodes + (int64_t)k * a.F0 + f);
   return __ldg(a.table + ((int64_t)t * a.B + (k % a.B)) * a.D + (f - a.F0));   // the `k mod B` broadcast of egno.py:66
+}
+
+// ein[row][0:64] = [ nodes | time embedding | zeros ]: the embedding Linear and its weight gradient then run through
+// the 64-wide GEMM / weight-gradient kernels (tcgen05 on the GPU).  One thread per (row, 4 columns).
+__global__ void __launch_bounds__(256) k_embed_inputs(NbEmbedArgs a, float* __restrict__ ein) {
+  const int F = a.F0 + a.D;
+  const int64_t total = (int64_t)a.T * a.Nn0 * 16;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx >> 4;
+    const int c0 = (int)(idx & 15) * 4;
+    const int t = (int)(row / a.Nn0), k = (int)(row % a.Nn0);
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = c0 + i < F ? nb_embed_feature(a, t, k, c0 + i) : 0.f;
+    nb_st4(ein + row * NB_H + c0, make_float4(v[0], v[1], v[2], v[3]));
+  }
 }
 
 __global__ void __launch_bounds__(256) k_embed_fwd(NbEmbedArgs a) {

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_gemm64_tc(NbGemmBatch batch, 
       float v[8];
       const float* w = src.W + (int64_t)n * src.sn + (int64_t)(8 * j) * src.sk;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(w + (int64_t)i * src.sk) * src.scale;
+      for (int i = 0; i < 8; ++i) v[i] = 8 * j + i < src.kmax ? __ldg(w + (int64_t)i * src.sk) * src.scale : 0.f;
       nb_tc_store8(Bh, Bl, n, j, v);
     }
   }

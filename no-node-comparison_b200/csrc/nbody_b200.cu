@@ -217,7 +217,7 @@ static int launch_gemm(const NbGemmArgs& a, void* st) { return launch_gemm_batch
 
 static NbGemmSrc gsrc(const float* A, int lda, int a_silu, const float* W, int64_t sk, int64_t sn, float scale = 1.f) {
   NbGemmSrc s;
-  s.A = A; s.lda = lda; s.a_silu = a_silu; s.W = W; s.sk = sk; s.sn = sn; s.scale = scale;
+  s.A = A; s.lda = lda; s.a_silu = a_silu; s.W = W; s.sk = sk; s.sn = sn; s.scale = scale; s.kmax = NB_H;
   return s;
 }
 
@@ -231,7 +231,7 @@ static NbGemmArgs gemm_args(int rows) {
 
 static NbFinSeg fseg(int start, int count, int inner, int64_t dst_off, int64_t so, int64_t si) {
   NbFinSeg s;
-  s.start = start; s.count = count; s.inner = inner; s.dst_off = dst_off; s.so = so; s.si = si;
+  s.start = start; s.count = count; s.inner = inner; s.dst_off = dst_off; s.so = so; s.si = si; s.klimit = 0;
   return s;
 }
 
@@ -242,6 +242,7 @@ struct WgradFin {
   int64_t w_off, so, si, b_off;
   float* dst;
   int accumulate;
+  int klimit;
 };
 struct LaunchQueue {
   float* pbase;
@@ -344,6 +345,7 @@ static int q_flush_wgrad(void* st) {
     f.partial = wb.job[j].partial; f.nparts = grid; f.plen = NB_WGRAD_PLEN; f.dst = wf.dst; f.accumulate = wf.accumulate;
     f.nseg = 0;
     f.seg[f.nseg++] = fseg(0, NB_H * NB_H, NB_H, wf.w_off, wf.so, wf.si);
+    f.seg[f.nseg - 1].klimit = wf.klimit;
     if (wf.b_off >= 0) f.seg[f.nseg++] = fseg(NB_H * NB_H, NB_H, NB_H, wf.b_off, 0, 1);
     NB_TRY(launch_finalize(f, st));
   }
@@ -357,14 +359,14 @@ static int q_flush(void* st) {
 // dst[w_off + o*so + k*si] (+)= sum_rows sum_p scale_p G_p[r][o] A_p[r][k];  dst[b_off + o] (+)= colsum(G_0) if b_off >= 0
 // (queued; executed at the next q_flush)
 static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* dst, int64_t w_off, int64_t so,
-                    int64_t si, int64_t b_off, int accumulate, void* st) {
+                    int64_t si, int64_t b_off, int accumulate, void* st, int klimit = 0) {
   if (rows <= 0) return NB_OK;
   if (g_q.wb.njobs == NB_MAX_WGRAD_JOBS) NB_TRY(q_flush_wgrad(st));
   NbWgradArgs a;
   memset(&a, 0, sizeof(a));
   a.rows = rows; a.npair = npair; a.pair[0] = p0; a.pair[1] = p1; a.colsum = b_off >= 0;
   WgradFin wf;
-  wf.w_off = w_off; wf.so = so; wf.si = si; wf.b_off = b_off; wf.dst = dst; wf.accumulate = accumulate;
+  wf.w_off = w_off; wf.so = so; wf.si = si; wf.b_off = b_off; wf.dst = dst; wf.accumulate = accumulate; wf.klimit = klimit;
   g_q.wfin[g_q.wb.njobs] = wf;
   g_q.wb.job[g_q.wb.njobs++] = a;
   return NB_OK;
@@ -801,9 +803,16 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       e.freq[k] = expf((float)k * -sc);
     }
     NB_TRY(egno_time_table(cfg, e, ttab, stream));
-    const size_t smem = ((size_t)X.lo.F * NB_H + 4 * X.lo.F) * sizeof(float);
-    NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
-    NB_TRY(nb_check_launch("k_embed_fwd"));
+    // h = Linear([nodes | time embedding]) (egno.py:72-76): inputs materialised 64 wide (scratch: P), then one GEMM
+    NB_LAUNCH_COUNTED(k_embed_inputs, (unsigned)ew_grid(Nn * 16), 256, 0, stream, e, P);
+    NB_TRY(nb_check_launch("k_embed_inputs"));
+    {
+      NbGemmArgs ga = gemm_args((int)Nn);
+      ga.nsrc = 1; ga.src[0] = gsrc(P, NB_H, 0, params + X.lo.emb_w, 1, X.lo.F);
+      ga.src[0].kmax = X.lo.F;
+      ga.bias = params + X.lo.emb_b; ga.out = b0.h0;
+      NB_TRY(launch_gemm(ga, stream));
+    }
     NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, x, b0.x0, (int)(Nn0 * 3), T);
     NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, v, b0.v0, (int)(Nn0 * 3), T);
     NB_TRY(nb_check_launch("k_replicate3"));
@@ -1131,20 +1140,12 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     }
     eb.g = gh_in;
     NB_TRY(egno_time_table(cfg, e, ttab, stream));
-    const int F = X.lo.F;
-    int grid = imin(cdiv(Nn, 32), 2 * nb_num_sms());
-    float* partial = q_alloc((int64_t)grid * (NB_H * F + NB_H), stream);
-    if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
-    eb.partial = partial;
-    const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
-    NB_LAUNCH_COUNTED(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
-    NB_TRY(nb_check_launch("k_embed_bwd"));
-    NbFinArgs f;
-    memset(&f, 0, sizeof(f));
-    f.partial = partial; f.nparts = grid; f.plen = NB_H * F + NB_H; f.dst = grad_params; f.nseg = 2;
-    f.seg[0] = fseg(0, NB_H * F, NB_H * F, X.lo.emb_w, 0, 1);
-    f.seg[1] = fseg(NB_H * F, NB_H, NB_H, X.lo.emb_b, 0, 1);
-    NB_TRY(launch_finalize(f, stream));
+    // dW_emb = gh^T [nodes | time embedding], db_emb = column sums of gh: the inputs are re-materialised 64 wide
+    // (scratch: P, free by now) and reduced by the weight-gradient kernel; columns >= F are not written.
+    NB_LAUNCH_COUNTED(k_embed_inputs, (unsigned)ew_grid(Nn * 16), 256, 0, stream, e, P);
+    NB_TRY(nb_check_launch("k_embed_inputs"));
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, P), wpair(nullptr, nullptr), grad_params, X.lo.emb_w, X.lo.F, 1, X.lo.emb_b, 0,
+                    stream, X.lo.F));
     NB_TRY(q_flush(stream));
   }
   if (g_x_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T);
