@@ -215,7 +215,7 @@ def run_ours(args):
         broadcast_parameters(model)
         model.enable_data_parallel()
     use_graph = not args.no_graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-8, capturable=use_graph)  # model_confs.yaml:15-17
+    opt = nb.FlatAdam(model.parameters(), lr=1e-4, weight_decay=1e-8)   # Adam of model_confs.yaml:15-17, one fused launch
 
     # ---- synthetic data: NB distinct batches per rank, raw states in pinned host memory
     NBATCH = 8
@@ -397,7 +397,7 @@ def run_ours(args):
         if world > 1:
             broadcast_parameters(seg)
             seg.enable_data_parallel()
-        sopt = torch.optim.Adam(seg.parameters(), lr=5e-3, weight_decay=1e-12)
+        sopt = nb.FlatAdam(seg.parameters(), lr=5e-3, weight_decay=1e-12)
         sb = []
         for i in range(NBATCH):
             s = synth.sample_state("gravity", B, N, seed=77 + 1000 * rank + i)
@@ -482,7 +482,7 @@ def small_configs(nb, synth, dev, K):
     T = 8
     torch.manual_seed(1)
     m = nb.EGNO(n_layers=4, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T, device=dev)
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4, weight_decay=1e-8, capturable=True)
+    opt = nb.FlatAdam(m.parameters(), lr=1e-4, weight_decay=1e-8)
     s = synth.sample_state("charged", B, N, seed=5)
     x, nodes, ea, v, lm = synth.egno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), edges[0], edges[1])
     tgt = x.repeat(T, 1) + 0.05 * torch.randn(T * B * N, 3, device=dev)
@@ -498,7 +498,7 @@ def small_configs(nb, synth, dev, K):
     T2 = 10
     torch.manual_seed(1)
     sg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=dev, n_layers=8, recurrent=True)
-    sopt = torch.optim.Adam(sg.parameters(), lr=5e-3, weight_decay=1e-12, capturable=True)
+    sopt = nb.FlatAdam(sg.parameters(), lr=5e-3, weight_decay=1e-12)
     his, x2, v2, ea2 = synth.segno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), edges[0], edges[1])
     tgt2 = x2 + 0.05 * torch.randn_like(x2)
 

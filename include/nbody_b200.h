@@ -195,6 +195,13 @@ int nb_nbody_features(int32_t B, int32_t N, int32_t with_charge, const float* lo
 int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, float G, const float* loc, const float* vel,
                     const float* charges, float* energy, void* stream);
 
+/* Fused Adam over flat buffers: torch.optim.Adam semantics (amsgrad = False), one launch for n
+ * elements; `step` is a device float counting the steps taken (incremented first when tick != 0), so the call is
+ * CUDA-graph capturable.  Replaces the per-tensor optimizer launches of main.py:150 for models whose parameters and
+ * gradients are the flat buffers of this ABI. */
+int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
+                 int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, void* stream);
+
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]
  * and dumps the raw 128 TMEM lanes x 64 columns into out[128*64]. */

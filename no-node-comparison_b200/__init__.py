@@ -12,7 +12,8 @@ from .segno import SEGNO  # noqa: F401
 from .build import build_library  # noqa: F401
 from ._lib import load_library, library_path  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
 from .rollout import prepare_inputs, conserved_energy, egno_rollout, segno_rollout  # noqa: F401
 
-__all__ = ["EGNO", "SEGNO", "GraphedStep", "prepare_inputs", "conserved_energy", "egno_rollout", "segno_rollout",
+__all__ = ["EGNO", "SEGNO", "GraphedStep", "FlatAdam", "prepare_inputs", "conserved_energy", "egno_rollout", "segno_rollout",
            "build_library", "load_library", "library_path"]

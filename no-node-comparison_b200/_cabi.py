@@ -36,6 +36,7 @@ EXPORTS = {
     "nb_egcl_edge_backward": (C.c_int, [C.c_int32] * 5 + [c_f] * 5 + [C.c_int32] * 3 + [c_f] * 14),
     "nb_nbody_features": (C.c_int, [C.c_int32] * 3 + [c_f] * 8),
     "nb_nbody_energy": (C.c_int, [C.c_int32] * 4 + [C.c_float] + [c_f] * 5),
+    "nb_adam_step": (C.c_int, [C.c_int64] + [c_f] * 5 + [C.c_int32] + [C.c_double] * 5 + [c_f]),
     "nb_launch_count": (C.c_longlong, []),
     "nb_profile_enable": (C.c_int, [C.c_int]),
     "nb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -529,3 +529,36 @@ __global__ void __launch_bounds__(256) k_check_edges(const int64_t* __restrict__
     if (row[e] != b * N + i || col[e] != b * N + j) atomicCAS(flag, 0, (int)(e % 2147483646) + 1);
   }
 }
+
+// ============================================================================= fused Adam over the flat buffers
+// torch.optim.Adam semantics (amsgrad = False, maximize = False): g += wd p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  The step counter lives on the device (k_adam_tick), so
+// the pair of launches is CUDA-graph capturable; parameters and gradients are ONE flat buffer each (the layout of the
+// C ABI), so one launch updates the whole model.
+__global__ void k_adam_tick(float* step) { *step += 1.0f; }
+
+struct NbAdamArgs {
+  int64_t n;
+  float* p;
+  const float* g;
+  float *m, *v;
+  const float* step;   // already incremented
+  double lr, beta1, beta2, eps, weight_decay;   // hyper-parameters in double, like the Python scalars torch uses
+};
+__global__ void __launch_bounds__(256) k_adam(NbAdamArgs a) {
+  const double t = (double)*a.step;
+  const double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
+  const float step_size = (float)(a.lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+  const float b1 = (float)a.beta1, b2 = (float)a.beta2, omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
+  const float eps = (float)a.eps, wd = (float)a.weight_decay;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = a.p[i];
+    const float g = fmaf(wd, p, a.g[i]);                 // grad.add(param, alpha=weight_decay)
+    const float m = fmaf(omb1, g - a.m[i], a.m[i]);      // exp_avg.lerp_(grad, 1 - beta1)
+    const float v = fmaf(omb2 * g, g, b2 * a.v[i]);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    a.m[i] = m;
+    a.v[i] = v;
+    a.p[i] = p - step_size * (m / (sqrtf(v) / bc2_sqrt + eps));   // param.addcdiv_(exp_avg, denom, value=-step_size)
+    (void)b1;
+  }
+}

@@ -1556,6 +1556,24 @@ extern "C" int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, fl
   return nb_check_launch("k_nbody_energy");
 }
 
+// fused Adam: `step` is a device float holding the number of steps taken so far (incremented here when tick != 0);
+// [params, grads, exp_avg, exp_avg_sq] are flat fp32 buffers of n elements
+extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
+                            int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, void* stream) {
+  if (n < 0 || !params || !grads || !exp_avg || !exp_avg_sq || !step) {
+    nb_set_error("nb_adam_step: null pointer or negative size");
+    return NB_ERR_INVALID;
+  }
+  if (tick) NB_LAUNCH_COUNTED(k_adam_tick, 1, 1, 0, stream, step);
+  if (n > 0) {
+    NbAdamArgs a;
+    a.n = n; a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.step = step;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    NB_LAUNCH_COUNTED(k_adam, (unsigned)imin(cdiv(n, 256), 4 * nb_num_sms()), 256, 0, stream, a);
+  }
+  return nb_check_launch("k_adam");
+}
+
 // tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.
 extern "C" int nb_tc_selftest(int32_t mode, const float* A, const float* W, float* out, void* stream) {
 #ifdef NB_EMU

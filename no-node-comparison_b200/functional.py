@@ -191,6 +191,9 @@ class SegnoFunction(torch.autograd.Function):
             n = shp.numel()
             grads.append(grad_flat[o:o + n].view(shp))
             o += n
+        # coord_mlp_vel (the last four tensors) never enters the computation: its gradients are None in the reference
+        # (gcl.py:64-67 builds it, forward never calls it), so optimizers leave it untouched
+        grads[-4:] = [None] * 4
         return (None, None, None, None, gx_in, gv_in, None, *grads)
 
 

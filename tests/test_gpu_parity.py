@@ -493,3 +493,40 @@ def test_device_resident_rollouts_match_a_stepwise_loop_with_oracle_features_and
             loc, vel = xo, vo
     assert rel_err(preds.cpu(), torch.stack(ref_p).cpu()) < 1e-5
     assert rel_err(en.cpu(), torch.stack(ref_e)) < 1e-4
+
+
+def test_flat_adam_matches_torch_adam_and_skips_inert_parameters():
+    """FlatAdam (one fused launch over the flat parameter / gradient buffers) follows torch.optim.Adam step for step on
+    EGNO; on SEGNO the never-used coord_mlp_vel tensors keep grad None (as in the reference) and are not updated."""
+    d = dev()
+    c = _egno_case(8, 5, 6, L=2, seed=21)
+    tgt = torch.randn(6 * 8 * 5, 3, generator=torch.Generator().manual_seed(1)).to(d)
+    finals = {}
+    for kind in ("torch", "flat"):
+        m = make_egno(c, seed=7)
+        opt = (torch.optim.Adam if kind == "torch" else nb.FlatAdam)(m.parameters(), lr=2e-3, weight_decay=1e-4)
+        for _ in range(4):
+            opt.zero_grad(set_to_none=True)
+            _, _, (xo, vo, ho) = run_egno(m, c, requires_grad=False)
+            ((xo - tgt) ** 2).mean().backward()
+            if kind == "flat":
+                assert len(opt._runs(list(m.parameters()))) == 1   # parameters and gradients are each one flat buffer
+            opt.step()
+        finals[kind] = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu()
+    assert rel_err(finals["flat"], finals["torch"]) < 1e-5, rel_err(finals["flat"], finals["torch"])
+    # SEGNO: inert tensors
+    B, N = 4, 5
+    s = synth.sample_state("gravity", B, N, seed=3)
+    row, col = synth.canonical_edges(B, N)
+    his, x, v, ea = synth.segno_features(s["loc"], s["vel"], s["charges"], row, col)
+    sg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
+    before = {k: p.detach().clone() for k, p in sg.named_parameters()}
+    opt = nb.FlatAdam(sg.parameters(), lr=1e-2, weight_decay=1e-2)
+    xo, _, _ = sg(his.to(d), x.to(d), [row, col], v.to(d), ea.to(d), T=3)
+    xo.square().mean().backward()
+    opt.step()
+    for k, p in sg.named_parameters():
+        if "coord_mlp_vel" in k:
+            assert p.grad is None and torch.equal(p.detach(), before[k]), k
+        else:
+            assert p.grad is not None and not torch.equal(p.detach(), before[k]), k
