@@ -404,12 +404,20 @@ def run_ours(args):
             his, x, v, ea = synth.segno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), row_d, col_d)
             sb.append(dict(his=his, x=x, v=v, ea=ea, target=x + 0.05 * torch.randn_like(x)))
 
-        def seg_step(i):
-            b = sb[i % NBATCH]
-            sopt.zero_grad(set_to_none=True)
-            xo, ho, vo = seg(b["his"], b["x"], edges, b["v"], b["ea"], T=T)
-            ((xo - b["target"]) ** 2).mean().backward()
-            sopt.step()
+        def seg_loss(his, x, v, ea, target):
+            xo, ho, vo = seg(his, x, edges, v, ea, T=T)
+            return ((xo - target) ** 2).mean()
+
+        if use_graph:
+            g_seg = nb.GraphedStep(seg_loss, sb[0], sopt)
+
+            def seg_step(i):
+                g_seg(**sb[i % NBATCH])
+        else:
+            def seg_step(i):
+                sopt.zero_grad(set_to_none=True)
+                seg_loss(**sb[i % NBATCH]).backward()
+                sopt.step()
 
         for i in range(3):
             seg_step(i)

@@ -51,6 +51,8 @@ typedef struct NbEgnoConfig {
   int32_t in_edge_nf;    /* 2 */
   int32_t time_emb_dim;  /* 32 */
   int32_t use_time_conv; /* 1 */
+  int32_t num_inputs;    /* 0 / 1: one input frame; L > 1: L input frames (egno.py:13-16,42-47: the embedding then takes
+                            in_node_nf + 2 * time_emb_dim features and frame t reads input min(t / (T / L), L - 1)) */
 } NbEgnoConfig;
 
 /* SEGNO(**params) as resolved by main.py:110-114 / model_confs.yaml:20-29 (SEGNO/models/model.py:7-26). */
@@ -104,14 +106,17 @@ int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int backward);
  * `saved` may be NULL for inference (then nothing is kept for backward). */
 int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, const float* x, const float* nodes,
                     const float* edge_fea, const float* v, const float* loc_mean, const int64_t* timesteps_out,
-                    float* x_out, float* v_out, float* h_out, float* saved, float* workspace, void* stream);
+                    const int64_t* timesteps_in, float* x_out, float* v_out, float* h_out, float* saved,
+                    float* workspace, void* stream);
+/* num_inputs = L > 1: x, v, loc_mean are [L][BN][3], nodes [L][BN][in_node_nf], edge_fea [L][B*N*(N-1)][in_edge_nf],
+ * timesteps_in [B][L] int64 (NULL otherwise); the backward's g_x_in / g_v_in are then [L][BN][3]. */
 
 /* Backward of the above (the reference relies on autograd).  g_*_out may be NULL (= zero).
  * grad_params (same layout as params) is OVERWRITTEN; g_x_in / g_v_in [BN,3] may be NULL. */
 int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, const float* nodes, const float* edge_fea,
-                     const float* loc_mean, const int64_t* timesteps_out, const float* saved, const float* g_x_out,
-                     const float* g_v_out, const float* g_h_out, float* grad_params, float* g_x_in, float* g_v_in,
-                     float* workspace, void* stream);
+                     const float* loc_mean, const int64_t* timesteps_out, const int64_t* timesteps_in,
+                     const float* saved, const float* g_x_out, const float* g_v_out, const float* g_h_out,
+                     float* grad_params, float* g_x_in, float* g_v_in, float* workspace, void* stream);
 
 /* Replaces SEGNO.forward_step applied to embedding(his) (SEGNO/models/model.py:73,95-102) with
  * SEGNO_GCL.forward (SEGNO/models/models/gcl.py:111-119), unsorted_segment_sum / _mean (:7-23).

@@ -9,7 +9,7 @@ c_f = C.c_void_p  # device (or, under the test emulator, host) pointers travel a
 class NbEgnoConfig(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("n_layers", C.c_int32),
                 ("num_modes", C.c_int32), ("in_node_nf", C.c_int32), ("in_edge_nf", C.c_int32),
-                ("time_emb_dim", C.c_int32), ("use_time_conv", C.c_int32)]
+                ("time_emb_dim", C.c_int32), ("use_time_conv", C.c_int32), ("num_inputs", C.c_int32)]
 
 
 class NbSegnoConfig(C.Structure):
@@ -26,8 +26,8 @@ EXPORTS = {
     "nb_egno_workspace_floats": (C.c_int64, [C.POINTER(NbEgnoConfig), C.c_int]),
     "nb_segno_saved_floats": (C.c_int64, [C.POINTER(NbSegnoConfig)]),
     "nb_segno_workspace_floats": (C.c_int64, [C.POINTER(NbSegnoConfig), C.c_int]),
-    "nb_egno_forward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 13),
-    "nb_egno_backward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 14),
+    "nb_egno_forward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 14),
+    "nb_egno_backward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 15),
     "nb_segno_forward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 11),
     "nb_segno_backward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 12),
     "nb_check_canonical_edges": (C.c_int, [c_f, c_f, C.c_int64, C.c_int32, C.c_int32, c_f, c_f]),

@@ -32,7 +32,14 @@ struct NbEdgeGeom {
   int N, EPG, NGT, B, G, n_units, nef;
   int clamp_edge;  // SEGNO: clamp(rij*c, +-100) per edge before the mean (gcl.py:100)
   int blk, nI, nJ, IB, JB;  // selector kernels, N > 27: a graph is walked in (IB receivers x JB senders) blocks, one tile each
+  int multi;                // EGNO num_inputs > 1: edge features are per input frame, [L][B*EPG][nef]
+  int tmap[NB_MAX_T];       // frame t -> input index (EGNO/utils.py:115-131)
 };
+// graph index into the edge-feature array of graph-instance gt = t*B + b  (shared across time unless `multi`)
+__device__ __forceinline__ int nb_ef_graph(const NbEdgeGeom& g, int gt) {
+  const int b = gt % g.B;
+  return g.multi ? g.tmap[gt / g.B] * g.B + b : b;
+}
 
 struct NbEdgeFwdArgs {
   NbEdgeGeom g;
@@ -74,7 +81,7 @@ __device__ __forceinline__ void nb_row_setup(const NbEdgeGeom& g, const float* _
       dx = __ldg(x + (int64_t)ni * 3 + 0) - __ldg(x + (int64_t)nj * 3 + 0);
       dy = __ldg(x + (int64_t)ni * 3 + 1) - __ldg(x + (int64_t)nj * 3 + 1);
       dz = __ldg(x + (int64_t)ni * 3 + 2) - __ldg(x + (int64_t)nj * 3 + 2);
-      int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
+      int64_t eoff = ((int64_t)nb_ef_graph(g, gt) * g.EPG + rem) * g.nef;
 #pragma unroll
       for (int f = 0; f < NB_MAX_EF; ++f)
         if (f < g.nef) e[f] = __ldg(ef + eoff + f);

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         dy = xs[li * 3 + 1] - xsnd[lj * 3 + 1];
         dz = xs[li * 3 + 2] - xsnd[lj * 3 + 2];
         r2 = dx * dx + dy * dy + dz * dz;
-        const int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
+        const int64_t eoff = ((int64_t)nb_ef_graph(g, gt) * g.EPG + rem) * g.nef;
 #pragma unroll
         for (int f = 0; f < NB_MAX_EF; ++f)
           if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         gfy = gfs[li * 3 + 1];
         gfz = gfs[li * 3 + 2];
         if (cq == 1) {
-          const int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
+          const int64_t eoff = ((int64_t)nb_ef_graph(g, gt) * g.EPG + rem) * g.nef;
 #pragma unroll
           for (int f = 0; f < NB_MAX_EF; ++f)
             if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);

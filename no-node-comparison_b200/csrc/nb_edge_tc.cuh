@@ -40,7 +40,7 @@ __device__ __forceinline__ NbRowRegs nb_row_regs(const NbEdgeGeom& g, const floa
     R.dy = __ldg(x + (int64_t)R.ni * 3 + 1) - __ldg(x + (int64_t)R.nj * 3 + 1);
     R.dz = __ldg(x + (int64_t)R.ni * 3 + 2) - __ldg(x + (int64_t)R.nj * 3 + 2);
     R.r2 = R.dx * R.dx + R.dy * R.dy + R.dz * R.dz;
-    int64_t eoff = ((int64_t)(gt % g.B) * g.EPG + rem) * g.nef;
+    int64_t eoff = ((int64_t)nb_ef_graph(g, gt) * g.EPG + rem) * g.nef;
 #pragma unroll
     for (int f = 0; f < NB_MAX_EF; ++f)
       if (f < g.nef) R.e[f] = __ldg(ef + eoff + f);

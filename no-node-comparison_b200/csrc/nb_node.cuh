@@ -282,28 +282,44 @@ struct NbEmbedArgs {
   float* out;            // [T*Nn0][64]
   float freq[32];        // D/2 frequencies
   float* table;          // [T][B][D] sinusoidal embedding of timesteps[b][t] (k_time_table), read by the kernels below
+  // EGNO num_inputs = L > 1 (egno.py:42-47,59-61,68-70): node features per input frame, a second embedding of the
+  // input times; frame t reads input tmap[t]
+  int L;                       // 0 / 1: single input
+  const int64_t* tsteps_in;    // [B][L]
+  float* table_in;             // [T][B][D]: embedding of timesteps_in[b][tmap[t]]
+  int tmap[NB_MAX_T];
 };
 
 // table[t][b][j] = sin(ts * freq[j]) (j < D/2) | cos(ts * freq[j - D/2]),  ts = timesteps[b][t]   (layer_no.py:8-17)
-__global__ void __launch_bounds__(256) k_time_table(NbEmbedArgs a) {
+__global__ void __launch_bounds__(256) k_time_table(NbEmbedArgs a, int input_times) {
   const int total = a.T * a.B * a.D, half = a.D >> 1;
+  float* tab = input_times ? a.table_in : a.table;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int j = idx % a.D, tb = idx / a.D, b = tb % a.B, t = tb / a.B;
-    const float ts = (float)__ldg(a.tsteps + (int64_t)b * a.T + t);
+    const float ts = input_times ? (float)__ldg(a.tsteps_in + (int64_t)b * a.L + a.tmap[t])
+                                 : (float)__ldg(a.tsteps + (int64_t)b * a.T + t);
     const float arg = ts * a.freq[j < half ? j : j - half];
-    a.table[idx] = j < half ? sinf(arg) : cosf(arg);
+    tab[idx] = j < half ? sinf(arg) : cosf(arg);
   }
 }
 
+// feature f of the embedding input of node k at frame t: [ nodes | (emb of the input time) | emb of the output time ]
 __device__ __forceinline__ float nb_embed_feature(const NbEmbedArgs& a, int t, int k, int f) {
-  if (f < a.F0) return __ldg(a.nodes + (int64_t)k * a.F0 + f);
-  return __ldg(a.table + ((int64_t)t * a.B + (k % a.B)) * a.D + (f - a.F0));   // the `k mod B` broadcast of egno.py:66
+  const bool multi = a.L > 1;
+  if (f < a.F0) return __ldg(a.nodes + ((int64_t)(multi ? a.tmap[t] : 0) * a.Nn0 + k) * a.F0 + f);
+  f -= a.F0;
+  const int64_t tb = ((int64_t)t * a.B + (k % a.B)) * a.D;   // the `k mod B` broadcast of egno.py:66,69
+  if (multi) {
+    if (f < a.D) return __ldg(a.table_in + tb + f);
+    f -= a.D;
+  }
+  return __ldg(a.table + tb + f);
 }
 
 // ein[row][0:64] = [ nodes | time embedding | zeros ]: the embedding Linear and its weight gradient then run through
 // the 64-wide GEMM / weight-gradient kernels (tcgen05 on the GPU).  One thread per (row, 4 columns).
-__global__ void __launch_bounds__(256) k_embed_inputs(NbEmbedArgs a, float* __restrict__ ein) {
-  const int F = a.F0 + a.D;
+__global__ void __launch_bounds__(256) k_embed_inputs(NbEmbedArgs a, float* __restrict__ ein, int foff) {
+  const int F = a.F0 + a.D * (a.L > 1 ? 2 : 1) - foff;   // features foff .. foff + 63 of the input row
   const int64_t total = (int64_t)a.T * a.Nn0 * 16;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = idx >> 4;
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(256) k_embed_inputs(NbEmbedArgs a, float* __re
     const int t = (int)(row / a.Nn0), k = (int)(row % a.Nn0);
     float v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = c0 + i < F ? nb_embed_feature(a, t, k, c0 + i) : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = c0 + i < F ? nb_embed_feature(a, t, k, foff + c0 + i) : 0.f;
     nb_st4(ein + row * NB_H + c0, make_float4(v[0], v[1], v[2], v[3]));
   }
 }
@@ -398,20 +414,28 @@ __global__ void __launch_bounds__(256) k_embed_bwd(NbEmbedBwdArgs a) {
 }
 
 // ============================================================================= small row-wise kernels
-// dst[t][k][0:3] = src[k][0:3]
+// frame t of the T output frames is fed by input tmap[t] (all zeros for a single input)
+struct NbFrameMap {
+  int L;
+  int m[NB_MAX_T];
+};
+// dst[t][k][0:3] = src[tmap[t]][k][0:3]
 __global__ void __launch_bounds__(256) k_replicate3(const float* __restrict__ src, float* __restrict__ dst, int n3,
-                                                    int T) {
+                                                    int T, NbFrameMap fm) {
   int64_t total = (int64_t)n3 * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = src[i % n3];
+    dst[i] = src[(int64_t)fm.m[i / n3] * n3 + i % n3];
 }
-// dst[k] = sum_t src[t][k]
+// dst[l][k] = sum over the frames t fed by input l of src[t][k]
 __global__ void __launch_bounds__(256) k_sum_over_t(const float* __restrict__ src, float* __restrict__ dst, int n3,
-                                                    int T) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
+                                                    int T, NbFrameMap fm) {
+  const int64_t total = (int64_t)n3 * fm.L;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(idx / n3), i = (int)(idx - (int64_t)l * n3);
     float s = 0.f;
-    for (int t = 0; t < T; ++t) s += src[(int64_t)t * n3 + i];
-    dst[i] = s;
+    for (int t = 0; t < T; ++t)
+      if (fm.m[t] == l) s += src[(int64_t)t * n3 + i];
+    dst[idx] = s;
   }
 }
 

@@ -187,7 +187,8 @@ struct NbTcxArgs {
   int n3;              // Nn0 * 3
   const float* x0;     // [T][n3]
   const float* v0;     // [T][n3]
-  const float* mean;   // [n3]
+  const float* mean;   // [L][n3]: frame t uses mean[tmap[t]]  (single input: L = 1, tmap = 0)
+  int tmap[NB_MAX_T];
   const float* W;      // [2][2][modes][2]
   float *x1, *v1;      // [T][n3]
   // backward
@@ -203,12 +204,12 @@ __device__ __forceinline__ float nb_tcx_w(const NbTcxArgs& a, int i, int o, int 
 __global__ void __launch_bounds__(256) k_tcx_fwd(NbTcxArgs a) {
   const float invT = 1.0f / (float)a.tw.T;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.n3; idx += gridDim.x * blockDim.x) {
-    const float mean = a.mean[idx];
-    float X[2][NB_MAX_T], Y[2][NB_MAX_T];
+    float X[2][NB_MAX_T], Y[2][NB_MAX_T], mean[NB_MAX_T];
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
       if (t < a.tw.T) {
-        X[0][t] = a.x0[(int64_t)t * a.n3 + idx] - mean;
+        mean[t] = a.mean[(int64_t)a.tmap[t] * a.n3 + idx];
+        X[0][t] = a.x0[(int64_t)t * a.n3 + idx] - mean[t];
         X[1][t] = a.v0[(int64_t)t * a.n3 + idx];
         Y[0][t] = 0.f;
         Y[1][t] = 0.f;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) k_tcx_fwd(NbTcxArgs a) {
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
       if (t < a.tw.T) {
-        a.x1[(int64_t)t * a.n3 + idx] = (X[0][t] + Y[0][t]) + mean;
+        a.x1[(int64_t)t * a.n3 + idx] = (X[0][t] + Y[0][t]) + mean[t];
         a.v1[(int64_t)t * a.n3 + idx] = X[1][t] + Y[1][t];
       }
   }
@@ -262,11 +263,10 @@ __global__ void __launch_bounds__(256) k_tcx_bwd(NbTcxArgs a) {
     const int idx = base + threadIdx.x;
     const bool act = idx < a.n3;
     float X[2][NB_MAX_T], G[2][NB_MAX_T], GX[2][NB_MAX_T];
-    const float mean = act ? a.mean[idx] : 0.f;
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
       if (t < a.tw.T) {
-        X[0][t] = act ? a.x0[(int64_t)t * a.n3 + idx] - mean : 0.f;
+        X[0][t] = act ? a.x0[(int64_t)t * a.n3 + idx] - a.mean[(int64_t)a.tmap[t] * a.n3 + idx] : 0.f;
         X[1][t] = act ? a.v0[(int64_t)t * a.n3 + idx] : 0.f;
         G[0][t] = act ? a.gx1[(int64_t)t * a.n3 + idx] : 0.f;
         G[1][t] = act ? a.gv1[(int64_t)t * a.n3 + idx] : 0.f;

@@ -383,8 +383,8 @@ static int ew_grid(int64_t n) { return imin(cdiv(n, 256), 8 * nb_num_sms()); }
 // ============================================================================= edge tile launches
 static NbEdgeGeom edge_geom(int n_gt, int B, int N, int nef, int clamp_edge) {
   NbEdgeGeom g;
+  memset(&g, 0, sizeof(g));
   g.N = N; g.EPG = N * (N - 1); g.NGT = n_gt; g.B = B; g.nef = nef; g.clamp_edge = clamp_edge;
-  g.blk = 0; g.nI = g.nJ = g.IB = g.JB = 0;
   int G = NB_TILE / g.EPG;            // pack small graphs so a tile is (nearly) full
   if (G < 1) G = 1;
   if (G * N > 128) G = 128 / N;
@@ -582,8 +582,10 @@ static int egno_validate(const NbEgnoConfig* c) {
   if (c->T < 1 || c->T > NB_MAX_T) { nb_set_error("unsupported num_timesteps=%d (<= %d)", c->T, NB_MAX_T); return NB_ERR_INVALID; }
   if (c->use_time_conv && (c->num_modes < 1 || c->num_modes > c->T / 2 + 1)) { nb_set_error("num_modes=%d must be in [1, T/2+1] for T=%d", c->num_modes, c->T); return NB_ERR_INVALID; }
   if (c->in_edge_nf < 0 || c->in_edge_nf > NB_MAX_EDGE_FEA) { nb_set_error("unsupported in_edge_nf=%d", c->in_edge_nf); return NB_ERR_INVALID; }
-  if (c->in_node_nf < 1 || c->time_emb_dim < 0 || c->time_emb_dim > 64 || (c->time_emb_dim & 1) || c->in_node_nf + c->time_emb_dim > 64) {
-    nb_set_error("unsupported in_node_nf=%d time_emb_dim=%d", c->in_node_nf, c->time_emb_dim);
+  if (c->num_inputs < 0 || c->num_inputs > c->T) { nb_set_error("num_inputs=%d must be in [1, num_timesteps=%d]", c->num_inputs, c->T); return NB_ERR_INVALID; }
+  if (c->in_node_nf < 1 || c->time_emb_dim < 0 || c->time_emb_dim > 64 || (c->time_emb_dim & 1) ||
+      c->in_node_nf + c->time_emb_dim * (c->num_inputs > 1 ? 2 : 1) > 128 || (c->num_inputs > 1 && c->time_emb_dim == 0)) {
+    nb_set_error("unsupported in_node_nf=%d time_emb_dim=%d num_inputs=%d", c->in_node_nf, c->time_emb_dim, c->num_inputs);
     return NB_ERR_INVALID;
   }
   if ((int64_t)c->T * c->B * c->N * (c->N - 1) > 2000000000LL) { nb_set_error("too many edges for 32-bit indexing"); return NB_ERR_INVALID; }
@@ -592,7 +594,7 @@ static int egno_validate(const NbEgnoConfig* c) {
 
 static void egno_layout(const NbEgnoConfig* c, EgnoLayout* lo) {
   const int H = NB_H;
-  lo->F = c->in_node_nf + c->time_emb_dim;
+  lo->F = c->in_node_nf + c->time_emb_dim * (c->num_inputs > 1 ? 2 : 1);   // egno.py:13-16
   lo->E = 1 + 2 * H + c->in_edge_nf;
   int64_t o = 0;
   // named_parameters() order of the reference: `layers` is registered before `embedding` (basic.py:193-197)
@@ -649,13 +651,52 @@ extern "C" int64_t nb_egno_saved_floats(const NbEgnoConfig* cfg) {
   return align64(egno_layer_floats(Nn)) * cfg->n_layers;
 }
 
-static inline int64_t egno_table_floats(const NbEgnoConfig* c) { return align64((int64_t)c->T * c->B * (c->time_emb_dim > 0 ? c->time_emb_dim : 1)); }
-// sinusoidal time-embedding table shared by the embedding forward / backward kernels (first region of the workspace)
-static int egno_time_table(const NbEgnoConfig* cfg, NbEmbedArgs& e, float* table, void* stream) {
+// two tables (output times, input times) of T*B*D floats each: first region of the workspace
+static inline int64_t egno_table_floats(const NbEgnoConfig* c) { return 2 * align64((int64_t)c->T * c->B * (c->time_emb_dim > 0 ? c->time_emb_dim : 1)); }
+static inline int egno_L(const NbEgnoConfig* c) { return c->num_inputs > 1 ? c->num_inputs : 1; }
+// frame -> input map of repeat_elements_to_exact_shape (EGNO/utils.py:115-131)
+static NbFrameMap egno_frame_map(const NbEgnoConfig* c) {
+  NbFrameMap fm;
+  memset(&fm, 0, sizeof(fm));
+  fm.L = egno_L(c);
+  const int reps = c->T / fm.L;
+  for (int t = 0; t < c->T && t < NB_MAX_T; ++t) fm.m[t] = fm.L > 1 ? (t / reps < fm.L - 1 ? t / reps : fm.L - 1) : 0;
+  return fm;
+}
+static void egno_geom_frames(const NbEgnoConfig* c, NbEdgeGeom& g) {
+  const NbFrameMap fm = egno_frame_map(c);
+  g.multi = fm.L > 1;
+  for (int t = 0; t < NB_MAX_T; ++t) g.tmap[t] = fm.m[t];
+}
+// embedding inputs (egno.py:50,59-76): fills the kernel arguments, builds the time table(s), materialises the input
+// rows 64 wide into ein0 (features 0..63) and ein1 (features 64.., only when F > 64)
+static int egno_embed_inputs(const NbEgnoConfig* cfg, const EgnoLayout& lo, NbEmbedArgs& e, const float* nodes,
+                             const int64_t* ts_out, const int64_t* ts_in, float* table, float* ein0, float* ein1,
+                             void* stream) {
+  memset(&e, 0, sizeof(e));
+  e.T = cfg->T; e.Nn0 = cfg->B * cfg->N; e.B = cfg->B; e.F0 = cfg->in_node_nf; e.D = cfg->time_emb_dim;
+  e.nodes = nodes; e.tsteps = ts_out; e.tsteps_in = ts_in;
+  const NbFrameMap fm = egno_frame_map(cfg);
+  e.L = fm.L;
+  for (int t = 0; t < NB_MAX_T; ++t) e.tmap[t] = fm.m[t];
+  if (fm.L > 1 && !ts_in) { nb_set_error("num_inputs > 1 needs timesteps_in"); return NB_ERR_INVALID; }
+  const int half = e.D / 2;
+  for (int k = 0; k < half; ++k) {
+    float sc = (float)(log(10000.0) / (double)(half - 1));  // layer_no.py:10-11 (fp32 arange * python scalar)
+    e.freq[k] = expf((float)k * -sc);
+  }
   e.table = table;
-  if (cfg->time_emb_dim <= 0) return NB_OK;
-  NB_LAUNCH_COUNTED(k_time_table, (unsigned)imin(cdiv((int64_t)e.T * e.B * e.D, 256), 4 * nb_num_sms()), 256, 0, stream, e);
-  return nb_check_launch("k_time_table");
+  e.table_in = table + egno_table_floats(cfg) / 2;
+  const int64_t Nn = (int64_t)e.T * e.Nn0;
+  if (e.D > 0) {
+    const unsigned tg = (unsigned)imin(cdiv((int64_t)e.T * e.B * e.D, 256), 4 * nb_num_sms());
+    NB_LAUNCH_COUNTED(k_time_table, tg, 256, 0, stream, e, 0);
+    if (fm.L > 1) NB_LAUNCH_COUNTED(k_time_table, tg, 256, 0, stream, e, 1);
+    NB_TRY(nb_check_launch("k_time_table"));
+  }
+  NB_LAUNCH_COUNTED(k_embed_inputs, (unsigned)ew_grid(Nn * 16), 256, 0, stream, e, ein0, 0);
+  if (lo.F > NB_H) NB_LAUNCH_COUNTED(k_embed_inputs, (unsigned)ew_grid(Nn * 16), 256, 0, stream, e, ein1, NB_H);
+  return nb_check_launch("k_embed_inputs");
 }
 
 static int64_t egno_coef_floats(const NbEgnoConfig* c) {
@@ -775,8 +816,8 @@ static NbEdgeW egno_edge_w(const EgnoCtx& X, int l) {
 
 extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, const float* x, const float* nodes,
                                const float* edge_fea, const float* v, const float* loc_mean,
-                               const int64_t* timesteps_out, float* x_out, float* v_out, float* h_out, float* saved,
-                               float* workspace, void* stream) {
+                               const int64_t* timesteps_out, const int64_t* timesteps_in, float* x_out, float* v_out,
+                               float* h_out, float* saved, float* workspace, void* stream) {
   EgnoCtx X;
   NB_TRY(egno_ctx_init(&X, cfg, params, stream));
   const int T = cfg->T, Ln = cfg->n_layers;
@@ -793,28 +834,23 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
   // ---- embedding (egno.py:50,63-76) + replication of x, v over T (egno.py:89-96)
   EgnoLayerBufs b0 = bufs(0);
   {
+    // h = Linear([nodes | time embeddings]) (egno.py:72-76): inputs materialised 64 wide (scratch: P, Q), then one GEMM
     NbEmbedArgs e;
-    memset(&e, 0, sizeof(e));
-    e.T = T; e.Nn0 = (int)Nn0; e.B = cfg->B; e.F0 = cfg->in_node_nf; e.D = cfg->time_emb_dim;
-    e.nodes = nodes; e.tsteps = timesteps_out; e.W = params + X.lo.emb_w; e.bias = params + X.lo.emb_b; e.out = b0.h0;
-    int half = e.D / 2;
-    for (int k = 0; k < half; ++k) {
-      float sc = (float)(log(10000.0) / (double)(half - 1));  // layer_no.py:10-11 (fp32 arange * python scalar)
-      e.freq[k] = expf((float)k * -sc);
-    }
-    NB_TRY(egno_time_table(cfg, e, ttab, stream));
-    // h = Linear([nodes | time embedding]) (egno.py:72-76): inputs materialised 64 wide (scratch: P), then one GEMM
-    NB_LAUNCH_COUNTED(k_embed_inputs, (unsigned)ew_grid(Nn * 16), 256, 0, stream, e, P);
-    NB_TRY(nb_check_launch("k_embed_inputs"));
+    NB_TRY(egno_embed_inputs(cfg, X.lo, e, nodes, timesteps_out, timesteps_in, ttab, P, Q, stream));
     {
       NbGemmArgs ga = gemm_args((int)Nn);
       ga.nsrc = 1; ga.src[0] = gsrc(P, NB_H, 0, params + X.lo.emb_w, 1, X.lo.F);
-      ga.src[0].kmax = X.lo.F;
+      ga.src[0].kmax = X.lo.F < NB_H ? X.lo.F : NB_H;
+      if (X.lo.F > NB_H) {
+        ga.nsrc = 2; ga.src[1] = gsrc(Q, NB_H, 0, params + X.lo.emb_w + NB_H, 1, X.lo.F);
+        ga.src[1].kmax = X.lo.F - NB_H;
+      }
       ga.bias = params + X.lo.emb_b; ga.out = b0.h0;
       NB_TRY(launch_gemm(ga, stream));
     }
-    NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, x, b0.x0, (int)(Nn0 * 3), T);
-    NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, v, b0.v0, (int)(Nn0 * 3), T);
+    const NbFrameMap fm = egno_frame_map(cfg);
+    NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, x, b0.x0, (int)(Nn0 * 3), T, fm);
+    NB_LAUNCH_COUNTED(k_replicate3, (unsigned)ew_grid(Nn * 3), 256, 0, stream, v, b0.v0, (int)(Nn0 * 3), T, fm);
     NB_TRY(nb_check_launch("k_replicate3"));
   }
 
@@ -848,6 +884,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       NbTcxArgs t;
       memset(&t, 0, sizeof(t));
       t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
+      { const NbFrameMap fmx = egno_frame_map(cfg); for (int tt = 0; tt < NB_MAX_T; ++tt) t.tmap[tt] = fmx.m[tt]; }
       t.x1 = x1; t.v1 = v1;
       NB_LAUNCH_COUNTED(k_tcx_fwd, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, t);
       NB_TRY(nb_check_launch("k_tcx_fwd"));
@@ -859,6 +896,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
     NB_TRY(egno_pq(X, l, h1, P, Q));
     NbEdgeFwdArgs ea;
     ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
+    egno_geom_frames(cfg, ea.g);
     ea.w = egno_edge_w(X, l);
     ea.x = x1; ea.P = P; ea.Q = Q; ea.ef = edge_fea; ea.M = b.M; ea.Fsum = b.Fsum;
     NB_TRY(launch_edge_fwd(ea, stream));
@@ -893,9 +931,9 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
 }
 
 extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, const float* nodes, const float* edge_fea,
-                                const float* loc_mean, const int64_t* timesteps_out, const float* saved,
-                                const float* g_x_out, const float* g_v_out, const float* g_h_out, float* grad_params,
-                                float* g_x_in, float* g_v_in, float* workspace, void* stream) {
+                                const float* loc_mean, const int64_t* timesteps_out, const int64_t* timesteps_in,
+                                const float* saved, const float* g_x_out, const float* g_v_out, const float* g_h_out,
+                                float* grad_params, float* g_x_in, float* g_v_in, float* workspace, void* stream) {
   EgnoCtx X;
   NB_TRY(egno_ctx_init(&X, cfg, params, stream));
   if (!saved) { nb_set_error("nb_egno_backward needs the saved buffer of a forward call"); return NB_ERR_INVALID; }
@@ -992,6 +1030,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       NbEdgeBwdArgs ea;
       memset(&ea, 0, sizeof(ea));
       ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
+      egno_geom_frames(cfg, ea.g);
       ea.w = egno_edge_w(X, l);
       ea.x = x1; ea.P = P; ea.Q = Q; ea.ef = edge_fea; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
       EdgeGradDst d;
@@ -1019,6 +1058,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         NbTcxArgs t;
         memset(&t, 0, sizeof(t));
         t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
+      { const NbFrameMap fmx = egno_frame_map(cfg); for (int tt = 0; tt < NB_MAX_T; ++tt) t.tmap[tt] = fmx.m[tt]; }
         t.gx1 = gx; t.gv1 = gvB; t.gx0 = gx0; t.gv0 = gvA;
         int grid = imin(cdiv(Nn0 * 3, 256), 2 * nb_num_sms());
         float* partial = q_alloc((int64_t)grid * 2 * 2 * modes * 2, stream);
@@ -1128,28 +1168,21 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   }
   // ---- embedding backward and the reduction of the T replicas of x, v
   {
-    NbEmbedBwdArgs eb;
-    memset(&eb, 0, sizeof(eb));
-    NbEmbedArgs& e = eb.e;
-    e.T = T; e.Nn0 = (int)Nn0; e.B = cfg->B; e.F0 = cfg->in_node_nf; e.D = cfg->time_emb_dim;
-    e.nodes = nodes; e.tsteps = timesteps_out;
-    int half = e.D / 2;
-    for (int k = 0; k < half; ++k) {
-      float sc = (float)(log(10000.0) / (double)(half - 1));
-      e.freq[k] = expf((float)k * -sc);
-    }
-    eb.g = gh_in;
-    NB_TRY(egno_time_table(cfg, e, ttab, stream));
-    // dW_emb = gh^T [nodes | time embedding], db_emb = column sums of gh: the inputs are re-materialised 64 wide
-    // (scratch: P, free by now) and reduced by the weight-gradient kernel; columns >= F are not written.
-    NB_LAUNCH_COUNTED(k_embed_inputs, (unsigned)ew_grid(Nn * 16), 256, 0, stream, e, P);
-    NB_TRY(nb_check_launch("k_embed_inputs"));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, P), wpair(nullptr, nullptr), grad_params, X.lo.emb_w, X.lo.F, 1, X.lo.emb_b, 0,
-                    stream, X.lo.F));
+    // dW_emb = gh^T [nodes | time embeddings], db_emb = column sums of gh: the inputs are re-materialised 64 wide
+    // (scratch: P, Q, free by now) and reduced by the weight-gradient kernel; columns >= F are not written.
+    NbEmbedArgs e;
+    NB_TRY(egno_embed_inputs(cfg, X.lo, e, nodes, timesteps_out, timesteps_in, ttab, P, Q, stream));
+    const int F = X.lo.F;
+    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, P), wpair(nullptr, nullptr), grad_params, X.lo.emb_w, F, 1, X.lo.emb_b, 0,
+                    stream, F < NB_H ? F : NB_H));
+    if (F > NB_H)
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, Q), wpair(nullptr, nullptr), grad_params, X.lo.emb_w + NB_H, F, 1, -1, 0,
+                      stream, F - NB_H));
     NB_TRY(q_flush(stream));
   }
-  if (g_x_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T);
-  if (g_v_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T);
+  const NbFrameMap fm = egno_frame_map(cfg);
+  if (g_x_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3 * fm.L), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T, fm);
+  if (g_v_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3 * fm.L), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T, fm);
   return nb_check_launch("nb_egno_backward");
 }
 

@@ -73,8 +73,8 @@ class EGNO(nn.Module):
             raise ValueError("flat=True / norm=True are not implemented (model_confs.yaml:4-5 use False)")
         if not isinstance(activation, nn.SiLU):
             raise ValueError("only the SiLU activation (reference default) is implemented")
-        if num_inputs != 1:
-            raise NotImplementedError("num_inputs > 1 (multi-input EGNO, egno.py:42-47) is not implemented yet")
+        if num_inputs < 1:
+            raise ValueError("num_inputs must be >= 1")
         self.time_emb_dim = time_emb_dim
         self.num_inputs = num_inputs
         self.varDT = varDT
@@ -84,7 +84,8 @@ class EGNO(nn.Module):
         self.with_v = with_v
         # --- EGNN.__init__ order (basic.py:193-203): `layers` registered first, `embedding` created first
         self.layers = nn.ModuleList()
-        self.embedding = nn.Linear(in_node_nf + time_emb_dim, hidden_nf)
+        # egno.py:13-16: one time embedding, or two (input and output times) when there are several input frames
+        self.embedding = nn.Linear(in_node_nf + time_emb_dim * (2 if num_inputs > 1 else 1), hidden_nf)
         for _ in range(n_layers):
             self.layers.append(_EGNNLayerHolder(in_edge_nf, hidden_nf, activation))
         self.use_time_conv = use_time_conv
@@ -115,10 +116,19 @@ class EGNO(nn.Module):
         T = self.num_timesteps
         if v is None or loc_mean is None:
             raise ValueError("v and loc_mean are required (with_v=True path, main_simulation_simple_no.py:267)")
-        if x.dim() != 2 or x.shape[1] != 3:
+        L = self.num_inputs
+        if L > 1:   # several input frames (egno.py:42-47, main_simulation_simple_no.py:313-327): leading dimension L
+            if x.dim() != 3 or x.shape[0] != L or x.shape[2] != 3:
+                raise ValueError(f"x must be [num_inputs={L}, B*N, 3], got {tuple(x.shape)}")
+            if timesteps_in is None or timesteps_in.dim() != 2 or timesteps_in.shape[1] != L:
+                raise ValueError(f"timesteps_in must be [B, {L}] when num_inputs > 1")
+            if L > T:
+                raise ValueError(f"num_inputs={L} exceeds num_timesteps={T}")
+        elif x.dim() != 2 or x.shape[1] != 3:
             raise ValueError(f"x must be [B*N, 3], got {tuple(x.shape)}")
         dev = x.device
-        n0 = x.shape[0]
+        n0 = x.shape[-2]
+        lead = (L,) if L > 1 else ()
         if timesteps_out is None:
             # the reference's default (egno.py:40) is 1-D and crashes in get_timestep_embedding; require [B, T]
             raise ValueError("timesteps_out [B, T] is required")
@@ -133,15 +143,20 @@ class EGNO(nn.Module):
         for name, t in (("h", h), ("edge_fea", edge_fea)):
             if t.requires_grad:
                 raise ValueError(f"gradients w.r.t. {name} are not implemented (the reference callers detach it)")
-        x = _require_cuda_f32("x", x, (n0, 3))
-        v = _require_cuda_f32("v", v, (n0, 3))
-        h = _require_cuda_f32("h", h, (n0, self.in_node_nf))
-        loc_mean = _require_cuda_f32("loc_mean", loc_mean, (n0, 3))
-        edge_fea = _require_cuda_f32("edge_fea", edge_fea, (B * N * (N - 1), self.in_edge_nf))
+        x = _require_cuda_f32("x", x, lead + (n0, 3))
+        v = _require_cuda_f32("v", v, lead + (n0, 3))
+        h = _require_cuda_f32("h", h, lead + (n0, self.in_node_nf))
+        loc_mean = _require_cuda_f32("loc_mean", loc_mean, lead + (n0, 3))
+        edge_fea = _require_cuda_f32("edge_fea", edge_fea, lead + (B * N * (N - 1), self.in_edge_nf))
         self._edges.validate(edge_index, B, N, dev)
         tsteps = timesteps_out.to(device=dev, dtype=torch.int64).contiguous()
+        tsteps_in = None
+        if L > 1:
+            if timesteps_in.shape[0] != B:
+                raise ValueError(f"timesteps_in must be [B={B}, {L}], got {tuple(timesteps_in.shape)}")
+            tsteps_in = timesteps_in.to(device=dev, dtype=torch.int64).contiguous()
         cfg = (B, N, T, self.n_layers, self.num_modes if self.use_time_conv else 1, self.in_node_nf, self.in_edge_nf,
-               self.time_emb_dim, 1 if self.use_time_conv else 0)
+               self.time_emb_dim, 1 if self.use_time_conv else 0, L)
         from ._lib import load_library
         from . import _cabi
         import ctypes
@@ -150,4 +165,4 @@ class EGNO(nn.Module):
             from ._lib import check
             check(-1, "EGNO configuration")
         flat, params = self._pack.flat_params(expected, dev)
-        return EgnoFunction.apply(cfg, self.process_group, flat, x, h, edge_fea, v, loc_mean, tsteps, *params)
+        return EgnoFunction.apply(cfg, self.process_group, flat, x, h, edge_fea, v, loc_mean, tsteps, tsteps_in, *params)

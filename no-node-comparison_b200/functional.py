@@ -93,7 +93,7 @@ class EgnoFunction(torch.autograd.Function):
     """x, v, h = EGNO.forward(...)   (reference: EGNO/model/egno.py:37-111)."""
 
     @staticmethod
-    def forward(ctx, cfg_tuple, dp_group, flat, x, nodes, edge_fea, v, loc_mean, tsteps, *params):
+    def forward(ctx, cfg_tuple, dp_group, flat, x, nodes, edge_fea, v, loc_mean, tsteps, tsteps_in, *params):
         lib = load_library()
         cfg = _cabi.NbEgnoConfig(*cfg_tuple)
         dev = x.device
@@ -105,18 +105,18 @@ class EgnoFunction(torch.autograd.Function):
         saved = torch.empty(lib.nb_egno_saved_floats(ctypes.byref(cfg)), device=dev, dtype=torch.float32) if need_grad else None
         ws = torch.empty(lib.nb_egno_workspace_floats(ctypes.byref(cfg), 0), device=dev, dtype=torch.float32)
         check(lib.nb_egno_forward(ctypes.byref(cfg), _ptr(flat), _ptr(x), _ptr(nodes), _ptr(edge_fea), _ptr(v),
-                                  _ptr(loc_mean), _ptr(tsteps), _ptr(x_out), _ptr(v_out), _ptr(h_out), _ptr(saved),
-                                  _ptr(ws), _stream_ptr(dev)), "nb_egno_forward")
+                                  _ptr(loc_mean), _ptr(tsteps), _ptr(tsteps_in), _ptr(x_out), _ptr(v_out), _ptr(h_out),
+                                  _ptr(saved), _ptr(ws), _stream_ptr(dev)), "nb_egno_forward")
         ctx.cfg_tuple = cfg_tuple
         ctx.dp_group = dp_group
         ctx.param_shapes = [p.shape for p in params]
-        ctx.save_for_backward(flat, nodes, edge_fea, loc_mean, tsteps, saved)
+        ctx.save_for_backward(flat, nodes, edge_fea, loc_mean, tsteps, tsteps_in, saved)
         return x_out, v_out, h_out
 
     @staticmethod
     def backward(ctx, gx_out, gv_out, gh_out):
         lib = load_library()
-        flat, nodes, edge_fea, loc_mean, tsteps, saved = ctx.saved_tensors
+        flat, nodes, edge_fea, loc_mean, tsteps, tsteps_in, saved = ctx.saved_tensors
         if saved is None:
             raise RuntimeError("EGNO forward ran without autograd state; cannot run backward")
         cfg = _cabi.NbEgnoConfig(*ctx.cfg_tuple)
@@ -126,11 +126,12 @@ class EgnoFunction(torch.autograd.Function):
         gv_out = None if gv_out is None else gv_out.contiguous()
         gh_out = None if gh_out is None else gh_out.contiguous()
         grad_flat = torch.empty_like(flat)
-        gx_in = torch.empty((n0, 3), device=dev, dtype=torch.float32)
-        gv_in = torch.empty((n0, 3), device=dev, dtype=torch.float32)
+        in_shape = (cfg.num_inputs, n0, 3) if cfg.num_inputs > 1 else (n0, 3)
+        gx_in = torch.empty(in_shape, device=dev, dtype=torch.float32)
+        gv_in = torch.empty(in_shape, device=dev, dtype=torch.float32)
         ws = torch.empty(lib.nb_egno_workspace_floats(ctypes.byref(cfg), 1), device=dev, dtype=torch.float32)
         check(lib.nb_egno_backward(ctypes.byref(cfg), _ptr(flat), _ptr(nodes), _ptr(edge_fea), _ptr(loc_mean),
-                                   _ptr(tsteps), _ptr(saved), _ptr(gx_out), _ptr(gv_out), _ptr(gh_out),
+                                   _ptr(tsteps), _ptr(tsteps_in), _ptr(saved), _ptr(gx_out), _ptr(gv_out), _ptr(gh_out),
                                    _ptr(grad_flat), _ptr(gx_in), _ptr(gv_in), _ptr(ws), _stream_ptr(dev)),
               "nb_egno_backward")
         _maybe_allreduce(grad_flat, ctx.dp_group)
@@ -139,7 +140,7 @@ class EgnoFunction(torch.autograd.Function):
             n = shp.numel()
             grads.append(grad_flat[o:o + n].view(shp))
             o += n
-        return (None, None, None, gx_in, None, None, gv_in, None, None, *grads)
+        return (None, None, None, gx_in, None, None, gv_in, None, None, None, *grads)
 
 
 class SegnoFunction(torch.autograd.Function):

@@ -145,6 +145,64 @@ def egno_forward(p: Dict[str, Tensor], x: Tensor, h: Tensor, row: Tensor, col: T
     return xx, vv, hh
 
 
+def frame_to_input(num_timesteps: int, num_inputs: int):
+    """repeat_elements_to_exact_shape (EGNO/utils.py:115-131): frame t of the T outputs is fed by input
+    min(t // (T // L), L - 1) — every input T // L times, the last one also covers the remainder."""
+    reps = num_timesteps // num_inputs
+    return [min(t // reps, num_inputs - 1) for t in range(num_timesteps)]
+
+
+def egno_forward_multi(p: Dict[str, Tensor], x: Tensor, h: Tensor, row: Tensor, col: Tensor, edge_fea: Tensor,
+                       v: Tensor, loc_mean: Tensor, timesteps_in: Tensor, timesteps_out: Tensor, *, n_layers: int,
+                       num_timesteps: int, time_emb_dim: int = 32) -> Tuple[Tensor, Tensor, Tensor]:
+    """EGNO.forward, EGNO/model/egno.py:37-111, num_inputs > 1.
+
+    x, v, loc_mean [L,BN,3]; h [L,BN,F]; edge_fea [L,E,2]; timesteps_in [B,L]; timesteps_out [B,T]."""
+    T, L = num_timesteps, x.shape[0]
+    nn_ = h.shape[1]
+    ne = row.shape[0]
+    B = timesteps_out.shape[0]
+    tmap = frame_to_input(T, L)
+    ts_in = timesteps_in[:, tmap]                                                  # :45  [B,T]
+    temb_in = timestep_embedding(ts_in, time_emb_dim).to(x.dtype)                 # :46
+    temb_out = timestep_embedding(timesteps_out, time_emb_dim).to(x.dtype)        # :50
+    bc = lambda e: e.transpose(0, 1).unsqueeze(1).repeat(1, nn_ // B, 1, 1).reshape(T, -1, time_emb_dim)  # :66,:69
+    hh = torch.cat([h[tmap], bc(temb_in), bc(temb_out)], dim=-1).reshape(T * nn_, -1)   # :59-61,:70,:74
+    hh = linear(hh, p, "embedding")
+    node_off = (torch.arange(T) * nn_).repeat_interleave(ne)
+    rr = row.repeat(T) + node_off
+    cc = col.repeat(T) + node_off
+    xx = x[tmap].reshape(T * nn_, 3)                                               # :80-83
+    vv = v[tmap].reshape(T * nn_, 3)
+    lm = loc_mean[tmap].reshape(T * nn_, 3)
+    ef = edge_fea[tmap].reshape(T * ne, -1)
+    H = hh.shape[-1]
+    for i in range(n_layers):
+        h3 = hh.view(T, nn_, H)
+        conv = spectral_conv(h3, p[f"time_conv_modules.{i}.t_conv.weights1"])
+        hh = (h3 + torch.nn.functional.leaky_relu(conv, 0.01)).reshape(T * nn_, H)
+        X = torch.stack([xx - lm, vv], dim=-1).view(T, nn_, 3, 2)
+        X = X + spectral_conv(X, p[f"time_conv_x_modules.{i}.t_conv.weights1"])
+        xx = X[..., 0].reshape(T * nn_, 3) + lm
+        vv = X[..., 1].reshape(T * nn_, 3)
+        xx, vv, hh = egnn_layer(p, f"layers.{i}", xx, hh, rr, cc, ef, vv)
+    return xx, vv, hh
+
+
+def egno_features_multi(loc: Tensor, vel: Tensor, charges: Tensor, row: Tensor, col: Tensor):
+    """prepare_inputs, EGNO/main_simulation_simple_no.py:313-327 (num_inputs > 1).
+    loc, vel [L,B,N,3]; charges [B,N,1] -> (loc [L,BN,3], vel, edge_attr [L,E,2], nodes [L,BN,2], loc_mean [L,BN,3])."""
+    L, B, N, _ = loc.shape
+    loc_mean = loc.mean(dim=2, keepdim=True).repeat(1, 1, N, 1).reshape(L, -1, 3)
+    loc = loc.reshape(L, -1, 3)
+    vel = vel.reshape(L, -1, 3)
+    q = charges.reshape(-1, 1)
+    nodes = torch.cat([torch.sqrt((vel ** 2).sum(-1, keepdim=True)), q.repeat(L, 1, 1).reshape(L, -1, 1)], dim=-1)
+    qq = (q[row] * q[col]).unsqueeze(0).repeat(L, 1, 1)
+    dist = ((loc[:, row] - loc[:, col]) ** 2).sum(2, keepdim=True)
+    return loc, vel, torch.cat([qq, dist], 2), nodes, loc_mean
+
+
 # ----------------------------------------------------------------------------- SEGNO pieces
 def segno_gcl(p: Dict[str, Tensor], h: Tensor, row: Tensor, col: Tensor, x: Tensor, v: Tensor,
               edge_attr: Tensor, n_layers: int, recurrent: bool = True,

@@ -75,7 +75,7 @@ def flat_params(weights: dict, order) -> np.ndarray:
     return np.concatenate([np.asarray(weights[k], dtype=np.float32).reshape(-1) for k in order])
 
 
-def egno_run(cfg_kw: dict, params: np.ndarray, x, nodes, edge_fea, v, loc_mean, t_out, Gx=None, Gv=None, Gh=None):
+def egno_run(cfg_kw: dict, params: np.ndarray, x, nodes, edge_fea, v, loc_mean, t_out, Gx=None, Gv=None, Gh=None, t_in=None):
     """forward (+ backward when cotangents are given) through the emulated C ABI."""
     L = lib()
     cfg = cabi.NbEgnoConfig(**cfg_kw)
@@ -89,16 +89,18 @@ def egno_run(cfg_kw: dict, params: np.ndarray, x, nodes, edge_fea, v, loc_mean, 
     ws = np.zeros(L.nb_egno_workspace_floats(ctypes.byref(cfg), 0), np.float32)
     x, nodes, edge_fea, v, loc_mean = f32(x), f32(nodes), f32(edge_fea), f32(v), f32(loc_mean)
     t_out = np.ascontiguousarray(np.asarray(t_out, dtype=np.int64))
+    t_in = None if t_in is None else np.ascontiguousarray(np.asarray(t_in, dtype=np.int64))
     check(L.nb_egno_forward(ctypes.byref(cfg), ptr(params), ptr(x), ptr(nodes), ptr(edge_fea), ptr(v), ptr(loc_mean),
-                            ptr(t_out), ptr(x_out), ptr(v_out), ptr(h_out), ptr(saved), ptr(ws), None))
+                            ptr(t_out), ptr(t_in), ptr(x_out), ptr(v_out), ptr(h_out), ptr(saved), ptr(ws), None))
     res = dict(x_out=x_out, v_out=v_out, h_out=h_out)
     if Gx is not None:
         ws2 = np.zeros(L.nb_egno_workspace_floats(ctypes.byref(cfg), 1), np.float32)
         gp = np.full(npar, np.nan, np.float32)
-        gx = np.zeros((cfg.B * cfg.N, 3), np.float32)
-        gv = np.zeros((cfg.B * cfg.N, 3), np.float32)
+        lead = (cfg.num_inputs,) if cfg.num_inputs > 1 else ()
+        gx = np.zeros(lead + (cfg.B * cfg.N, 3), np.float32)
+        gv = np.zeros(lead + (cfg.B * cfg.N, 3), np.float32)
         check(L.nb_egno_backward(ctypes.byref(cfg), ptr(params), ptr(nodes), ptr(edge_fea), ptr(loc_mean), ptr(t_out),
-                                 ptr(saved), ptr(f32(Gx)), ptr(f32(Gv)), ptr(f32(Gh)), ptr(gp), ptr(gx), ptr(gv),
+                                 ptr(t_in), ptr(saved), ptr(f32(Gx)), ptr(f32(Gv)), ptr(f32(Gh)), ptr(gp), ptr(gx), ptr(gv),
                                  ptr(ws2), None))
         res.update(grad_params=gp, gx_in=gx, gv_in=gv)
     return res

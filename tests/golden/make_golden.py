@@ -84,6 +84,44 @@ def run_egno(ref, name, n_balls, B, T, n_layers, num_modes, frame0=30):
     print(name, "x_out", tuple(xo.shape), "params", sum(p.numel() for p in model.parameters()))
 
 
+def run_egno_multi(ref, name, n_balls, B, T, n_layers, num_modes, num_inputs, var_dt, frames):
+    """num_inputs > 1 (the PRO sweep, _schedule.yaml:38-68): several input frames, optional per-trajectory output times."""
+    np.random.seed(43)
+    loc, vel, q = simulate(ref, "charged", n_balls, B)
+    locL = torch.tensor(loc[:, frames]).transpose(0, 1).contiguous()   # [L,B,N,3]
+    velL = torch.tensor(vel[:, frames]).transpose(0, 1).contiguous()
+    row, col = O.canonical_edges(B, n_balls)
+    x, v, edge_attr, nodes, loc_mean = O.egno_features_multi(locL, velL, torch.tensor(q), row, col)
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref.EGNO(n_layers=n_layers, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, flat=False,
+                         norm=False, num_modes=num_modes, num_timesteps=T, time_emb_dim=32, num_inputs=num_inputs,
+                         varDT=var_dt, device="cpu")
+    gen = torch.Generator().manual_seed(11)
+    t_in = torch.arange(-num_inputs + 1, 1)[None].repeat(B, 1)
+    if var_dt:   # per-trajectory ascending output times (utils.py:15-31 random_ascending_tensor)
+        t_out = torch.stack([torch.sort(torch.randperm(3 * T, generator=gen)[:T] + 1).values for _ in range(B)])
+    else:
+        t_out = torch.arange(1, T + 1)[None].repeat(B, 1)
+    x = x.clone().requires_grad_(True)
+    v = v.clone().requires_grad_(True)
+    xo, vo, ho = model(x, nodes, [row, col], edge_attr, v=v, loc_mean=loc_mean, timesteps_in=t_in, timesteps_out=t_out)
+    gen = torch.Generator().manual_seed(7)
+    Gx, Gv, Gh = cot(xo.shape, gen), cot(vo.shape, gen), cot(ho.shape, gen) * 0.1
+    ((xo * Gx).sum() + (vo * Gv).sum() + (ho * Gh).sum()).backward()
+    out = dict(meta=np.array([n_balls, B, T, n_layers, num_modes, num_inputs], dtype=np.int64),
+               loc=locL.numpy(), vel=velL.numpy(), charges=q, t_out=t_out.numpy(), t_in=t_in.numpy(),
+               x_out=xo.detach().numpy(), v_out=vo.detach().numpy(), h_out=ho.detach().numpy(),
+               Gx=Gx.numpy(), Gv=Gv.numpy(), Gh=Gh.numpy(),
+               gx_in=x.grad.numpy(), gv_in=v.grad.numpy())
+    for k, p in model.state_dict().items():
+        out["w:" + k] = p.numpy()
+    for k, p in model.named_parameters():
+        out["g:" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "x_out", tuple(xo.shape), "params", sum(p.numel() for p in model.parameters()))
+
+
 def run_segno(ref, name, kind, n_balls, B, T, frame0):
     np.random.seed(43)
     loc, vel, q = simulate(ref, kind, n_balls, B)
@@ -119,6 +157,10 @@ def main():
     run_egno(ref, "egno_n20_t10", n_balls=20, B=2, T=10, n_layers=4, num_modes=2)
     run_egno(ref, "egno_n5_t6_m4", n_balls=5, B=3, T=6, n_layers=2, num_modes=4)   # modes == T//2+1 (Nyquist)
     run_egno(ref, "egno_n7_t10_m5", n_balls=7, B=2, T=10, n_layers=1, num_modes=5)
+    run_egno_multi(ref, "egno_n5_t10_in3", n_balls=5, B=3, T=10, n_layers=2, num_modes=2, num_inputs=3, var_dt=False,
+                   frames=[26, 28, 30])
+    run_egno_multi(ref, "egno_n5_t8_in2_vardt", n_balls=5, B=4, T=8, n_layers=2, num_modes=2, num_inputs=2, var_dt=True,
+                   frames=[25, 30])
     run_segno(ref, "segno_n5_t10", "charged", n_balls=5, B=4, T=10, frame0=30)
     run_segno(ref, "segno_n20_t10_gravity", "gravity", n_balls=20, B=2, T=10, frame0=0)
 

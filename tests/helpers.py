@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 EGNO_CASES = ["egno_n5_t8", "egno_n20_t10", "egno_n5_t6_m4", "egno_n7_t10_m5"]
+EGNO_MULTI_CASES = ["egno_n5_t10_in3", "egno_n5_t8_in2_vardt"]   # num_inputs > 1 (and per-trajectory output times)
 SEGNO_CASES = ["segno_n5_t10", "segno_n20_t10_gravity"]
 
 
@@ -43,6 +44,16 @@ def egno_inputs_from_case(d):
                                                        torch.tensor(d["charges"]), row, col)
     return dict(n=n, B=B, T=T, L=L, modes=modes, row=row, col=col, x=x, v=v, edge_attr=edge_attr, nodes=nodes,
                 loc_mean=loc_mean, t_out=torch.tensor(d["t_out"]))
+
+
+def egno_multi_inputs_from_case(d):
+    n, B, T, L, modes, nin = [int(v) for v in d["meta"]]
+    row, col = O.canonical_edges(B, n)
+    x, v, edge_attr, nodes, loc_mean = O.egno_features_multi(torch.tensor(d["loc"]), torch.tensor(d["vel"]),
+                                                             torch.tensor(d["charges"]), row, col)
+    return dict(n=n, B=B, T=T, L=L, modes=modes, num_inputs=nin, row=row, col=col, x=x.contiguous(), v=v.contiguous(),
+                edge_attr=edge_attr.contiguous(), nodes=nodes.contiguous(), loc_mean=loc_mean.contiguous(),
+                t_out=torch.tensor(d["t_out"]), t_in=torch.tensor(d["t_in"]))
 
 
 def segno_inputs_from_case(d):

@@ -7,7 +7,8 @@ import torch
 
 from oracle import nbody_oracle as O
 from tests import emu_harness as E
-from tests.helpers import load_case, egno_inputs_from_case, segno_inputs_from_case, rel_err
+from tests.helpers import (load_case, egno_inputs_from_case, egno_multi_inputs_from_case, segno_inputs_from_case, rel_err,
+                           EGNO_MULTI_CASES)
 
 TOL = 2e-5  # fp32 kernels vs fp32 reference: summation-order noise only
 
@@ -32,6 +33,22 @@ def test_egno_emulated_kernels_match_reference_golden(name):
                time_emb_dim=32, use_time_conv=1)
     r = E.egno_run(cfg, params, c["x"].numpy(), c["nodes"].numpy(), c["edge_attr"].numpy(), c["v"].numpy(),
                    c["loc_mean"].numpy(), c["t_out"].numpy(), d["Gx"], d["Gv"], d["Gh"])
+    for k in ("x_out", "v_out", "h_out", "gx_in", "gv_in"):
+        assert rel_err(torch.tensor(r[k]), torch.tensor(d[k])) < TOL, k
+    _check_grads(r, w, g, order)
+
+
+@pytest.mark.parametrize("name", EGNO_MULTI_CASES)
+def test_egno_multi_input_emulated_kernels_match_reference_golden(name):
+    """num_inputs > 1 (egno.py:42-47,59-61,68-70,79-86) and per-trajectory output times (varDT) against the reference."""
+    d, w, g = load_case(name)
+    c = egno_multi_inputs_from_case(d)
+    order = list(w.keys())
+    params = E.flat_params({k: v.numpy() for k, v in w.items()}, order)
+    cfg = dict(B=c["B"], N=c["n"], T=c["T"], n_layers=c["L"], num_modes=c["modes"], in_node_nf=2, in_edge_nf=2,
+               time_emb_dim=32, use_time_conv=1, num_inputs=c["num_inputs"])
+    r = E.egno_run(cfg, params, c["x"].numpy(), c["nodes"].numpy(), c["edge_attr"].numpy(), c["v"].numpy(),
+                   c["loc_mean"].numpy(), c["t_out"].numpy(), d["Gx"], d["Gv"], d["Gh"], t_in=c["t_in"].numpy())
     for k in ("x_out", "v_out", "h_out", "gx_in", "gv_in"):
         assert rel_err(torch.tensor(r[k]), torch.tensor(d[k])) < TOL, k
     _check_grads(r, w, g, order)

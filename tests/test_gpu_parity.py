@@ -20,8 +20,8 @@ import torch
 import no_node_comparison_b200 as nb
 from no_node_comparison_b200 import synth
 from oracle import nbody_oracle as O
-from tests.helpers import (EGNO_CASES, SEGNO_CASES, load_case, rel_err, rel_l2, egno_inputs_from_case,
-                           segno_inputs_from_case)
+from tests.helpers import (EGNO_CASES, EGNO_MULTI_CASES, SEGNO_CASES, load_case, rel_err, rel_l2, egno_inputs_from_case,
+                           egno_multi_inputs_from_case, segno_inputs_from_case)
 
 pytestmark = pytest.mark.gpu
 TOL_OUT = 1e-4
@@ -64,6 +64,35 @@ def test_egno_matches_reference_golden(name):
     loss = (xo * torch.tensor(dd["Gx"], device=d)).sum() + (vo * torch.tensor(dd["Gv"], device=d)).sum() + \
         (ho * torch.tensor(dd["Gh"], device=d)).sum()
     loss.backward()
+    assert rel_err(x.grad.cpu(), torch.tensor(dd["gx_in"])) < TOL_GRAD
+    assert rel_err(v.grad.cpu(), torch.tensor(dd["gv_in"])) < TOL_GRAD
+    for k, p in m.named_parameters():
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g[k])
+        assert rel_err(got, g[k]) < TOL_GRAD, k
+
+
+@pytest.mark.parametrize("name", EGNO_MULTI_CASES)
+def test_egno_multi_input_matches_reference_golden(name):
+    """num_inputs > 1 (several input frames, a second time embedding, per-frame edge features) and per-trajectory output
+    times (varDT), the PRO half of the reference's sweep (_schedule.yaml:38-68): golden vectors of the real reference."""
+    dd, w, g = load_case(name)
+    c = egno_multi_inputs_from_case(dd)
+    d = dev()
+    torch.manual_seed(1)
+    m = nb.EGNO(n_layers=c["L"], in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=c["modes"],
+                num_timesteps=c["T"], num_inputs=c["num_inputs"], device=d)
+    m.load_state_dict(w)
+    x = c["x"].to(d).requires_grad_(True)
+    v = c["v"].to(d).requires_grad_(True)
+    xo, vo, ho = m(x, c["nodes"].to(d), [c["row"].to(d), c["col"].to(d)], c["edge_attr"].to(d), v=v,
+                   loc_mean=c["loc_mean"].to(d), timesteps_in=c["t_in"].to(d), timesteps_out=c["t_out"].to(d))
+    assert rel_err(xo.cpu(), torch.tensor(dd["x_out"])) < TOL_OUT
+    assert rel_err(vo.cpu(), torch.tensor(dd["v_out"])) < TOL_OUT
+    assert rel_err(ho.cpu(), torch.tensor(dd["h_out"])) < TOL_OUT
+    loss = (xo * torch.tensor(dd["Gx"], device=d)).sum() + (vo * torch.tensor(dd["Gv"], device=d)).sum() + \
+        (ho * torch.tensor(dd["Gh"], device=d)).sum()
+    loss.backward()
+    assert x.grad.shape == x.shape and v.grad.shape == v.shape
     assert rel_err(x.grad.cpu(), torch.tensor(dd["gx_in"])) < TOL_GRAD
     assert rel_err(v.grad.cpu(), torch.tensor(dd["gv_in"])) < TOL_GRAD
     for k, p in m.named_parameters():

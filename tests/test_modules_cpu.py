@@ -67,8 +67,10 @@ def test_unsupported_configurations_raise():
         _egno(hidden_nf=32)
     with pytest.raises(ValueError):
         _egno(with_v=False)
-    with pytest.raises(NotImplementedError):
-        _egno(num_inputs=2)
+    with pytest.raises(ValueError):
+        _egno(num_inputs=0)
+    # several input frames: two time embeddings feed the embedding Linear (egno.py:13-16)
+    assert _egno(num_inputs=2).embedding.weight.shape == (64, 2 + 2 * 32)
     with pytest.raises(ValueError):
         nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, tanh=True)
 
