@@ -64,6 +64,9 @@ typedef struct NbSegnoConfig {
   int32_t in_edge_nf;   /* 2 */
   int32_t recurrent;    /* h += phi_h(...) (gcl.py:93-94) */
   float coords_weight;  /* gcl.py:102 */
+  int32_t h_given;      /* 0: `his` are raw node features, embedded inside (single-input forward, model.py:73);
+                           1: `his` IS the hidden state h0[BN,64] of forward_step (the segments of the multi-input forward,
+                              model.py:79-90): no embedding, and the backward returns dL/dh0 in g_h_in */
 } NbSegnoConfig;
 
 int nb_version(void);
@@ -127,7 +130,7 @@ int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, const float*
 
 int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, const float* his, const float* edge_attr,
                       const float* saved, const float* g_x_out, const float* g_h_out, const float* g_v_out,
-                      float* grad_params, float* g_x_in, float* g_v_in, float* workspace, void* stream);
+                      float* grad_params, float* g_x_in, float* g_v_in, float* g_h_in, float* workspace, void* stream);
 
 /* Validates that (row, col) is the canonical fully connected list for B graphs of N bodies.
  * Writes 0 to *flag_dev if so, else the (1-based) index of a mismatching edge.  No host sync. */

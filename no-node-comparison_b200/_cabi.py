@@ -14,7 +14,8 @@ class NbEgnoConfig(C.Structure):
 
 class NbSegnoConfig(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("in_node_nf", C.c_int32),
-                ("in_edge_nf", C.c_int32), ("recurrent", C.c_int32), ("coords_weight", C.c_float)]
+                ("in_edge_nf", C.c_int32), ("recurrent", C.c_int32), ("coords_weight", C.c_float),
+                ("h_given", C.c_int32)]
 
 
 EXPORTS = {
@@ -29,7 +30,7 @@ EXPORTS = {
     "nb_egno_forward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 14),
     "nb_egno_backward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 15),
     "nb_segno_forward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 11),
-    "nb_segno_backward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 12),
+    "nb_segno_backward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 13),
     "nb_check_canonical_edges": (C.c_int, [c_f, c_f, C.c_int64, C.c_int32, C.c_int32, c_f, c_f]),
     "nb_egcl_edge_forward": (C.c_int, [C.c_int32] * 5 + [c_f] * 5 + [C.c_int32] * 3 + [c_f] * 9),
     "nb_egcl_edge_backward_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32]),

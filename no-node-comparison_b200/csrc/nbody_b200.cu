@@ -1310,12 +1310,14 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
     NbEdgeGeom fg = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
     if (g_segno_fused && g_edge_impl == 2 && g_node_impl == 1 && sel_geom(fg) && !fg.blk) {
       // embedding into scratch (the fused kernel writes h_k of every sub-step into `saved` itself)
-      NbEmbedArgs e;
-      segno_embed_args(X, his, &e);
-      e.out = P;
-      const size_t esm = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
-      NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, esm, stream, e);
-      NB_TRY(nb_check_launch("k_embed_fwd"));
+      if (!cfg->h_given) {
+        NbEmbedArgs e;
+        segno_embed_args(X, his, &e);
+        e.out = P;
+        const size_t esm = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
+        NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, esm, stream, e);
+        NB_TRY(nb_check_launch("k_embed_fwd"));
+      }
       NbSegnoFusedArgs fa;
       memset(&fa, 0, sizeof(fa));
       fa.g = fg; fa.T = T; fa.recurrent = cfg->recurrent; fa.inv_T = (float)(1.0 / (double)T); fa.cw = cfg->coords_weight;
@@ -1323,7 +1325,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
       fa.W2 = params + X.lo.e_w2; fa.b2 = params + X.lo.e_b2; fa.W3 = params + X.lo.c_w1; fa.b3 = params + X.lo.c_b1;
       fa.w4 = params + X.lo.c_w2; fa.b4 = params + X.lo.c_b2;
       fa.W5 = params + X.lo.n_w1; fa.b5 = params + X.lo.n_b1; fa.W6 = params + X.lo.n_w2; fa.b6 = params + X.lo.n_b2;
-      fa.h_in = P; fa.x_in = x; fa.v_in = v; fa.ef = edge_attr;
+      fa.h_in = cfg->h_given ? his : P; fa.x_in = x; fa.v_in = v; fa.ef = edge_attr;
       fa.h_out = h_out; fa.x_out = x_out; fa.v_out = v_out; fa.saved = saved; fa.iter_stride = itf;
       const size_t fsm = NB_SEGNO_FUSED_SMEM(fg.G * fg.EPG);
       NB_SET_SMEM(k_segno_fused_fwd, fsm);
@@ -1336,12 +1338,16 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
 #endif
   SegnoIterBufs b0 = bufs(0);
   {
-    NbEmbedArgs e;
-    segno_embed_args(X, his, &e);
-    e.out = b0.h;
-    const size_t smem = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
-    NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
-    NB_TRY(nb_check_launch("k_embed_fwd"));
+    if (cfg->h_given) {
+      cudaMemcpyAsync(b0.h, his, Nn * NB_H * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+    } else {
+      NbEmbedArgs e;
+      segno_embed_args(X, his, &e);
+      e.out = b0.h;
+      const size_t smem = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
+      NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(Nn, 4), 8 * nb_num_sms()), 256, smem, stream, e);
+      NB_TRY(nb_check_launch("k_embed_fwd"));
+    }
     cudaMemcpyAsync(b0.x, x, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, cst);
   }
   const float* vcur = v;
@@ -1381,7 +1387,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
 extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, const float* his,
                                  const float* edge_attr, const float* saved, const float* g_x_out,
                                  const float* g_h_out, const float* g_v_out, float* grad_params, float* g_x_in,
-                                 float* g_v_in, float* workspace, void* stream) {
+                                 float* g_v_in, float* g_h_in, float* workspace, void* stream) {
   NB_TRY(segno_validate(cfg));
   if (!saved) { nb_set_error("nb_segno_backward needs the saved buffer of a forward call"); return NB_ERR_INVALID; }
   SegnoCtx X;
@@ -1469,6 +1475,10 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     gh_in = gh_new;
     ghi ^= 1;
   }
+  if (cfg->h_given) {
+    NB_TRY(q_flush(stream));
+    if (g_h_in) cudaMemcpyAsync(g_h_in, gh_in, Nn * NB_H * sizeof(float), cudaMemcpyDeviceToDevice, cst);
+  } else
   {
     NbEmbedBwdArgs eb;
     memset(&eb, 0, sizeof(eb));

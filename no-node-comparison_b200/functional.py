@@ -40,13 +40,14 @@ class _ParamPack:
     the order of named_parameters()).  The views survive optimizer steps and load_state_dict (both
     in-place); `.to()` / `.cuda()` replace parameter storage, which is detected and re-flattened."""
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, skip_prefix: Optional[str] = None):
         self.module = module
+        self.skip_prefix = skip_prefix      # parameters outside the C layout (kept as ordinary torch parameters)
         self.flat: Optional[torch.Tensor] = None
         self.offsets: List[int] = []
 
     def params(self) -> List[torch.nn.Parameter]:
-        return [p for _, p in self.module.named_parameters()]
+        return [p for k, p in self.module.named_parameters() if not (self.skip_prefix and k.startswith(self.skip_prefix))]
 
     def _views_ok(self, ps) -> bool:
         f = self.flat
@@ -183,9 +184,10 @@ class SegnoFunction(torch.autograd.Function):
         gx_in = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         gv_in = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 1), device=dev, dtype=torch.float32)
+        gh_in = torch.empty((Nn, 64), device=dev, dtype=torch.float32) if cfg.h_given else None
         check(lib.nb_segno_backward(ctypes.byref(cfg), _ptr(flat), _ptr(his), _ptr(edge_attr), _ptr(saved),
                                     _ptr(gx_out), _ptr(gh_out), _ptr(gv_out), _ptr(grad_flat), _ptr(gx_in),
-                                    _ptr(gv_in), _ptr(ws), _stream_ptr(dev)), "nb_segno_backward")
+                                    _ptr(gv_in), _ptr(gh_in), _ptr(ws), _stream_ptr(dev)), "nb_segno_backward")
         _maybe_allreduce(grad_flat, ctx.dp_group)
         grads, o = [], 0
         for shp in ctx.param_shapes:
@@ -195,7 +197,9 @@ class SegnoFunction(torch.autograd.Function):
         # coord_mlp_vel (the last four tensors) never enters the computation: its gradients are None in the reference
         # (gcl.py:64-67 builds it, forward never calls it), so optimizers leave it untouched
         grads[-4:] = [None] * 4
-        return (None, None, None, None, gx_in, gv_in, None, *grads)
+        if cfg.h_given:   # a segment of the multi-input forward: `his` is the hidden state, the embedding is outside
+            grads[0] = grads[1] = None
+        return (None, None, None, gh_in, gx_in, gv_in, None, *grads)
 
 
 class _EdgeCache:

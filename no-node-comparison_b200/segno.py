@@ -31,6 +31,18 @@ class _GCLHolder(nn.Module):
         self.n_layers = 8
 
 
+class InvariantTemporalAttention(nn.Module):
+    """model.py:127-139: softmax over the frames of an MLP on (|v|, h).  Per-node, two frames: plain torch."""
+
+    def __init__(self, in_dim, hidden_dim=32):
+        super().__init__()
+        self.attn_mlp = nn.Sequential(nn.Linear(in_dim + 1, hidden_dim), nn.Tanh(), nn.Linear(hidden_dim, 1))
+
+    def forward(self, vel_seq, his_seq):
+        speed = vel_seq.norm(dim=-1, keepdim=True)
+        return self.attn_mlp(torch.cat([speed, his_seq], dim=-1)).softmax(dim=1)
+
+
 class SEGNO(nn.Module):
     def __init__(self, in_node_nf, in_edge_nf, hidden_nf, device='cpu', act_fn=nn.SiLU(), n_layers=4, coords_weight=1.0,
                  recurrent=False, norm_diff=False, tanh=False, invariant=True, norm_vel=True, varDT=False,
@@ -42,11 +54,13 @@ class SEGNO(nn.Module):
             raise ValueError("only the SiLU activation (reference default) is implemented")
         if tanh:
             raise ValueError("tanh=True (gcl.py:57-59) is not implemented (model_confs.yaml:27 uses False)")
-        if multiple_agg is not None:
-            raise NotImplementedError("multi-input SEGNO (multiple_agg, model.py:70-90,105-139) is not implemented yet")
+        if multiple_agg not in (None, 'sum', 'attn'):
+            raise ValueError(f"multiple_agg must be None, 'sum' or 'attn' (model.py:82-90), got {multiple_agg!r}")
         self.hidden_nf = hidden_nf
         self.varDT = varDT
         self.multiple_agg = multiple_agg
+        if multiple_agg == 'attn':   # registered (and initialised) before everything else, as in model.py:14-15
+            self.enc_attn_net = InvariantTemporalAttention(hidden_nf, hidden_dim=hidden_nf)
         self.device = device
         self.n_layers = n_layers
         self.in_node_nf = in_node_nf
@@ -59,7 +73,7 @@ class SEGNO(nn.Module):
         self.module = _GCLHolder(hidden_nf, in_edge_nf, act_fn)
         self.module.n_layers = n_layers
         self.to(self.device)
-        self._pack = _ParamPack(self)
+        self._pack = _ParamPack(self, skip_prefix="enc_attn_net")   # the C layout: embedding + module
         self._edges = _EdgeCache()
         self.process_group = None
 
@@ -71,15 +85,52 @@ class SEGNO(nn.Module):
 
     def forward(self, his, x, edges, v, edge_attr, T=10, in_steps=None):
         if x.dim() == 3:
-            raise NotImplementedError("multi-input SEGNO (x of shape [BN, n_inputs, 3]) is not implemented yet")
-        if edge_attr.requires_grad or his.requires_grad:
+            return self._forward_multi(his, x, edges, v, edge_attr, int(T), in_steps)
+        return self._segment(his, x, edges, v, edge_attr, int(T), h_given=False)
+
+    def _forward_multi(self, his, x, edges, v, edge_attr, T, in_steps):
+        """Several input frames (model.py:65-90): integrate from frame i to frame i+1 (`diff(in_steps)` sub-steps),
+        merge the result with the observed frame ('sum': add; 'attn': invariant temporal attention over the pair,
+        model.py:105-139), and finally integrate T sub-steps from the last frame.  The integration segments are the
+        fused CUDA path; the embedding Linear and the (tiny, per-node) merges are ordinary torch ops.  Returns the
+        integrated state of the last segment (the intended semantics, see the module docstring)."""
+        if in_steps is None or x.shape[1] < 2:
+            raise ValueError("multi-input SEGNO needs x, v, his of shape [BN, n_inputs >= 2, .] and in_steps [n_inputs]")
+        if self.multiple_agg is None:
+            raise ValueError("multi-input SEGNO needs multiple_agg='sum' or 'attn' (main.py:110-114)")
+        if self.process_group is not None:
+            raise NotImplementedError("data-parallel multi-input SEGNO: the torch-side parameters (embedding, attention) "
+                                      "are not part of the flat-bucket all-reduce yet")
+        steps = torch.diff(torch.as_tensor(in_steps).cpu()).tolist() + [T]
+        if len(steps) != x.shape[1]:
+            raise ValueError(f"in_steps has {len(steps)} entries for {x.shape[1]} input frames")
+        h = self.embedding(his)                       # [BN, L, H]
+        h_, x_, v_ = h[:, 0, :], x[:, 0, :], v[:, 0, :]
+        out = None
+        for i, step in enumerate(steps):
+            xi, hi, vi = self._segment(h_.contiguous(), x_.contiguous(), edges, v_.contiguous(), edge_attr, int(step),
+                                       h_given=True)
+            out = (xi, hi, vi)
+            if i < len(steps) - 1:
+                if self.multiple_agg == 'sum':
+                    h_, x_, v_ = h[:, i + 1, :] + hi, x[:, i + 1, :] + xi, v[:, i + 1, :] + vi
+                else:
+                    hs = torch.stack([h[:, i + 1, :], hi], dim=1)
+                    xs = torch.stack([x[:, i + 1, :], xi], dim=1)
+                    vs = torch.stack([v[:, i + 1, :], vi], dim=1)
+                    attn = self.enc_attn_net(vs, hs)                                   # [BN, 2, 1]
+                    x_, v_, h_ = (attn * xs).sum(1), (attn * vs).sum(1), (attn * hs).sum(1)
+        return out
+
+    def _segment(self, his, x, edges, v, edge_attr, T, h_given):
+        if edge_attr.requires_grad or (his.requires_grad and not h_given):
             raise ValueError("gradients w.r.t. his / edge_attr are not implemented (the reference callers detach them)")
         T = int(T)
         n0 = x.shape[0]
         dev = x.device
         x = _require_cuda_f32("x", x, (n0, 3))
         v = _require_cuda_f32("v", v, (n0, 3))
-        his = _require_cuda_f32("his", his, (n0, self.in_node_nf))
+        his = _require_cuda_f32("his", his, (n0, _HIDDEN if h_given else self.in_node_nf))
         E = edge_attr.shape[0]
         # E = B*N*(N-1) and n0 = B*N  ->  N - 1 = E / n0
         if n0 == 0 or E % n0 != 0:
@@ -93,7 +144,8 @@ class SEGNO(nn.Module):
         # forward_step mutates these on every call (model.py:96-97)
         self.module.n_layers = T
         self.n_layers = T
-        cfg = (B, N, T, self.in_node_nf, self.in_edge_nf, 1 if self.recurrent else 0, float(self.coords_weight))
+        cfg = (B, N, T, self.in_node_nf, self.in_edge_nf, 1 if self.recurrent else 0, float(self.coords_weight),
+               1 if h_given else 0)
         from ._lib import load_library, check
         from . import _cabi
         import ctypes

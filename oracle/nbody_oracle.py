@@ -236,6 +236,46 @@ def segno_forward(p: Dict[str, Tensor], his: Tensor, x: Tensor, row: Tensor, col
     return x, h, v
 
 
+def segno_forward_multi(p: Dict[str, Tensor], his: Tensor, x: Tensor, row: Tensor, col: Tensor, v: Tensor,
+                        edge_attr: Tensor, T: int, in_steps, multiple_agg: str, recurrent: bool = True
+                        ) -> Tuple[Tensor, Tensor, Tensor]:
+    """The intended multi-input SEGNO forward (SEGNO/models/model.py:65-90 with :105-139): his [BN,L,F], x, v [BN,L,3].
+    Integrate `diff(in_steps)` sub-steps between consecutive input frames, merge the prediction with the observed frame
+    ('sum': add, 'attn': InvariantTemporalAttention over the pair), then T sub-steps from the last frame; returns the
+    integrated state of the last segment (HEAD returns the segment's *inputs*)."""
+    steps = torch.diff(torch.as_tensor(in_steps)).tolist() + [T]
+    h = linear(his, p, "embedding")                                   # :73
+    h_, x_, v_ = h[:, 0, :], x[:, 0, :], v[:, 0, :]
+    xi = hi = vi = None
+    for i, step in enumerate(steps):
+        hi, xi, vi = h_, x_, v_
+        for _ in range(int(step)):                                    # forward_step, :95-102
+            hi, xi, vi = segno_gcl(p, hi, row, col, xi, vi, edge_attr, n_layers=int(step), recurrent=recurrent)
+        if i < len(steps) - 1:
+            if multiple_agg == "sum":                                 # :83-86
+                h_, x_, v_ = h[:, i + 1, :] + hi, x[:, i + 1, :] + xi, v[:, i + 1, :] + vi
+            else:                                                     # :87-90, :105-139
+                hs = torch.stack([h[:, i + 1, :], hi], dim=1)
+                xs = torch.stack([x[:, i + 1, :], xi], dim=1)
+                vs = torch.stack([v[:, i + 1, :], vi], dim=1)
+                feats = torch.cat([vs.norm(dim=-1, keepdim=True), hs], dim=-1)
+                a = linear(torch.tanh(linear(feats, p, "enc_attn_net.attn_mlp.0")), p, "enc_attn_net.attn_mlp.2").softmax(dim=1)
+                x_, v_, h_ = (a * xs).sum(1), (a * vs).sum(1), (a * hs).sum(1)
+    return xi, hi, vi
+
+
+def segno_features_multi(loc: Tensor, vel: Tensor, charges: Tensor, row: Tensor, col: Tensor):
+    """SEGNO/train_nbody.py:110-118 (several input frames): loc, vel [L,B,N,3] -> his [BN,L,1], x, v [BN,L,3],
+    edge_attr [E,2] (charge products and squared distances of the LAST input frame)."""
+    L, B, N, _ = loc.shape
+    x = loc.reshape(L, B * N, 3).transpose(0, 1).contiguous()
+    v = vel.reshape(L, B * N, 3).transpose(0, 1).contiguous()
+    q = charges.reshape(-1, 1)
+    his = torch.sqrt((v ** 2).sum(-1, keepdim=True))
+    dist = ((x[row, -1, :] - x[col, -1, :]) ** 2).sum(1, keepdim=True)
+    return his, x, v, torch.cat([q[row] * q[col], dist], 1)
+
+
 # ----------------------------------------------------------------------------- featurisation (callers)
 def egno_features(loc: Tensor, vel: Tensor, charges: Tensor, row: Tensor, col: Tensor
                   ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:

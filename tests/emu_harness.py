@@ -127,6 +127,6 @@ def segno_run(cfg_kw: dict, params: np.ndarray, his, x, v, edge_attr, Gx=None, G
         gx = np.zeros((Nn, 3), np.float32)
         gv = np.zeros((Nn, 3), np.float32)
         check(L.nb_segno_backward(ctypes.byref(cfg), ptr(params), ptr(his), ptr(edge_attr), ptr(saved), ptr(f32(Gx)),
-                                  ptr(f32(Gh)), ptr(f32(Gv)), ptr(gp), ptr(gx), ptr(gv), ptr(ws2), None))
+                                  ptr(f32(Gh)), ptr(f32(Gv)), ptr(gp), ptr(gx), ptr(gv), None, ptr(ws2), None))
         res.update(grad_params=gp, gx_in=gx, gv_in=gv)
     return res

@@ -149,6 +149,49 @@ def run_segno(ref, name, kind, n_balls, B, T, frame0):
     print(name, "x_out", tuple(xo.shape), "params", sum(p.numel() for p in model.parameters()))
 
 
+def run_segno_multi(ref, name, n_balls, B, T, frames, agg):
+    """Several input frames (model.py:65-90).  HEAD's forward returns the last segment's inputs; the
+    vectors pin the intended result, computed with the reference's own forward_step / prepare_node_inputs."""
+    np.random.seed(43)
+    loc, vel, q = simulate(ref, "charged", n_balls, B)
+    locL = torch.tensor(loc[:, frames]).transpose(0, 1).contiguous()
+    velL = torch.tensor(vel[:, frames]).transpose(0, 1).contiguous()
+    row, col = O.canonical_edges(B, n_balls)
+    his, x, v, edge_attr = O.segno_features_multi(locL, velL, torch.tensor(q), row, col)
+    torch.manual_seed(1)
+    model = ref.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device="cpu", n_layers=8, recurrent=True,
+                      norm_diff=False, tanh=False, multiple_agg=agg)
+    in_steps = torch.tensor([f - frames[0] for f in frames])
+    x = x.clone().requires_grad_(True)
+    v = v.clone().requires_grad_(True)
+    steps = torch.diff(in_steps).tolist() + [T]
+    h = model.embedding(his)
+    h_, x_, v_ = h[:, 0, :], x[:, 0, :], v[:, 0, :]
+    for i, step in enumerate(steps):
+        xi, hi, vi = model.forward_step(h_, x_, [row, col], v_, edge_attr, T=step)
+        if i < len(steps) - 1:
+            if agg == "sum":
+                h_, x_, v_ = h[:, i + 1, :] + hi, x[:, i + 1, :] + xi, v[:, i + 1, :] + vi
+            else:
+                x_, v_, h_ = model.prepare_node_inputs(torch.stack([x[:, i + 1, :], xi], dim=1),
+                                                       torch.stack([v[:, i + 1, :], vi], dim=1),
+                                                       torch.stack([h[:, i + 1, :], hi], dim=1))
+    xo, ho, vo = xi, hi, vi
+    gen = torch.Generator().manual_seed(7)
+    Gx, Gv, Gh = cot(xo.shape, gen), cot(vo.shape, gen), cot(ho.shape, gen) * 0.1
+    ((xo * Gx).sum() + (vo * Gv).sum() + (ho * Gh).sum()).backward()
+    out = dict(meta=np.array([n_balls, B, T, len(frames)], dtype=np.int64), loc=locL.numpy(), vel=velL.numpy(), charges=q,
+               in_steps=in_steps.numpy(), agg=np.array([0 if agg == "sum" else 1]),
+               x_out=xo.detach().numpy(), v_out=vo.detach().numpy(), h_out=ho.detach().numpy(),
+               Gx=Gx.numpy(), Gv=Gv.numpy(), Gh=Gh.numpy(), gx_in=x.grad.numpy(), gv_in=v.grad.numpy())
+    for k, p in model.state_dict().items():
+        out["w:" + k] = p.numpy()
+    for k, p in model.named_parameters():
+        out["g:" + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "x_out", tuple(xo.shape), "params", sum(p.numel() for p in model.parameters()))
+
+
 def main():
     ref = ref_loader.load_reference()
     torch.set_num_threads(4)
@@ -163,6 +206,8 @@ def main():
                    frames=[25, 30])
     run_segno(ref, "segno_n5_t10", "charged", n_balls=5, B=4, T=10, frame0=30)
     run_segno(ref, "segno_n20_t10_gravity", "gravity", n_balls=20, B=2, T=10, frame0=0)
+    run_segno_multi(ref, "segno_n5_t6_in3_attn", n_balls=5, B=3, T=6, frames=[24, 27, 30], agg="attn")
+    run_segno_multi(ref, "segno_n5_t5_in2_sum", n_balls=5, B=4, T=5, frames=[26, 30], agg="sum")
 
 
 if __name__ == "__main__":

@@ -56,6 +56,18 @@ def egno_multi_inputs_from_case(d):
                 t_out=torch.tensor(d["t_out"]), t_in=torch.tensor(d["t_in"]))
 
 
+SEGNO_MULTI_CASES = ["segno_n5_t6_in3_attn", "segno_n5_t5_in2_sum"]
+
+
+def segno_multi_inputs_from_case(d):
+    n, B, T, L = [int(v) for v in d["meta"]]
+    row, col = O.canonical_edges(B, n)
+    his, x, v, edge_attr = O.segno_features_multi(torch.tensor(d["loc"]), torch.tensor(d["vel"]),
+                                                  torch.tensor(d["charges"]), row, col)
+    return dict(n=n, B=B, T=T, L=L, row=row, col=col, his=his, x=x, v=v, edge_attr=edge_attr,
+                in_steps=torch.tensor(d["in_steps"]), agg="sum" if int(d["agg"][0]) == 0 else "attn")
+
+
 def segno_inputs_from_case(d):
     n, B, T = [int(v) for v in d["meta"]]
     row, col = O.canonical_edges(B, n)

@@ -20,8 +20,9 @@ import torch
 import no_node_comparison_b200 as nb
 from no_node_comparison_b200 import synth
 from oracle import nbody_oracle as O
-from tests.helpers import (EGNO_CASES, EGNO_MULTI_CASES, SEGNO_CASES, load_case, rel_err, rel_l2, egno_inputs_from_case,
-                           egno_multi_inputs_from_case, segno_inputs_from_case)
+from tests.helpers import (EGNO_CASES, EGNO_MULTI_CASES, SEGNO_CASES, SEGNO_MULTI_CASES, load_case, rel_err, rel_l2,
+                           egno_inputs_from_case, egno_multi_inputs_from_case, segno_inputs_from_case,
+                           segno_multi_inputs_from_case)
 
 pytestmark = pytest.mark.gpu
 TOL_OUT = 1e-4
@@ -559,3 +560,32 @@ def test_flat_adam_matches_torch_adam_and_skips_inert_parameters():
             assert p.grad is None and torch.equal(p.detach(), before[k]), k
         else:
             assert p.grad is not None and not torch.equal(p.detach(), before[k]), k
+
+
+@pytest.mark.parametrize("name", SEGNO_MULTI_CASES)
+def test_segno_multi_input_matches_reference_golden(name):
+    """Several input frames (model.py:65-90): CUDA integration segments (hidden state handed in, dL/dh handed back)
+    composed with the torch-side embedding and 'sum' / attention merges, against golden vectors of the reference."""
+    dd, w, g = load_case(name)
+    c = segno_multi_inputs_from_case(dd)
+    d = dev()
+    torch.manual_seed(1)
+    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True, multiple_agg=c["agg"])
+    assert [k for k, _ in m.named_parameters()] == list(w.keys())
+    m.load_state_dict(w)
+    x = c["x"].to(d).requires_grad_(True)
+    v = c["v"].to(d).requires_grad_(True)
+    xo, ho, vo = m(c["his"].to(d), x, [c["row"], c["col"]], v, c["edge_attr"].to(d), T=c["T"], in_steps=c["in_steps"])
+    assert rel_err(xo.cpu(), torch.tensor(dd["x_out"])) < TOL_OUT
+    assert rel_err(vo.cpu(), torch.tensor(dd["v_out"])) < TOL_OUT
+    assert rel_err(ho.cpu(), torch.tensor(dd["h_out"])) < TOL_OUT
+    loss = (xo * torch.tensor(dd["Gx"], device=d)).sum() + (vo * torch.tensor(dd["Gv"], device=d)).sum() + \
+        (ho * torch.tensor(dd["Gh"], device=d)).sum()
+    loss.backward()
+    assert rel_err(x.grad.cpu(), torch.tensor(dd["gx_in"])) < TOL_GRAD
+    assert rel_err(v.grad.cpu(), torch.tensor(dd["gv_in"])) < TOL_GRAD
+    for k, p in m.named_parameters():
+        if k == "enc_attn_net.attn_mlp.2.bias":   # softmax is shift invariant: rounding noise in the reference too
+            continue
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g[k])
+        assert rel_err(got, g[k]) < TOL_GRAD, k
