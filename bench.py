@@ -518,6 +518,28 @@ def small_configs(nb, synth, dev, K):
     g2 = nb.GraphedStep(f2, ins2, sopt)
     out["segno_n5_t10_b100_train_traj_per_s"] = run(lambda: g2(**ins2), 4 * K)
     out["small_configs_note"] = "BASELINE.json configs[0] / [1] (B=100): launch-bound; whole step replayed as one CUDA graph"
+    del g1, g2, m, sg
+    # BASELINE.json configs[4] shape: 100-body EGNO, the per-GPU share (64) of the batch of 512 at 8 GPUs
+    B5, N5, T5 = 64, 100, 10
+    row5, col5 = synth.canonical_edges(B5, N5)
+    e5 = [row5.to(dev), col5.to(dev)]
+    torch.manual_seed(1)
+    m5 = nb.EGNO(n_layers=4, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T5, device=dev)
+    o5 = nb.FlatAdam(m5.parameters(), lr=1e-4, weight_decay=1e-8)
+    s5 = synth.sample_state("charged", B5, N5, seed=9)
+    x5, n5, ea5, v5, lm5 = synth.egno_features(s5["loc"].to(dev), s5["vel"].to(dev), s5["charges"].to(dev), e5[0], e5[1])
+    tg5 = x5.repeat(T5, 1) + 0.05 * torch.randn(T5 * B5 * N5, 3, device=dev)
+    to5 = torch.arange(1, T5 + 1, device=dev)[None].repeat(B5, 1)
+
+    def step5():
+        o5.zero_grad(set_to_none=True)
+        xo, _, _ = m5(x5, n5, e5, ea5, v=v5, loc_mean=lm5, timesteps_out=to5)
+        ((xo - tg5) ** 2).mean().backward()
+        o5.step()
+
+    B = B5
+    out["egno_n100_b64_train_traj_per_s"] = run(step5, 5)
+    out["egno_n100_note"] = "BASELINE.json configs[4] shape per GPU (B=512 over 8 GPUs): N=100, T=10, L=4, 6.3M edges per layer"
     return out
 
 
