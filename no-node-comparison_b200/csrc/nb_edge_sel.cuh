@@ -43,7 +43,8 @@ struct NbSelUnit {
   int send0, nsend;    // same for the senders
   int RC;              // selector column / node-tile row of sender slot 0
   int I0, J0;          // blocked mode: first receiver / sender index inside the graph
-  bool racc, sacc;     // read-out adds onto the receiver / sender outputs already in global memory
+  bool first_j, last_j;  // blocked mode: first / last sender block of this receiver block
+  bool first_i, last_i;  //               first / last receiver block of this graph-instance
 };
 template <bool BLK>
 __device__ __forceinline__ NbSelUnit nb_sel_unit(const NbEdgeGeom& g, int uo, int sub) {
@@ -56,7 +57,7 @@ __device__ __forceinline__ NbSelUnit nb_sel_unit(const NbEdgeGeom& g, int uo, in
     U.nrecv = U.nsend = ngt * g.N;
     U.RC = g.G * g.N;
     U.I0 = U.J0 = 0;
-    U.racc = U.sacc = false;
+    U.first_j = U.last_j = U.first_i = U.last_i = true;
   } else {
     const int ib = sub / g.nJ, jb = sub - ib * g.nJ;
     U.gt0 = uo;
@@ -68,8 +69,10 @@ __device__ __forceinline__ NbSelUnit nb_sel_unit(const NbEdgeGeom& g, int uo, in
     U.send0 = uo * g.N + U.J0;
     U.nsend = min(g.JB, g.N - U.J0);
     U.RC = g.IB;
-    U.racc = jb > 0;
-    U.sacc = ib > 0;
+    U.first_j = jb == 0;
+    U.last_j = jb == g.nJ - 1;
+    U.first_i = ib == 0;
+    U.last_i = ib == g.nI - 1;
   }
   return U;
 }
@@ -260,9 +263,10 @@ __device__ __forceinline__ void nb_sel_stage_nodes(unsigned char* Nh, unsigned c
 }
 // general unit: rows [0, nrecv) <- P of the receiver list, rows [RC, RC + nsend) <- Q of the sender list
 __device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned char* Nl, const float* __restrict__ P,
-                                                  const float* __restrict__ Q, const NbSelUnit& U, int tid, int nthreads) {
+                                                  const float* __restrict__ Q, const NbSelUnit& U, int tid, int nthreads,
+                                                  bool with_recv = true) {
   const int total = (U.nrecv + U.nsend) * 8;
-  for (int idx = tid; idx < total; idx += nthreads) {
+  for (int idx = tid + (with_recv ? 0 : U.nrecv * 8); idx < total; idx += nthreads) {
     const int n = idx >> 3, j = idx & 7;
     const bool snd = n >= U.nrecv;
     const float* src = snd ? Q + (int64_t)(U.send0 + n - U.nrecv) * NB_H + 8 * j : P + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
@@ -369,10 +373,10 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
     const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
     // every MMA of the previous unit has completed (its read-out waited for the last commit)
-    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_THREADS);
+    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_THREADS, U.first_j);
     {  // positions of the receiver and (blocked mode: distinct) sender lists, one pass
       const int n3r = U.nrecv * 3, n3 = n3r + (BLK ? U.nsend * 3 : 0);
-      for (int idx = tid; idx < n3; idx += NB_THREADS) {
+      for (int idx = tid + (U.first_j ? 0 : n3r); idx < n3; idx += NB_THREADS) {
         if (idx < n3r) xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
         else xq[idx - n3r] = __ldg(a.x + (int64_t)U.send0 * 3 + (idx - n3r));
       }
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         nb_issue_w3(tm, sTh, sTl, sW3h, sW3l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
         // M_i += Sel^T m  (runs underneath the phi_x epilogue)
-        nb_issue_scatter(tm + 64, sSel, sTh, sTl, idesc_sc, r0 > 0 ? 1u : 0u);
+        nb_issue_scatter(tm + 64, sSel, sTh, sTl, idesc_sc, (r0 > 0 || !U.first_j) ? 1u : 0u);
       }
       nb_mbar_wait(bar, phase);
       phase ^= 1;
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
       __syncthreads();
       if (tid == 0) {
         nb_tc_fence_after();
-        nb_issue_scatter8(tm + 128, sSel, sFh, sFl, idesc_sc8, r0 > 0 ? 1u : 0u);
+        nb_issue_scatter8(tm + 128, sSel, sFh, sFl, idesc_sc8, (r0 > 0 || !U.first_j) ? 1u : 0u);
         nb_mma_commit(bar);  // waited for at the top of the next tile / at the unit read-out
       }
     }
@@ -495,29 +499,22 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
     nb_mbar_wait(bar, phase);
     phase ^= 1;
     nb_tc_fence_after();
-    {
+    if (U.last_j) {  // blocked mode: the receivers' accumulators collect all sender blocks in TMEM first
       const int nl = 16 * q + lane;
       float v[32];
       nb_tmem_ld32(tm + ((uint32_t)(32 * q) << 16) + 64 + (uint32_t)cb, v);
       if (lane < 16 && nl < U.nrecv) {
         float* dst = a.M + (int64_t)(U.recv0 + nl) * NB_H + cb;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          if (U.racc) {
-            const float4 old = nb_ld4(dst + 4 * k);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          nb_st4(dst + 4 * k, o);
-        }
+        for (int k = 0; k < 8; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
       }
       float f4[4];
       nb_tmem_ld4(tm + ((uint32_t)(32 * q) << 16) + 128, f4);
       if (hf == 0 && lane < 16 && nl < U.nrecv) {
         float* dst = a.Fsum + (int64_t)(U.recv0 + nl) * 3;
-        dst[0] = U.racc ? dst[0] + f4[0] : f4[0];
-        dst[1] = U.racc ? dst[1] + f4[1] : f4[1];
-        dst[2] = U.racc ? dst[2] + f4[2] : f4[2];
+        dst[0] = f4[0];
+        dst[1] = f4[1];
+        dst[2] = f4[2];
       }
     }
     nb_tc_fence_before();
@@ -554,6 +551,8 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 #define NB_SB_FL (NB_SB_RG + 2 * NB_TILE * 16)
 #define NB_SB_NFLOAT (4 * NB_H + 4 * NB_TILE + 3 * 32 * 3 + 10 * NB_H + NB_H * 4)
 #define NB_EDGE_BWD_SEL_SMEM(RU) (NB_SB_FL + NB_SB_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
+#define NB_SB_GXACC(N) (((N) * 3 + 3) / 4 * 4)
+#define NB_EDGE_BWD_SEL_BLK_EXTRA(N) ((32 * NB_H + (N) * NB_H + NB_SB_GXACC(N)) * 4)
 #define NB_SB_TMEM_COLS 512
 
 __device__ __forceinline__ void nb_tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -643,7 +642,11 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   float* gfs = xq + 32 * 3;           // [32][3] dL/dFsum of the unit's receivers
   float* gwacc = gfs + 32 * 3;        // [10][64]: rows 0,1 w_rad (hi, lo piece) ; 2 + 2f, 3 + 2f w_ef[f]
   float* gxst = gwacc + 10 * NB_H;    // [64][4]
-  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(gxst + NB_H * 4);
+  // blocked mode: per-graph accumulators, so that nothing is read-modified-written in global memory per tile
+  float* gPacc = gxst + NB_H * 4;                          // [32][64]  receivers of the current receiver block
+  float* gQacc = gPacc + (BLK ? 32 * NB_H : 0);            // [N][64]   all senders of the graph-instance
+  float* gxacc = gQacc + (BLK ? a.g.N * NB_H : 0);         // [N][3] (+ pad)
+  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(gxacc + (BLK ? NB_SB_GXACC(a.g.N) : 0));
   const NbEdgeGeom g = a.g;
   const int RU = BLK ? 0 : g.G * g.EPG;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
@@ -733,17 +736,20 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
     // every MMA of the previous unit has completed (the read-out waited for the last side commit)
-    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_SB_THREADS);
-    for (int idx = tid; idx < U.nrecv * 8; idx += NB_SB_THREADS) {
-      int n = idx >> 3, j = idx & 7;
-      const float* src = a.gM + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
-      float4 p0 = nb_ld4(src), p1 = nb_ld4(src + 4);
-      float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-      nb_tc_store8(GMh, GMl, n, j, v);
-    }
+    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_SB_THREADS, U.first_j);   // receivers change with the receiver block only
+    if (U.first_j)
+      for (int idx = tid; idx < U.nrecv * 8; idx += NB_SB_THREADS) {
+        int n = idx >> 3, j = idx & 7;
+        const float* src = a.gM + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
+        float4 p0 = nb_ld4(src), p1 = nb_ld4(src + 4);
+        float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        nb_tc_store8(GMh, GMl, n, j, v);
+      }
+    if (BLK && U.first_i && U.first_j)
+      for (int idx = tid; idx < g.N * 3; idx += NB_SB_THREADS) gxacc[idx] = 0.f;
     {
       const int n3r = U.nrecv * 3, n3 = n3r + (BLK ? U.nsend * 3 : 0);
-      for (int idx = tid; idx < n3; idx += NB_SB_THREADS) {
+      for (int idx = tid + (U.first_j ? 0 : n3r); idx < n3; idx += NB_SB_THREADS) {
         if (idx < n3r) {
           xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
           gfs[idx] = __ldg(a.gFsum + (int64_t)U.recv0 * 3 + idx);
@@ -960,15 +966,23 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         const bool is_recv = i < U.nrecv, is_send = i >= U.RC && i < U.RC + U.nsend;
         if (is_recv || is_send) {
           float* dst = is_recv ? a.gP + (int64_t)(U.recv0 + i) * NB_H + cb : a.gQ + (int64_t)(U.send0 + i - U.RC) * NB_H + cb;
-          const bool acc = is_recv ? U.racc : U.sacc;
+          if (!BLK) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-            if (acc) {
-              const float4 old = nb_ld4(dst + 4 * k);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+          } else {
+            // this thread is the only one that ever touches this accumulator slice: gP collects the sender blocks of
+            // the receiver block, gQ the receiver blocks of the graph-instance; global memory is written once
+            float* acc = is_recv ? gPacc + i * NB_H + cb : gQacc + (U.J0 + i - U.RC) * NB_H + cb;
+            const bool first = is_recv ? U.first_j : U.first_i, last = is_recv ? U.last_j : U.last_i;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float4 o = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              if (!first) {
+                const float4 old = nb_ld4(acc + 4 * k);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              nb_st4(last ? dst + 4 * k : acc + 4 * k, o);
             }
-            nb_st4(dst + 4 * k, o);
           }
         } else if (i >= NB_SEL_XC0) {
           float* dst = gwacc + (i - NB_SEL_XC0) * NB_H + cb;  // exclusive owner of these 16 accumulators
@@ -992,15 +1006,19 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         int n = idx / 3, dd = idx - 3 * n;
         a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd] - gxst[(U.RC + n) * 4 + dd];
       }
-    } else {       // two lists that may overlap: two passes
+    } else {       // two lists that may overlap: two passes, into the per-graph accumulator
       for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
         int n = idx / 3, dd = idx - 3 * n;
-        a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd];
+        gxacc[U.I0 * 3 + idx] += gxst[n * 4 + dd];
       }
       __syncthreads();
       for (int idx = tid; idx < U.nsend * 3; idx += NB_SB_THREADS) {
         int n = idx / 3, dd = idx - 3 * n;
-        a.gx[(int64_t)U.send0 * 3 + idx] -= gxst[(U.RC + n) * 4 + dd];
+        gxacc[U.J0 * 3 + idx] -= gxst[(U.RC + n) * 4 + dd];
+      }
+      if (U.last_i && U.last_j) {
+        __syncthreads();
+        for (int idx = tid; idx < g.N * 3; idx += NB_SB_THREADS) a.gx[(int64_t)U.gt0 * g.N * 3 + idx] += gxacc[idx];
       }
     }
     __syncthreads();

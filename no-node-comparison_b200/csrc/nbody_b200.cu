@@ -498,7 +498,7 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
   bool done = false;
 #ifndef NB_EMU
   if (use_sel) {
-    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG);
+    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG) + (a.g.blk ? NB_EDGE_BWD_SEL_BLK_EXTRA(a.g.N) : 0);
     int pi_sel = prof_begin(1, st);
     if (a.g.blk) {
       NB_SET_SMEM(k_edge_bwd_sel<true>, smem_sel);
