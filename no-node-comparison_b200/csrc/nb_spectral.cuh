@@ -370,18 +370,28 @@ struct NbTconvArgs {
 #define NB_TCV_LDT 68
 __device__ __forceinline__ void nb_tconv_stage_w(float* B0, float* B1, float* B2, float* T0, float* T1, float* T2,
                                                  const float* __restrict__ W, int modes, int tid) {
-  for (int idx = tid; idx < NB_H * NB_H; idx += 256) {
-    const int i = idx >> 6, o = idx & 63;
-    const float2 w0 = __ldg(reinterpret_cast<const float2*>(W + (int64_t)idx * modes * 2));
-    float2 w1 = make_float2(0.f, 0.f);
-    if (modes > 1) w1 = __ldg(reinterpret_cast<const float2*>(W + (int64_t)idx * modes * 2 + 2));
-    B0[idx] = w0.x;
-    B1[idx] = w1.x;
-    B2[idx] = w1.y;
-    if (T0) {
-      T0[o * NB_TCV_LDT + i] = w0.x;
-      T1[o * NB_TCV_LDT + i] = w1.x;
-      T2[o * NB_TCV_LDT + i] = w1.y;
+  // two batches of 8 iterations: 16 independent 8-byte loads in flight per thread before the first store
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float2 w0[8], w1[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + (half * 8 + it) * 256;
+      w0[it] = __ldg(reinterpret_cast<const float2*>(W + (int64_t)idx * modes * 2));
+      w1[it] = modes > 1 ? __ldg(reinterpret_cast<const float2*>(W + (int64_t)idx * modes * 2 + 2)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + (half * 8 + it) * 256;
+      const int i = idx >> 6, o = idx & 63;
+      B0[idx] = w0[it].x;
+      B1[idx] = w1[it].x;
+      B2[idx] = w1[it].y;
+      if (T0) {
+        T0[o * NB_TCV_LDT + i] = w0[it].x;
+        T1[o * NB_TCV_LDT + i] = w1[it].x;
+        T2[o * NB_TCV_LDT + i] = w1[it].y;
+      }
     }
   }
 }
