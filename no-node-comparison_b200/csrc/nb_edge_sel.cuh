@@ -373,12 +373,16 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
     const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
     // every MMA of the previous unit has completed (its read-out waited for the last commit)
-    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_THREADS, U.first_j);
-    {  // positions of the receiver and (blocked mode: distinct) sender lists, one pass
+    {  // positions of the receiver and (blocked mode: distinct) sender lists: at most one per thread, loaded before the
+       // node-tile staging below so that the unit pays one memory round trip
       const int n3r = U.nrecv * 3, n3 = n3r + (BLK ? U.nsend * 3 : 0);
-      for (int idx = tid + (U.first_j ? 0 : n3r); idx < n3; idx += NB_THREADS) {
-        if (idx < n3r) xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
-        else xq[idx - n3r] = __ldg(a.x + (int64_t)U.send0 * 3 + (idx - n3r));
+      const int t_x = tid + (U.first_j ? 0 : n3r);
+      float xv = 0.f;
+      if (t_x < n3) xv = t_x < n3r ? __ldg(a.x + (int64_t)U.recv0 * 3 + t_x) : __ldg(a.x + (int64_t)U.send0 * 3 + (t_x - n3r));
+      nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_THREADS, U.first_j);
+      if (t_x < n3) {
+        if (t_x < n3r) xs[t_x] = xv;
+        else xq[t_x - n3r] = xv;
       }
     }
     const float* xsnd = BLK ? xq : xs;  // whole-graph units: senders = receivers
@@ -736,25 +740,54 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
     // every MMA of the previous unit has completed (the read-out waited for the last side commit)
-    nb_sel_stage_unit(Nh, Nl, a.P, a.Q, U, tid, NB_SB_THREADS, U.first_j);   // receivers change with the receiver block only
-    if (U.first_j)
-      for (int idx = tid; idx < U.nrecv * 8; idx += NB_SB_THREADS) {
-        int n = idx >> 3, j = idx & 7;
-        const float* src = a.gM + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
-        float4 p0 = nb_ld4(src), p1 = nb_ld4(src + 4);
-        float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        nb_tc_store8(GMh, GMl, n, j, v);
-      }
-    if (BLK && U.first_i && U.first_j)
-      for (int idx = tid; idx < g.N * 3; idx += NB_SB_THREADS) gxacc[idx] = 0.f;
+    // unit staging: every global load is issued before the first dependent store (one memory round trip, not three).
+    // (nrecv + nsend) * 8 <= 432 node-tile tasks and nrecv * 8 <= 256 gM tasks: at most one of each per thread.
     {
+      const int n_nt = (U.nrecv + U.nsend) * 8, n_gm = U.first_j ? U.nrecv * 8 : 0;
+      const int t_nt = tid + (U.first_j ? 0 : U.nrecv * 8);          // receivers change with the receiver block only
+      const bool do_nt = t_nt < n_nt, do_gm = tid < n_gm;
       const int n3r = U.nrecv * 3, n3 = n3r + (BLK ? U.nsend * 3 : 0);
-      for (int idx = tid + (U.first_j ? 0 : n3r); idx < n3; idx += NB_SB_THREADS) {
-        if (idx < n3r) {
-          xs[idx] = __ldg(a.x + (int64_t)U.recv0 * 3 + idx);
-          gfs[idx] = __ldg(a.gFsum + (int64_t)U.recv0 * 3 + idx);
+      const int t_x = tid + (U.first_j ? 0 : n3r);
+      float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, m0 = p0, m1 = p0;
+      float xv = 0.f, gv = 0.f;
+      int nt_row = 0;
+      if (do_nt) {
+        const int n = t_nt >> 3, j = t_nt & 7;
+        const bool snd = n >= U.nrecv;
+        const float* src = snd ? a.Q + (int64_t)(U.send0 + n - U.nrecv) * NB_H + 8 * j : a.P + (int64_t)(U.recv0 + n) * NB_H + 8 * j;
+        p0 = nb_ld4(src);
+        p1 = nb_ld4(src + 4);
+        nt_row = snd ? U.RC + n - U.nrecv : n;
+      }
+      if (do_gm) {
+        const float* src = a.gM + (int64_t)(U.recv0 + (tid >> 3)) * NB_H + 8 * (tid & 7);
+        m0 = nb_ld4(src);
+        m1 = nb_ld4(src + 4);
+      }
+      if (t_x < n3) {
+        if (t_x < n3r) {
+          xv = __ldg(a.x + (int64_t)U.recv0 * 3 + t_x);
+          gv = __ldg(a.gFsum + (int64_t)U.recv0 * 3 + t_x);
         } else {
-          xq[idx - n3r] = __ldg(a.x + (int64_t)U.send0 * 3 + (idx - n3r));
+          xv = __ldg(a.x + (int64_t)U.send0 * 3 + (t_x - n3r));
+        }
+      }
+      if (BLK && U.first_i && U.first_j)
+        for (int idx = tid; idx < g.N * 3; idx += NB_SB_THREADS) gxacc[idx] = 0.f;
+      if (do_nt) {
+        float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        nb_tc_store8(Nh, Nl, nt_row, t_nt & 7, v);
+      }
+      if (do_gm) {
+        float v[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        nb_tc_store8(GMh, GMl, tid >> 3, tid & 7, v);
+      }
+      if (t_x < n3) {
+        if (t_x < n3r) {
+          xs[t_x] = xv;
+          gfs[t_x] = gv;
+        } else {
+          xq[t_x - n3r] = xv;
         }
       }
     }
