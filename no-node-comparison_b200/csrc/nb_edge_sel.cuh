@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_gat, 0u);
         nb_mma_commit(bar);
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm, sTh, sTl, sW2h, sW2l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm, sTh, sTl, sW3h, sW3l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
       }
       nb_fence_async_smem();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_scatter8(tm + 128, sSel, sFh, sFl, idesc_sc8, (r0 > 0 || !U.first_j) ? 1u : 0u);
         nb_mma_commit(bar);  // waited for at the top of the next tile / at the unit read-out
@@ -537,8 +537,9 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 //   S3  phi_x head, g3                                 -> dgrad 3 + gM broadcast  | side: dW3, db3
 //   S4  g2 = (gm + gM_i) SiLU'(pre2)                   -> dgrad 2                 | side: dW2, db2
 //   S5  g1 = gz1 SiLU'(pre1), dL/drij                  ->                           side: gP|gQ|gw += Sel^T g1, gx += Sel^T rG
-// The critical-path MMAs are issued by thread 0 (mbarrier `bar`), the side MMAs by thread 32 (`bar2`); the side MMAs
-// run underneath the next stage's CUDA-core work.
+// One elected lane of warp 0 issues every MMA: first the critical-path ones (mbarrier `bar`), then the side ones
+// (`bar2`) -- the tensor pipe runs them in issue order, so the side MMAs execute underneath the next stage's CUDA-core
+// work and never ahead of the MMA the CTA is waiting for.
 //
 // TMEM columns: [0,64) pre1 -> SiLU'(pre1) | [64,128) pre2 -> SiLU'(pre2) | [128,192) pre3 -> gm -> gz1 |
 //               [192,256) dW3 | [256,320) dW2 | [320,328) db3 | [328,336) db2 | [336,400) node sums | [400,408) x sums
@@ -826,7 +827,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_dg, 0u);
         nb_mma_commit(bar);
@@ -847,7 +848,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 64, sTzh, sTzl, sW2h, sW2l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
@@ -868,7 +869,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 128, sTmh, sTml, sW3h, sW3l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
@@ -913,13 +914,11 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 128, sTgh, sTgl, sW3h, sW3l, true, idesc_dg, 0u);          // gm = g3 W3
         nb_issue_gather(tm + 128, sSel, sGMh, sGMl, ks_recv, idesc_dg, 1u);          //    + gM_i
         nb_mma_commit(bar);
-      } else if (tid == 32) {
-        nb_tc_fence_after();
         nb_issue_wgrad(tm + 192, tm + 320, sTgh, sTgl, sTmh, sTml, sOnes, idesc_wg, idesc_bs, wacc);  // dW3, db3
         nb_mma_commit(bar2);
       }
@@ -941,12 +940,10 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 128, sTgh, sTgl, sW2h, sW2l, true, idesc_dg, 0u);  // gz1 = g2 W2
         nb_mma_commit(bar);
-      } else if (tid == 32) {
-        nb_tc_fence_after();
         nb_issue_wgrad(tm + 256, tm + 328, sTgh, sTgl, sTzh, sTzl, sOnes, idesc_wg, idesc_bs, wacc);  // dW2, db2
       }
       wacc = 1;
@@ -979,7 +976,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       }
       nb_fence_async_smem();
       __syncthreads();
-      if (tid == 32) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         const uint32_t uacc = r0 > 0 ? 1u : 0u;
         nb_issue_scatter(tm + 336, sSel, sTmh, sTml, idesc_wg, uacc);    // gP | gQ | gw partials += Sel^T g1

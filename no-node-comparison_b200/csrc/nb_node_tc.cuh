@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_gemm64_tc(NbGemmBatch batch, 
     nb_fence_async_smem();
     nb_tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (NB_ISSUER(0)) {
       nb_tc_fence_after();
       for (int s = 0; s < a.nsrc; ++s) {
         const uint32_t sa = nb_smem_u32(base + NB_GT_A(s)), sb = nb_smem_u32(base + NB_GT_B(s));
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_wgrad64_tc(NbWgradBatch batch
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         if (a.colsum && p == 0) {
           nb_issue_wgrad(tm, tm + 64, sGh, sGl, sAh, sAl, sOnes, idesc_wg, idesc_bs, wacc);

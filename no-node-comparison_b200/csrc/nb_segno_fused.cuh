@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       nb_tc_fence_before();
       __syncthreads();
       // ---- (b) P = h W1r^T, Q = h W1c^T -> node tile rows [0, GN) and [GN, 2 GN)
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 192, sHh, sHl, NB_FS_SWH(2), NB_FS_SWL(2), false, idesc_node, 0u);
         nb_issue_w3(tm + 256, sHh, sHl, NB_FS_SWH(3), NB_FS_SWL(3), false, idesc_node, 0u);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
         nb_fence_async_smem();
         nb_tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (NB_ISSUER(0)) {
           nb_tc_fence_after();
           nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_gat, 0u);
           nb_mma_commit(bar);
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
         nb_fence_async_smem();
         nb_tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (NB_ISSUER(0)) {
           nb_tc_fence_after();
           nb_issue_w3(tm, sTh, sTl, NB_FS_SWH(0), NB_FS_SWL(0), false, idesc_fwd, 0u);
           nb_mma_commit(bar);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
         nb_fence_async_smem();
         nb_tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (NB_ISSUER(0)) {
           nb_tc_fence_after();
           nb_issue_w3(tm, sTh, sTl, NB_FS_SWH(1), NB_FS_SWL(1), false, idesc_fwd, 0u);
           nb_mma_commit(bar);
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
         }
         nb_fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (NB_ISSUER(0)) {
           nb_tc_fence_after();
           nb_issue_scatter8(tm + 128, sSel, sFh, sFl, idesc_sc8, r0 > 0 ? 1u : 0u);
           nb_mma_commit(bar);
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       nb_tc_fence_before();
       __syncthreads();
       // ---- (e) U5 = [h, M] W5^T + b5 ; h <- h + SiLU(U5) W6^T + b6
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 192, sHh, sHl, NB_FS_SWH(4), NB_FS_SWL(4), false, idesc_node, 0u);
         nb_issue_w3(tm + 192, sUh, sUl, NB_FS_SWH(5), NB_FS_SWL(5), false, idesc_node, 1u);
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_w3(tm + 192, sUh, sUl, NB_FS_SWH(6), NB_FS_SWL(6), false, idesc_node, 0u);
         nb_mma_commit(bar);

@@ -55,6 +55,21 @@ __device__ __forceinline__ void nb_tmem_dealloc(uint32_t taddr, uint32_t ncols) 
 __device__ __forceinline__ void nb_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void nb_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+// One lane of a fully converged warp (call under a warp-uniform condition only).  MMAs issued under
+// `if (warp == W && nb_elect_one())` compile to back-to-back UTCHMMA; under `if (tid == 0)` the compiler wraps every
+// single MMA in an ELECT / BRA.U.ANY loop (about ten instructions per MMA, all on the critical path of the issuing warp).
+__device__ __forceinline__ bool nb_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+#define NB_ISSUER(w) (warp == (w) && nb_elect_one())
 __device__ __forceinline__ void nb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread l of warp w reads TMEM lane 32*(w%4)+l
