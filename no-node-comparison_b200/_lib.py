@@ -11,7 +11,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libnbody_b200.so")
+    # NB_B200_LIBRARY: a profiling build of the same sources (tools/stage_clocks.py); never a different implementation
+    return os.environ.get("NB_B200_LIBRARY") or os.path.join(_HERE, "libnbody_b200.so")
 
 
 def load_library() -> ctypes.CDLL:

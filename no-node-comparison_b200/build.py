@@ -26,20 +26,24 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/nbody_b200.cu -> libnbody_b200.so.  Returns the library path."""
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compile csrc/nbody_b200.cu -> libnbody_b200.so.  Returns the library path.
+    `defines` / `out`: profiling builds (e.g. -DNB_STAGE_CLOCKS) written next to the product library."""
+    if out is not None:
+        force = True
+    out = out or OUT
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.isfile(nvcc):
         raise RuntimeError("nvcc not found: cannot build libnbody_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), SRC, "-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-I", os.path.join(ROOT, "include"), SRC, "-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

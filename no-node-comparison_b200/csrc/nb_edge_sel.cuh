@@ -142,6 +142,39 @@ __device__ __forceinline__ void nb_issue_w3(uint32_t tmem_d, uint32_t a_hi, uint
   }
 }
 
+// the same product with the activation operand in tensor memory (hi pieces at columns ta_hi .., lo pieces at ta_lo ..,
+// 8 columns per k-step): only the 2 KB weight slice of a k-step is fetched from shared memory
+__device__ __forceinline__ void nb_issue_w3_ta(uint32_t tmem_d, uint32_t ta_hi, uint32_t ta_lo, uint32_t w_hi, uint32_t w_lo,
+                                               bool w_mn, uint32_t idesc, uint32_t acc0) {
+  const uint32_t bstep = w_mn ? NB_KSTEP_MN : NB_KSTEP_K;
+  uint32_t acc = acc0;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t a = pass == 1 ? ta_lo : ta_hi;
+    const uint32_t b = w_mn ? nb_desc_lo_mn(pass == 2 ? w_lo : w_hi) : nb_desc_lo_k(pass == 2 ? w_lo : w_hi);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      nb_mma_bf16_ta(tmem_d, a + 8u * s, b + bstep * s, NB_DESC_HI_SW128, idesc, acc);
+      acc = 1u;
+    }
+  }
+}
+// 16 consecutive fp32 values of row r (column quarter cq) -> split bf16 pieces into the shared-memory tiles (chunks
+// 2 cq, 2 cq + 1: the side MMAs' copy) and into this thread's TMEM lane (8 packed columns each: the A operand's copy)
+__device__ __forceinline__ void nb_store16_ta(unsigned char* hi, unsigned char* lo, int r, int cq, const float* v,
+                                              uint32_t ta_hi, uint32_t ta_lo) {
+  uint32_t h0[4], l0[4], h1[4], l1[4];
+  nb_split8(v, h0, l0);
+  nb_split8(v + 8, h1, l1);
+  const uint32_t o0 = nb_tc_chunk_off(r, 2 * cq), o1 = nb_tc_chunk_off(r, 2 * cq + 1);
+  *reinterpret_cast<uint4*>(hi + o0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+  *reinterpret_cast<uint4*>(hi + o1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+  *reinterpret_cast<uint4*>(lo + o0) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+  *reinterpret_cast<uint4*>(lo + o1) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+  nb_tmem_st44(ta_hi, h0, h1);
+  nb_tmem_st44(ta_lo, l0, l1);
+}
+
 // gather: D[128 x 64] (+)= Sel[128 x 16 ksteps] . (Nh + Nl),  Sel K-major, node tile MN-major (K = node-tile rows)
 __device__ __forceinline__ void nb_issue_gather(uint32_t tmem_d, uint32_t sel, uint32_t n_hi, uint32_t n_lo, int ksteps,
                                                 uint32_t idesc, uint32_t acc0) {
@@ -542,7 +575,12 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 // work and never ahead of the MMA the CTA is waiting for.
 //
 // TMEM columns: [0,64) pre1 -> SiLU'(pre1) | [64,128) pre2 -> SiLU'(pre2) | [128,192) pre3 -> gm -> gz1 |
-//               [192,256) dW3 | [256,320) dW2 | [320,328) db3 | [328,336) db2 | [336,400) node sums | [400,408) x sums
+//               [192,256) dW3 | [256,320) dW2 | [320,328) db3 | [328,336) db2 | [336,400) node sums | [400,408) x sums |
+//               [448,480) hi pieces, [480,512) lo pieces of the current A operand (z1 -> m -> g3 -> g2; packed bf16 pairs)
+// The four critical products read their activation operand from tensor memory (nb_issue_w3_ta): a 128x64x16 MMA with both
+// operands in shared memory is bound by the 6 KB operand fetch (~85 cycles measured, tools/stage_clocks.py and the
+// timed modes of k_tc_selftest), not by the tensor pipe (32 cycles).  The shared-memory copies stay: the weight-gradient
+// and scatter MMAs need the activations as MN-major / B operands, which cannot come from tensor memory.
 #define NB_SB_THREADS 512
 #define NB_SB_W 0
 #define NB_SB_TZ (4 * NB_TC_TILE_BYTES(64))
@@ -613,8 +651,30 @@ __device__ __forceinline__ void nb_issue_wgrad(uint32_t tmem_w, uint32_t tmem_b,
   }
 }
 
+// Optional per-stage cycle counters of CTA 0 (profiling builds only: -DNB_STAGE_CLOCKS, tools/stage_clocks.py)
+#ifdef NB_STAGE_CLOCKS
+__device__ long long nb_dbg_clk[32];
+#define NB_CLK(i)                                   \
+  if (dbg_on) {                                     \
+    const long long t_now = clock64();              \
+    dbg_acc[i] += t_now - dbg_last;                 \
+    dbg_last = t_now;                               \
+  }
+#else
+#define NB_CLK(i)
+#endif
+
 template <bool BLK>
 __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs a) {
+#ifdef NB_STAGE_CLOCKS
+  __shared__ long long dbg_acc[32];
+  const bool dbg_on = blockIdx.x == 0 && threadIdx.x == 0;
+  long long dbg_last = 0;
+  if (dbg_on) {
+    for (int i = 0; i < 32; ++i) dbg_acc[i] = 0;
+    dbg_last = clock64();
+  }
+#endif
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
   unsigned char* W2h = base + NB_SB_W;
@@ -716,6 +776,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   const uint32_t t1 = tm + lane_base + 0 + (uint32_t)cb;    // pre1 / SiLU'(pre1)
   const uint32_t t2 = tm + lane_base + 64 + (uint32_t)cb;   // pre2 / SiLU'(pre2)
   const uint32_t t3 = tm + lane_base + 128 + (uint32_t)cb;  // pre3 / gm / gz1
+  const uint32_t ta_h = tm + 448, ta_l = tm + 480;            // A operand in tensor memory (issuer's view)
+  const uint32_t ta_hm = ta_h + lane_base + 8u * (uint32_t)cq, ta_lm = ta_l + lane_base + 8u * (uint32_t)cq;  // this thread's slice
   const uint32_t idesc_fwd = nb_idesc_bf16(128, 64, 0, 0);
   const uint32_t idesc_dg = nb_idesc_bf16(128, 64, 0, 1);   // also the gathers
   const uint32_t idesc_wg = nb_idesc_bf16(64, 64, 1, 1);    // also the 64-wide scatters
@@ -740,6 +802,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   for (int sub = 0; sub < n_sub; ++sub) {
     const NbSelUnit U = nb_sel_unit<BLK>(g, uo, sub);
     const int R = U.R;
+    NB_CLK(0)
     // every MMA of the previous unit has completed (the read-out waited for the last side commit)
     // unit staging: every global load is issued before the first dependent store (one memory round trip, not three).
     // (nrecv + nsend) * 8 <= 432 node-tile tasks and nrecv * 8 <= 256 gM tasks: at most one of each per thread.
@@ -794,6 +857,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     }
     const float* xsnd = BLK ? xq : xs;  // whole-graph units: senders = receivers
     __syncthreads();
+    NB_CLK(1)
 
     for (int r0 = 0; r0 < R; r0 += NB_TILE) {
       // ---- T0: geometry + selector row
@@ -818,23 +882,28 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
             if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
         }
       }
+      NB_CLK(2)
       if (r0 > 0) {  // the side MMAs of the previous tile (dW2, scatters) have consumed Sel, Tz, Tm, Tg, rG
         nb_mbar_wait(bar2, phase2);
         phase2 ^= 1;
         nb_tc_fence_after();
       }
+      NB_CLK(3)
       if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, U.RC + lj, r2, e);
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
+      NB_CLK(4)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_dg, 0u);
         nb_mma_commit(bar);
       }
+      NB_CLK(5)
       nb_mbar_wait(bar, phase);
       phase ^= 1;
       nb_tc_fence_after();
+      NB_CLK(6)
       // ---- S1: z1 -> tile, SiLU'(pre1) -> TMEM
       {
         float v[16], d[16];
@@ -842,20 +911,23 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
 #pragma unroll
         for (int i = 0; i < 16; ++i) nb_silu_grad(v[i], v[i], d[i]);
         nb_tmem_st16(t1, d);
-        nb_tc_store8(Tzh, Tzl, row, 2 * cq, v);
-        nb_tc_store8(Tzh, Tzl, row, 2 * cq + 1, v + 8);
+        nb_store16_ta(Tzh, Tzl, row, cq, v, ta_hm, ta_lm);
+        nb_tmem_st_wait();
       }
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
+      NB_CLK(7)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3(tm + 64, sTzh, sTzl, sW2h, sW2l, false, idesc_fwd, 0u);
+        nb_issue_w3_ta(tm + 64, ta_h, ta_l, sW2h, sW2l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
       }
+      NB_CLK(8)
       nb_mbar_wait(bar, phase);
       phase ^= 1;
       nb_tc_fence_after();
+      NB_CLK(9)
       // ---- S2: m -> tile, SiLU'(pre2) -> TMEM
       {
         float v[16], d[16];
@@ -863,20 +935,23 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
 #pragma unroll
         for (int i = 0; i < 16; ++i) nb_silu_grad(v[i] + vb2[cb + i], v[i], d[i]);
         nb_tmem_st16(t2, d);
-        nb_tc_store8(Tmh, Tml, row, 2 * cq, v);
-        nb_tc_store8(Tmh, Tml, row, 2 * cq + 1, v + 8);
+        nb_store16_ta(Tmh, Tml, row, cq, v, ta_hm, ta_lm);
+        nb_tmem_st_wait();
       }
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
+      NB_CLK(10)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3(tm + 128, sTmh, sTml, sW3h, sW3l, false, idesc_fwd, 0u);
+        nb_issue_w3_ta(tm + 128, ta_h, ta_l, sW3h, sW3l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
       }
+      NB_CLK(11)
       nb_mbar_wait(bar, phase);
       phase ^= 1;
       nb_tc_fence_after();
+      NB_CLK(12)
       // ---- S3: phi_x head, g3 = dL/dpre3
       float rgx, rgy, rgz;
       {
@@ -908,23 +983,27 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
           gw4acc[i] = fmaf(gc, v[i], gw4acc[i]);
           v[i] = gc * vw4[cb + i] * d[i];  // g3
         }
-        nb_tc_store8(Tgh, Tgl, row, 2 * cq, v);
-        nb_tc_store8(Tgh, Tgl, row, 2 * cq + 1, v + 8);
+        nb_store16_ta(Tgh, Tgl, row, cq, v, ta_hm, ta_lm);
+        nb_tmem_st_wait();
       }
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
+      NB_CLK(13)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3(tm + 128, sTgh, sTgl, sW3h, sW3l, true, idesc_dg, 0u);          // gm = g3 W3
+        nb_issue_w3_ta(tm + 128, ta_h, ta_l, sW3h, sW3l, true, idesc_dg, 0u);        // gm = g3 W3
         nb_issue_gather(tm + 128, sSel, sGMh, sGMl, ks_recv, idesc_dg, 1u);          //    + gM_i
         nb_mma_commit(bar);
+        NB_CLK(14)
         nb_issue_wgrad(tm + 192, tm + 320, sTgh, sTgl, sTmh, sTml, sOnes, idesc_wg, idesc_bs, wacc);  // dW3, db3
         nb_mma_commit(bar2);
       }
+      NB_CLK(15)
       nb_mbar_wait(bar, phase);
       phase ^= 1;
       nb_tc_fence_after();
+      NB_CLK(16)
       // ---- S4: g2 = (gm + gM_i) * SiLU'(pre2)    (padded rows: gm = 0 and the gathered gM = 0)
       {
         float v[16], d[16];
@@ -932,24 +1011,30 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_tmem_ld16(t2, d);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= d[i];
+        NB_CLK(17)
         nb_mbar_wait(bar2, phase2);  // dW3 / db3 have consumed the g3 and m tiles
         phase2 ^= 1;
-        nb_tc_store8(Tgh, Tgl, row, 2 * cq, v);
-        nb_tc_store8(Tgh, Tgl, row, 2 * cq + 1, v + 8);
+        NB_CLK(18)
+        nb_store16_ta(Tgh, Tgl, row, cq, v, ta_hm, ta_lm);
+        nb_tmem_st_wait();
       }
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
+      NB_CLK(19)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3(tm + 128, sTgh, sTgl, sW2h, sW2l, true, idesc_dg, 0u);  // gz1 = g2 W2
+        nb_issue_w3_ta(tm + 128, ta_h, ta_l, sW2h, sW2l, true, idesc_dg, 0u);  // gz1 = g2 W2
         nb_mma_commit(bar);
+        NB_CLK(20)
         nb_issue_wgrad(tm + 256, tm + 328, sTgh, sTgl, sTzh, sTzl, sOnes, idesc_wg, idesc_bs, wacc);  // dW2, db2
       }
       wacc = 1;
+      NB_CLK(21)
       nb_mbar_wait(bar, phase);
       phase ^= 1;
       nb_tc_fence_after();
+      NB_CLK(22)
       // ---- S5: g1 = gz1 * SiLU'(pre1) -> the (free) m tile ; dL/drij -> rG tile
       {
         float v[16], d[16];
@@ -976,6 +1061,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       }
       nb_fence_async_smem();
       __syncthreads();
+      NB_CLK(23)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         const uint32_t uacc = r0 > 0 ? 1u : 0u;
@@ -983,11 +1069,13 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_issue_scatter8(tm + 400, sSel, sRGh, sRGl, idesc_bs, uacc);   // x sums += Sel^T rG
         nb_mma_commit(bar2);  // also covers dW2 / db2; waited for at the top of the next tile / at the read-out
       }
+      NB_CLK(24)
     }
     // ---- unit read-out (accumulator row i <-> TMEM lane (i % 16) + 32 (i / 16): thread (q, lane < 16) owns row 16 q + lane)
     nb_mbar_wait(bar2, phase2);
     phase2 ^= 1;
     nb_tc_fence_after();
+    NB_CLK(25)
     {
       const int i = 16 * q + lane;
       float v[16];
@@ -1054,6 +1142,11 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     __syncthreads();
   }
 
+  NB_CLK(26)
+#ifdef NB_STAGE_CLOCKS
+  if (dbg_on)
+    for (int i = 0; i < 32; ++i) nb_dbg_clk[i] += dbg_acc[i];
+#endif
   // ---- CTA epilogue: weight-gradient accumulators (TMEM), register / shared accumulators -> this CTA's partial slice
   float* out = a.partial + (int64_t)blockIdx.x * NB_EB_PLEN;
   nb_tc_fence_after();

@@ -155,6 +155,47 @@ __device__ __forceinline__ void nb_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on the 128 lanes, K-major: the 16 bf16 of a k-step packed
+// two per 32-bit column, 8 columns per k-step) is read from tensor memory instead of shared memory.  A 128x64x16 MMA
+// with both operands in shared memory is bound by the operand fetch (6 KB per MMA), not by the tensor pipe.
+__device__ __forceinline__ void nb_mma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane <- 8 packed words (no wait: pair with nb_tmem_st_wait)
+__device__ __forceinline__ void nb_tmem_st8(uint32_t taddr, const uint32_t (&w)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(w[0]),
+               "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void nb_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// split 8 consecutive fp32 values into packed bf16 pairs: hi[i] = (v[2i], v[2i+1]) leading pieces, lo[i] = the remainders
+__device__ __forceinline__ void nb_split8(const float* v, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b1 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    float2 f1 = __bfloat1622float2(b1);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i] - f1.x, v[2 * i + 1] - f1.y);
+    hi[i] = *reinterpret_cast<uint32_t*>(&b1);
+    lo[i] = *reinterpret_cast<uint32_t*>(&b2);
+  }
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane <- two groups of 4 packed words
+__device__ __forceinline__ void nb_tmem_st44(uint32_t taddr, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a[0]),
+               "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+               : "memory");
+}
+
 // all MMAs issued so far by this thread arrive on `bar` when complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void nb_mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(nb_smem_u32(bar)) : "memory");
@@ -203,7 +244,10 @@ __device__ __forceinline__ void nb_tc_issue3(uint32_t tmem_d, uint32_t a_hi, uin
 // mode 1: D[128x64] = A[128x64] * W        (A K-major, B = W[o][k] MN-major)       data-gradient form
 // mode 3: D[ 64x 8] = A^T * ones[128x8]  (column sums; dense no-swizzle B operand)
 // mode 2: D[ 64x64] = A^T * G              (A = A[r][c] MN-major (M = c), B = G[r][c] MN-major (N = c), K = 128 rows)
-// out: raw dump of the 128 TMEM lanes x 64 columns
+// mode 4 / 5: modes 0 / 1 with the A operand in tensor memory (nb_mma_bf16_ta)
+// mode 6 .. 9: modes 0 .. 3 (shared-memory A), timed like 4 / 5
+// out: raw dump of the 128 TMEM lanes x 64 columns; modes >= 4 append out[8192] = cycles of one 12-MMA group (issue ->
+//      commit observed), out[8193] = cycles of four groups issued back to back
 __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ W,
                                                      float* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char tsm[];
@@ -219,7 +263,9 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
     nb_mbar_init(&bar, 1);
     nb_mbar_fence_init();
   }
-  if (warp == 0) nb_tmem_alloc(&tmem_base, 64);
+  if (warp == 0) nb_tmem_alloc(&tmem_base, 128);
+  const bool timed = mode >= 4, a_tmem = mode == 4 || mode == 5;
+  if (mode >= 6) mode -= 6;
   // operand tiles: this thread owns row `tid`
   {
     const float* ar = A + (size_t)tid * 64;
@@ -238,6 +284,71 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
   __syncthreads();
   nb_tc_fence_after();
   const uint32_t tm = tmem_base;
+  if (a_tmem) {  // A row `tid` -> TMEM lane tid, columns [64, 96) hi pieces, [96, 128) lo pieces
+    const float* ar = A + (size_t)tid * 64;
+    const uint32_t la = tm + ((uint32_t)(warp * 32) << 16);
+    for (int ks = 0; ks < 4; ++ks) {  // k-step ks = columns 16 ks .. 16 ks + 15 = 8 packed words
+      uint32_t h0[4], l0[4], h1[4], l1[4];
+      nb_split8(ar + 16 * ks, h0, l0);
+      nb_split8(ar + 16 * ks + 8, h1, l1);
+      nb_tmem_st44(la + 64 + 8 * ks, h0, h1);
+      nb_tmem_st44(la + 96 + 8 * ks, l0, l1);
+    }
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();
+    nb_tc_fence_after();
+    mode -= 4;
+  }
+  if (timed) {
+    long long c1 = 0, c4 = 0;
+    const uint32_t idesc = mode == 0 ? nb_idesc_bf16(128, 64, 0, 0) : nb_idesc_bf16(128, 64, 0, 1);
+    const uint32_t sah = nb_smem_u32(a_hi), sal = nb_smem_u32(a_lo), sbh = nb_smem_u32(b_hi), sbl = nb_smem_u32(b_lo);
+    uint32_t ph = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      const int groups = rep == 0 ? 4 : 1;   // the single group last: its result is the one dumped
+      long long t0 = 0;
+      if (warp == 0 && nb_elect_one()) {
+        t0 = clock64();
+        for (int gi = 0; gi < groups; ++gi) {
+          uint32_t acc = 0;
+          if (mode == 2) {
+            nb_tc_issue3(tm, sah, sal, 1, sbh, sbl, 1, 8, nb_idesc_bf16(64, 64, 1, 1), false);
+          } else if (mode == 3) {
+            for (int pass = 0; pass < 2; ++pass)
+              for (int s = 0; s < 8; ++s) {
+                nb_mma_bf16(tm, nb_desc_mnmajor(pass ? sal : sah, s), nb_desc_mn8_noswizzle(sbh, s), nb_idesc_bf16(64, 8, 1, 1), acc);
+                acc = 1;
+              }
+          } else
+          for (int pass = 0; pass < 3; ++pass)
+            for (int s = 0; s < 4; ++s) {
+              const uint32_t bt = pass == 2 ? sbl : sbh;
+              const uint64_t bd = mode == 0 ? nb_desc_kmajor(bt, s) : nb_desc_mnmajor(bt, s);
+              if (a_tmem)
+                nb_mma_bf16_ta(tm, tm + (pass == 1 ? 96u : 64u) + 8u * s, (uint32_t)bd, (uint32_t)(bd >> 32), idesc, acc);
+              else
+                nb_mma_bf16(tm, nb_desc_kmajor(pass == 1 ? sal : sah, s), bd, idesc, acc);
+              acc = 1;
+            }
+        }
+        nb_mma_commit(&bar);
+      }
+      nb_mbar_wait(&bar, ph);
+      ph ^= 1;
+      nb_tc_fence_after();
+      if (tid == 0) {
+        const long long dt = clock64() - t0;
+        if (rep == 0) c4 = dt; else c1 = dt;
+      }
+      nb_tc_fence_before();
+      __syncthreads();
+    }
+    if (tid == 0) {
+      out[8192] = (float)c1;
+      out[8193] = (float)c4;
+    }
+  } else
   if (tid == 0) {
     if (mode == 0)
       nb_tc_issue3(tm, nb_smem_u32(a_hi), nb_smem_u32(a_lo), 0, nb_smem_u32(b_hi), nb_smem_u32(b_lo), 0, 4,
@@ -259,7 +370,7 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
     }
     nb_mma_commit(&bar);
   }
-  nb_mbar_wait(&bar, 0);
+  if (!timed) nb_mbar_wait(&bar, 0);
   nb_tc_fence_after();
   float v[32];
   const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
@@ -269,6 +380,6 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
   for (int i = 0; i < 32; ++i) out[(size_t)tid * 64 + 32 + i] = v[i];
   nb_tc_fence_before();
   __syncthreads();
-  if (warp == 0) nb_tmem_dealloc(tm, 64);
+  if (warp == 0) nb_tmem_dealloc(tm, 128);
 }
 #endif  // NB_EMU

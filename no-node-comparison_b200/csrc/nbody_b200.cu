@@ -92,6 +92,19 @@ static void prof_end(int, int, void*) {}
 extern "C" long long nb_launch_count(void) { return g_launches; }
 
 // enable != 0: start timing the dominant kernels with CUDA events on their launch stream (counters reset)
+#ifdef NB_STAGE_CLOCKS
+// profiling builds only (tools/stage_clocks.py): per-stage cycle totals of CTA 0 of k_edge_bwd_sel since the last reset
+extern "C" int nb_debug_stage_clocks(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, nb_dbg_clk, sizeof(long long) * 32);
+  if (reset) {
+    long long z[32] = {0};
+    cudaMemcpyToSymbol(nb_dbg_clk, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 extern "C" int nb_profile_enable(int enable) {
 #ifndef NB_EMU
   g_prof_on = enable;
@@ -1624,7 +1637,7 @@ extern "C" int nb_tc_selftest(int32_t mode, const float* A, const float* W, floa
   nb_set_error("tcgen05 is not available in the host emulator");
   return NB_ERR_INVALID;
 #else
-  if (mode < 0 || mode > 3) { nb_set_error("mode must be 0..3"); return NB_ERR_INVALID; }
+  if (mode < 0 || mode > 9) { nb_set_error("mode must be 0..9"); return NB_ERR_INVALID; }
   const size_t smem = 4 * NB_TC_TILE_BYTES(128) + 1024;
   NB_SET_SMEM(k_tc_selftest, smem);
   NB_LAUNCH_COUNTED(k_tc_selftest, 1, 128, smem, stream, (int)mode, A, W, out);

@@ -14,12 +14,14 @@ def _run(mode, A, W):
     lib = nb.load_library()
     d = torch.device("cuda:0")
     Ad, Wd = A.to(d).contiguous(), W.to(d).contiguous()
-    out = torch.zeros(128, 64, device=d)
+    out = torch.zeros(128 * 64 + 64, device=d)  # modes >= 4 append cycle counts behind the 128 x 64 dump
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = lib.nb_tc_selftest(mode, P(Ad), P(Wd), P(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.nb_last_error()
     torch.cuda.synchronize()
-    return out.cpu()
+    if mode >= 4:
+        print(f"tcgen05 selftest mode {mode}: one 12-MMA group {out[8192].item():.0f} cycles, four groups {out[8193].item():.0f}")
+    return out[:128 * 64].reshape(128, 64).cpu()
 
 
 def _relerr(a, b):
@@ -60,3 +62,26 @@ def test_tcgen05_column_sum_form_noswizzle_operand():
     lanes = torch.tensor([(i % 16) + 32 * (i // 16) for i in range(64)])
     for col in range(8):
         assert _relerr(out[lanes, col], ref) < 3e-5, (col, _relerr(out[lanes, col], ref))
+
+
+@pytest.mark.parametrize("mode", [4, 5, 6, 7])
+def test_tcgen05_a_operand_in_tensor_memory(mode):
+    """modes 4 / 5: forward / data-gradient forms with the A operand read from TMEM (packed bf16 pairs, one row per
+    lane); modes 6 / 7: the shared-memory-A forms through the same timed path."""
+    g = torch.Generator().manual_seed(10 + mode)
+    A, W = torch.randn(128, 64, generator=g), torch.randn(64, 64, generator=g)
+    out = _run(mode, A, W)
+    ref = A.double() @ (W.double().t() if mode in (4, 6) else W.double())
+    assert _relerr(out, ref) < 3e-5, _relerr(out, ref)
+
+
+def test_tcgen05_timed_wgrad_and_column_sum_forms():
+    """modes 8 / 9 = modes 2 / 3 through the timed path (prints the cycles of the 24- and 16-MMA groups)."""
+    g = torch.Generator().manual_seed(3)
+    A, G = torch.randn(128, 64, generator=g), torch.randn(128, 64, generator=g)
+    out = _run(8, A, G)
+    ref = A.double().t() @ G.double()
+    rows = torch.tensor([(o % 16) + 32 * (o // 16) for o in range(64)])
+    assert _relerr(out[rows], ref) < 3e-5
+    out = _run(9, A, G)
+    assert _relerr(out[rows, 0], A.double().sum(0)) < 3e-5
