@@ -669,6 +669,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
 #ifdef NB_STAGE_CLOCKS
   __shared__ long long dbg_acc[32];
   const bool dbg_on = blockIdx.x == 0 && threadIdx.x == 0;
+  const long long dbg_t0 = clock64();
+  unsigned long long dbg_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
   long long dbg_last = 0;
   if (dbg_on) {
     for (int i = 0; i < 32; ++i) dbg_acc[i] = 0;
@@ -1204,5 +1207,15 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   nb_tc_fence_before();
   __syncthreads();
   if (warp == 0) nb_tmem_dealloc(tm, NB_SB_TMEM_COLS);
+#ifdef NB_STAGE_CLOCKS
+  if (threadIdx.x == 0) {  // whole-CTA cycles: [27] max over CTAs and launches, [28] sum over CTAs; [29] the same span in ns
+    const long long dt = clock64() - dbg_t0;
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    atomicMax((unsigned long long*)&nb_dbg_clk[27], (unsigned long long)dt);
+    atomicAdd((unsigned long long*)&nb_dbg_clk[28], (unsigned long long)dt);
+    atomicAdd((unsigned long long*)&nb_dbg_clk[29], g1 - dbg_g0);  // [28] / [29] = effective SM clock in GHz
+  }
+#endif
 }
 #endif  // NB_EMU

@@ -57,6 +57,7 @@ def run(B=256, N=20, T=10, L=4, steps=3):
     step()
     buf = (ctypes.c_longlong * 32)()
     fn(buf, 1)
+    lib.nb_profile_enable(1)
     for _ in range(steps):
         step()
     fn(buf, 0)
@@ -66,6 +67,12 @@ def run(B=256, N=20, T=10, L=4, steps=3):
     tiles = units * -(-N * (N - 1) // 128) if N <= 27 else None
     print(f"k_edge_bwd_sel, CTA 0: {launches} launches, {tot / launches:.0f} cycles per launch"
           + (f", {units} units, {tiles} tiles per launch" if tiles else ""))
+    print(f"  whole CTA: slowest CTA of any launch {buf[27]} cycles, mean over CTAs and launches {buf[28] / launches / 148:.0f}"
+          f" = {buf[29] / launches / 148 / 1e3:.1f} us (globaltimer): effective SM clock {buf[28] / max(buf[29], 1):.3f} GHz")
+    import ctypes as C
+    ms = (C.c_double * 8)(); cnt = (C.c_longlong * 8)()
+    lib.nb_profile_read(ms, cnt)
+    print("  CUDA-event times per category (ms per launch):", [round(ms[i] / max(cnt[i], 1), 4) for i in range(8)], list(cnt))
     for i in range(27):
         if buf[i]:
             per = f"{buf[i] / launches / tiles:8.0f} /tile" if tiles else ""
