@@ -175,6 +175,27 @@ __device__ __forceinline__ void nb_store16_ta(unsigned char* hi, unsigned char* 
   nb_tmem_st44(ta_lo, l0, l1);
 }
 
+// 32 consecutive fp32 values of row r (column half hf) -> this thread's TMEM lane (2 x 8 packed columns per piece) and,
+// when `hi` is given, the shared-memory tiles (chunks 4 hf .. 4 hf + 3)
+__device__ __forceinline__ void nb_store32_ta(unsigned char* hi, unsigned char* lo, int r, int hf, const float* v, uint32_t ta_hi,
+                                              uint32_t ta_lo) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint32_t h0[4], l0[4], h1[4], l1[4];
+    nb_split8(v + 16 * k, h0, l0);
+    nb_split8(v + 16 * k + 8, h1, l1);
+    if (hi) {
+      const uint32_t o0 = nb_tc_chunk_off(r, 4 * hf + 2 * k), o1 = nb_tc_chunk_off(r, 4 * hf + 2 * k + 1);
+      *reinterpret_cast<uint4*>(hi + o0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+      *reinterpret_cast<uint4*>(hi + o1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+      *reinterpret_cast<uint4*>(lo + o0) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+      *reinterpret_cast<uint4*>(lo + o1) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+    }
+    nb_tmem_st44(ta_hi + 8u * k, h0, h1);
+    nb_tmem_st44(ta_lo + 8u * k, l0, l1);
+  }
+}
+
 // gather: D[128 x 64] (+)= Sel[128 x 16 ksteps] . (Nh + Nl),  Sel K-major, node tile MN-major (K = node-tile rows)
 __device__ __forceinline__ void nb_issue_gather(uint32_t tmem_d, uint32_t sel, uint32_t n_hi, uint32_t n_lo, int ksteps,
                                                 uint32_t idesc, uint32_t acc0) {
@@ -320,7 +341,8 @@ __device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned ch
 #define NB_SF_FL (NB_SF_F + 2 * NB_TILE * 16)
 #define NB_SF_NFLOAT (3 * NB_H + 2 * NB_TILE + 2 * 32 * 3)
 #define NB_EDGE_FWD_SEL_SMEM(RU) (NB_SF_FL + NB_SF_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
-#define NB_SF_TMEM_COLS 256  // [0,64) pre-activations | [64,128) M accumulators | [128,136) Fsum accumulators
+#define NB_SF_TMEM_COLS 256  // [0,64) pre-activations | [64,128) M accumulators | [128,136) Fsum accumulators |
+                             // [192,224) hi, [224,256) lo pieces of the A operand (z1, then m) as packed bf16 pairs
 
 template <bool BLK>
 __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a) {
@@ -390,6 +412,9 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
   nb_tc_fence_after();
   const uint32_t tm = *tmem_slot;
   const uint32_t tm_mine = tm + ((uint32_t)(32 * q) << 16) + (uint32_t)cb;
+  // the two 64-deep products read their activation operand from tensor memory (see the backward kernel's note)
+  const uint32_t ta_h = tm + 192, ta_l = tm + 224;
+  const uint32_t ta_hm = ta_h + ((uint32_t)(32 * q) << 16) + 16u * (uint32_t)hf, ta_lm = ta_l + ((uint32_t)(32 * q) << 16) + 16u * (uint32_t)hf;
   const uint32_t idesc_fwd = nb_idesc_bf16(128, 64, 0, 0);  // A K-major, B K-major (W^T)
   const uint32_t idesc_gat = nb_idesc_bf16(128, 64, 0, 1);  // A K-major, B MN-major
   const uint32_t idesc_sc = nb_idesc_bf16(64, 64, 1, 1);    // Sel^T . tile
@@ -465,15 +490,14 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         nb_tmem_ld32(tm_mine, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Th, Tl, row, 4 * hf + jj, v + 8 * jj);
+        nb_store32_ta(nullptr, nullptr, row, hf, v, ta_hm, ta_lm);  // z1 is only ever an A operand: no shared-memory copy
+        nb_tmem_st_wait();
       }
-      nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3(tm, sTh, sTl, sW2h, sW2l, false, idesc_fwd, 0u);
+        nb_issue_w3_ta(tm, ta_h, ta_l, sW2h, sW2l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
       }
       nb_mbar_wait(bar, phase);
@@ -485,15 +509,15 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         nb_tmem_ld32(tm_mine, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i] + vb2[cb + i]);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Th, Tl, row, 4 * hf + jj, v + 8 * jj);
+        nb_store32_ta(Th, Tl, row, hf, v, ta_hm, ta_lm);  // shared-memory copy: B operand of the scatter M_i += Sel^T m
+        nb_tmem_st_wait();
       }
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3(tm, sTh, sTl, sW3h, sW3l, false, idesc_fwd, 0u);
+        nb_issue_w3_ta(tm, ta_h, ta_l, sW3h, sW3l, false, idesc_fwd, 0u);
         nb_mma_commit(bar);
         // M_i += Sel^T m  (runs underneath the phi_x epilogue)
         nb_issue_scatter(tm + 64, sSel, sTh, sTl, idesc_sc, (r0 > 0 || !U.first_j) ? 1u : 0u);

@@ -640,13 +640,16 @@ static void egno_layout(const NbEgnoConfig* c, EgnoLayout* lo) {
 }
 
 struct EgnoLayerBufs {
-  float *h0, *h1, *M, *U5, *UV, *x0, *v0, *x1, *v1, *Fsum;
+  float *h0, *h1, *M, *U5, *UV, *P, *Q, *x0, *v0, *x1, *v1, *Fsum;
 };
-static inline int64_t egno_layer_floats(int64_t Nn) { return Nn * (5 * NB_H + 5 * 3); }
+// P, Q (the per-node halves of the first edge layer) are kept for the backward edge tile: 26 MB per layer at B = 256
+// instead of one more two-job GEMM launch per layer in the backward pass
+static inline int64_t egno_layer_floats(int64_t Nn) { return Nn * (7 * NB_H + 5 * 3); }
 static EgnoLayerBufs egno_layer_bufs(float* base, int64_t Nn) {
   EgnoLayerBufs b;
   b.h0 = base; b.h1 = b.h0 + Nn * NB_H; b.M = b.h1 + Nn * NB_H; b.U5 = b.M + Nn * NB_H; b.UV = b.U5 + Nn * NB_H;
-  b.x0 = b.UV + Nn * NB_H; b.v0 = b.x0 + Nn * 3; b.x1 = b.v0 + Nn * 3; b.v1 = b.x1 + Nn * 3; b.Fsum = b.v1 + Nn * 3;
+  b.P = b.UV + Nn * NB_H; b.Q = b.P + Nn * NB_H;
+  b.x0 = b.Q + Nn * NB_H; b.v0 = b.x0 + Nn * 3; b.x1 = b.v0 + Nn * 3; b.v1 = b.x1 + Nn * 3; b.Fsum = b.v1 + Nn * 3;
   return b;
 }
 static inline int64_t align64(int64_t v) { return (v + 63) / 64 * 64; }
@@ -906,12 +909,14 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       cudaMemcpyAsync(v1, v0, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     }
     // ---- EGNN layer (basic.py:167-186)
-    NB_TRY(egno_pq(X, l, h1, P, Q));
+    float* Pl = saved ? b.P : P;  // training: kept for the backward edge tile
+    float* Ql = saved ? b.Q : Q;
+    NB_TRY(egno_pq(X, l, h1, Pl, Ql));
     NbEdgeFwdArgs ea;
     ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
     egno_geom_frames(cfg, ea.g);
     ea.w = egno_edge_w(X, l);
-    ea.x = x1; ea.P = P; ea.Q = Q; ea.ef = edge_fea; ea.M = b.M; ea.Fsum = b.Fsum;
+    ea.x = x1; ea.P = Pl; ea.Q = Ql; ea.ef = edge_fea; ea.M = b.M; ea.Fsum = b.Fsum;
     NB_TRY(launch_edge_fwd(ea, stream));
     float* h_next = (l + 1 < Ln) ? bufs(l + 1).h0 : h_out;
     float* x_next = (l + 1 < Ln) ? bufs(l + 1).x0 : x_out;
@@ -1037,15 +1042,14 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       NB_TRY(wgrad_to((int)Nn, 1, wpair(GUV, h1), wpair(nullptr, nullptr), grad_params, L.v_w1, NB_H, 1,
                       L.v_b1, 0, stream));
     }
-    // 3. edge tile backward (recompute)
-    NB_TRY(egno_pq(X, l, h1, P, Q));
+    // 3. edge tile backward (recompute from the saved P, Q)
     {
       NbEdgeBwdArgs ea;
       memset(&ea, 0, sizeof(ea));
       ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
       egno_geom_frames(cfg, ea.g);
       ea.w = egno_edge_w(X, l);
-      ea.x = x1; ea.P = P; ea.Q = Q; ea.ef = edge_fea; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
+      ea.x = x1; ea.P = b.P; ea.Q = b.Q; ea.ef = edge_fea; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
       EdgeGradDst d;
       d.w1 = L.e_w1; d.W2 = L.e_w2; d.b2 = L.e_b2; d.W3 = L.c_w1; d.b3 = L.c_b1; d.w4 = L.c_w2; d.b4 = L.c_b2;
       d.ldw1 = X.lo.E; d.col_rad = 0; d.col_ef = 1 + 2 * NB_H; d.b_unused = 0;
