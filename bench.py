@@ -236,7 +236,7 @@ def run_ours(args):
 
     def loss_fn(x, nodes, ea, v, lm, target):
         xo, vo, ho = model(x, nodes, edges, ea, v=v, loc_mean=lm, timesteps_out=t_out)
-        return ((xo - target) ** 2).mean()
+        return nb.trajectory_mse(xo, target, T)[0]      # the callers' MSE (main_simulation_simple_no.py:273-276), fused
 
     def loss_from_raw(loc, vel, charges, target):
         # prepare_inputs on the device: one featurisation kernel (nb_nbody_features)

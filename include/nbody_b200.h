@@ -203,6 +203,16 @@ int nb_nbody_features(int32_t B, int32_t N, int32_t with_charge, const float* lo
 int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, float G, const float* loc, const float* vel,
                     const float* charges, float* energy, void* stream);
 
+/* Trajectory MSE and its gradient: the callers' loss
+ *   losses[t] = mean over (rows, xyz) of (pred - target)^2,   loss = mean_t losses[t]  (only_first: losses[0])
+ * (EGNO/main_simulation_simple_no.py:273-276: MSELoss(reduction='none')(...).mean((0, 1, 3)) then .mean() / [0];
+ * SEGNO/train_nbody.py:163-165 is the T = 1 case) with grad = d loss / d pred written in the same pass (nullable).
+ * pred is [T][rows][3] (the models' frame-major output); target_layout 0: [T][rows][3], 1: [rows][T][3] (the data
+ * loader's [B, N, T, 3]).  workspace: nb_traj_mse_workspace_floats(T) floats.  Two launches, deterministic. */
+int64_t nb_traj_mse_workspace_floats(int32_t T);
+int nb_traj_mse(int32_t T, int64_t rows, int32_t target_layout, int32_t only_first, const float* pred, const float* target,
+                float* losses, float* loss, float* grad, float* workspace, void* stream);
+
 /* Fused Adam over flat buffers: torch.optim.Adam semantics (amsgrad = False), one launch for n
  * elements; `step` is a device float counting the steps taken (incremented first when tick != 0), so the call is
  * CUDA-graph capturable.  Replaces the per-tensor optimizer launches of main.py:150 for models whose parameters and

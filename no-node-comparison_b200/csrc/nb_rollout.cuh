@@ -116,3 +116,65 @@ __global__ void __launch_bounds__(128) k_nbody_energy(NbEnergyArgs a) {
     }
   }
 }
+
+// ----------------------------------------------------------------------------- trajectory MSE
+// The callers' loss: MSELoss(reduction='none')(pred, target).mean((0, 1, 3)) -> losses[T], then losses.mean() or
+// losses[0] (EGNO/main_simulation_simple_no.py:273-276; SEGNO/train_nbody.py:163-165 with T = 1), and its gradient
+// with respect to the prediction, in two launches instead of ~10 element-wise / reduction kernels.  Deterministic:
+// per-CTA partial sums in a fixed order, no atomics.
+struct NbMseArgs {
+  int T, layout, only_first, nchunk;
+  int64_t R;                   // rows per frame (B*N)
+  const float* pred;           // [T][R][3], frame-major (the models' output layout)
+  const float* target;         // layout 0: [T][R][3] ; layout 1: [R][T][3] (the data loader's [B, N, T, 3])
+  float* grad;                 // [T][R][3] or null: d loss / d pred
+  float* partial;              // [T][nchunk]
+  float* losses;               // [T]
+  float* loss;                 // [1]
+};
+
+__global__ void __launch_bounds__(256) k_traj_mse(NbMseArgs a) {
+  __shared__ float part[256];
+  const int t = blockIdx.y, tid = threadIdx.x;
+  const int64_t n = a.R * 3;   // elements of one frame
+  const float gs = a.only_first ? (t == 0 ? 2.f / (float)n : 0.f) : 2.f / ((float)n * (float)a.T);
+  float acc = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + tid; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / 3;
+    const int k = (int)(e - 3 * r);
+    const float p = a.pred[(int64_t)t * n + e];
+    const float y = a.layout ? a.target[(r * a.T + t) * 3 + k] : a.target[(int64_t)t * n + e];
+    const float d = p - y;
+    acc = fmaf(d, d, acc);
+    if (a.grad) a.grad[(int64_t)t * n + e] = gs * d;
+  }
+  part[tid] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {   // fixed-shape tree: bitwise reproducible
+    if (tid < w) part[tid] += part[tid + w];
+    __syncthreads();
+  }
+  if (tid == 0) a.partial[(int64_t)t * a.nchunk + blockIdx.x] = part[0];
+}
+
+__global__ void __launch_bounds__(32) k_traj_mse_fin(NbMseArgs a) {
+  __shared__ float ls[NB_MAX_T];
+  const int t = threadIdx.x;
+  if (t < a.T) {
+    float s = 0.f;
+    for (int c = 0; c < a.nchunk; ++c) s += a.partial[(int64_t)t * a.nchunk + c];
+    s /= (float)(a.R * 3);
+    ls[t] = s;
+    a.losses[t] = s;
+  }
+  __syncthreads();
+  if (t == 0) {
+    float s = 0.f;
+    if (a.only_first) s = ls[0];
+    else {
+      for (int k = 0; k < a.T; ++k) s += ls[k];
+      s /= (float)a.T;
+    }
+    a.loss[0] = s;
+  }
+}

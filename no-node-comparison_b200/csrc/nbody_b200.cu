@@ -1616,6 +1616,26 @@ extern "C" int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, fl
   return nb_check_launch("k_nbody_energy");
 }
 
+#define NB_MSE_CHUNKS 64
+extern "C" int64_t nb_traj_mse_workspace_floats(int32_t T) { return (int64_t)(T > 0 ? T : 0) * NB_MSE_CHUNKS; }
+extern "C" int nb_traj_mse(int32_t T, int64_t rows, int32_t target_layout, int32_t only_first, const float* pred,
+                           const float* target, float* losses, float* loss, float* grad, float* workspace, void* stream) {
+  if (T < 1 || T > NB_MAX_T || rows < 1 || (target_layout != 0 && target_layout != 1) || !pred || !target || !losses ||
+      !loss || !workspace) {
+    nb_set_error("nb_traj_mse: unsupported arguments (T=%d (<= %d), rows=%lld, layout=%d) or null pointer", T, NB_MAX_T,
+                 (long long)rows, target_layout);
+    return NB_ERR_INVALID;
+  }
+  NbMseArgs a;
+  memset(&a, 0, sizeof(a));
+  a.T = T; a.layout = target_layout; a.only_first = only_first ? 1 : 0; a.R = rows; a.pred = pred; a.target = target;
+  a.grad = grad; a.partial = workspace; a.losses = losses; a.loss = loss;
+  a.nchunk = (int)imin(cdiv(rows * 3, 256), NB_MSE_CHUNKS);
+  NB_LAUNCH_COUNTED(k_traj_mse, dim3((unsigned)a.nchunk, (unsigned)T), 256, 0, stream, a);
+  NB_LAUNCH_COUNTED(k_traj_mse_fin, 1, 32, 0, stream, a);
+  return nb_check_launch("k_traj_mse");
+}
+
 // fused Adam: `step` is a device float holding the number of steps taken so far (incremented here when tick != 0);
 // [params, grads, exp_avg, exp_avg_sq] are flat fp32 buffers of n elements
 extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,

@@ -325,3 +325,13 @@ def energy_gravity(loc: Tensor, vel: Tensor, mass: Tensor, G: float = 1.0) -> Te
     pe = -(m[:, :, None] * m[:, None, :]) * inv
     PE = G * torch.triu(pe, 1).sum((-1, -2))
     return KE + PE
+
+
+def trajectory_mse(pred_tmajor: Tensor, target_bnt3: Tensor, only_first: bool = False) -> Tuple[Tensor, Tensor]:
+    """The callers' loss (EGNO/main_simulation_simple_no.py:268-276): pred [T*B*N, 3] frame-major as the model returns
+    it, target [B*N, T, 3] as the loader holds it -> (loss, losses[T]) with
+    losses = MSELoss(reduction='none')(pred, target).mean over (nodes, xyz); loss = losses[0] | losses.mean()."""
+    bn, T = target_bnt3.shape[0], target_bnt3.shape[1]
+    pred = pred_tmajor.reshape(T, bn, 3).transpose(0, 1)          # [BN, T, 3]   (:269)
+    losses = ((pred - target_bnt3) ** 2).mean((0, 2))             # [T]          (:273)
+    return (losses[0] if only_first else losses.mean()), losses   # (:276)

@@ -195,3 +195,25 @@ def test_fused_adam_kernel_vs_torch_adam():
                                ctypes.c_double(0.9), ctypes.c_double(0.99), ctypes.c_double(1e-8), ctypes.c_double(1e-2), None))
         np.testing.assert_allclose(p, ref.detach().numpy(), rtol=5e-7, atol=5e-8)
     assert step[0] == 5.0
+
+
+@pytest.mark.parametrize("T,R,layout,only_first", [(8, 25, 1, False), (10, 400, 0, False), (10, 40, 1, True), (1, 100, 0, False)])
+def test_trajectory_mse_kernel_vs_oracle(T, R, layout, only_first):
+    """nb_traj_mse (the callers' loss and its gradient) against the oracle's restatement of
+    main_simulation_simple_no.py:268-276 and torch autograd."""
+    L = E.lib()
+    g = torch.Generator().manual_seed(T * 1000 + R)
+    pred = torch.randn(T * R, 3, generator=g, requires_grad=True)
+    tgt_bnt3 = torch.randn(R, T, 3, generator=g)
+    loss_r, losses_r = O.trajectory_mse(pred, tgt_bnt3, only_first)
+    loss_r.backward()
+    tgt = tgt_bnt3 if layout == 1 else tgt_bnt3.transpose(0, 1).reshape(T * R, 3)
+    losses, loss = np.zeros(T, np.float32), np.zeros(1, np.float32)
+    grad = np.zeros((T * R, 3), np.float32)
+    ws = np.zeros(int(L.nb_traj_mse_workspace_floats(T)), np.float32)
+    E.check(L.nb_traj_mse(T, R, layout, int(only_first), E.ptr(E.f32(pred.detach())), E.ptr(E.f32(tgt)), E.ptr(losses),
+                          E.ptr(loss), E.ptr(grad), E.ptr(ws), None))
+    np.testing.assert_allclose(losses, losses_r.detach().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(loss[0], loss_r.item(), rtol=2e-6)
+    np.testing.assert_allclose(grad, pred.grad.numpy(), rtol=1e-6, atol=1e-9)
+    assert L.nb_traj_mse(0, R, layout, 0, E.ptr(grad), E.ptr(grad), E.ptr(losses), E.ptr(loss), None, E.ptr(ws), None) < 0

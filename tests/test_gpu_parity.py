@@ -661,3 +661,29 @@ def test_blocked_selector_walk_is_deterministic_and_batch_independent():
     ho3 = outs[0][1].view(T, 3 * N, -1)[:, :N].reshape(T * N, -1)
     assert rel_err(xo1.cpu(), xo3.cpu()) < 1e-6
     assert rel_err(ho1.cpu(), ho3.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("only_first", [False, True])
+def test_fused_trajectory_mse_matches_the_callers_loss(only_first):
+    """nb.trajectory_mse on a model output at BASELINE sizes: loss, per-frame losses and the gradient that
+    reaches the model against the oracle's restatement of main_simulation_simple_no.py:268-276 under autograd; both
+    target layouts; bitwise reproducible."""
+    dev = torch.device("cuda:0")
+    T, B, N = 10, 256, 20
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn(T * B * N, 3, generator=g)
+    tgt = torch.randn(B * N, T, 3, generator=g)
+    pr = pred.clone().requires_grad_(True)
+    loss_r, losses_r = O.trajectory_mse(pr, tgt, only_first)
+    loss_r.backward()
+    for target in (tgt.to(dev), tgt.reshape(B, N, T, 3).to(dev), tgt.transpose(0, 1).reshape(T * B * N, 3).contiguous().to(dev)):
+        pd = pred.to(dev).requires_grad_(True)
+        loss, losses = nb.trajectory_mse(pd, target, T, only_first)
+        (3.0 * loss).backward()
+        assert rel_err(losses.cpu(), losses_r.detach()) < 1e-5
+        assert abs(loss.item() - loss_r.item()) < 1e-5 * abs(loss_r.item())
+        assert rel_err(pd.grad.cpu(), 3.0 * pr.grad) < 1e-5
+        loss2, _ = nb.trajectory_mse(pd.detach(), target, T, only_first)
+        assert torch.equal(loss2, loss.detach())
+    with pytest.raises(ValueError):
+        nb.trajectory_mse(pred.to(dev), tgt.to(dev)[:, :5], T)
