@@ -688,6 +688,26 @@ __device__ long long nb_dbg_clk[32];
 #define NB_CLK(i)
 #endif
 
+// dW | db (+)= G^T [A | 1]: the bias column sums ride in the weight-gradient MMAs as a second MN block of the B operand
+// (N = 72: the 64 columns of A, then 8 columns of an all-ones SW128 tile `lbo` bytes above a_hi) for the passes
+// (g_hi, a_hi), (g_lo, a_hi); the pass (g_hi, a_lo) stays N = 64.  24 MMAs instead of 24 + 16 (an N = 8 MMA costs 23 cycles).
+__device__ __forceinline__ void nb_issue_wgrad_fold(uint32_t tmem_w, uint32_t g_hi, uint32_t g_lo, uint32_t a_hi, uint32_t a_lo,
+                                                    uint32_t lbo, uint32_t idesc64, uint32_t idesc72, uint32_t acc0) {
+  uint32_t acc = acc0;
+  const uint32_t b72 = ((a_hi >> 4) & 0x3FFFu) | ((lbo >> 4) << 16);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t ga = nb_desc_lo_mn(pass == 1 ? g_lo : g_hi);
+    const uint32_t ab = pass == 2 ? nb_desc_lo_mn(a_lo) : b72;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      nb_mma2(tmem_w, ga + NB_KSTEP_MN * s, NB_DESC_HI_SW128, ab + NB_KSTEP_MN * s, NB_DESC_HI_SW128, pass == 2 ? idesc64 : idesc72, acc);
+      acc = 1u;
+    }
+  }
+}
+#define NB_SB_ONES64_BYTES NB_TC_TILE_BYTES(128)  // whole-graph units only: all-ones SW128 tile (second MN block of the fold)
+
 template <bool BLK>
 __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs a) {
 #ifdef NB_STAGE_CLOCKS
@@ -723,7 +743,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   unsigned char* RGh = base + NB_SB_RG;
   unsigned char* RGl = RGh + NB_TILE * 16;
   float* scratch = reinterpret_cast<float*>(Tzh);  // fp32 [128][64] view, CTA epilogue only
-  float* fl = reinterpret_cast<float*>(base + NB_SB_FL);
+  constexpr bool FOLD = !BLK;  // bias sums folded into the weight-gradient MMAs (needs 16 KB the blocked walk does not have)
+  unsigned char* ones64 = base + NB_SB_FL;  // FOLD only
+  float* fl = reinterpret_cast<float*>(base + NB_SB_FL + (FOLD ? NB_SB_ONES64_BYTES : 0));
   float* vb2 = fl;
   float* vb3 = vb2 + NB_H;
   float* vw4 = vb3 + NB_H;
@@ -768,6 +790,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     uint32_t one2 = 0x3F803F80u;  // bf16 (1.0, 1.0)
     *reinterpret_cast<uint4*>(ones + tid * 16) = make_uint4(one2, one2, one2, one2);
   }
+  if (FOLD)
+    for (int idx = tid; idx < (int)(NB_SB_ONES64_BYTES / 16); idx += NB_SB_THREADS)
+      reinterpret_cast<uint4*>(ones64)[idx] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (tid < NB_H) {
     vb2[tid] = __ldg(a.w.b2 + tid);
     vb3[tid] = __ldg(a.w.b3 + tid);
@@ -809,6 +834,10 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   const uint32_t idesc_dg = nb_idesc_bf16(128, 64, 0, 1);   // also the gathers
   const uint32_t idesc_wg = nb_idesc_bf16(64, 64, 1, 1);    // also the 64-wide scatters
   const uint32_t idesc_bs = nb_idesc_bf16(64, 8, 1, 1);
+  const uint32_t idesc_wg72 = nb_idesc_bf16(64, 72, 1, 1);
+  // TMEM columns of the weight-gradient accumulators: dW3 | db3 | dW2 | db2 contiguous when folded
+  constexpr uint32_t cW3 = 192, cW2 = FOLD ? 264 : 256, cB3 = FOLD ? 256 : 320, cB2 = 328;
+  const uint32_t sOnes64 = nb_smem_u32(ones64);
   const uint32_t sTzh = nb_smem_u32(Tzh), sTzl = nb_smem_u32(Tzl), sTmh = nb_smem_u32(Tmh), sTml = nb_smem_u32(Tml),
                  sTgh = nb_smem_u32(Tgh), sTgl = nb_smem_u32(Tgl), sSel = nb_smem_u32(Sel), sNh = nb_smem_u32(Nh),
                  sNl = nb_smem_u32(Nl), sGMh = nb_smem_u32(GMh), sGMl = nb_smem_u32(GMl), sOnes = nb_smem_u32(ones),
@@ -1023,7 +1052,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_issue_gather(tm + 128, sSel, sGMh, sGMl, ks_recv, idesc_dg, 1u);          //    + gM_i
         nb_mma_commit(bar);
         NB_CLK(14)
-        nb_issue_wgrad(tm + 192, tm + 320, sTgh, sTgl, sTmh, sTml, sOnes, idesc_wg, idesc_bs, wacc);  // dW3, db3
+        if (FOLD) nb_issue_wgrad_fold(tm + cW3, sTgh, sTgl, sTmh, sTml, sOnes64 - sTmh, idesc_wg, idesc_wg72, wacc);
+        else nb_issue_wgrad(tm + cW3, tm + cB3, sTgh, sTgl, sTmh, sTml, sOnes, idesc_wg, idesc_bs, wacc);  // dW3, db3
         nb_mma_commit(bar2);
       }
       NB_CLK(15)
@@ -1054,7 +1084,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_issue_w3_ta(tm + 128, ta_h, ta_l, sW2h, sW2l, true, idesc_dg, 0u);  // gz1 = g2 W2
         nb_mma_commit(bar);
         NB_CLK(20)
-        nb_issue_wgrad(tm + 256, tm + 328, sTgh, sTgl, sTzh, sTzl, sOnes, idesc_wg, idesc_bs, wacc);  // dW2, db2
+        if (FOLD) nb_issue_wgrad_fold(tm + cW2, sTgh, sTgl, sTzh, sTzl, sOnes64 - sTzh, idesc_wg, idesc_wg72, wacc);
+        else nb_issue_wgrad(tm + cW2, tm + cB2, sTgh, sTgl, sTzh, sTzl, sOnes, idesc_wg, idesc_bs, wacc);  // dW2, db2
       }
       wacc = 1;
       NB_CLK(21)
@@ -1185,15 +1216,17 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
 #pragma unroll
       for (int k = 0; k < 4; ++k) nb_st4(out + NB_EB_GW3 + o * NB_H + cb + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
     }
-    nb_tmem_ld16(tm + lane_base + 256 + (uint32_t)cb, v);  // dW2[o][cb..]
+    nb_tmem_ld16(tm + lane_base + cW2 + (uint32_t)cb, v);  // dW2[o][cb..]
     if (lane < 16 && wacc) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) nb_st4(out + NB_EB_GW2 + o * NB_H + cb + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
     }
-    nb_tmem_ld16(tm + lane_base + 320, v);  // db3 in column 0, db2 in column 8
+    float b3v[4], b2v[4];
+    nb_tmem_ld4(tm + lane_base + cB3, b3v);  // db3 / db2: every column of the 8-wide block holds the sum
+    nb_tmem_ld4(tm + lane_base + cB2, b2v);
     if (lane < 16 && cq == 0 && wacc) {
-      out[NB_EB_GB3 + o] = v[0];
-      out[NB_EB_GB2 + o] = v[8];
+      out[NB_EB_GB3 + o] = b3v[0];
+      out[NB_EB_GB2 + o] = b2v[0];
     }
   }
   if (!wacc) {  // a CTA that processed no tile contributes zeros

@@ -246,6 +246,10 @@ __device__ __forceinline__ void nb_tc_issue3(uint32_t tmem_d, uint32_t a_hi, uin
 // mode 2: D[ 64x64] = A^T * G              (A = A[r][c] MN-major (M = c), B = G[r][c] MN-major (N = c), K = 128 rows)
 // mode 4 / 5: modes 0 / 1 with the A operand in tensor memory (nb_mma_bf16_ta)
 // mode 6 .. 9: modes 0 .. 3 (shared-memory A), timed like 4 / 5
+// mode 10: D[64 x 72] = A^T * [G | 1]: the weight-gradient form with the bias column sums folded in as a second MN block
+//          of the B operand (N = 72: 64 columns of G, then 8 columns of an all-ones SW128 tile LBO bytes further on);
+//          hi*hi + lo*hi with N = 72, hi*lo with N = 64.  Dump: columns 0..63 of the accumulator, then out[8192 + 64 l + c]
+//          = columns 64..71 (c < 8) of lane l
 // out: raw dump of the 128 TMEM lanes x 64 columns; modes >= 4 append out[8192] = cycles of one 12-MMA group (issue ->
 //      commit observed), out[8193] = cycles of four groups issued back to back
 __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ W,
@@ -264,6 +268,8 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
     nb_mbar_fence_init();
   }
   if (warp == 0) nb_tmem_alloc(&tmem_base, 128);
+  const bool fold = mode == 10;
+  if (fold) mode = 2;
   const bool timed = mode >= 4, a_tmem = mode == 4 || mode == 5;
   if (mode >= 6) mode -= 6;
   // operand tiles: this thread owns row `tid`
@@ -279,11 +285,42 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
       for (int j = 0; j < 8; ++j) nb_tc_store8(b_hi, b_lo, tid, j, wr + 8 * j);
     }
   }
+  unsigned char* ones_t = b_lo + NB_TC_TILE_BYTES(128);  // mode 10 only (the host sizes shared memory for it)
+  if (fold) {
+    const uint32_t one2 = 0x3F803F80u;
+    for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(ones_t + tid * NB_TC_ROW_BYTES + 16 * c) = make_uint4(one2, one2, one2, one2);
+  }
   nb_fence_async_smem();
   nb_tc_fence_before();
   __syncthreads();
   nb_tc_fence_after();
   const uint32_t tm = tmem_base;
+  if (fold) {
+    if (tid == 0) {
+      const uint32_t sah = nb_smem_u32(a_hi), sal = nb_smem_u32(a_lo), sbh = nb_smem_u32(b_hi), sbl = nb_smem_u32(b_lo);
+      const uint32_t lbo = nb_smem_u32(ones_t) - sbh;  // second MN block of the B operand: the ones tile
+      uint32_t acc = 0;
+      for (int pass = 0; pass < 3; ++pass)
+        for (int s = 0; s < 8; ++s) {
+          const uint64_t ad = nb_desc_mnmajor(pass == 1 ? sal : sah, s);
+          const uint64_t bd = pass == 2 ? nb_desc_mnmajor(sbl, s) : nb_make_desc(sbh + 2048 * s, lbo, 1024);
+          nb_mma_bf16(tm, ad, bd, pass == 2 ? nb_idesc_bf16(64, 64, 1, 1) : nb_idesc_bf16(64, 72, 1, 1), acc);
+          acc = 1;
+        }
+      nb_mma_commit(&bar);
+    }
+    nb_mbar_wait(&bar, 0);
+    nb_tc_fence_after();
+    float v8[4];
+    const uint32_t la = tm + ((uint32_t)(warp * 32) << 16);
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[4];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(la + 64 + 4 * h) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int i = 0; i < 4; ++i) v8[i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 4; ++i) out[8192 + (size_t)tid * 64 + 4 * h + i] = v8[i];
+    }
+  } else
   if (a_tmem) {  // A row `tid` -> TMEM lane tid, columns [64, 96) hi pieces, [96, 128) lo pieces
     const float* ar = A + (size_t)tid * 64;
     const uint32_t la = tm + ((uint32_t)(warp * 32) << 16);
@@ -370,7 +407,7 @@ __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __re
     }
     nb_mma_commit(&bar);
   }
-  if (!timed) nb_mbar_wait(&bar, 0);
+  if (!timed && !fold) nb_mbar_wait(&bar, 0);
   nb_tc_fence_after();
   float v[32];
   const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);

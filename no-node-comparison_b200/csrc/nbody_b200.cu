@@ -511,7 +511,8 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
   bool done = false;
 #ifndef NB_EMU
   if (use_sel) {
-    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG) + (a.g.blk ? NB_EDGE_BWD_SEL_BLK_EXTRA(a.g.N) : 0);
+    const size_t smem_sel = NB_EDGE_BWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG) +
+                            (a.g.blk ? NB_EDGE_BWD_SEL_BLK_EXTRA(a.g.N) : NB_SB_ONES64_BYTES);
     int pi_sel = prof_begin(1, st);
     if (a.g.blk) {
       NB_SET_SMEM(k_edge_bwd_sel<true>, smem_sel);
@@ -1661,8 +1662,8 @@ extern "C" int nb_tc_selftest(int32_t mode, const float* A, const float* W, floa
   nb_set_error("tcgen05 is not available in the host emulator");
   return NB_ERR_INVALID;
 #else
-  if (mode < 0 || mode > 9) { nb_set_error("mode must be 0..9"); return NB_ERR_INVALID; }
-  const size_t smem = 4 * NB_TC_TILE_BYTES(128) + 1024;
+  if (mode < 0 || mode > 10) { nb_set_error("mode must be 0..10"); return NB_ERR_INVALID; }
+  const size_t smem = 5 * NB_TC_TILE_BYTES(128) + 1024;
   NB_SET_SMEM(k_tc_selftest, smem);
   NB_LAUNCH_COUNTED(k_tc_selftest, 1, 128, smem, stream, (int)mode, A, W, out);
   return nb_check_launch("k_tc_selftest");

@@ -14,11 +14,13 @@ def _run(mode, A, W):
     lib = nb.load_library()
     d = torch.device("cuda:0")
     Ad, Wd = A.to(d).contiguous(), W.to(d).contiguous()
-    out = torch.zeros(128 * 64 + 64, device=d)  # modes >= 4 append cycle counts behind the 128 x 64 dump
+    out = torch.zeros(2 * 128 * 64, device=d)  # modes >= 4 append cycle counts (mode 10: columns 64..71) behind the dump
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = lib.nb_tc_selftest(mode, P(Ad), P(Wd), P(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.nb_last_error()
     torch.cuda.synchronize()
+    if mode == 10:
+        return out[:128 * 64].reshape(128, 64).cpu(), out[128 * 64:].reshape(128, 64)[:, :8].cpu()
     if mode >= 4:
         print(f"tcgen05 selftest mode {mode}: one 12-MMA group {out[8192].item():.0f} cycles, four groups {out[8193].item():.0f}")
     return out[:128 * 64].reshape(128, 64).cpu()
@@ -85,3 +87,15 @@ def test_tcgen05_timed_wgrad_and_column_sum_forms():
     assert _relerr(out[rows], ref) < 3e-5
     out = _run(9, A, G)
     assert _relerr(out[rows, 0], A.double().sum(0)) < 3e-5
+
+
+def test_tcgen05_wgrad_form_with_folded_column_sums():
+    """mode 10: D[64 x 72] = A^T [G | 1] — an N = 72 MN-major B operand whose second block (LBO) is an all-ones tile, so
+    the bias gradient (column sums of A) rides in the weight-gradient MMAs."""
+    g = torch.Generator().manual_seed(4)
+    A, G = torch.randn(128, 64, generator=g), torch.randn(128, 64, generator=g)
+    out, tail = _run(10, A, G)
+    rows = torch.tensor([(o % 16) + 32 * (o // 16) for o in range(64)])
+    assert _relerr(out[rows], A.double().t() @ G.double()) < 3e-5
+    for c in range(8):
+        assert _relerr(tail[rows, c], A.double().sum(0)) < 3e-5, c
