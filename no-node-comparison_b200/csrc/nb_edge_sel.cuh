@@ -591,8 +591,8 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 //   T0  selector row                                   -> gather  pre1            (MMA, waited)
 //   S1  z1, SiLU'(pre1) parked in TMEM                 -> MMA 1   pre2
 //   S2  m,  SiLU'(pre2) parked in TMEM                 -> MMA 2   pre3
-//   S3  phi_x head, g3                                 -> dgrad 3 + gM broadcast  | side: dW3, db3
-//   S4  g2 = (gm + gM_i) SiLU'(pre2)                   -> dgrad 2                 | side: dW2, db2
+//   S3  phi_x head, g3                                 -> dgrad 3                 | side: dW3, db3
+//   S4  g2 = (gm + gM_i) SiLU'(pre2), gM_i from smem   -> dgrad 2                 | side: dW2, db2
 //   S5  g1 = gz1 SiLU'(pre1), dL/drij                  ->                           side: gP|gQ|gw += Sel^T g1, gx += Sel^T rG
 // One elected lane of warp 0 issues every MMA: first the critical-path ones (mbarrier `bar`), then the side ones
 // (`bar2`) -- the tensor pipe runs them in issue order, so the side MMAs execute underneath the next stage's CUDA-core
@@ -737,8 +737,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   unsigned char* Sel = base + NB_SB_SEL;
   unsigned char* Nh = base + NB_SB_NT;
   unsigned char* Nl = Nh + NB_TC_TILE_BYTES(64);
-  unsigned char* GMh = base + NB_SB_GM;
-  unsigned char* GMl = GMh + NB_TC_TILE_BYTES(64);
+  float* gMs = reinterpret_cast<float*>(base + NB_SB_GM);  // [32][64] fp32: dL/dM_i of the unit's receivers (added in S4)
   unsigned char* ones = base + NB_SB_ONES;
   unsigned char* RGh = base + NB_SB_RG;
   unsigned char* RGl = RGh + NB_TILE * 16;
@@ -840,11 +839,10 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   const uint32_t sOnes64 = nb_smem_u32(ones64);
   const uint32_t sTzh = nb_smem_u32(Tzh), sTzl = nb_smem_u32(Tzl), sTmh = nb_smem_u32(Tmh), sTml = nb_smem_u32(Tml),
                  sTgh = nb_smem_u32(Tgh), sTgl = nb_smem_u32(Tgl), sSel = nb_smem_u32(Sel), sNh = nb_smem_u32(Nh),
-                 sNl = nb_smem_u32(Nl), sGMh = nb_smem_u32(GMh), sGMl = nb_smem_u32(GMl), sOnes = nb_smem_u32(ones),
+                 sNl = nb_smem_u32(Nl), sOnes = nb_smem_u32(ones),
                  sRGh = nb_smem_u32(RGh), sRGl = nb_smem_u32(RGl), sW2h = nb_smem_u32(W2h), sW2l = nb_smem_u32(W2l),
                  sW3h = nb_smem_u32(W3h), sW3l = nb_smem_u32(W3l);
   const float b4 = __ldg(a.w.b4);
-  const int ks_recv = ((BLK ? g.IB : g.G * g.N) + 15) >> 4;  // k-steps holding the receiver columns
   uint32_t phase = 0, phase2 = 0;
   uint32_t wacc = 0;
 
@@ -899,8 +897,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_tc_store8(Nh, Nl, nt_row, t_nt & 7, v);
       }
       if (do_gm) {
-        float v[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        nb_tc_store8(GMh, GMl, tid >> 3, tid & 7, v);
+        nb_st4(gMs + (tid >> 3) * NB_H + 8 * (tid & 7), m0);
+        nb_st4(gMs + (tid >> 3) * NB_H + 8 * (tid & 7) + 4, m1);
       }
       if (t_x < n3) {
         if (t_x < n3r) {
@@ -1048,8 +1046,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       NB_CLK(13)
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
-        nb_issue_w3_ta(tm + 128, ta_h, ta_l, sW3h, sW3l, true, idesc_dg, 0u);        // gm = g3 W3
-        nb_issue_gather(tm + 128, sSel, sGMh, sGMl, ks_recv, idesc_dg, 1u);          //    + gM_i
+        nb_issue_w3_ta(tm + 128, ta_h, ta_l, sW3h, sW3l, true, idesc_dg, 0u);        // gm = g3 W3  (+ gM_i: added in S4)
         nb_mma_commit(bar);
         NB_CLK(14)
         if (FOLD) nb_issue_wgrad_fold(tm + cW3, sTgh, sTgl, sTmh, sTml, sOnes64 - sTmh, idesc_wg, idesc_wg72, wacc);
@@ -1066,6 +1063,20 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         float v[16], d[16];
         nb_tmem_ld16(t3, v);
         nb_tmem_ld16(t2, d);
+        {  // + dL/dM of the row's receiver, straight from shared memory (exact; 4 gather MMAs less on the critical path)
+          int li4 = 0, lj4, gt4, rem4;
+          const bool ok4 = nb_sel_row<BLK>(g, U, rowinfo, r0 + row, li4, lj4, gt4, rem4);
+          const float* gmr = gMs + (ok4 ? li4 : 0) * NB_H + cb;
+          const float msk = ok4 ? 1.f : 0.f;  // padded rows: g2 = 0 (their SiLU' values are arbitrary)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 gq = nb_ld4(gmr + 4 * k);
+            v[4 * k + 0] = fmaf(msk, gq.x, v[4 * k + 0]);
+            v[4 * k + 1] = fmaf(msk, gq.y, v[4 * k + 1]);
+            v[4 * k + 2] = fmaf(msk, gq.z, v[4 * k + 2]);
+            v[4 * k + 3] = fmaf(msk, gq.w, v[4 * k + 3]);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= d[i];
         NB_CLK(17)
