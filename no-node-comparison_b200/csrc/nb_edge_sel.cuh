@@ -635,6 +635,16 @@ __device__ __forceinline__ void nb_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void nb_tmem_st16_nowait(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
 __device__ __forceinline__ void nb_tmem_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -964,9 +974,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_tmem_ld16(t1, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) nb_silu_grad(v[i], v[i], d[i]);
-        nb_tmem_st16(t1, d);
+        nb_tmem_st16_nowait(t1, d);
         nb_store16_ta(Tzh, Tzl, row, cq, v, ta_hm, ta_lm);
-        nb_tmem_st_wait();
+        nb_tmem_st_wait();  // one wait for the parked SiLU' values and the A operand
       }
       nb_fence_async_smem();
       nb_tc_fence_before();
@@ -988,7 +998,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_tmem_ld16(t2, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) nb_silu_grad(v[i] + vb2[cb + i], v[i], d[i]);
-        nb_tmem_st16(t2, d);
+        nb_tmem_st16_nowait(t2, d);
         nb_store16_ta(Tmh, Tml, row, cq, v, ta_hm, ta_lm);
         nb_tmem_st_wait();
       }
@@ -1145,6 +1155,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     phase2 ^= 1;
     nb_tc_fence_after();
     NB_CLK(25)
+    float gx_old = 0.f;  // whole-graph units: issued here, consumed after the read-out's barrier (latency hidden)
+    if (!BLK && tid < U.nrecv * 3) gx_old = a.gx[(int64_t)U.recv0 * 3 + tid];
     {
       const int i = 16 * q + lane;
       float v[16];
@@ -1189,9 +1201,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     __syncthreads();
     // dL/dx: + receiver sums - sender sums
     if (!BLK) {  // one node list
-      for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
-        int n = idx / 3, dd = idx - 3 * n;
-        a.gx[(int64_t)U.recv0 * 3 + idx] += gxst[n * 4 + dd] - gxst[(U.RC + n) * 4 + dd];
+      if (tid < U.nrecv * 3) {  // nrecv * 3 <= 81 < blockDim.x
+        const int n = tid / 3, dd = tid - 3 * n;
+        a.gx[(int64_t)U.recv0 * 3 + tid] = gx_old + (gxst[n * 4 + dd] - gxst[(U.RC + n) * 4 + dd]);
       }
     } else {       // two lists that may overlap: two passes, into the per-graph accumulator
       for (int idx = tid; idx < U.nrecv * 3; idx += NB_SB_THREADS) {
