@@ -588,8 +588,8 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 
 // ----------------------------------------------------------------------------- backward
 // 512 threads: thread (warp w, lane l) owns row 32 (w & 3) + l and the 16 columns of quarter (w >> 2).
-//   T0  selector row                                   -> gather  pre1            (MMA, waited)
-//   S1  z1, SiLU'(pre1) parked in TMEM                 -> MMA 1   pre2
+//   S1  selector row (for the scatters); pre1 = P_i + Q_j + w_rad r2 + W_e e summed in fp32 from shared-memory
+//       copies of the unit's P / Q rows (no gather MMA, no round trip); z1, SiLU'(pre1) parked in TMEM -> MMA 1   pre2
 //   S2  m,  SiLU'(pre2) parked in TMEM                 -> MMA 2   pre3
 //   S3  phi_x head, g3                                 -> dgrad 3                 | side: dW3, db3
 //   S4  g2 = (gm + gM_i) SiLU'(pre2), gM_i from smem   -> dgrad 2                 | side: dW2, db2
@@ -616,7 +616,8 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
 #define NB_SB_ONES (NB_SB_GM + 2 * NB_TC_TILE_BYTES(64))
 #define NB_SB_RG (NB_SB_ONES + NB_TILE * 16)
 #define NB_SB_FL (NB_SB_RG + 2 * NB_TILE * 16)
-#define NB_SB_NFLOAT (4 * NB_H + 4 * NB_TILE + 3 * 32 * 3 + 10 * NB_H + NB_H * 4)
+#define NB_SB_NFLOAT (4 * NB_H + 4 * NB_TILE + 3 * 32 * 3 + 10 * NB_H + NB_H * 4 + NB_MAX_EF * NB_H)
+#define NB_SB_QLD 68  // row stride of the sender rows: lanes of a warp read 16 B of DIFFERENT rows at the same column offset
 #define NB_EDGE_BWD_SEL_SMEM(RU) (NB_SB_FL + NB_SB_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
 #define NB_SB_GXACC(N) (((N) * 3 + 3) / 4 * 4)
 #define NB_EDGE_BWD_SEL_BLK_EXTRA(N) ((32 * NB_H + (N) * NB_H + NB_SB_GXACC(N)) * 4)
@@ -745,8 +746,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   unsigned char* Tgh = base + NB_SB_TG;
   unsigned char* Tgl = Tgh + NB_TC_TILE_BYTES(128);
   unsigned char* Sel = base + NB_SB_SEL;
-  unsigned char* Nh = base + NB_SB_NT;
-  unsigned char* Nl = Nh + NB_TC_TILE_BYTES(64);
+  float* Pf = reinterpret_cast<float*>(base + NB_SB_NT);  // [receivers][64] fp32: P rows of the unit (P includes b1)
+  float* Qf = Pf + (BLK ? a.g.IB : a.g.G * a.g.N) * NB_H; // [senders][NB_SB_QLD] fp32: Q rows; receivers + senders <= 54: 14.7 KB
   float* gMs = reinterpret_cast<float*>(base + NB_SB_GM);  // [32][64] fp32: dL/dM_i of the unit's receivers (added in S4)
   unsigned char* ones = base + NB_SB_ONES;
   unsigned char* RGh = base + NB_SB_RG;
@@ -765,8 +766,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   float* gfs = xq + 32 * 3;           // [32][3] dL/dFsum of the unit's receivers
   float* gwacc = gfs + 32 * 3;        // [10][64]: rows 0,1 w_rad (hi, lo piece) ; 2 + 2f, 3 + 2f w_ef[f]
   float* gxst = gwacc + 10 * NB_H;    // [64][4]
+  float* Wef = gxst + NB_H * 4;       // [NB_MAX_EF][64] edge-feature columns of W1
   // blocked mode: per-graph accumulators, so that nothing is read-modified-written in global memory per tile
-  float* gPacc = gxst + NB_H * 4;                          // [32][64]  receivers of the current receiver block
+  float* gPacc = Wef + NB_MAX_EF * NB_H;                   // [32][64]  receivers of the current receiver block
   float* gQacc = gPacc + (BLK ? 32 * NB_H : 0);            // [N][64]   all senders of the graph-instance
   float* gxacc = gQacc + (BLK ? a.g.N * NB_H : 0);         // [N][3] (+ pad)
   uint32_t* rowinfo = reinterpret_cast<uint32_t*>(gxacc + (BLK ? NB_SB_GXACC(a.g.N) : 0));
@@ -792,8 +794,12 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
     nb_tc_store8(W2h, W2l, o, j, v2);
     nb_tc_store8(W3h, W3l, o, j, v3);
   }
-  for (int idx = tid; idx < 4 * NB_TC_TILE_BYTES(64) / 16; idx += NB_SB_THREADS)  // node tile + gM tile (contiguous)
-    reinterpret_cast<uint4*>(Nh)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  for (int idx = tid; idx < 4 * NB_TC_TILE_BYTES(64) / 16; idx += NB_SB_THREADS)  // P / Q rows + gM rows (contiguous)
+    reinterpret_cast<uint4*>(Pf)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  for (int idx = tid; idx < NB_MAX_EF * NB_H; idx += NB_SB_THREADS) {
+    const int f = idx >> 6, c = idx & 63;
+    Wef[idx] = f < g.nef ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_ef + f) : 0.f;
+  }
   nb_sel_build_rowinfo(rowinfo, g, tid, NB_SB_THREADS);
   if (tid < NB_TILE) {
     uint32_t one2 = 0x3F803F80u;  // bf16 (1.0, 1.0)
@@ -816,18 +822,6 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   }
   if (warp == 0) nb_tmem_alloc(tmem_slot, NB_SB_TMEM_COLS);
   __syncthreads();
-  for (int idx = tid; idx < 10 * 8; idx += NB_SB_THREADS) {
-    int k = idx >> 3, j = idx & 7;
-    int f = (k >> 1) - 1;  // -1: radial
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int c = 8 * j + i;
-      v[i] = f < 0 ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_rad)
-                   : (f < g.nef ? __ldg(a.w.W1 + (int64_t)c * a.w.ldw1 + a.w.col_ef + f) : 0.f);
-    }
-    nb_tc_store8(Nh, Nl, NB_SEL_XC0 + k, j, v);
-  }
   nb_fence_async_smem();
   nb_tc_fence_before();
   __syncthreads();
@@ -848,8 +842,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
   constexpr uint32_t cW3 = 192, cW2 = FOLD ? 264 : 256, cB3 = FOLD ? 256 : 320, cB2 = 328;
   const uint32_t sOnes64 = nb_smem_u32(ones64);
   const uint32_t sTzh = nb_smem_u32(Tzh), sTzl = nb_smem_u32(Tzl), sTmh = nb_smem_u32(Tmh), sTml = nb_smem_u32(Tml),
-                 sTgh = nb_smem_u32(Tgh), sTgl = nb_smem_u32(Tgl), sSel = nb_smem_u32(Sel), sNh = nb_smem_u32(Nh),
-                 sNl = nb_smem_u32(Nl), sOnes = nb_smem_u32(ones),
+                 sTgh = nb_smem_u32(Tgh), sTgl = nb_smem_u32(Tgl), sSel = nb_smem_u32(Sel), sOnes = nb_smem_u32(ones),
                  sRGh = nb_smem_u32(RGh), sRGl = nb_smem_u32(RGl), sW2h = nb_smem_u32(W2h), sW2l = nb_smem_u32(W2l),
                  sW3h = nb_smem_u32(W3h), sW3l = nb_smem_u32(W3l);
   const float b4 = __ldg(a.w.b4);
@@ -902,9 +895,10 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       }
       if (BLK && U.first_i && U.first_j)
         for (int idx = tid; idx < g.N * 3; idx += NB_SB_THREADS) gxacc[idx] = 0.f;
-      if (do_nt) {
-        float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        nb_tc_store8(Nh, Nl, nt_row, t_nt & 7, v);
+      if (do_nt) {  // nt_row: receivers [0, nrecv), senders [RC, RC + nsend)
+        float* dst = nt_row < U.RC ? Pf + nt_row * NB_H + 8 * (t_nt & 7) : Qf + (nt_row - U.RC) * NB_SB_QLD + 8 * (t_nt & 7);
+        nb_st4(dst, p0);
+        nb_st4(dst + 4, p1);
       }
       if (do_gm) {
         nb_st4(gMs + (tid >> 3) * NB_H + 8 * (tid & 7), m0);
@@ -939,7 +933,7 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         gfx = gfs[li * 3 + 0];
         gfy = gfs[li * 3 + 1];
         gfz = gfs[li * 3 + 2];
-        if (cq == 1) {
+        {
           const int64_t eoff = ((int64_t)nb_ef_graph(g, gt) * g.EPG + rem) * g.nef;
 #pragma unroll
           for (int f = 0; f < NB_MAX_EF; ++f)
@@ -953,25 +947,36 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         nb_tc_fence_after();
       }
       NB_CLK(3)
-      if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, U.RC + lj, r2, e);
-      nb_fence_async_smem();
-      nb_tc_fence_before();
-      __syncthreads();
-      NB_CLK(4)
-      if (NB_ISSUER(0)) {
-        nb_tc_fence_after();
-        nb_issue_gather(tm, sSel, sNh, sNl, 4, idesc_dg, 0u);
-        nb_mma_commit(bar);
-      }
-      NB_CLK(5)
-      nb_mbar_wait(bar, phase);
-      phase ^= 1;
-      nb_tc_fence_after();
-      NB_CLK(6)
-      // ---- S1: z1 -> tile, SiLU'(pre1) -> TMEM
+      if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, U.RC + lj, r2, e);  // consumed by the scatters of S5
+      // ---- S1: pre1 in fp32 from the unit's P / Q rows; z1 -> tile, SiLU'(pre1) -> TMEM
       {
         float v[16], d[16];
-        nb_tmem_ld16(t1, v);
+        const float* pr = Pf + (valid ? li : 0) * NB_H + cb;
+        const float* qr = Qf + (valid ? lj : 0) * NB_SB_QLD + cb;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 pp = nb_ld4(pr + 4 * k), qq = nb_ld4(qr + 4 * k), wr = nb_ld4(vwr + cb + 4 * k);
+          v[4 * k + 0] = fmaf(r2, wr.x, pp.x + qq.x);
+          v[4 * k + 1] = fmaf(r2, wr.y, pp.y + qq.y);
+          v[4 * k + 2] = fmaf(r2, wr.z, pp.z + qq.z);
+          v[4 * k + 3] = fmaf(r2, wr.w, pp.w + qq.w);
+        }
+#pragma unroll
+        for (int f = 0; f < NB_MAX_EF; ++f)
+          if (f < g.nef) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 we = nb_ld4(Wef + f * NB_H + cb + 4 * k);
+              v[4 * k + 0] = fmaf(e[f], we.x, v[4 * k + 0]);
+              v[4 * k + 1] = fmaf(e[f], we.y, v[4 * k + 1]);
+              v[4 * k + 2] = fmaf(e[f], we.z, v[4 * k + 2]);
+              v[4 * k + 3] = fmaf(e[f], we.w, v[4 * k + 3]);
+            }
+          }
+        if (!valid) {  // padded rows: pre1 = 0 (what their all-zero selector row used to gather)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) nb_silu_grad(v[i], v[i], d[i]);
         nb_tmem_st16_nowait(t1, d);
