@@ -25,6 +25,18 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+_STDOUT_FD = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 METRIC = "train trajectories/s (EGNO 20-body, fwd+bwd+Adam)"
 UNIT = "trajectories/s"
 
@@ -164,7 +176,7 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, per_step=None, note=None):
@@ -314,7 +326,7 @@ def run_ours(args):
         lib.nb_profile_enable(0)
         per = {c: round(1e3 * qm[i] / max(qc[i], 1), 1) for i, c in enumerate(["edge_fwd", "edge_bwd", "gemm64", "wgrad64", "tconv"])}
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            emit(dict({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                               "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True,
                               "us_per_launch": per, "ms_in_kernels_per_step": round(sum(qm[:5]) / K, 3)}))
         finish(world, dist)
@@ -354,18 +366,18 @@ def run_ours(args):
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "peak_source": peak_src,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
-                # (profiles/r01_edge_bwd_sel_digest.txt); valid for the default workload only
-                "traffic": 43.2e6 if (N, T, B) == (20, 10, 256) else None,
+                # (profiles/r01b_edge_bwd_sel_digest.txt); valid for the default workload only
+                "traffic": 46.1e6 if (N, T, B) == (20, 10, 256) else None,
                 "flop_per_launch": flop_kernel, "flop_per_launch_reference_formula": 2 * 2 * MAC_EDGE_REF * ne,
-                "tensor_pipe_active_pct_ncu": 23.0 if (N, T, B) == (20, 10, 256) else None,
+                "tensor_pipe_active_pct_ncu": 26.7 if (N, T, B) == (20, 10, 256) else None,
                 "note": "achieved = ALGORITHMIC fp32 FLOPs the edge kernel owns (8448 MAC/edge forward, x2 for backward; the "
                         "recompute is not credited) / its mean launch time (CUDA events on the launch stream).  The reference's "
                         "dense 131-wide first layer would count 16640 MAC/edge (second figure).  Every logical fp32 MMA is "
                         "three bf16 tcgen05 passes (hi*hi + lo*hi + hi*lo) and the backward executes ~2x the credited MACs "
-                        "(recompute, bias/one-hot gather/scatter MMAs), so the tensor pipe is ~8x busier than `frac` suggests: "
-                        "ncu reports 23 % tensor-pipe active for this launch.  The kernel is bound by its dependent "
-                        "MMA -> TMEM -> SiLU -> smem -> MMA chain (5 round trips per 128-edge tile), not by HBM "
-                        "(43 MB per launch = 75 GB/s).",
+                        "(recompute, weight-gradient and one-hot scatter MMAs), so the tensor pipe is ~8x busier than `frac` "
+                        "suggests: ncu reports 27 % tensor-pipe active for this launch.  The kernel is bound by its dependent "
+                        "MMA -> TMEM -> SiLU -> smem -> MMA chain (4 round trips per 128-edge tile; per-stage cycles in "
+                        "DESIGN.md / tools/stage_clocks.py), not by HBM (46 MB per launch = 105 GB/s).",
                 "hbm_peak_gbs": hbm}
 
     # HBM-bound side of the path: the fused temporal convolution (forward reads h and writes h once; the backward reads h
@@ -464,7 +476,7 @@ def run_ours(args):
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
                 "cpu_baseline": cpu_baseline,
                 "kernels": kern, "extras": extras}
-        print(json.dumps(line), flush=True)
+        emit(line)
     finish(world, dist)
 
 
@@ -545,6 +557,12 @@ def small_configs(nb, synth, dev, K):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL's "NCCL version ..." banner when
+    # NCCL_DEBUG is set in the environment) are sent to stderr; emit() writes the line to the real stdout
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
