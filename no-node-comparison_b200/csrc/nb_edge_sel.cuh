@@ -717,6 +717,23 @@ __device__ __forceinline__ void nb_issue_wgrad_fold(uint32_t tmem_w, uint32_t g_
     }
   }
 }
+// gP | gQ | gw | x sums (+)= Sel^T [g1 | rG]: the [128][8] dL/dr tile rides as the second MN block of the B operand
+// (N = 72); its hi / lo pieces live in logical chunks 1 / 2 of the all-ones tile (whose chunk 0 serves the bias fold), so
+// the second block starts lbo_* bytes above the g1 piece of the pass.  16 MMAs instead of 16 + 16.
+__device__ __forceinline__ void nb_issue_scatter_fold(uint32_t tmem_d, uint32_t sel, uint32_t v_hi, uint32_t v_lo, uint32_t lbo_hi,
+                                                      uint32_t lbo_lo, uint32_t idesc72, uint32_t acc0) {
+  uint32_t acc = acc0;
+  const uint32_t a = nb_desc_lo_mn(sel);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t b = (((pass ? v_lo : v_hi) >> 4) & 0x3FFFu) | (((pass ? lbo_lo : lbo_hi) >> 4) << 16);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      nb_mma2(tmem_d, a + NB_KSTEP_MN * s, NB_DESC_HI_SW128, b + NB_KSTEP_MN * s, NB_DESC_HI_SW128, idesc72, acc);
+      acc = 1u;
+    }
+  }
+}
 #define NB_SB_ONES64_BYTES NB_TC_TILE_BYTES(128)  // whole-graph units only: all-ones SW128 tile (second MN block of the fold)
 
 template <bool BLK>
@@ -1140,8 +1157,15 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
         const float gr2 = 2.f * ((cpart[row] + cpart[NB_TILE + row]) + (cpart[2 * NB_TILE + row] + cpart[3 * NB_TILE + row]));
         const uint32_t px = nb_pack_split(fmaf(dx, gr2, rgx)), py = nb_pack_split(fmaf(dy, gr2, rgy)),
                        pz = nb_pack_split(fmaf(dz, gr2, rgz));
-        *reinterpret_cast<uint4*>(RGh + row * 16) = make_uint4((px & 0xffffu) | (py << 16), pz & 0xffffu, 0u, 0u);
-        *reinterpret_cast<uint4*>(RGl + row * 16) = make_uint4((px >> 16) | (py & 0xffff0000u), pz >> 16, 0u, 0u);
+        const uint4 rh = make_uint4((px & 0xffffu) | (py << 16), pz & 0xffffu, 0u, 0u);
+        const uint4 rl = make_uint4((px >> 16) | (py & 0xffff0000u), pz >> 16, 0u, 0u);
+        if (FOLD) {  // logical chunks 1 (hi) and 2 (lo) of this row of the all-ones tile
+          *reinterpret_cast<uint4*>(ones64 + nb_tc_chunk_off(row, 1)) = rh;
+          *reinterpret_cast<uint4*>(ones64 + nb_tc_chunk_off(row, 2)) = rl;
+        } else {
+          *reinterpret_cast<uint4*>(RGh + row * 16) = rh;
+          *reinterpret_cast<uint4*>(RGl + row * 16) = rl;
+        }
       }
       nb_fence_async_smem();
       __syncthreads();
@@ -1149,8 +1173,12 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs
       if (NB_ISSUER(0)) {
         nb_tc_fence_after();
         const uint32_t uacc = r0 > 0 ? 1u : 0u;
-        nb_issue_scatter(tm + 336, sSel, sTmh, sTml, idesc_wg, uacc);    // gP | gQ | gw partials += Sel^T g1
-        nb_issue_scatter8(tm + 400, sSel, sRGh, sRGl, idesc_bs, uacc);   // x sums += Sel^T rG
+        if (FOLD) {  // [gP | gQ | gw partials | x sums] += Sel^T [g1 | rG]: accumulator columns [336, 408)
+          nb_issue_scatter_fold(tm + 336, sSel, sTmh, sTml, sOnes64 + 16 - sTmh, sOnes64 + 32 - sTml, idesc_wg72, uacc);
+        } else {
+          nb_issue_scatter(tm + 336, sSel, sTmh, sTml, idesc_wg, uacc);    // gP | gQ | gw partials += Sel^T g1
+          nb_issue_scatter8(tm + 400, sSel, sRGh, sRGl, idesc_bs, uacc);   // x sums += Sel^T rG
+        }
         nb_mma_commit(bar2);  // also covers dW2 / db2; waited for at the top of the next tile / at the read-out
       }
       NB_CLK(24)
