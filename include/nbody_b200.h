@@ -213,6 +213,20 @@ int64_t nb_traj_mse_workspace_floats(int32_t T);
 int nb_traj_mse(int32_t T, int64_t rows, int32_t target_layout, int32_t only_first, const float* pred, const float* target,
                 float* losses, float* loss, float* grad, float* workspace, void* stream);
 
+/* Trajectory simulators (data generation): float64 leapfrog integration of B independent systems of
+ * N <= 128 bodies, one CTA per trajectory; random draws stay on the host, in the reference's order.
+ * nb_sim_charged = ChargedParticlesSim.sample_trajectory (synthetic_sim.py:220-296): loc0 / vel0 [B][3][N], charges
+ *   [B][N] -> loc / vel [B][T / sample_freq - 1][3][N] (the frames the reference keeps; velocities at half steps);
+ *   the reference's constants are dt = 1e-3, strength = 1, max_force = 0.1 / dt, box_size = 5.
+ * nb_sim_gravity = GravitySim.sample_trajectory (synthetic_sim.py:360-405): pos0 / vel0 [B][N][3], mass [B][N] ->
+ *   pos / vel / force [B][T / sample_freq][N][3]; reference constants dt = 1e-3, G = 1, softening = 0.1. */
+int nb_sim_charged(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double dt, double strength, double max_force,
+                   double box_size, const double* loc0, const double* vel0, const double* charges, double* loc, double* vel,
+                   void* stream);
+int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double dt, double G, double softening,
+                   const double* pos0, const double* vel0, const double* mass, double* pos, double* vel, double* force,
+                   void* stream);
+
 /* Fused Adam over flat buffers: torch.optim.Adam semantics (amsgrad = False), one launch for n
  * elements; `step` is a device float counting the steps taken (incremented first when tick != 0), so the call is
  * CUDA-graph capturable.  Replaces the per-tensor optimizer launches of main.py:150 for models whose parameters and

@@ -15,6 +15,7 @@ from .graph import GraphedStep  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
 from .rollout import prepare_inputs, conserved_energy, egno_rollout, segno_rollout  # noqa: F401
 from .loss import trajectory_mse  # noqa: F401
+from .simulate import simulate_charged, simulate_gravity  # noqa: F401
 
 __all__ = ["EGNO", "SEGNO", "GraphedStep", "FlatAdam", "prepare_inputs", "conserved_energy", "egno_rollout", "segno_rollout",
-           "trajectory_mse", "build_library", "load_library", "library_path"]
+           "trajectory_mse", "simulate_charged", "simulate_gravity", "build_library", "load_library", "library_path"]

@@ -37,6 +37,8 @@ EXPORTS = {
     "nb_egcl_edge_backward": (C.c_int, [C.c_int32] * 5 + [c_f] * 5 + [C.c_int32] * 3 + [c_f] * 14),
     "nb_nbody_features": (C.c_int, [C.c_int32] * 3 + [c_f] * 8),
     "nb_nbody_energy": (C.c_int, [C.c_int32] * 4 + [C.c_float] + [c_f] * 5),
+    "nb_sim_charged": (C.c_int, [C.c_int32] * 4 + [C.c_double] * 4 + [c_f] * 6),
+    "nb_sim_gravity": (C.c_int, [C.c_int32] * 4 + [C.c_double] * 3 + [c_f] * 7),
     "nb_traj_mse_workspace_floats": (C.c_int64, [C.c_int32]),
     "nb_traj_mse": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [c_f] * 7),
     "nb_adam_step": (C.c_int, [C.c_int64] + [c_f] * 5 + [C.c_int32] + [C.c_double] * 5 + [c_f]),

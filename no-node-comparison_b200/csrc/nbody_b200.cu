@@ -9,6 +9,7 @@
 #include "nb_node.cuh"
 #include "nb_spectral.cuh"
 #include "nb_rollout.cuh"
+#include "nb_sim.cuh"
 #include "nb_edge.cuh"
 #include "nb_tc.cuh"
 #include "nb_edge_tc.cuh"
@@ -1635,6 +1636,40 @@ extern "C" int nb_traj_mse(int32_t T, int64_t rows, int32_t target_layout, int32
   NB_LAUNCH_COUNTED(k_traj_mse, dim3((unsigned)a.nchunk, (unsigned)T), 256, 0, stream, a);
   NB_LAUNCH_COUNTED(k_traj_mse_fin, 1, 32, 0, stream, a);
   return nb_check_launch("k_traj_mse");
+}
+
+// trajectory simulators (float64; see nb_sim.cuh)
+extern "C" int nb_sim_charged(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double dt, double strength, double max_force,
+                              double box_size, const double* loc0, const double* vel0, const double* charges, double* loc,
+                              double* vel, void* stream) {
+  if (B < 1 || N < 1 || N > NB_SIM_MAX_N || T < 2 || sample_freq < 1 || T % sample_freq || !loc0 || !vel0 || !charges ||
+      (T / sample_freq > 1 && (!loc || !vel))) {
+    nb_set_error("nb_sim_charged: unsupported arguments (B=%d, N=%d (<= %d), T=%d, sample_freq=%d) or null pointer", B, N,
+                 NB_SIM_MAX_N, T, sample_freq);
+    return NB_ERR_INVALID;
+  }
+  NbSimChargedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.sample_freq = sample_freq; a.dt = dt; a.strength = strength; a.max_f = max_force;
+  a.box = box_size; a.loc0 = loc0; a.vel0 = vel0; a.charges = charges; a.loc = loc; a.vel = vel;
+  NB_LAUNCH_COUNTED(k_sim_charged, (unsigned)B, NB_SIM_MAX_N, 0, stream, a);
+  return nb_check_launch("k_sim_charged");
+}
+extern "C" int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double dt, double G, double softening,
+                              const double* pos0, const double* vel0, const double* mass, double* pos, double* vel,
+                              double* force, void* stream) {
+  if (B < 1 || N < 1 || N > NB_SIM_MAX_N || T < 1 || sample_freq < 1 || T % sample_freq || !pos0 || !vel0 || !mass || !pos ||
+      !vel || !force) {
+    nb_set_error("nb_sim_gravity: unsupported arguments (B=%d, N=%d (<= %d), T=%d, sample_freq=%d) or null pointer", B, N,
+                 NB_SIM_MAX_N, T, sample_freq);
+    return NB_ERR_INVALID;
+  }
+  NbSimGravityArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = N; a.T = T; a.sample_freq = sample_freq; a.dt = dt; a.G = G; a.soft2 = softening * softening;
+  a.pos0 = pos0; a.vel0 = vel0; a.mass = mass; a.pos = pos; a.vel = vel; a.force = force;
+  NB_LAUNCH_COUNTED(k_sim_gravity, (unsigned)B, NB_SIM_MAX_N, 0, stream, a);
+  return nb_check_launch("k_sim_gravity");
 }
 
 // fused Adam: `step` is a device float holding the number of steps taken so far (incremented here when tick != 0);
