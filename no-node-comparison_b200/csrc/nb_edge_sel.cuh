@@ -303,18 +303,6 @@ __device__ __forceinline__ void nb_sel_write_row(unsigned char* Sel, int row, in
   }
 }
 
-// rows [0, GN) and [GN, 2 GN) of the node tile <- P, Q of the unit's nodes (split bf16)
-__device__ __forceinline__ void nb_sel_stage_nodes(unsigned char* Nh, unsigned char* Nl, const float* __restrict__ P,
-                                                   const float* __restrict__ Q, int64_t node0, int nnode, int GN, int tid,
-                                                   int nthreads) {
-  for (int idx = tid; idx < nnode * 16; idx += nthreads) {
-    int n = idx >> 4, which = (idx >> 3) & 1, j = idx & 7;
-    const float* src = (which ? Q : P) + (node0 + n) * NB_H + 8 * j;
-    float4 a = nb_ld4(src), b = nb_ld4(src + 4);
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    nb_tc_store8(Nh, Nl, which ? GN + n : n, j, v);
-  }
-}
 // general unit: rows [0, nrecv) <- P of the receiver list, rows [RC, RC + nsend) <- Q of the sender list
 __device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned char* Nl, const float* __restrict__ P,
                                                   const float* __restrict__ Q, const NbSelUnit& U, int tid, int nthreads,
@@ -645,17 +633,6 @@ __device__ __forceinline__ void nb_tmem_st16_nowait(uint32_t taddr, const float 
       "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
-}
-__device__ __forceinline__ void nb_tmem_st16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // dW (+)= G^T A  (both MN-major, K = 128 rows, three split passes) and db (+)= G^T 1

@@ -171,12 +171,6 @@ __device__ __forceinline__ void nb_mma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a,
       "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 8 consecutive 32-bit columns of this thread's TMEM lane <- 8 packed words (no wait: pair with nb_tmem_st_wait)
-__device__ __forceinline__ void nb_tmem_st8(uint32_t taddr, const uint32_t (&w)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(w[0]),
-               "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-               : "memory");
-}
 __device__ __forceinline__ void nb_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // split 8 consecutive fp32 values into packed bf16 pairs: hi[i] = (v[2i], v[2i+1]) leading pieces, lo[i] = the remainders
 __device__ __forceinline__ void nb_split8(const float* v, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
