@@ -126,3 +126,26 @@ def test_param_pack_keeps_views_through_optimizer_and_load():
     m.double().float()                                                        # storage replaced -> repacked
     flat3, _ = pack.flat_params(n, torch.device("cpu"))
     assert flat3.data_ptr() != flat.data_ptr()
+
+
+def test_helper_apis_refuse_cpu_tensors_and_bad_shapes():
+    """trajectory_mse / simulate_* have no CPU path: host tensors and malformed arguments raise before any launch."""
+    import no_node_comparison_b200 as nb
+    T, R = 4, 10
+    pred, tgt = torch.randn(T * R, 3), torch.randn(R, T, 3)
+    with pytest.raises(ValueError, match="CUDA"):
+        nb.trajectory_mse(pred, tgt, T)
+    with pytest.raises(ValueError):
+        nb.trajectory_mse(torch.randn(T * R + 1, 3), tgt, T)          # rows not a multiple of T
+    with pytest.raises(ValueError):
+        nb.trajectory_mse(pred, torch.randn(R, T + 1, 3), T)          # target frame count
+    with pytest.raises(ValueError):
+        nb.trajectory_mse(pred, tgt.requires_grad_(True), T)          # no gradient w.r.t. the target
+    loc0 = torch.randn(2, 3, 5, dtype=torch.float64)
+    with pytest.raises(ValueError, match="CUDA"):
+        nb.simulate_charged(loc0, loc0.clone(), torch.ones(2, 5, dtype=torch.float64), 200, 100)
+    with pytest.raises(ValueError):
+        nb.simulate_charged(loc0, loc0.clone(), torch.ones(2, 5, dtype=torch.float64), 250, 100)   # T % sample_freq
+    with pytest.raises(ValueError, match="CUDA"):
+        nb.simulate_gravity(torch.randn(2, 5, 3, dtype=torch.float64), torch.randn(2, 5, 3, dtype=torch.float64),
+                            torch.ones(2, 5, dtype=torch.float64), 100, 100)
