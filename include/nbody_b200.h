@@ -95,11 +95,16 @@ const char* nb_last_error(void);
 int64_t nb_egno_param_count(const NbEgnoConfig* cfg);
 int64_t nb_segno_param_count(const NbSegnoConfig* cfg);
 
-/* floats the caller must provide */
+/* floats the caller must provide.  `mode` of the workspace queries: 0 = forward without a `saved` buffer (inference:
+ * includes the two ping-pong layer sets that stand in for it), 1 = backward, 2 = forward WITH a `saved` buffer
+ * (training: no ping-pong region). */
+#define NB_WS_FORWARD_INFER 0
+#define NB_WS_BACKWARD 1
+#define NB_WS_FORWARD_TRAIN 2
 int64_t nb_egno_saved_floats(const NbEgnoConfig* cfg);
-int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int backward);
+int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int mode);
 int64_t nb_segno_saved_floats(const NbSegnoConfig* cfg);
-int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int backward);
+int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int mode);
 
 /* Replaces EGNO.forward (EGNO/model/egno.py:37-111, num_inputs == 1) including every
  * EGNN_Layer.forward (EGNO/model/basic.py:167-186), aggregate (basic.py:6-31),
@@ -176,9 +181,11 @@ int nb_profile_enable(int enable);
 int nb_profile_read(double* ms /*[NB_PROFILE_CATEGORIES]*/, long long* counts /*[NB_PROFILE_CATEGORIES]*/);
 
 /* Edge-tile implementation: 2 = tcgen05 tensor-core tiles whose node gathers and receiver / sender reductions are
- * one-hot MMAs (default, product path; graphs with more than 27 nodes run variant 1), 1 = tcgen05 tiles with
- * CUDA-core gathers / reductions, 0 = fp32 SIMT tiles (kept as an independent cross-check and for the host emulator
- * of the test suite).  All are CUDA kernels of this library. */
+ * one-hot MMAs (default, product path; graphs with more than 27 nodes are walked in receiver x sender blocks by the same
+ * kernels, template parameter BLK), 1 = tcgen05 tiles with CUDA-core gathers / reductions, 0 = fp32 SIMT tiles (kept as
+ * an independent cross-check and for the host emulator of the test suite).  All are CUDA kernels of this library.
+ * The three nb_set_* switches below are process-wide TEST hooks (variant cross-checks); they are not meant to be flipped
+ * while another thread is inside a forward / backward call. */
 int nb_set_edge_impl(int impl);
 int nb_get_edge_impl(void);
 /* Node-level 64-wide GEMMs and weight-gradient reductions: 1 = tcgen05 kernels (default, product path), 0 = fp32 SIMT
@@ -230,9 +237,11 @@ int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double 
 /* Fused Adam over flat buffers: torch.optim.Adam semantics (amsgrad = False), one launch for n
  * elements; `step` is a device float counting the steps taken (incremented first when tick != 0), so the call is
  * CUDA-graph capturable.  Replaces the per-tensor optimizer launches of main.py:150 for models whose parameters and
- * gradients are the flat buffers of this ABI. */
+ * gradients are the flat buffers of this ABI.  grad_scale multiplies the gradients first: 1 / world size when the bucket
+ * holds the all-reduced SUM (the data-parallel mean costs no launch of its own), 1 otherwise. */
 int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
-                 int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, void* stream);
+                 int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                 void* stream);
 
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]

@@ -568,6 +568,7 @@ struct NbAdamArgs {
   float *m, *v;
   const float* step;   // already incremented
   double lr, beta1, beta2, eps, weight_decay;   // hyper-parameters in double, like the Python scalars torch uses
+  float grad_scale;    // gradients are multiplied by it first (data parallel: 1 / world over the summed bucket)
 };
 __global__ void __launch_bounds__(256) k_adam(NbAdamArgs a) {
   const double t = (double)*a.step;
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(256) k_adam(NbAdamArgs a) {
   const float eps = (float)a.eps, wd = (float)a.weight_decay;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     const float p = a.p[i];
-    const float g = fmaf(wd, p, a.g[i]);                 // grad.add(param, alpha=weight_decay)
+    const float g = fmaf(wd, p, a.g[i] * a.grad_scale);  // grad.add(param, alpha=weight_decay)
     const float m = fmaf(omb1, g - a.m[i], a.m[i]);      // exp_avg.lerp_(grad, 1 - beta1)
     const float v = fmaf(omb2 * g, g, b2 * a.v[i]);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     a.m[i] = m;

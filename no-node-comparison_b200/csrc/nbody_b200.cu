@@ -18,12 +18,12 @@
 #include "nb_segno_fused.cuh"
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
-#define NB_LAUNCH_COUNTED(...) \
-  do {                         \
-    ++g_launches_ref();        \
-    NB_LAUNCH(__VA_ARGS__);    \
+#define NB_LAUNCH_COUNTED(...)                             \
+  do {                                                     \
+    __atomic_fetch_add(&g_launches, 1LL, __ATOMIC_RELAXED); \
+    NB_LAUNCH(__VA_ARGS__);                                \
   } while (0)
-static long long& g_launches_ref();
+static long long g_launches = 0;
 
 // ============================================================================= errors / device info
 static thread_local char g_err[512] = "";
@@ -38,7 +38,8 @@ void nb_set_error(const char* fmt, ...) {
 int nb_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    nb_set_error("CUDA error after %s: %s", what, cudaGetErrorString(e));
+    nb_set_error("CUDA error reported after %s (it may stem from earlier asynchronous work on this device): %s", what,
+                 cudaGetErrorString(e));
     return NB_ERR_CUDA;
   }
   return NB_OK;
@@ -48,20 +49,22 @@ int nb_num_sms() {
 #ifdef NB_EMU
   return 3;
 #else
-  static thread_local int cached = 0;
-  if (!cached) {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
+  // cached per device ordinal: a thread may drive different GPUs over its lifetime
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cached[dev];
+  if (!n) {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    cached = n > 0 ? n : 148;
+    n = n > 0 ? n : 148;
+    cached[dev] = n;   // benign race: every writer stores the same value
   }
-  return cached;
+  return n;
 #endif
 }
 
 // ---- launch accounting and optional per-kernel CUDA-event timing (used by bench.py for the roofline)
-static long long g_launches = 0;
-static long long& g_launches_ref() { return g_launches; }
 #define NB_PROF_CATS 5  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64, 4 temporal conv */
 #define NB_PROF_MAX 8192
 #ifndef NB_EMU
@@ -90,7 +93,7 @@ static int prof_begin(int, void*) { return -1; }
 static void prof_end(int, int, void*) {}
 #endif
 
-extern "C" long long nb_launch_count(void) { return g_launches; }
+extern "C" long long nb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 // enable != 0: start timing the dominant kernels with CUDA events on their launch stream (counters reset)
 #ifdef NB_STAGE_CLOCKS
@@ -461,7 +464,9 @@ static bool sel_geom(NbEdgeGeom& g) {
 
 static int launch_edge_fwd(NbEdgeFwdArgs& a, void* st) {
 #ifndef NB_EMU
-  if (g_edge_impl == 2 && sel_geom(a.g)) {
+  if (g_edge_impl == 2) {
+    // no silent switch to another variant: a shape the selector kernels cannot walk is an error
+    if (!sel_geom(a.g)) { nb_set_error("selector edge kernels support at most 255 nodes per graph (N=%d)", a.g.N); return NB_ERR_INVALID; }
     const size_t smem_sel = NB_EDGE_FWD_SEL_SMEM(a.g.blk ? 0 : a.g.G * a.g.EPG);
     int grid_sel = imin(a.g.n_units, 2 * nb_num_sms());
     int pi_sel = prof_begin(0, st);
@@ -503,7 +508,10 @@ struct EdgeGradDst {
 static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, int accumulate, void* st) {
   bool use_sel = false;
 #ifndef NB_EMU
-  use_sel = g_edge_impl == 2 && sel_geom(a.g);
+  if (g_edge_impl == 2) {
+    if (!sel_geom(a.g)) { nb_set_error("selector edge kernels support at most 255 nodes per graph (N=%d)", a.g.N); return NB_ERR_INVALID; }
+    use_sel = true;
+  }
 #endif
   int grid = imin(a.g.n_units, use_sel ? nb_num_sms() : edge_bwd_grid_cap());
   float* partial = q_alloc((int64_t)grid * NB_EB_PLEN, st);
@@ -722,12 +730,14 @@ static int64_t egno_coef_floats(const NbEgnoConfig* c) {
   return align64((int64_t)ncoef * c->B * c->N * NB_H);
 }
 
-extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int backward) {
+extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int mode) {
   if (egno_validate(cfg) != NB_OK) return -1;
+  if (mode < 0 || mode > 2) { nb_set_error("workspace mode must be 0 (inference), 1 (backward) or 2 (training forward)"); return -1; }
   int64_t Nn = (int64_t)cfg->T * cfg->B * cfg->N;
   int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
   const int64_t tab = egno_table_floats(cfg);
-  if (!backward) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // last term: inference ping-pong
+  if (mode == NB_WS_FORWARD_TRAIN) return tab + 2 * nh + 2 * cf;                     // `saved` holds the layer sets
+  if (mode == NB_WS_FORWARD_INFER) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // + ping-pong
   return tab + 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
          NB_PARTIAL_FLOATS;
 }
@@ -1267,11 +1277,13 @@ extern "C" int64_t nb_segno_saved_floats(const NbSegnoConfig* cfg) {
   if (segno_validate(cfg) != NB_OK) return -1;
   return segno_iter_floats((int64_t)cfg->B * cfg->N) * cfg->T;
 }
-extern "C" int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int backward) {
+extern "C" int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int mode) {
   if (segno_validate(cfg) != NB_OK) return -1;
+  if (mode < 0 || mode > 2) { nb_set_error("workspace mode must be 0 (inference), 1 (backward) or 2 (training forward)"); return -1; }
   int64_t Nn = (int64_t)cfg->B * cfg->N;
   int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3);
-  if (!backward) return 2 * nh /*P,Q*/ + 3 * n3 /*Fsum, v ping-pong*/ + 2 * segno_iter_floats(Nn);
+  if (mode == NB_WS_FORWARD_TRAIN) return 2 * nh /*P,Q*/ + 3 * n3 /*Fsum, v ping-pong*/;
+  if (mode == NB_WS_FORWARD_INFER) return 2 * nh + 3 * n3 + 2 * segno_iter_floats(Nn);
   return 2 * nh + 2 * nh /*gh*/ + 4 * nh /*GU5 gM gP gQ*/ + 4 * n3 + NB_PARTIAL_FLOATS;
 }
 
@@ -1675,7 +1687,8 @@ extern "C" int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_fr
 // fused Adam: `step` is a device float holding the number of steps taken so far (incremented here when tick != 0);
 // [params, grads, exp_avg, exp_avg_sq] are flat fp32 buffers of n elements
 extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
-                            int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, void* stream) {
+                            int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                            void* stream) {
   if (n < 0 || !params || !grads || !exp_avg || !exp_avg_sq || !step) {
     nb_set_error("nb_adam_step: null pointer or negative size");
     return NB_ERR_INVALID;
@@ -1684,7 +1697,7 @@ extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float*
   if (n > 0) {
     NbAdamArgs a;
     a.n = n; a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.step = step;
-    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = (float)grad_scale;
     NB_LAUNCH_COUNTED(k_adam, (unsigned)imin(cdiv(n, 256), 4 * nb_num_sms()), 256, 0, stream, a);
   }
   return nb_check_launch("k_adam");

@@ -105,12 +105,22 @@ class EGNO(nn.Module):
         self._edges = _EdgeCache()
         self.process_group = None   # set by enable_data_parallel(): one flat-bucket all-reduce per backward
 
-    def enable_data_parallel(self, group=None):
-        """Average parameter gradients over `group` with ONE all-reduce of the flat gradient buffer."""
+    def enable_data_parallel(self, group=None, average=True):
+        """Reduce parameter gradients over `group` with ONE all-reduce of the flat gradient buffer.  average=True leaves
+        the mean in `.grad` (any optimizer); average=False leaves the sum, for FlatAdam(grad_scale=1 / world), which
+        applies the factor inside its update kernel."""
         import torch.distributed as dist
 
-        self.process_group = group if group is not None else dist.group.WORLD
+        self.process_group = (group if group is not None else dist.group.WORLD, bool(average))
         return self
+
+    @staticmethod
+    def _integral_times(name, t, dev):
+        """The reference embeds `timesteps.float()` (layer_no.py:12); the kernels take int64 frame indices (what every
+        reference caller passes).  Floating-point times are accepted only when they are integral."""
+        if t.is_floating_point() and not bool((t == t.round()).all()):
+            raise ValueError(f"{name} holds non-integral times; only integer frame indices are implemented")
+        return t.to(device=dev, dtype=torch.int64).contiguous()
 
     def forward(self, x, h, edge_index, edge_fea, v=None, loc_mean=None, timesteps_in=None, timesteps_out=None):
         T = self.num_timesteps
@@ -149,12 +159,12 @@ class EGNO(nn.Module):
         loc_mean = _require_cuda_f32("loc_mean", loc_mean, lead + (n0, 3))
         edge_fea = _require_cuda_f32("edge_fea", edge_fea, lead + (B * N * (N - 1), self.in_edge_nf))
         self._edges.validate(edge_index, B, N, dev)
-        tsteps = timesteps_out.to(device=dev, dtype=torch.int64).contiguous()
+        tsteps = self._integral_times("timesteps_out", timesteps_out, dev)
         tsteps_in = None
         if L > 1:
             if timesteps_in.shape[0] != B:
                 raise ValueError(f"timesteps_in must be [B={B}, {L}], got {tuple(timesteps_in.shape)}")
-            tsteps_in = timesteps_in.to(device=dev, dtype=torch.int64).contiguous()
+            tsteps_in = self._integral_times("timesteps_in", timesteps_in, dev)
         cfg = (B, N, T, self.n_layers, self.num_modes if self.use_time_conv else 1, self.in_node_nf, self.in_edge_nf,
                self.time_emb_dim, 1 if self.use_time_conv else 0, L)
         from ._lib import load_library

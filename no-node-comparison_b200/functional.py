@@ -80,14 +80,18 @@ class _ParamPack:
         return self.flat, ps
 
 
-def _maybe_allreduce(grad_flat: torch.Tensor, group) -> None:
-    """Data parallel: ONE all-reduce of the flat gradient bucket (NCCL over NVLink), then the mean."""
-    if group is None:
+def _maybe_allreduce(grad_flat: torch.Tensor, dp) -> None:
+    """Data parallel: ONE all-reduce of the flat gradient bucket (NCCL over NVLink).  `dp` = (group, average): with
+    average the bucket is divided by the world size here (any optimizer sees the mean gradient); without, the SUM is left
+    in place and the 1 / world factor rides inside the fused optimizer kernel (FlatAdam(grad_scale=1 / world))."""
+    if dp is None:
         return
     import torch.distributed as dist
 
+    group, average = dp
     dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=group)
-    grad_flat.div_(dist.get_world_size(group))
+    if average:
+        grad_flat.div_(dist.get_world_size(group))
 
 
 class EgnoFunction(torch.autograd.Function):
@@ -104,7 +108,7 @@ class EgnoFunction(torch.autograd.Function):
         v_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         h_out = torch.empty((Nn, 64), device=dev, dtype=torch.float32)
         saved = torch.empty(lib.nb_egno_saved_floats(ctypes.byref(cfg)), device=dev, dtype=torch.float32) if need_grad else None
-        ws = torch.empty(lib.nb_egno_workspace_floats(ctypes.byref(cfg), 0), device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.nb_egno_workspace_floats(ctypes.byref(cfg), 2 if need_grad else 0), device=dev, dtype=torch.float32)
         check(lib.nb_egno_forward(ctypes.byref(cfg), _ptr(flat), _ptr(x), _ptr(nodes), _ptr(edge_fea), _ptr(v),
                                   _ptr(loc_mean), _ptr(tsteps), _ptr(tsteps_in), _ptr(x_out), _ptr(v_out), _ptr(h_out),
                                   _ptr(saved), _ptr(ws), _stream_ptr(dev)), "nb_egno_forward")
@@ -158,7 +162,7 @@ class SegnoFunction(torch.autograd.Function):
         v_out = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         h_out = torch.empty((Nn, 64), device=dev, dtype=torch.float32)
         saved = torch.empty(lib.nb_segno_saved_floats(ctypes.byref(cfg)), device=dev, dtype=torch.float32) if need_grad else None
-        ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 0), device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 2 if need_grad else 0), device=dev, dtype=torch.float32)
         check(lib.nb_segno_forward(ctypes.byref(cfg), _ptr(flat), _ptr(his), _ptr(x), _ptr(v), _ptr(edge_attr),
                                    _ptr(x_out), _ptr(h_out), _ptr(v_out), _ptr(saved), _ptr(ws), _stream_ptr(dev)),
               "nb_segno_forward")
@@ -203,20 +207,33 @@ class SegnoFunction(torch.autograd.Function):
 
 
 class _EdgeCache:
-    """Validates `edge_index` against the canonical fully connected list once per distinct tensor
-    (key: storage address, length, version).  Non-canonical graphs raise: the kernels reduce each
-    receiver's N-1 contiguous edge rows and have no general scatter path."""
+    """Validates `edge_index` against the canonical fully connected list once per distinct tensor OBJECT: the cache holds
+    weak references to the validated row / col tensors and their `_version`s, so a new tensor that happens to reuse a
+    freed tensor's address is checked again.  Non-canonical graphs raise: the kernels reduce each receiver's N-1
+    contiguous edge rows and have no general scatter path."""
 
     def __init__(self):
-        self._ok = {}
+        self._ok = []   # [(weakref(row), weakref(col), row._version, col._version, E, B, N)]
+
+    def _hit(self, row, col, E, B, N) -> bool:
+        alive = []
+        hit = False
+        for ent in self._ok:
+            r, c = ent[0](), ent[1]()
+            if r is None or c is None:
+                continue
+            alive.append(ent)
+            if r is row and c is col and ent[2:] == (row._version, col._version, E, B, N):
+                hit = True
+        self._ok = alive[-16:]
+        return hit
 
     def validate(self, edge_index, B: int, N: int, device: torch.device) -> None:
         row, col = edge_index[0], edge_index[1]
         E = B * N * (N - 1)
         if row.dim() != 1 or row.numel() != E or col.numel() != E:
             raise ValueError(f"edge_index must hold B*N*(N-1) = {E} edges of a fully connected graph; got {row.numel()}")
-        key = (row.data_ptr(), col.data_ptr(), E, B, N, row._version, col._version, str(row.device))
-        if self._ok.get(key):
+        if self._hit(row, col, E, B, N):
             return
         if row.dtype != torch.int64 or col.dtype != torch.int64:
             raise ValueError("edge_index must be int64")
@@ -236,6 +253,9 @@ class _EdgeCache:
         if bad:
             raise ValueError(f"edge_index is not the canonical fully connected list (first mismatch at edge {bad - 1}); "
                              "only `for i: for j != i` graphs offset by N*b are supported")
-        if len(self._ok) > 64:
-            self._ok.clear()
-        self._ok[key] = True
+        import weakref
+
+        try:
+            self._ok.append((weakref.ref(row), weakref.ref(col), row._version, col._version, E, B, N))
+        except TypeError:   # objects that cannot be weakly referenced are simply re-validated next time
+            pass

@@ -20,11 +20,13 @@ from .functional import _ptr, _stream_ptr
 
 class FlatAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0):
+                 weight_decay: float = 0.0, grad_scale: float = 1.0):
+        """`grad_scale`: the gradients are multiplied by it inside the update kernel (data parallel: 1 / world size when
+        the flat gradient bucket holds the SUM over ranks)."""
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._flat_state = {}
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale))
+        self._flat = {}     # group index -> dict(m, v, step, offs): flat moment buffers; self.state[p] holds views of them
 
     @staticmethod
     def _runs(ps: List[torch.nn.Parameter]):
@@ -48,6 +50,53 @@ class FlatAdam(torch.optim.Optimizer):
             runs.append((cur, n))
         return runs
 
+    def _group_state(self, gi: int, ps: List[torch.nn.Parameter]):
+        """Flat exp_avg / exp_avg_sq / step of a parameter group.  `self.state[p]` holds views of the flat buffers under
+        torch.optim.Adam's keys, so `state_dict()` / `load_state_dict()` round-trip them; whenever the per-parameter
+        state no longer aliases the flat buffers (after load_state_dict, add_param_group or a re-ordered group) the flat
+        buffers are rebuilt from it."""
+        st = self._flat.get(gi)
+        dev = ps[0].device
+        total = sum(p.numel() for p in ps)
+
+        def aliased():
+            if st is None or st["m"].numel() != total or st["m"].device != dev or len(st["offs"]) != len(ps):
+                return False
+            o = 0
+            for p in ps:
+                s = self.state.get(p)
+                if st["offs"].get(id(p)) != o:
+                    return False
+                if s:   # parameters that never received a gradient have no state yet
+                    if (s["exp_avg"].data_ptr() != st["m"].data_ptr() + 4 * o or s["exp_avg_sq"].data_ptr() != st["v"].data_ptr() + 4 * o
+                            or s["step"].data_ptr() != st["step"].data_ptr()):
+                        return False
+                o += p.numel()
+            return True
+
+        if aliased():
+            return st
+        new = dict(m=torch.zeros(total, device=dev), v=torch.zeros(total, device=dev), step=torch.zeros(1, device=dev), offs={})
+        o, step_src = 0, None
+        for p in ps:
+            new["offs"][id(p)] = o
+            s = self.state.get(p)
+            if s:   # carry over what a checkpoint (or an earlier layout) holds
+                new["m"][o:o + p.numel()].copy_(s["exp_avg"].reshape(-1))
+                new["v"][o:o + p.numel()].copy_(s["exp_avg_sq"].reshape(-1))
+                if step_src is None:
+                    step_src = s["step"]
+            o += p.numel()
+        if step_src is not None:
+            new["step"].copy_(torch.as_tensor(step_src, dtype=torch.float32).reshape(1))
+        self._flat[gi] = new
+        return new
+
+    def _publish(self, st, p):
+        o = st["offs"][id(p)]
+        self.state[p] = dict(step=st["step"], exp_avg=st["m"][o:o + p.numel()].view(p.shape),
+                             exp_avg_sq=st["v"][o:o + p.numel()].view(p.shape))
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -65,16 +114,10 @@ class FlatAdam(torch.optim.Optimizer):
                 if p.grad is not None and (p.grad.dtype != torch.float32 or p.grad.is_sparse):
                     raise ValueError("FlatAdam needs dense float32 gradients")
             dev = ps[0].device
-            st = self._flat_state.get(gi)
-            total = sum(p.numel() for p in ps)
-            if st is None:
-                st = dict(m=torch.zeros(total, device=dev), v=torch.zeros(total, device=dev),
-                          step=torch.zeros(1, device=dev), offs={})
-                o = 0
-                for p in ps:
-                    st["offs"][id(p)] = o
-                    o += p.numel()
-                self._flat_state[gi] = st
+            st = self._group_state(gi, ps)
+            for p in ps:
+                if p.grad is not None and not self.state.get(p):
+                    self._publish(st, p)
             b1, b2 = group["betas"]
             tick = 1
             for first, n in self._runs(ps):
@@ -82,6 +125,6 @@ class FlatAdam(torch.optim.Optimizer):
                 check(lib.nb_adam_step(n, _ptr(first.data), _ptr(first.grad), _ptr(st["m"][o:o + n]), _ptr(st["v"][o:o + n]),
                                        _ptr(st["step"]), tick, ctypes.c_double(group["lr"]), ctypes.c_double(b1),
                                        ctypes.c_double(b2), ctypes.c_double(group["eps"]), ctypes.c_double(group["weight_decay"]),
-                                       _stream_ptr(dev)), "nb_adam_step")
+                                       ctypes.c_double(group.get("grad_scale", 1.0)), _stream_ptr(dev)), "nb_adam_step")
                 tick = 0
         return loss

@@ -77,10 +77,11 @@ class SEGNO(nn.Module):
         self._edges = _EdgeCache()
         self.process_group = None
 
-    def enable_data_parallel(self, group=None):
+    def enable_data_parallel(self, group=None, average=True):
+        """See EGNO.enable_data_parallel: one all-reduce of the flat gradient bucket per backward."""
         import torch.distributed as dist
 
-        self.process_group = group if group is not None else dist.group.WORLD
+        self.process_group = (group if group is not None else dist.group.WORLD, bool(average))
         return self
 
     def forward(self, his, x, edges, v, edge_attr, T=10, in_steps=None):
@@ -156,4 +157,6 @@ class SEGNO(nn.Module):
         return SegnoFunction.apply(cfg, self.process_group, flat, his, x, v, edge_attr, *params)
 
     def forward_step(self, h, x, edges, v, edge_attr, T=10):
-        raise NotImplementedError("call forward(his, ...): embedding and the T integration steps run as one fused call")
+        """model.py:95-102: T weight-shared SEGNO_GCL sub-steps from an already embedded hidden state `h` [BN, 64];
+        returns (x, h, v).  Differentiable w.r.t. h, x and v (dL/dh is handed back by the C call)."""
+        return self._segment(h, x, edges, v, edge_attr, int(T), h_given=True)

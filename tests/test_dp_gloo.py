@@ -26,9 +26,11 @@ def _worker(rank, world, port, out):
     from no_node_comparison_b200.dataparallel import shard_range
 
     g = torch.arange(10, dtype=torch.float32) * (rank + 1)          # per-rank "flat gradient bucket"
-    _maybe_allreduce(g, dist.group.WORLD)
+    _maybe_allreduce(g, (dist.group.WORLD, True))                   # mean (any optimizer)
+    s = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    _maybe_allreduce(s, (dist.group.WORLD, False))                  # sum (1 / world rides in FlatAdam's kernel)
     lo, hi = shard_range(11, rank, world)
-    out.put((rank, g.tolist(), (lo, hi)))
+    out.put((rank, g.tolist(), (lo, hi), s.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -47,3 +49,5 @@ def test_flat_bucket_allreduce_and_sharding_world2():
     expect = (torch.arange(10, dtype=torch.float32) * 1.5).tolist()   # mean of 1x and 2x
     assert res[0][1] == expect and res[1][1] == expect
     assert res[0][2] == (0, 6) and res[1][2] == (6, 11)               # contiguous, covering, near-equal shards
+    total = (torch.arange(10, dtype=torch.float32) * 3.0).tolist()
+    assert res[0][3] == total and res[1][3] == total

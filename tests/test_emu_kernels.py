@@ -191,8 +191,10 @@ def test_fused_adam_kernel_vs_torch_adam():
         grad = torch.randn(n, generator=g)
         ref.grad = grad.clone()
         opt.step()
-        E.check(L.nb_adam_step(n, E.ptr(p), E.ptr(E.f32(grad)), E.ptr(m), E.ptr(v), E.ptr(step), 1, ctypes.c_double(3e-3),
-                               ctypes.c_double(0.9), ctypes.c_double(0.99), ctypes.c_double(1e-8), ctypes.c_double(1e-2), None))
+        # the kernel multiplies the gradient by grad_scale first (data parallel: 1 / world over the summed bucket)
+        E.check(L.nb_adam_step(n, E.ptr(p), E.ptr(E.f32(grad * 4.0)), E.ptr(m), E.ptr(v), E.ptr(step), 1, ctypes.c_double(3e-3),
+                               ctypes.c_double(0.9), ctypes.c_double(0.99), ctypes.c_double(1e-8), ctypes.c_double(1e-2),
+                               ctypes.c_double(0.25), None))
         np.testing.assert_allclose(p, ref.detach().numpy(), rtol=5e-7, atol=5e-8)
     assert step[0] == 5.0
 
