@@ -4,8 +4,9 @@ vectors of the reference and against the oracle; plus size-independent propertie
 Tolerances (fp32 everywhere; BASELINE.json: predicted positions rel. err <= 1e-4):
   outputs   : max|a-b| / max|b| <= 1e-4   (observed ~1e-6 .. 1e-5: summation order + split-bf16 operands)
   gradients : <= 1e-3                       (observed ~1e-5)
-EGNO parameter gradients are held to 1e-3 (scale-relative) on at least 99 % of the entries of every tensor and to 1e-2 in
-the max norm: TimeConv applies LeakyReLU to the
+EGNO parameter gradients are held to 1e-3 (scale-relative) on EVERY entry of every tensor except TimeConv's own weights,
+where a counted budget applies (helpers.param_grads_within_kink_budget: at most 1e-4 of the layer's activations may take
+the other LeakyReLU slope, each moving at most 64 gradient entries, none by more than 2e-2): TimeConv applies LeakyReLU to the
 spectral convolution of h (layer_no.py:125-126), and an element whose pre-activation is within rounding distance of the
 kink takes the other slope under ANY change of summation order or operand rounding upstream (the reference itself does
 so between CPU and GPU, or with TF32).  One flipped element moves one column of that layer's weight gradient by
@@ -21,6 +22,7 @@ import no_node_comparison_b200 as nb
 from no_node_comparison_b200 import synth
 from oracle import nbody_oracle as O
 from tests.helpers import (EGNO_CASES, EGNO_MULTI_CASES, SEGNO_CASES, SEGNO_MULTI_CASES, load_case, rel_err, rel_l2,
+                           param_grads_within_kink_budget,
                            egno_inputs_from_case, egno_multi_inputs_from_case, segno_inputs_from_case,
                            segno_multi_inputs_from_case)
 
@@ -153,10 +155,7 @@ def test_egno_vs_oracle_various_shapes(B, N, T, L):
     assert rel_err(vo.cpu(), vo_r.detach()) < TOL_OUT
     assert rel_err(ho.cpu(), ho_r.detach()) < TOL_OUT
     assert rel_err(x.grad.cpu(), xr.grad) < TOL_GRAD
-    for k, q in m.named_parameters():
-        ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
-        bad = ((q.grad.cpu() - ref).abs() > TOL_GRAD * ref.abs().max()).float().mean().item()
-        assert bad < 0.01 and rel_err(q.grad.cpu(), ref) < 10 * TOL_GRAD, (k, bad)
+    param_grads_within_kink_budget(m, p, n_rows=T * B * N, tol=TOL_GRAD)
 
 
 @pytest.mark.parametrize("B,N,T", [(16, 20, 10), (2, 100, 2), (9, 3, 5)])
@@ -631,10 +630,7 @@ def test_egno_multi_input_vs_oracle_larger_graphs(B, N, T, nin):
             return ref.abs().max()
         tail = k.split(".", 2)[-1]
         return max(float(p[j].grad.abs().max()) for j in p if j.endswith(tail) and p[j].grad is not None)
-    for k, qp in m.named_parameters():
-        ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
-        bad = ((qp.grad.cpu() - ref).abs() > TOL_GRAD * scale(k, ref)).float().mean().item()
-        assert bad < 0.01 and rel_err(qp.grad.cpu(), ref) < 10 * TOL_GRAD, (k, bad)
+    param_grads_within_kink_budget(m, p, n_rows=T * B * N, tol=TOL_GRAD, scale=scale)
 
 
 def test_blocked_selector_walk_is_deterministic_and_batch_independent():
