@@ -122,44 +122,97 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_arm(args, steps, warmup, sample):
-    """The reference's CPU implementation of the path: the oracle port (oracle/nbody_oracle.py, pinned to the
-    reference by golden vectors; /root/reference itself is not on the GPU box) with all host threads."""
+def _reference_or_port():
+    """The reference's own modules when the unmodified copy is installed (oracle/_ref, made by oracle/make_ref.py in the
+    build container; it travels to the GPU box), else None (the oracle port is timed instead)."""
+    try:
+        from oracle import ref_loader as RL
+
+        if RL.reference_available():
+            return RL.load_reference(), RL
+    except Exception as e:       # a broken install must not take the bench down: fall back to the port and say so
+        print(f"reference import failed ({e}); timing the oracle port", file=sys.stderr)
+    return None, None
+
+
+def cpu_reference_arm(args, steps, warmup, sample, model="egno", device="cpu"):
+    """The reference's implementation of the path on the host cores: the reference's real `EGNO` / `SEGNO` modules
+    (kind "reference") when oracle/_ref is installed, else the oracle port (kind "port"); forward + the callers' MSE +
+    backward + torch.optim.Adam with all host threads, on a bounded sample of the workload.  With device="cuda" the
+    oracle port runs the same PyTorch eager ops on the B200 (same-GPU context for the hand-written kernels)."""
     from oracle import nbody_oracle as O
-    import no_node_comparison_b200 as nb
     from no_node_comparison_b200 import synth
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     N, T, L = args.n_balls, args.timesteps, args.layers
+    R, RL = _reference_or_port() if device == "cpu" else (None, None)
     torch.manual_seed(1)
-    holder = nb.EGNO(n_layers=L, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T,
-                     device="cpu")
-    p = {k: t.detach().clone().requires_grad_(True) for k, t in holder.state_dict().items()}
-    opt = torch.optim.Adam(list(p.values()), lr=1e-4, weight_decay=1e-8)
-    s = synth.sample_state("charged", sample, N, seed=0)
+    dev = torch.device(device)
     row, col = synth.canonical_edges(sample, N)
-    x, nodes, ea, v, lm = synth.egno_features(s["loc"], s["vel"], s["charges"], row, col)
-    t_out = torch.arange(1, T + 1)[None].repeat(sample, 1)
-    target = x.repeat(T, 1) + 0.05 * torch.randn(T * sample * N, 3, generator=torch.Generator().manual_seed(1))
+    if model == "egno":
+        s = synth.sample_state("charged", sample, N, seed=0)
+        x, nodes, ea, v, lm = synth.egno_features(s["loc"], s["vel"], s["charges"], row, col)
+        t_out = torch.arange(1, T + 1)[None].repeat(sample, 1)
+        target = x.repeat(T, 1) + 0.05 * torch.randn(T * sample * N, 3, generator=torch.Generator().manual_seed(1))
+        x, nodes, ea, v, lm, t_out, target, row, col = (t.to(dev) for t in (x, nodes, ea, v, lm, t_out, target, row, col))
+        if R is not None:
+            m = R.EGNO(n_layers=L, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T,
+                       device="cpu")
+            params = list(m.parameters())
+            fwd = lambda: m(x, nodes, [row, col], ea, v=v, loc_mean=lm, timesteps_out=t_out)[0]
+        else:
+            import no_node_comparison_b200 as nb
+
+            holder = nb.EGNO(n_layers=L, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2,
+                             num_timesteps=T, device="cpu")
+            p = {k: t.detach().clone().to(dev).requires_grad_(True) for k, t in holder.state_dict().items()}
+            params = list(p.values())
+            fwd = lambda: O.egno_forward(p, x, nodes, row, col, ea, v, lm, t_out, n_layers=L, num_timesteps=T)[0]
+        opt = torch.optim.Adam(params, lr=1e-4, weight_decay=1e-8)
+        what = f"EGNO N={N}, T={T}, L={L}"
+    else:
+        s = synth.sample_state("gravity", sample, N, seed=0)
+        his, x, v, ea = synth.segno_features(s["loc"], s["vel"], s["charges"], row, col)
+        target = x + 0.05 * torch.randn(sample * N, 3, generator=torch.Generator().manual_seed(1))
+        his, x, v, ea, target, row, col = (t.to(dev) for t in (his, x, v, ea, target, row, col))
+        if R is not None:
+            m = R.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device="cpu", n_layers=8, recurrent=True)
+            params = [q for k, q in m.named_parameters()]
+            # SEGNO.forward at reference HEAD returns its inputs (SURVEY.md 0); the semantics its callers assume:
+            fwd = lambda: m.forward_step(m.embedding(his), x, [row, col], v, ea, T=T)[0]
+        else:
+            import no_node_comparison_b200 as nb
+
+            holder = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device="cpu", n_layers=8, recurrent=True)
+            p = {k: t.detach().clone().to(dev).requires_grad_(True) for k, t in holder.state_dict().items()}
+            params = [q for k, q in p.items() if "coord_mlp_vel" not in k]
+            fwd = lambda: O.segno_forward(p, his, x, row, col, v, ea, T)[0]
+        opt = torch.optim.Adam(params, lr=5e-3, weight_decay=1e-12)
+        what = f"SEGNO N={N}, {T} sub-steps, dense-M segment mean included"
 
     def step():
         opt.zero_grad()
-        xo, _, _ = O.egno_forward(p, x, nodes, row, col, ea, v, lm, t_out, n_layers=L, num_timesteps=T)
-        loss = ((xo - target) ** 2).mean()
+        loss = ((fwd() - target) ** 2).mean()
         loss.backward()
         opt.step()
         return float(loss.detach())
 
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
     for _ in range(warmup):
         step()
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
+    sync()
     dt = time.perf_counter() - t0
-    return {"value": sample * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps x {sample} trajectories (N={N}, T={T}, L={L}) fwd+bwd+Adam, torch CPU fp32, "
-                      f"{cores} threads, {warmup} warm-up", "ms_per_step": 1e3 * dt / steps}
+    kind = "reference" if R is not None else "port"
+    where = f"torch CPU fp32, {cores} threads" if dev.type == "cpu" else "torch eager fp32 on the B200 (TF32 off)"
+    return {"value": sample * steps / dt, "unit": UNIT, "cores": cores if dev.type == "cpu" else 0, "kind": kind,
+            "sample": f"{steps} steps x {sample} trajectories ({what}) fwd+bwd+Adam, {where}, {warmup} warm-up; "
+                      + ("the reference's own nn.Module from oracle/_ref" if R is not None else "oracle port (oracle/nbody_oracle.py)"),
+            "ms_per_step": 1e3 * dt / steps}
 
 
 def run_reference(args):
@@ -177,6 +230,16 @@ def run_reference(args):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def load_digest():
+    """profiles/ncu_digest.json: per-kernel numbers read from committed ncu captures (tools/ncu_digest.py)."""
+    path = os.path.join(ROOT, "profiles", "ncu_digest.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
 
 
 def workload_config(args, per_step=None, note=None):
@@ -236,10 +299,17 @@ def run_ours(args):
     edges = [row_d, col_d]
     t_out = torch.arange(1, T + 1, device=dev)[None].repeat(B, 1)
     host, resident = [], []
+    F0 = 30      # input frame of the reference's loader for the charged data set (dataset_simple.py:123); targets = the next T
     for i in range(NBATCH):
-        s = synth.sample_state("charged", B, N, seed=1000 * rank + i)
-        tgt = (s["loc"].reshape(1, B * N, 3) + 0.05 * torch.randn(T, B * N, 3, generator=torch.Generator().manual_seed(i))
-               ).reshape(T * B * N, 3)
+        # synthetic trajectories of synthetic_sim.py's charged system, integrated by this repo's device simulator
+        # (nb.simulate_charged, pinned to the reference by tests/test_sim.py) from its initial-condition distribution
+        s0 = synth.sample_state("charged", B, N, seed=1000 * rank + i)
+        f64 = lambda t: t.to(dev, torch.float64)
+        loc_f, vel_f = nb.simulate_charged(f64(s0["loc"]).transpose(1, 2).contiguous(), f64(s0["vel"]).transpose(1, 2).contiguous(),
+                                           f64(s0["charges"]), (F0 + T + 2) * 100, 100)        # [B, frames, 3, N]
+        s = dict(loc=loc_f[:, F0].transpose(1, 2).float().cpu().contiguous(), vel=vel_f[:, F0].transpose(1, 2).float().cpu().contiguous(),
+                 charges=s0["charges"])
+        tgt = loc_f[:, F0 + 1:F0 + T + 1].permute(1, 0, 3, 2).reshape(T * B * N, 3).float().cpu()   # frame-major like the output
         hb = {k: v.contiguous().pin_memory() for k, v in dict(loc=s["loc"], vel=s["vel"], charges=s["charges"], target=tgt).items()}
         host.append(hb)
         x, nodes, ea, v, lm = synth.egno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), row_d, col_d)
@@ -358,6 +428,8 @@ def run_ours(args):
     else:
         peak_tf, peak_src, hbm = 1400.0, "fallback (B200_PROFILING.md sustained bf16)", 6650.0
     ne = T * B * N * (N - 1)
+    digest = load_digest()
+    dg = digest.get("k_edge_bwd_sel", {}) if (N, T, B) == (20, 10, 256) else {}
     t_bwd = kern["edge_bwd"]["ms_per_launch"]
     flop_kernel = 2 * 2 * MAC_EDGE_KERNEL * ne           # backward = 2 x forward; recompute is not credited
     achieved = flop_kernel / (t_bwd * 1e-3) / 1e12 if t_bwd else None
@@ -365,19 +437,21 @@ def run_ours(args):
                           "all on tcgen05 with split-bf16 operands and fp32 TMEM accumulators)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "peak_source": peak_src,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full
-                # (profiles/r01b_edge_bwd_sel_digest.txt); valid for the default workload only
-                "traffic": 46.1e6 if (N, T, B) == (20, 10, 256) else None,
+                # every logical fp32 product is three bf16 passes: the ceiling for fp32-accurate work on this pipe
+                "peak_3pass": peak_tf / 3.0, "frac_3pass": (achieved / (peak_tf / 3.0)) if achieved else None,
+                "frac_reference_formula": (2 * 2 * MAC_EDGE_REF * ne / (t_bwd * 1e-3) / 1e12 / peak_tf) if t_bwd else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch and tensor-pipe activity from the committed ncu
+                # digest of this kernel (profiles/ncu_digest.json, written by tools/ncu_digest.py); default workload only
+                "traffic": dg.get("dram_bytes"), "tensor_pipe_active_pct_ncu": dg.get("tensor_pipe_active_pct"),
+                "ncu_source": dg.get("source"),
                 "flop_per_launch": flop_kernel, "flop_per_launch_reference_formula": 2 * 2 * MAC_EDGE_REF * ne,
-                "tensor_pipe_active_pct_ncu": 28.0 if (N, T, B) == (20, 10, 256) else None,
                 "note": "achieved = ALGORITHMIC fp32 FLOPs the edge kernel owns (8448 MAC/edge forward, x2 for backward; the "
                         "recompute is not credited) / its mean launch time (CUDA events on the launch stream).  The reference's "
                         "dense 131-wide first layer would count 16640 MAC/edge (second figure).  Every logical fp32 MMA is "
                         "three bf16 tcgen05 passes (hi*hi + lo*hi + hi*lo) and the backward executes ~2x the credited MACs "
                         "(recompute, weight-gradient and one-hot scatter MMAs), so the tensor pipe is ~8x busier than `frac` "
-                        "suggests: ncu reports 28 % tensor-pipe active for this launch.  The kernel is bound by its dependent "
-                        "MMA -> TMEM -> SiLU -> smem -> MMA chain (4 round trips per 128-edge tile; per-stage cycles in "
-                        "DESIGN.md / tools/stage_clocks.py), not by HBM (46 MB per launch = 105 GB/s).",
+                        "suggests (tensor_pipe_active_pct_ncu).  frac_3pass is the same figure against peak / 3, the ceiling "
+                        "of fp32-accurate products on this pipe.  Not HBM-bound: `traffic` is ~1.1x the node-level bytes.",
                 "hbm_peak_gbs": hbm}
 
     # HBM-bound side of the path: the fused temporal convolution (forward reads h and writes h once; the backward reads h
@@ -393,7 +467,7 @@ def run_ours(args):
                     "note": "mean over the forward and backward launches of a step (CUDA events); algorithmic bytes = "
                             "2*T*64*4 B per node-trajectory forward, (3*T + 6)*64*4 B backward"}
 
-    extras = {}
+    extras, segno = {}, None
     if not args.no_extras:
         # inference throughput (no_grad forward) of the same model
         with torch.no_grad():
@@ -403,44 +477,108 @@ def run_ours(args):
                 f(i)
             ms_inf = timed(f, K)
         extras["egno_infer_traj_per_s"] = world * B * K / (ms_inf / 1e3)
-        # SEGNO, BASELINE.json configs[3] shape (N=20, T=10, B=256): train step and forward
+        # SEGNO, BASELINE.json configs[3] shape (gravity, N=20, 10 sub-steps, B=256): the second half of the metric
         torch.manual_seed(1)
         seg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=dev, n_layers=8, recurrent=True)
         if world > 1:
             broadcast_parameters(seg)
             seg.enable_data_parallel()
         sopt = nb.FlatAdam(seg.parameters(), lr=5e-3, weight_decay=1e-12)
-        sb = []
+        sb, shost = [], []
         for i in range(NBATCH):
-            s = synth.sample_state("gravity", B, N, seed=77 + 1000 * rank + i)
-            his, x, v, ea = synth.segno_features(s["loc"].to(dev), s["vel"].to(dev), s["charges"].to(dev), row_d, col_d)
-            sb.append(dict(his=his, x=x, v=v, ea=ea, target=x + 0.05 * torch.randn_like(x)))
+            # trajectories of synthetic_sim.py's gravitational system (nb.simulate_gravity): frame 0 in, frame 1 out
+            s0 = synth.sample_state("gravity", B, N, seed=77 + 1000 * rank + i)
+            f64 = lambda t: t.to(dev, torch.float64)
+            pos_f, vel_f, _ = nb.simulate_gravity(f64(s0["loc"]), f64(s0["vel"]), f64(s0["charges"]), 200, 100)   # [B, 2, N, 3]
+            loc0, vel0 = pos_f[:, 0].float().contiguous(), vel_f[:, 0].float().contiguous()
+            tgt = pos_f[:, 1].float().reshape(B * N, 3).contiguous()
+            his, x, v, ea = synth.segno_features(loc0, vel0, s0["charges"].to(dev), row_d, col_d)
+            sb.append(dict(his=his, x=x, v=v, ea=ea, target=tgt))
+            shost.append({k: t.cpu().contiguous().pin_memory() for k, t in dict(loc=loc0, vel=vel0, mass=s0["charges"], target=tgt).items()})
+        seg_h2d = sum(t.numel() * t.element_size() for t in shost[0].values())
 
         def seg_loss(his, x, v, ea, target):
             xo, ho, vo = seg(his, x, edges, v, ea, T=T)
-            return ((xo - target) ** 2).mean()
+            return nb.trajectory_mse(xo, target, 1)[0]          # MSELoss()(loc_pred, loc_end), train_nbody.py:163-165, fused
+
+        def seg_loss_raw(loc, vel, mass, target):
+            x, v = loc.reshape(-1, 3), vel.reshape(-1, 3)
+            his, _, ea = nb.prepare_inputs(x, v, mass, N, with_charge=False, want_mean=False)    # train_nbody.py:93,119-123
+            return seg_loss(his, x, v, ea, target)
+
+        def seg_eager(i):
+            sopt.zero_grad(set_to_none=True)
+            seg_loss(**sb[i % NBATCH]).backward()
+            sopt.step()
 
         if use_graph:
             g_seg = nb.GraphedStep(seg_loss, sb[0], sopt)
-
-            def seg_step(i):
-                g_seg(**sb[i % NBATCH])
+            g_seg_raw = nb.GraphedStep(seg_loss_raw, {k: t.to(dev) for k, t in shost[0].items()}, sopt)
+            seg_step = lambda i: g_seg(**sb[i % NBATCH])
+            seg_e2e = lambda i: g_seg_raw(**shost[i % NBATCH]).item()
+            seg_launches = g_seg.launches_per_replay
         else:
-            def seg_step(i):
+            seg_step = seg_eager
+
+            def seg_e2e(i):
+                d = {k: t.to(dev, non_blocking=True) for k, t in shost[i % NBATCH].items()}
                 sopt.zero_grad(set_to_none=True)
-                seg_loss(**sb[i % NBATCH]).backward()
+                loss = seg_loss_raw(**d)
+                loss.backward()
                 sopt.step()
+                return loss.item()
+            seg_launches = None
 
         for i in range(3):
             seg_step(i)
         ms_seg = timed(seg_step, K)
-        extras["segno_train_traj_per_s"] = world * B * K / (ms_seg / 1e3)
+        for i in range(2):
+            seg_e2e(i)
+        ms_seg_e2e = timed(seg_e2e, K)
         with torch.no_grad():
             g = lambda i: seg(sb[i % NBATCH]["his"], sb[i % NBATCH]["x"], edges, sb[i % NBATCH]["v"], sb[i % NBATCH]["ea"], T=T)
             for i in range(3):
                 g(i)
             ms_sinf = timed(g, K)
-        extras["segno_infer_traj_per_s"] = world * B * K / (ms_sinf / 1e3)
+        lib.nb_profile_enable(1)
+        ms_sprof = timed(seg_eager, K)
+        sm_, sc_ = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
+        lib.nb_profile_read(sm_, sc_)
+        lib.nb_profile_enable(0)
+        scat = {"edge_bwd": 1, "segno_fused_fwd": 5, "gemm64": 2, "wgrad64": 3}
+        skern = {c: {"ms_total": sm_[i], "launches": int(sc_[i]), "ms_per_launch": (sm_[i] / sc_[i]) if sc_[i] else None,
+                     "share_of_step": sm_[i] / ms_sprof if ms_sprof else None} for c, i in scat.items()}
+        ne_s = B * N * (N - 1)                                    # edges per sub-step
+        t_sb, t_sf = skern["edge_bwd"]["ms_per_launch"], skern["segno_fused_fwd"]["ms_per_launch"]
+        mac_node = 2 * 64 * 64 + 2 * 64 * 64 + 64 * 64            # P|Q, phi_h first layer ([h, M] 128-wide), second layer
+        flop_fused = 2 * T * (MAC_EDGE_KERNEL * ne_s + mac_node * B * N)
+        flop_sbwd = 2 * 2 * MAC_EDGE_KERNEL * ne_s
+        tf = lambda fl, ms_: fl / (ms_ * 1e-3) / 1e12 if ms_ else None
+        segno = {"config": {"workload": f"SEGNO gravity N-body, {N} particles, {T} sub-steps, hidden 64 (BASELINE.json configs[3])",
+                            "batch_per_gpu": B},
+                 "train_traj_per_s": world * B * K / (ms_seg / 1e3), "ms_per_step": ms_seg / K,
+                 "infer_traj_per_s": world * B * K / (ms_sinf / 1e3),
+                 "e2e": {"value": world * B * K / (ms_seg_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": seg_h2d,
+                         "d2h_bytes_per_step": 4, "ms_per_step": ms_seg_e2e / K},
+                 "gpu_launches_per_step": seg_launches,
+                 "roofline": {"kernel": "k_edge_bwd_sel at the SEGNO shape (one launch per sub-step of the backward sweep; "
+                                        f"{ne_s} edges = {-(-ne_s // 128)} tiles over the SMs)",
+                              "bound": "tensor", "achieved": tf(flop_sbwd, t_sb), "peak": peak_tf, "unit": "TFLOP/s",
+                              "frac": (tf(flop_sbwd, t_sb) / peak_tf) if t_sb else None,
+                              "frac_3pass": (tf(flop_sbwd, t_sb) / (peak_tf / 3)) if t_sb else None, "peak_source": peak_src,
+                              "traffic": digest.get("k_edge_bwd_sel_segno", {}).get("dram_bytes"),
+                              "ncu_source": digest.get("k_edge_bwd_sel_segno", {}).get("source")},
+                 "roofline_fused_fwd": {"kernel": "k_segno_fused_fwd (all sub-steps of the forward in one kernel, node state in "
+                                                  "shared memory)", "bound": "tensor", "achieved": tf(flop_fused, t_sf),
+                                        "peak": peak_tf, "unit": "TFLOP/s", "frac": (tf(flop_fused, t_sf) / peak_tf) if t_sf else None,
+                                        "frac_3pass": (tf(flop_fused, t_sf) / (peak_tf / 3)) if t_sf else None,
+                                        "traffic": digest.get("k_segno_fused_fwd", {}).get("dram_bytes"),
+                                        "tensor_pipe_active_pct_ncu": digest.get("k_segno_fused_fwd", {}).get("tensor_pipe_active_pct"),
+                                        "ncu_source": digest.get("k_segno_fused_fwd", {}).get("source"),
+                                        "note": f"one CTA per trajectory: {B} CTAs on {torch.cuda.get_device_properties(dev).multi_processor_count} SMs"},
+                 "kernels": skern}
+        extras["segno_train_traj_per_s"] = segno["train_traj_per_s"]
+        extras["segno_infer_traj_per_s"] = segno["infer_traj_per_s"]
         # long-horizon rollouts kept on the device (featurisation + model + energies; BASELINE.json configs[3]:
         # traj_len = 20 calls, main.py:42), one host read at the end
         TL = 20
@@ -462,22 +600,85 @@ def run_ours(args):
         if world == 1:
             extras.update(small_configs(nb, synth, dev, K))
 
+    # ---- BASELINE.json configs[4]: 100-body EGNO, GLOBAL batch 512 split over the ranks (strong scaling), at every N
+    cfg5 = None
+    if not args.no_extras:
+        cfg5 = config5_leg(nb, synth, dev, rank, world, timed, dist, use_graph)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_arm(args, steps=8, warmup=1, sample=args.cpu_sample)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_extras:
+            # same-GPU context: the plain PyTorch eager ops of the oracle port on this B200, same config
+            try:
+                eg = cpu_reference_arm(args, steps=5, warmup=2, sample=B, device="cuda")
+                cpu_baseline["torch_eager_b200"] = {"value": eg["value"], "unit": UNIT, "sample": eg["sample"]}
+                extras["torch_eager_b200_traj_per_s"] = eg["value"]
+            except Exception as e:
+                cpu_baseline["torch_eager_b200"] = {"error": str(e)[:200]}
+            cs = cpu_reference_arm(args, steps=8, warmup=1, sample=args.cpu_sample, model="segno")
+            segno["cpu_baseline"] = {k: cs[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "data": "synthetic (trajectories of the reference's charged simulator, integrated on the device)",
+                "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
                 "cpu_baseline": cpu_baseline,
-                "kernels": kern, "extras": extras}
+                "kernels": kern, "segno": segno, "config5": cfg5, "extras": extras}
         emit(line)
     finish(world, dist)
+
+
+def config5_leg(nb, synth, dev, rank, world, timed, dist, use_graph):
+    """BASELINE.json configs[4]: EGNO on a synthetic 100-particle charged system, batch 512, data-parallel over the ranks
+    (strong scaling: 512 / world trajectories per GPU; one flat-bucket all-reduce per step)."""
+    GB, N5, T5, L5 = 512, 100, 10, 4
+    B5 = GB // world
+    row5, col5 = synth.canonical_edges(B5, N5)
+    e5 = [row5.to(dev), col5.to(dev)]
+    torch.manual_seed(1)
+    m5 = nb.EGNO(n_layers=L5, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T5, device=dev)
+    if world > 1:
+        from no_node_comparison_b200.dataparallel import broadcast_parameters
+
+        broadcast_parameters(m5)
+        m5.enable_data_parallel()
+    o5 = nb.FlatAdam(m5.parameters(), lr=1e-4, weight_decay=1e-8)
+    s5 = synth.sample_state("charged", B5, N5, seed=9 + rank)
+    x5, n5, ea5, v5, lm5 = synth.egno_features(s5["loc"].to(dev), s5["vel"].to(dev), s5["charges"].to(dev), e5[0], e5[1])
+    tg5 = x5.repeat(T5, 1) + 0.05 * torch.randn(T5 * B5 * N5, 3, device=dev)
+    to5 = torch.arange(1, T5 + 1, device=dev)[None].repeat(B5, 1)
+
+    def loss5(x, nodes, ea, v, lm, tgt):
+        xo, _, _ = m5(x, nodes, e5, ea, v=v, loc_mean=lm, timesteps_out=to5)
+        return nb.trajectory_mse(xo, tgt, T5)[0]
+
+    ins = dict(x=x5, nodes=n5, ea=ea5, v=v5, lm=lm5, tgt=tg5)
+    if use_graph:
+        g5 = nb.GraphedStep(loss5, ins, o5, warmup=2)
+        step5 = lambda i: g5.graph.replay()
+    else:
+        def step5(i):
+            o5.zero_grad(set_to_none=True)
+            loss5(**ins).backward()
+            o5.step()
+        for _ in range(2):
+            step5(0)
+    K5 = 5
+    ms5 = timed(step5, K5)
+    out = {"workload": "EGNO synthetic 100-particle charged system, batch 512, data-parallel (BASELINE.json configs[4])",
+           "metric": "train trajectories/s (EGNO 100-body, fwd+bwd+Adam)", "value": GB * K5 / (ms5 / 1e3), "unit": UNIT,
+           "scaling": "strong", "global_batch": GB, "batch_per_gpu": B5, "n_gpus": world, "steps": K5,
+           "ms_per_step": ms5 / K5, "edges_per_layer_per_gpu": T5 * B5 * N5 * (N5 - 1),
+           "data": "synthetic (initial-condition distribution of the charged simulator; runtime is value-independent)"}
+    del m5, o5
+    torch.cuda.empty_cache()
+    return out
 
 
 def small_configs(nb, synth, dev, K):
@@ -531,27 +732,6 @@ def small_configs(nb, synth, dev, K):
     out["segno_n5_t10_b100_train_traj_per_s"] = run(lambda: g2(**ins2), 4 * K)
     out["small_configs_note"] = "BASELINE.json configs[0] / [1] (B=100): launch-bound; whole step replayed as one CUDA graph"
     del g1, g2, m, sg
-    # BASELINE.json configs[4] shape: 100-body EGNO, the per-GPU share (64) of the batch of 512 at 8 GPUs
-    B5, N5, T5 = 64, 100, 10
-    row5, col5 = synth.canonical_edges(B5, N5)
-    e5 = [row5.to(dev), col5.to(dev)]
-    torch.manual_seed(1)
-    m5 = nb.EGNO(n_layers=4, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T5, device=dev)
-    o5 = nb.FlatAdam(m5.parameters(), lr=1e-4, weight_decay=1e-8)
-    s5 = synth.sample_state("charged", B5, N5, seed=9)
-    x5, n5, ea5, v5, lm5 = synth.egno_features(s5["loc"].to(dev), s5["vel"].to(dev), s5["charges"].to(dev), e5[0], e5[1])
-    tg5 = x5.repeat(T5, 1) + 0.05 * torch.randn(T5 * B5 * N5, 3, device=dev)
-    to5 = torch.arange(1, T5 + 1, device=dev)[None].repeat(B5, 1)
-
-    def step5():
-        o5.zero_grad(set_to_none=True)
-        xo, _, _ = m5(x5, n5, e5, ea5, v=v5, loc_mean=lm5, timesteps_out=to5)
-        ((xo - tg5) ** 2).mean().backward()
-        o5.step()
-
-    B = B5
-    out["egno_n100_b64_train_traj_per_s"] = run(step5, 5)
-    out["egno_n100_note"] = "BASELINE.json configs[4] shape per GPU (B=512 over 8 GPUs): N=100, T=10, L=4, 6.3M edges per layer"
     return out
 
 

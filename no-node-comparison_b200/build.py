@@ -11,7 +11,7 @@ SRC = os.path.join(HERE, "csrc", "nbody_b200.cu")
 OUT = os.path.join(HERE, "libnbody_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-ldl"]
 
 
 def _sources():

@@ -25,6 +25,18 @@
   } while (0)
 static long long g_launches = 0;
 
+// NVTX ranges around every compute entry point of the C ABI (header-only NVTX3: a no-op unless a profiler injects itself)
+#ifndef NB_EMU
+#include <nvtx3/nvToolsExt.h>
+struct NbRange {
+  explicit NbRange(const char* name) { nvtxRangePushA(name); }
+  ~NbRange() { nvtxRangePop(); }
+};
+#define NB_RANGE(name) NbRange nb_range_guard_(name)
+#else
+#define NB_RANGE(name)
+#endif
+
 // ============================================================================= errors / device info
 static thread_local char g_err[512] = "";
 
@@ -65,13 +77,13 @@ int nb_num_sms() {
 }
 
 // ---- launch accounting and optional per-kernel CUDA-event timing (used by bench.py for the roofline)
-#define NB_PROF_CATS 5  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64, 4 temporal conv */
+#define NB_PROF_CATS 6  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64, 4 temporal conv, 5 fused SEGNO forward */
 #define NB_PROF_MAX 8192
 #ifndef NB_EMU
 static int g_prof_on = 0;
 static cudaEvent_t g_prof_ev[NB_PROF_CATS][NB_PROF_MAX][2];
-static int g_prof_made[NB_PROF_CATS] = {0, 0, 0, 0, 0};
-static int g_prof_n[NB_PROF_CATS] = {0, 0, 0, 0, 0};
+static int g_prof_made[NB_PROF_CATS] = {0};
+static int g_prof_n[NB_PROF_CATS] = {0};
 static int prof_begin(int cat, void* st) {
   if (!g_prof_on || g_prof_n[cat] >= NB_PROF_MAX) return -1;
   int i = g_prof_n[cat];
@@ -846,6 +858,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
                                const float* edge_fea, const float* v, const float* loc_mean,
                                const int64_t* timesteps_out, const int64_t* timesteps_in, float* x_out, float* v_out,
                                float* h_out, float* saved, float* workspace, void* stream) {
+  NB_RANGE("nb_egno_forward");
   EgnoCtx X;
   NB_TRY(egno_ctx_init(&X, cfg, params, stream));
   const int T = cfg->T, Ln = cfg->n_layers;
@@ -964,6 +977,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
                                 const float* loc_mean, const int64_t* timesteps_out, const int64_t* timesteps_in,
                                 const float* saved, const float* g_x_out, const float* g_v_out, const float* g_h_out,
                                 float* grad_params, float* g_x_in, float* g_v_in, float* workspace, void* stream) {
+  NB_RANGE("nb_egno_backward");
   EgnoCtx X;
   NB_TRY(egno_ctx_init(&X, cfg, params, stream));
   if (!saved) { nb_set_error("nb_egno_backward needs the saved buffer of a forward call"); return NB_ERR_INVALID; }
@@ -1323,6 +1337,7 @@ static void segno_embed_args(const SegnoCtx& X, const float* his, NbEmbedArgs* e
 extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, const float* his, const float* x,
                                 const float* v, const float* edge_attr, float* x_out, float* h_out, float* v_out,
                                 float* saved, float* workspace, void* stream) {
+  NB_RANGE("nb_segno_forward");
   NB_TRY(segno_validate(cfg));
   SegnoCtx X;
   X.c = cfg; segno_layout(cfg, &X.lo); X.Nn = (int64_t)cfg->B * cfg->N; X.params = params; X.st = stream;
@@ -1360,9 +1375,9 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
       fa.h_out = h_out; fa.x_out = x_out; fa.v_out = v_out; fa.saved = saved; fa.iter_stride = itf;
       const size_t fsm = NB_SEGNO_FUSED_SMEM(fg.G * fg.EPG);
       NB_SET_SMEM(k_segno_fused_fwd, fsm);
-      int pi = prof_begin(0, stream);
+      int pi = prof_begin(5, stream);
       NB_LAUNCH_COUNTED(k_segno_fused_fwd, (unsigned)imin(fg.n_units, nb_num_sms()), NB_THREADS, fsm, stream, fa);
-      prof_end(0, pi, stream);
+      prof_end(5, pi, stream);
       return nb_check_launch("k_segno_fused_fwd");
     }
   }
@@ -1419,6 +1434,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
                                  const float* edge_attr, const float* saved, const float* g_x_out,
                                  const float* g_h_out, const float* g_v_out, float* grad_params, float* g_x_in,
                                  float* g_v_in, float* g_h_in, float* workspace, void* stream) {
+  NB_RANGE("nb_segno_backward");
   NB_TRY(segno_validate(cfg));
   if (!saved) { nb_set_error("nb_segno_backward needs the saved buffer of a forward call"); return NB_ERR_INVALID; }
   SegnoCtx X;
@@ -1542,6 +1558,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
 // ============================================================================= exported building blocks
 extern "C" int nb_check_canonical_edges(const int64_t* row, const int64_t* col, int64_t n_edges, int32_t B, int32_t N,
                                         int32_t* flag_dev, void* stream) {
+  NB_RANGE("nb_check_canonical_edges");
   if (N < 2 || B < 1 || n_edges != (int64_t)B * N * (N - 1)) {
     nb_set_error("edge_index has %lld edges, expected B*N*(N-1) = %lld", (long long)n_edges, (long long)B * N * (N - 1));
     return NB_ERR_INVALID;
@@ -1556,6 +1573,7 @@ extern "C" int nb_egcl_edge_forward(int32_t n_gt, int32_t B, int32_t N, int32_t 
                                     const float* w1, int32_t ldw1, int32_t col_rad, int32_t col_ef, const float* W2,
                                     const float* b2, const float* W3, const float* b3, const float* w4, const float* b4,
                                     float* M, float* Fsum, void* stream) {
+  NB_RANGE("nb_egcl_edge_forward");
   if (N < 2 || N > NB_MAX_NODES || n_edge_fea < 0 || n_edge_fea > NB_MAX_EDGE_FEA || n_gt < 1 || B < 1) {
     nb_set_error("nb_egcl_edge_forward: unsupported shape");
     return NB_ERR_INVALID;
@@ -1579,6 +1597,7 @@ extern "C" int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t
                                      const float* b2, const float* W3, const float* b3, const float* w4, const float* b4,
                                      const float* gM, const float* gFsum, float* gP, float* gQ, float* gx,
                                      float* gw, float* workspace, void* stream) {
+  NB_RANGE("nb_egcl_edge_backward");
   if (N < 2 || N > NB_MAX_NODES || n_edge_fea < 0 || n_edge_fea > NB_MAX_EDGE_FEA || n_gt < 1 || B < 1) {
     nb_set_error("nb_egcl_edge_backward: unsupported shape");
     return NB_ERR_INVALID;
@@ -1604,6 +1623,7 @@ extern "C" int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t
 extern "C" int nb_nbody_features(int32_t B, int32_t N, int32_t with_charge, const float* loc, const float* vel,
                                  const float* charges, const float* edge_attr_o, float* nodes, float* loc_mean,
                                  float* edge_attr, void* stream) {
+  NB_RANGE("nb_nbody_features");
   if (B < 1 || N < 2 || N > 1024 || !loc || !vel || !charges || !nodes || !edge_attr) {
     nb_set_error("nb_nbody_features: unsupported shape or null pointer (B=%d, N=%d)", B, N);
     return NB_ERR_INVALID;
@@ -1618,6 +1638,7 @@ extern "C" int nb_nbody_features(int32_t B, int32_t N, int32_t with_charge, cons
 
 extern "C" int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, float G, const float* loc, const float* vel,
                                const float* charges, float* energy, void* stream) {
+  NB_RANGE("nb_nbody_energy");
   if ((kind != 0 && kind != 1) || F < 1 || B < 1 || N < 1 || N > 1024 || !loc || !vel || !charges || !energy) {
     nb_set_error("nb_nbody_energy: unsupported arguments (kind=%d, F=%d, B=%d, N=%d)", kind, F, B, N);
     return NB_ERR_INVALID;
@@ -1634,6 +1655,7 @@ extern "C" int nb_nbody_energy(int32_t kind, int32_t F, int32_t B, int32_t N, fl
 extern "C" int64_t nb_traj_mse_workspace_floats(int32_t T) { return (int64_t)(T > 0 ? T : 0) * NB_MSE_CHUNKS; }
 extern "C" int nb_traj_mse(int32_t T, int64_t rows, int32_t target_layout, int32_t only_first, const float* pred,
                            const float* target, float* losses, float* loss, float* grad, float* workspace, void* stream) {
+  NB_RANGE("nb_traj_mse");
   if (T < 1 || T > NB_MAX_T || rows < 1 || (target_layout != 0 && target_layout != 1) || !pred || !target || !losses ||
       !loss || !workspace) {
     nb_set_error("nb_traj_mse: unsupported arguments (T=%d (<= %d), rows=%lld, layout=%d) or null pointer", T, NB_MAX_T,
@@ -1654,6 +1676,7 @@ extern "C" int nb_traj_mse(int32_t T, int64_t rows, int32_t target_layout, int32
 extern "C" int nb_sim_charged(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double dt, double strength, double max_force,
                               double box_size, const double* loc0, const double* vel0, const double* charges, double* loc,
                               double* vel, void* stream) {
+  NB_RANGE("nb_sim_charged");
   if (B < 1 || N < 1 || N > NB_SIM_MAX_N || T < 2 || sample_freq < 1 || T % sample_freq || !loc0 || !vel0 || !charges ||
       (T / sample_freq > 1 && (!loc || !vel))) {
     nb_set_error("nb_sim_charged: unsupported arguments (B=%d, N=%d (<= %d), T=%d, sample_freq=%d) or null pointer", B, N,
@@ -1670,6 +1693,7 @@ extern "C" int nb_sim_charged(int32_t B, int32_t N, int32_t T, int32_t sample_fr
 extern "C" int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double dt, double G, double softening,
                               const double* pos0, const double* vel0, const double* mass, double* pos, double* vel,
                               double* force, void* stream) {
+  NB_RANGE("nb_sim_gravity");
   if (B < 1 || N < 1 || N > NB_SIM_MAX_N || T < 1 || sample_freq < 1 || T % sample_freq || !pos0 || !vel0 || !mass || !pos ||
       !vel || !force) {
     nb_set_error("nb_sim_gravity: unsupported arguments (B=%d, N=%d (<= %d), T=%d, sample_freq=%d) or null pointer", B, N,
@@ -1689,6 +1713,7 @@ extern "C" int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_fr
 extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
                             int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                             void* stream) {
+  NB_RANGE("nb_adam_step");
   if (n < 0 || !params || !grads || !exp_avg || !exp_avg_sq || !step) {
     nb_set_error("nb_adam_step: null pointer or negative size");
     return NB_ERR_INVALID;

@@ -46,6 +46,9 @@ class GraphedStep:
         if self.opt is not None:
             loss.backward()
             self.opt.step()
+            # keep no reference to the autograd graph: its AccumulateGrad nodes are bound to the capture stream and would
+            # otherwise outlive the capture (PyTorch warns about, and may synchronise on, the stream mismatch later)
+            loss = loss.detach()
         return loss
 
     def __call__(self, **inputs: torch.Tensor) -> torch.Tensor:

@@ -63,7 +63,7 @@ def timestep_embedding(timesteps: Tensor, dim: int, max_positions: int = 10000) 
     """EGNO/model/layer_no.py:8-17.  timesteps [B,T] -> [B,T,dim] = [sin | cos]."""
     half = dim // 2
     scale = math.log(max_positions) / (half - 1)
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -scale)
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=timesteps.device) * -scale)
     arg = timesteps.float()[:, :, None] * freq[None, None, :]
     emb = torch.cat([torch.sin(arg), torch.cos(arg)], dim=-1)
     if dim % 2 == 1:
@@ -122,7 +122,7 @@ def egno_forward(p: Dict[str, Tensor], x: Tensor, h: Tensor, row: Tensor, col: T
     temb = temb.transpose(0, 1).unsqueeze(1).repeat(1, nn_ // B, 1, 1).reshape(T, -1, time_emb_dim)
     hh = torch.cat([h.unsqueeze(0).repeat(T, 1, 1), temb], dim=-1).reshape(T * nn_, -1)  # :63,:72,:74
     hh = linear(hh, p, "embedding")                                               # :76
-    node_off = (torch.arange(T) * nn_).repeat_interleave(ne)                      # :53-55, :91-92
+    node_off = (torch.arange(T, device=row.device) * nn_).repeat_interleave(ne)   # :53-55, :91-92
     rr = row.repeat(T) + node_off
     cc = col.repeat(T) + node_off
     xx = x.repeat(T, 1)
@@ -169,7 +169,7 @@ def egno_forward_multi(p: Dict[str, Tensor], x: Tensor, h: Tensor, row: Tensor, 
     bc = lambda e: e.transpose(0, 1).unsqueeze(1).repeat(1, nn_ // B, 1, 1).reshape(T, -1, time_emb_dim)  # :66,:69
     hh = torch.cat([h[tmap], bc(temb_in), bc(temb_out)], dim=-1).reshape(T * nn_, -1)   # :59-61,:70,:74
     hh = linear(hh, p, "embedding")
-    node_off = (torch.arange(T) * nn_).repeat_interleave(ne)
+    node_off = (torch.arange(T, device=row.device) * nn_).repeat_interleave(ne)
     rr = row.repeat(T) + node_off
     cc = col.repeat(T) + node_off
     xx = x[tmap].reshape(T * nn_, 3)                                               # :80-83

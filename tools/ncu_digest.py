@@ -39,5 +39,23 @@ def main(path, top=30):
     for s, ie, f, ln, src in out[:top]:
         print(f"{100*s/max(tot,1):5.1f}% inst={ie/1e6:7.2f}M {f}:{ln}: {src}")
 
+def to_json(path, key, digest_txt, workload, out='profiles/ncu_digest.json'):
+    """Record the numbers bench.py quotes (DRAM bytes per launch, tensor-pipe activity) for kernel `key` in profiles/ncu_digest.json."""
+    import json, os
+    raw = list(csv.reader(io.StringIO(run([path, '--page', 'raw', '--csv']))))
+    hdr, units, vals = raw[0], raw[1], raw[2]
+    get = lambda name: next((float(v.replace(',', '')) * {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1}.get(u, 1)
+                             for h, u, v in zip(hdr, units, vals) if h == name), None)
+    d = json.load(open(out)) if os.path.isfile(out) else {}
+    d[key] = {'dram_bytes': (get('dram__bytes_read.sum') or 0) + (get('dram__bytes_write.sum') or 0),
+              'tensor_pipe_active_pct': get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'),
+              'xu_pipe_pct': get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'),
+              'duration_us': get('gpu__time_duration.sum'), 'workload': workload, 'source': digest_txt}
+    json.dump(d, open(out, 'w'), indent=1)
+
+
 if __name__ == '__main__':
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
+    if len(sys.argv) > 2 and sys.argv[2] == '--json':     # ncu_digest.py rep --json key digest.txt "workload"
+        to_json(sys.argv[1], sys.argv[3], sys.argv[4], sys.argv[5])
+    else:
+        main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
