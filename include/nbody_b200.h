@@ -249,6 +249,11 @@ int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, f
  * and dumps the raw 128 TMEM lanes x 64 columns into out[128*64]. */
 int nb_tc_selftest(int32_t mode, const float* A, const float* W, float* out, void* stream);
 
+/* SiLU self test: out_mufu[i] = x sigmoid(x) with ex2.approx + rcp.approx (two MUFU operations), out_fma[i] = the same
+ * with the reciprocal on the FMA pipe (bit-trick seed + three Newton steps), the variant the forward edge tile uses for
+ * a measured share of its elements (EGNO/model/basic.py:46-51: SiLU after every edge / coordinate MLP layer). */
+int nb_silu_selftest(int64_t n, const float* x, float* out_mufu, float* out_fma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

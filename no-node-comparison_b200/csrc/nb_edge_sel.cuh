@@ -332,6 +332,17 @@ __device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned ch
 #define NB_SF_TMEM_COLS 256  // [0,64) pre-activations | [64,128) M accumulators | [128,136) Fsum accumulators |
                              // [192,224) hi, [224,256) lo pieces of the A operand (z1, then m) as packed bf16 pairs
 
+// SiLU of the forward tile: elements whose index i satisfies (i % NB_FWD_FMA_DEN) < NB_FWD_FMA_NUM take their reciprocal
+// on the FMA pipe (nb_sigmoid_fma), the rest on the MUFU.  Measured on B200 (tools/ab_variants.py, cfg3, same box,
+// alternating): 0/1 -> 188.9 us per launch, 1/2 -> 188.6, 2/3 -> 193.4, 1/1 -> 201.3: halving the MUFU load buys
+// nothing (XU was 53 % of peak, the tile is bound by its dependent chain at two CTAs per SM, and the seven extra FMA-pipe
+// instructions per element cost issue slots), so the default stays 0 / 1; the variant remains as a build-time switch.
+#ifndef NB_FWD_FMA_NUM
+#define NB_FWD_FMA_NUM 0
+#define NB_FWD_FMA_DEN 1
+#endif
+#define NB_FWD_SILU(i, x) ((((i) % NB_FWD_FMA_DEN) < NB_FWD_FMA_NUM) ? nb_silu_fma(x) : nb_silu(x))
+
 template <bool BLK>
 __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a) {
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
@@ -477,7 +488,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         float v[32];
         nb_tmem_ld32(tm_mine, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = NB_FWD_SILU(i, v[i]);
         nb_store32_ta(nullptr, nullptr, row, hf, v, ta_hm, ta_lm);  // z1 is only ever an A operand: no shared-memory copy
         nb_tmem_st_wait();
       }
@@ -496,7 +507,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         float v[32];
         nb_tmem_ld32(tm_mine, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i] + vb2[cb + i]);
+        for (int i = 0; i < 32; ++i) v[i] = NB_FWD_SILU(i, v[i] + vb2[cb + i]);
         nb_store32_ta(Th, Tl, row, hf, v, ta_hm, ta_lm);  // shared-memory copy: B operand of the scatter M_i += Sel^T m
         nb_tmem_st_wait();
       }
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a)
         nb_tmem_ld32(tm_mine, v);
         float cp = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cp = fmaf(vw4[cb + i], nb_silu(v[i] + vb3[cb + i]), cp);
+        for (int i = 0; i < 32; ++i) cp = fmaf(vw4[cb + i], NB_FWD_SILU(i, v[i] + vb3[cb + i]), cp);
         cpart[hf * NB_TILE + row] = cp;
       }
       nb_tc_fence_before();

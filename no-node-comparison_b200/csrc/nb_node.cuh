@@ -16,6 +16,12 @@ struct NbGemmSrc {
   int64_t sk, sn;
   float scale;
   int kmax;    // valid k of this source (<= 64; operand rows beyond it are taken as zero)
+  // tcgen05 kernel only: a pre-split copy of the 64 x 64 weight block in the shared-memory tile layout (8 KB of hi
+  // pieces, then 8 KB of lo pieces, SW128; tile row = the block's row, tile column = its column), written once per call by
+  // k_weight_images.  A CTA then stages its B operand with 1 024 coalesced 16-byte copies instead of 4 096 strided scalar
+  // loads.  img_mn = 1: the product uses the block transposed (dgrad), i.e. reads the same image as an MN-major operand.
+  const unsigned char* img;
+  int img_mn;
 };
 enum { NB_EPI_NONE = 0, NB_EPI_SILU = 1, NB_EPI_MUL_DSILU = 2 };
 struct NbGemmArgs {

@@ -119,6 +119,16 @@ extern "C" int nb_debug_stage_clocks(long long* out, int reset) {
   }
   return 0;
 }
+// the same for k_gemm64_tc (CTA (0, 0), thread 0): out[0] = launches, out[1..12] = cycles per stage (NB_GCLK)
+extern "C" int nb_debug_gemm_clocks(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, nb_dbg_clk_gemm, sizeof(long long) * 16);
+  if (reset) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(nb_dbg_clk_gemm, z, sizeof(z));
+  }
+  return 0;
+}
 #endif
 
 extern "C" int nb_profile_enable(int enable) {
@@ -201,6 +211,57 @@ extern "C" int nb_get_segno_fused(void) { return g_segno_fused; }
 // mixing, whose result feeds LeakyReLU: split-bf16 rounding (1e-5) would flip the kink for ~1e-5 of the elements and
 // move the weight gradients by O(1/rows) per flip; fp32 keeps the forward mask and its backward recompute identical
 // to the reference's.  These GEMMs have T times fewer rows than every other node GEMM.
+#define EGNO_WIMG_PER_LAYER 6
+// ---- weight images of the current forward / backward call (tcgen05 node GEMMs): registered once per call by
+// wimg_prepare(), looked up by the weight block's address when a job is launched; a guard object clears the table when
+// the call returns.  Sources whose weights are not registered (odd shapes, scaled operands) stage them element-wise.
+#ifndef NB_EMU
+struct WimgTable {
+  const float* W[NB_MAX_WIMG];
+  int ld[NB_MAX_WIMG];
+  const unsigned char* img[NB_MAX_WIMG];
+  int n;
+};
+static thread_local WimgTable g_wimg = {{nullptr}, {0}, {nullptr}, 0};
+struct WimgGuard {
+  ~WimgGuard() { g_wimg.n = 0; }
+};
+static inline int64_t wimg_floats(int nblocks) { return ((int64_t)nblocks * 2 * NB_TC_TILE_BYTES(64) / 4 + 63) / 64 * 64; }
+// blocks: (address of element [0][0], leading dimension) of every 64 x 64 weight block the call's GEMMs multiply with
+static int wimg_prepare(const float* const* W, const int* ld, int n, float* scratch, void* st) {
+  g_wimg.n = 0;
+  if (g_node_impl != 1 || n <= 0) return NB_OK;
+  if (n > NB_MAX_WIMG) n = NB_MAX_WIMG;
+  NbWimgBatch b;
+  memset(&b, 0, sizeof(b));
+  b.out = reinterpret_cast<unsigned char*>(scratch);
+  for (int i = 0; i < n; ++i) {
+    b.W[i] = W[i]; b.ld[i] = ld[i];
+    g_wimg.W[i] = W[i]; g_wimg.ld[i] = ld[i]; g_wimg.img[i] = b.out + (size_t)i * 2 * NB_TC_TILE_BYTES(64);
+  }
+  g_wimg.n = n;
+  NB_LAUNCH_COUNTED(k_weight_images, (unsigned)n, 256, 0, st, b);
+  return nb_check_launch("k_weight_images");
+}
+static void wimg_attach(NbGemmArgs& a) {
+  for (int s = 0; s < a.nsrc; ++s) {
+    NbGemmSrc& src = a.src[s];
+    src.img = nullptr; src.img_mn = 0;
+    if (src.scale != 1.f || src.kmax != NB_H) continue;
+    for (int i = 0; i < g_wimg.n; ++i) {
+      if (g_wimg.W[i] != src.W) continue;
+      if (src.sk == 1 && src.sn == g_wimg.ld[i]) { src.img = g_wimg.img[i]; src.img_mn = 0; }        // y = x W^T
+      else if (src.sn == 1 && src.sk == g_wimg.ld[i]) { src.img = g_wimg.img[i]; src.img_mn = 1; }   // g = g' W
+      break;
+    }
+  }
+}
+#else
+struct WimgGuard {};
+static inline int64_t wimg_floats(int) { return 0; }
+static int wimg_prepare(const float* const*, const int*, int, float*, void*) { return NB_OK; }
+#endif
+
 static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st, bool exact_fp32 = false) {
   int i = 0;
   while (i < n) {
@@ -218,12 +279,15 @@ static int launch_gemm_batch(const NbGemmArgs* jobs, int n, void* st, bool exact
 #ifndef NB_EMU
     if (g_node_impl == 1 && !exact_fp32) {
       int nsrc_max = 1;
-      for (int j = 0; j < b.njobs; ++j)
+      for (int j = 0; j < b.njobs; ++j) {
         if (b.job[j].nsrc > nsrc_max) nsrc_max = b.job[j].nsrc;
+        wimg_attach(b.job[j]);
+      }
       const size_t smem_tc = NB_GEMM_TC_SMEM(nsrc_max);
       NB_SET_SMEM(k_gemm64_tc, NB_GEMM_TC_SMEM(2));
-      // persistent CTAs: about three co-resident CTAs per SM over the jobs of the batch
-      int per_job = 3 * nb_num_sms() / b.njobs;
+      // persistent CTAs: the two co-resident CTAs per SM (128 registers each) shared by the jobs of the batch, each
+      // pipelined over its tiles (next tile's rows in flight under the current tile's MMAs and epilogue)
+      int per_job = 2 * nb_num_sms() / b.njobs;
       if (per_job < 1) per_job = 1;
       const int gx = imin(cdiv(maxrows, NB_TILE), per_job);
       int pi_tc = prof_begin(2, st);
@@ -247,6 +311,7 @@ static int launch_gemm(const NbGemmArgs& a, void* st) { return launch_gemm_batch
 static NbGemmSrc gsrc(const float* A, int lda, int a_silu, const float* W, int64_t sk, int64_t sn, float scale = 1.f) {
   NbGemmSrc s;
   s.A = A; s.lda = lda; s.a_silu = a_silu; s.W = W; s.sk = sk; s.sn = sn; s.scale = scale; s.kmax = NB_H;
+  s.img = nullptr; s.img_mn = 0;
   return s;
 }
 
@@ -747,7 +812,7 @@ extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int mode) {
   if (mode < 0 || mode > 2) { nb_set_error("workspace mode must be 0 (inference), 1 (backward) or 2 (training forward)"); return -1; }
   int64_t Nn = (int64_t)cfg->T * cfg->B * cfg->N;
   int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
-  const int64_t tab = egno_table_floats(cfg);
+  const int64_t tab = egno_table_floats(cfg) + wimg_floats(EGNO_WIMG_PER_LAYER * cfg->n_layers);   // + weight images
   if (mode == NB_WS_FORWARD_TRAIN) return tab + 2 * nh + 2 * cf;                     // `saved` holds the layer sets
   if (mode == NB_WS_FORWARD_INFER) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // + ping-pong
   return tab + 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
@@ -762,6 +827,24 @@ struct EgnoCtx {
   const float* params;
   void* st;
 };
+
+// the 64 x 64 weight blocks the node GEMMs of a layer multiply with (forward: as stored; backward: transposed views of
+// the same images): first edge layer's h_row / h_col columns, node_net layer 1 (h | M halves) and 2, node_v_net layer 1
+static int egno_weight_images(const EgnoCtx& X, float* scratch) {
+  const float* W[NB_MAX_LAYERS * EGNO_WIMG_PER_LAYER];
+  int ld[NB_MAX_LAYERS * EGNO_WIMG_PER_LAYER];
+  int n = 0;
+  for (int l = 0; l < X.c->n_layers; ++l) {
+    const EgnoLayerOff& L = X.lo.L[l];
+    W[n] = X.params + L.e_w1 + 1; ld[n++] = X.lo.E;
+    W[n] = X.params + L.e_w1 + 1 + NB_H; ld[n++] = X.lo.E;
+    W[n] = X.params + L.n_w1; ld[n++] = 2 * NB_H;
+    W[n] = X.params + L.n_w1 + NB_H; ld[n++] = 2 * NB_H;
+    W[n] = X.params + L.n_w2; ld[n++] = NB_H;
+    W[n] = X.params + L.v_w1; ld[n++] = NB_H;
+  }
+  return wimg_prepare(W, ld, n, scratch, X.st);
+}
 
 static int egno_ctx_init(EgnoCtx* X, const NbEgnoConfig* cfg, const float* params, void* st) {
   NB_TRY(egno_validate(cfg));
@@ -864,7 +947,9 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
   const int T = cfg->T, Ln = cfg->n_layers;
   const int64_t Nn = X.Nn, Nn0 = X.Nn0;
   const int64_t nh = align64(Nn * NB_H), cf = egno_coef_floats(cfg), lf = align64(egno_layer_floats(Nn));
-  float* ttab = workspace;
+  WimgGuard wimg_guard;
+  NB_TRY(egno_weight_images(X, workspace));
+  float* ttab = workspace + wimg_floats(EGNO_WIMG_PER_LAYER * Ln);
   float* P = ttab + egno_table_floats(cfg);
   float* Q = P + nh;
   float* coef = Q + nh;
@@ -986,6 +1071,9 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   const int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
   const int64_t lf = align64(egno_layer_floats(Nn));
   float* w = workspace;
+  WimgGuard wimg_guard;
+  NB_TRY(egno_weight_images(X, w));
+  w += wimg_floats(EGNO_WIMG_PER_LAYER * Ln);
   float* ttab = w; w += egno_table_floats(cfg);
   float* P = w; w += nh;
   float* Q = w; w += nh;
@@ -1271,6 +1359,7 @@ static void segno_layout(const NbSegnoConfig* c, SegnoLayout* lo) {
   lo->total = o;
 }
 
+#define SEGNO_WIMG 5  /* edge layer 1 (h_row | h_col), node_mlp layer 1 (h | M), layer 2 */
 struct SegnoIterBufs {
   float *h, *M, *U5, *x;
 };
@@ -1296,9 +1385,10 @@ extern "C" int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int mode)
   if (mode < 0 || mode > 2) { nb_set_error("workspace mode must be 0 (inference), 1 (backward) or 2 (training forward)"); return -1; }
   int64_t Nn = (int64_t)cfg->B * cfg->N;
   int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3);
-  if (mode == NB_WS_FORWARD_TRAIN) return 2 * nh /*P,Q*/ + 3 * n3 /*Fsum, v ping-pong*/;
-  if (mode == NB_WS_FORWARD_INFER) return 2 * nh + 3 * n3 + 2 * segno_iter_floats(Nn);
-  return 2 * nh + 2 * nh /*gh*/ + 4 * nh /*GU5 gM gP gQ*/ + 4 * n3 + NB_PARTIAL_FLOATS;
+  const int64_t wi = wimg_floats(SEGNO_WIMG);
+  if (mode == NB_WS_FORWARD_TRAIN) return wi + 2 * nh /*P,Q*/ + 3 * n3 /*Fsum, v ping-pong*/;
+  if (mode == NB_WS_FORWARD_INFER) return wi + 2 * nh + 3 * n3 + 2 * segno_iter_floats(Nn);
+  return wi + 2 * nh + 2 * nh /*gh*/ + 4 * nh /*GU5 gM gP gQ*/ + 4 * n3 + NB_PARTIAL_FLOATS;
 }
 
 struct SegnoCtx {
@@ -1308,6 +1398,13 @@ struct SegnoCtx {
   const float* params;
   void* st;
 };
+
+static int segno_weight_images(const SegnoCtx& X, float* scratch) {
+  const float* W[SEGNO_WIMG] = {X.params + X.lo.e_w1, X.params + X.lo.e_w1 + NB_H, X.params + X.lo.n_w1, X.params + X.lo.n_w1 + NB_H,
+                                X.params + X.lo.n_w2};
+  const int ld[SEGNO_WIMG] = {X.lo.E, X.lo.E, 2 * NB_H, 2 * NB_H, NB_H};
+  return wimg_prepare(W, ld, SEGNO_WIMG, scratch, X.st);
+}
 
 static int segno_pq(const SegnoCtx& X, const float* h, float* P, float* Q) {
   NbGemmArgs a = gemm_args((int)X.Nn);  // cols: h_row | h_col | radial | edge_attr  (gcl.py:78)
@@ -1343,7 +1440,8 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
   X.c = cfg; segno_layout(cfg, &X.lo); X.Nn = (int64_t)cfg->B * cfg->N; X.params = params; X.st = stream;
   const int64_t Nn = X.Nn, nh = align64(Nn * NB_H), n3 = align64(Nn * 3), itf = segno_iter_floats(Nn);
   const int T = cfg->T;
-  float* P = workspace;
+  WimgGuard wimg_guard;
+  float* P = workspace + wimg_floats(SEGNO_WIMG);
   float* Q = P + nh;
   float* Fsum = Q + nh;
   float* vb[2] = {Fsum + n3, Fsum + 2 * n3};
@@ -1382,6 +1480,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
     }
   }
 #endif
+  NB_TRY(segno_weight_images(X, workspace));
   SegnoIterBufs b0 = bufs(0);
   {
     if (cfg->h_given) {
@@ -1443,6 +1542,9 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   const int64_t Nn = X.Nn, nh = align64(Nn * NB_H), n3 = align64(Nn * 3), itf = segno_iter_floats(Nn);
   const int T = cfg->T;
   float* w = workspace;
+  WimgGuard wimg_guard;
+  NB_TRY(segno_weight_images(X, w));
+  w += wimg_floats(SEGNO_WIMG);
   float* P = w; w += nh;
   float* Q = w; w += nh;
   float* ghb[2]; ghb[0] = w; w += nh; ghb[1] = w; w += nh;
@@ -1729,6 +1831,18 @@ extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float*
 }
 
 // tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.
+__global__ void k_silu_selftest(int64_t n, const float* x, float* a, float* b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    a[i] = nb_silu(x[i]);
+    b[i] = nb_silu_fma(x[i]);
+  }
+}
+extern "C" int nb_silu_selftest(int64_t n, const float* x, float* out_mufu, float* out_fma, void* stream) {
+  if (n < 0 || !x || !out_mufu || !out_fma) { nb_set_error("nb_silu_selftest: null pointer or negative size"); return NB_ERR_INVALID; }
+  if (n > 0) NB_LAUNCH_COUNTED(k_silu_selftest, (unsigned)imin(cdiv(n, 256), 4 * nb_num_sms()), 256, 0, stream, n, x, out_mufu, out_fma);
+  return nb_check_launch("k_silu_selftest");
+}
+
 extern "C" int nb_tc_selftest(int32_t mode, const float* A, const float* W, float* out, void* stream) {
 #ifdef NB_EMU
   (void)mode; (void)A; (void)W; (void)out; (void)stream;

@@ -99,3 +99,25 @@ def test_tcgen05_wgrad_form_with_folded_column_sums():
     assert _relerr(out[rows], A.double().t() @ G.double()) < 3e-5
     for c in range(8):
         assert _relerr(tail[rows, c], A.double().sum(0)) < 3e-5, c
+
+
+def test_silu_with_the_reciprocal_on_the_fma_pipe_matches_the_mufu_variant():
+    """nb_silu_fma (ex2.approx + bit-trick seed + three Newton steps; the forward edge tile uses it to halve its MUFU load)
+    against float64 SiLU and against the two-MUFU variant, over the whole range incl. the saturating ends."""
+    import ctypes
+
+    import no_node_comparison_b200 as nb
+    lib = nb.load_library()
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.randn(1 << 20, generator=g) * 4, torch.linspace(-120, 120, 100001), torch.tensor([0.0, -0.0, 88.0, -88.0, -104.0, 1e4, -1e4])]).to(d)
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.nb_silu_selftest(x.numel(), P(x), P(a), P(b), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    ref = (x.double() * torch.sigmoid(x.double()))
+    scale = ref.abs().clamp_min(1e-30)
+    err_mufu = ((a.double() - ref).abs() / torch.maximum(scale, torch.full_like(scale, 1e-3))).max().item()
+    err_fma = ((b.double() - ref).abs() / torch.maximum(scale, torch.full_like(scale, 1e-3))).max().item()
+    print(f"SiLU max rel. error vs float64: two-MUFU {err_mufu:.2e}, FMA-pipe reciprocal {err_fma:.2e}")
+    assert torch.isfinite(b).all()
+    assert err_fma < 1e-6 and err_fma < 2 * err_mufu + 2e-7

@@ -57,10 +57,23 @@ def run(B=256, N=20, T=10, L=4, steps=3):
     step()
     buf = (ctypes.c_longlong * 32)()
     fn(buf, 1)
+    gfn = lib.nb_debug_gemm_clocks
+    gfn.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+    gfn.restype = ctypes.c_int
+    gbuf = (ctypes.c_longlong * 16)()
+    gfn(gbuf, 1)
     lib.nb_profile_enable(1)
     for _ in range(steps):
         step()
     fn(buf, 0)
+    gfn(gbuf, 0)
+    gn = max(gbuf[0], 1)
+    GN = {1: "first tile's loads issued", 2: "mbarrier init + TMEM alloc", 3: "weight staging + sync", 4: "split + store tile (waits for its loads)",
+          5: "fence + sync", 6: "MMA issue + commit", 7: "prefetch next tile / epilogue operands", 8: "wait MMA", 9: "TMEM load", 10: "epilogue + stores",
+          11: "final sync", 12: "TMEM dealloc"}
+    print(f"k_gemm64_tc, CTA (0,0): {gn} launches, {sum(gbuf[1:13]) / gn:.0f} cycles per launch")
+    for i in range(1, 13):
+        print(f"  {i:2d} {gbuf[i] / gn:9.0f} cyc/launch  {GN[i]}")
     tot = sum(buf)
     launches = steps * L
     units = -(-T * B // 148)
