@@ -142,6 +142,7 @@ __device__ __forceinline__ void nb_load_w1_slices(const NbEdgeW& w, int nef, int
 #define NB_EDGE_FWD_SMEM_FLOATS (2 * NB_H * NB_H + 3 * NB_H + NB_TILE * NB_LDA + NB_TILE * (2 + 1 + 3 + NB_MAX_EF + 1))
 
 __global__ void __launch_bounds__(NB_THREADS) k_edge_fwd(NbEdgeFwdArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   float* W2t = sm;                  // [k][o]
   float* W3t = W2t + NB_H * NB_H;   // [k][o]
@@ -282,6 +283,7 @@ struct NbEdgeBwdArgs {
   (4 * NB_H * NB_H + 4 * NB_H + 3 * NB_TILE * NB_LDA + NB_TILE * (2 + 1 + 3 + NB_MAX_EF + 3 + 3) + (GN) * (NB_H + 3))
 
 __global__ void __launch_bounds__(NB_THREADS) k_edge_bwd(NbEdgeBwdArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   float* W2t = sm;                 // [k][o]  (forward recompute)
   float* W3t = W2t + NB_H * NB_H;

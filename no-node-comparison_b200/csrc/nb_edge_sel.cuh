@@ -345,6 +345,7 @@ __device__ __forceinline__ void nb_sel_stage_unit(unsigned char* Nh, unsigned ch
 
 template <bool BLK>
 __global__ void __launch_bounds__(NB_THREADS, 2) k_edge_fwd_sel(NbEdgeFwdArgs a) {
+  NB_PDL_ENTER();
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
   unsigned char* W2h = base + NB_SF_W;
@@ -726,6 +727,7 @@ __device__ __forceinline__ void nb_issue_scatter_fold(uint32_t tmem_d, uint32_t 
 
 template <bool BLK>
 __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_edge_bwd_sel(NbEdgeBwdArgs a) {
+  NB_PDL_ENTER();
 #ifdef NB_STAGE_CLOCKS
   __shared__ long long dbg_acc[32];
   const bool dbg_on = blockIdx.x == 0 && threadIdx.x == 0;

@@ -112,6 +112,7 @@ __device__ __forceinline__ float2 nb_tc_load_pair(const unsigned char* hi, const
 #define NB_EDGE_FWD_TC_SMEM (NB_EFT_F + NB_EFT_NFLOAT * 4 + 64 + 1024)
 
 __global__ void __launch_bounds__(NB_THREADS) k_edge_fwd_tc(NbEdgeFwdArgs a) {
+  NB_PDL_ENTER();
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared state space: LDS/STS, not LD/ST)
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
@@ -299,6 +300,7 @@ __device__ __forceinline__ float nb_scratch_get(const float* S, int r, int c) {
 }
 
 __global__ void __launch_bounds__(NB_THREADS, 1) k_edge_bwd_tc(NbEdgeBwdArgs a) {
+  NB_PDL_ENTER();
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared state space: LDS/STS, not LD/ST)
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);

@@ -49,6 +49,7 @@ struct NbGemmBatch {
 
 // blockIdx.y selects the job; blockIdx.x the 128-row tile (CTAs past a job's last tile exit)
 __global__ void __launch_bounds__(NB_THREADS) k_gemm64(NbGemmBatch batch) {
+  NB_PDL_ENTER();
   const NbGemmArgs& a = batch.job[blockIdx.y];
   if ((int)blockIdx.x * NB_TILE >= a.rows) return;
   NB_DYN_SMEM(sm);
@@ -139,7 +140,17 @@ struct NbWgradPair {
   int lda;
   int a_silu;
   float scale;
+  // segmented operands (seg_rows > 0): logical row r lives in segment r / seg_rows at offset r % seg_rows; segments
+  // are seg_g / seg_a floats apart.  Lets ONE reduction run over the same tensor of all SEGNO sub-steps (stored one
+  // block per sub-step) instead of one small reduction per sub-step.
+  int seg_rows;
+  int64_t seg_g, seg_a;
 };
+__device__ __forceinline__ const float* nb_wg_row(const float* base, int ld, int seg_rows, int64_t seg_stride, int64_t r) {
+  if (seg_rows <= 0) return base + r * ld;
+  const int64_t sgm = r / seg_rows;
+  return base + sgm * seg_stride + (r - sgm * seg_rows) * ld;
+}
 struct NbWgradArgs {
   int rows;
   int npair;
@@ -156,6 +167,7 @@ struct NbWgradBatch {
 
 // blockIdx.y selects the job; each job owns gridDim.x partial slices
 __global__ void __launch_bounds__(NB_THREADS) k_wgrad64(NbWgradBatch batch) {
+  NB_PDL_ENTER();
   const NbWgradArgs& a = batch.job[blockIdx.y];
   NB_DYN_SMEM(sm);
   float* Gs = sm;                     // [128][68]
@@ -174,8 +186,8 @@ __global__ void __launch_bounds__(NB_THREADS) k_wgrad64(NbWgradBatch batch) {
       const NbWgradPair pr = a.pair[p];
       for (int idx = tid; idx < nv * 16; idx += NB_THREADS) {
         int r = idx >> 4, c4 = idx & 15;
-        float4 g = nb_ld4(pr.G + (int64_t)(r0 + r) * pr.ldg + c4 * 4);
-        float4 v = nb_ld4(pr.A + (int64_t)(r0 + r) * pr.lda + c4 * 4);
+        float4 g = nb_ld4(nb_wg_row(pr.G, pr.ldg, pr.seg_rows, pr.seg_g, r0 + r) + c4 * 4);
+        float4 v = nb_ld4(nb_wg_row(pr.A, pr.lda, pr.seg_rows, pr.seg_a, r0 + r) + c4 * 4);
         if (pr.a_silu) {
           v.x = nb_silu(v.x);
           v.y = nb_silu(v.y);
@@ -230,6 +242,7 @@ struct NbFinBatch {
 };
 
 __global__ void __launch_bounds__(256) k_finalize(NbFinBatch batch) {
+  NB_PDL_ENTER();
   __shared__ float red[8][33];
   const NbFinArgs& a = batch.job[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,6 +311,7 @@ struct NbEmbedArgs {
 
 // table[t][b][j] = sin(ts * freq[j]) (j < D/2) | cos(ts * freq[j - D/2]),  ts = timesteps[b][t]   (layer_no.py:8-17)
 __global__ void __launch_bounds__(256) k_time_table(NbEmbedArgs a, int input_times) {
+  NB_PDL_ENTER();
   const int total = a.T * a.B * a.D, half = a.D >> 1;
   float* tab = input_times ? a.table_in : a.table;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -325,6 +339,7 @@ __device__ __forceinline__ float nb_embed_feature(const NbEmbedArgs& a, int t, i
 // ein[row][0:64] = [ nodes | time embedding | zeros ]: the embedding Linear and its weight gradient then run through
 // the 64-wide GEMM / weight-gradient kernels (tcgen05 on the GPU).  One thread per (row, 4 columns).
 __global__ void __launch_bounds__(256) k_embed_inputs(NbEmbedArgs a, float* __restrict__ ein, int foff) {
+  NB_PDL_ENTER();
   const int F = a.F0 + a.D * (a.L > 1 ? 2 : 1) - foff;   // features foff .. foff + 63 of the input row
   const int64_t total = (int64_t)a.T * a.Nn0 * 16;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -339,6 +354,7 @@ __global__ void __launch_bounds__(256) k_embed_inputs(NbEmbedArgs a, float* __re
 }
 
 __global__ void __launch_bounds__(256) k_embed_fwd(NbEmbedArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   const int F = a.F0 + a.D;
   float* Ws = sm;              // [F][64] transposed
@@ -376,6 +392,7 @@ struct NbEmbedBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) k_embed_bwd(NbEmbedBwdArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   const int F = a.e.F0 + a.e.D;
   float* ins = sm;            // [32][F]
@@ -428,6 +445,7 @@ struct NbFrameMap {
 // dst[t][k][0:3] = src[tmap[t]][k][0:3]
 __global__ void __launch_bounds__(256) k_replicate3(const float* __restrict__ src, float* __restrict__ dst, int n3,
                                                     int T, NbFrameMap fm) {
+  NB_PDL_ENTER();
   int64_t total = (int64_t)n3 * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = src[(int64_t)fm.m[i / n3] * n3 + i % n3];
@@ -435,6 +453,7 @@ __global__ void __launch_bounds__(256) k_replicate3(const float* __restrict__ sr
 // dst[l][k] = sum over the frames t fed by input l of src[t][k]
 __global__ void __launch_bounds__(256) k_sum_over_t(const float* __restrict__ src, float* __restrict__ dst, int n3,
                                                     int T, NbFrameMap fm) {
+  NB_PDL_ENTER();
   const int64_t total = (int64_t)n3 * fm.L;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int l = (int)(idx / n3), i = (int)(idx - (int64_t)l * n3);
@@ -458,6 +477,7 @@ struct NbXupdArgs {
 };
 
 __global__ void __launch_bounds__(256) k_egno_xupd_fwd(NbXupdArgs a) {
+  NB_PDL_ENTER();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float w0 = __ldg(a.w2 + 2 * lane), w1 = __ldg(a.w2 + 2 * lane + 1), b2 = __ldg(a.b2);
   const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
@@ -476,6 +496,7 @@ __global__ void __launch_bounds__(256) k_egno_xupd_fwd(NbXupdArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_egno_xupd_bwd(NbXupdArgs a) {
+  NB_PDL_ENTER();
   __shared__ float red[8][65];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float w0 = __ldg(a.w2 + 2 * lane), w1 = __ldg(a.w2 + 2 * lane + 1), b2 = __ldg(a.b2);
@@ -529,6 +550,7 @@ struct NbIntegArgs {
   float *gx_out, *gv_out, *gFsum;  // backward out (gx_out may alias gx)
 };
 __global__ void __launch_bounds__(256) k_segno_integ_fwd(NbIntegArgs a) {
+  NB_PDL_ENTER();
   const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n3; i += (int64_t)gridDim.x * blockDim.x) {
     float acc = a.Fsum[i] / cnt * a.cw;
@@ -538,6 +560,7 @@ __global__ void __launch_bounds__(256) k_segno_integ_fwd(NbIntegArgs a) {
   }
 }
 __global__ void __launch_bounds__(256) k_segno_integ_bwd(NbIntegArgs a) {
+  NB_PDL_ENTER();
   const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n3; i += (int64_t)gridDim.x * blockDim.x) {
     float gxi = a.gx ? a.gx[i] : 0.f;
@@ -551,6 +574,7 @@ __global__ void __launch_bounds__(256) k_segno_integ_bwd(NbIntegArgs a) {
 // Canonical fully connected edge list check (dataset_simple.py:64-71, :101-111).
 __global__ void __launch_bounds__(256) k_check_edges(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
                                                      int64_t E, int B, int N, int* flag) {
+  NB_PDL_ENTER();
   const int64_t epg = (int64_t)N * (N - 1);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = e / epg, rem = e - b * epg;
@@ -565,7 +589,8 @@ __global__ void __launch_bounds__(256) k_check_edges(const int64_t* __restrict__
 // p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  The step counter lives on the device (k_adam_tick), so
 // the pair of launches is CUDA-graph capturable; parameters and gradients are ONE flat buffer each (the layout of the
 // C ABI), so one launch updates the whole model.
-__global__ void k_adam_tick(float* step) { *step += 1.0f; }
+__global__ void k_adam_tick(float* step) {
+  NB_PDL_ENTER(); *step += 1.0f; }
 
 struct NbAdamArgs {
   int64_t n;
@@ -577,6 +602,7 @@ struct NbAdamArgs {
   float grad_scale;    // gradients are multiplied by it first (data parallel: 1 / world over the summed bucket)
 };
 __global__ void __launch_bounds__(256) k_adam(NbAdamArgs a) {
+  NB_PDL_ENTER();
   const double t = (double)*a.step;
   const double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
   const float step_size = (float)(a.lr / bc1), bc2_sqrt = (float)sqrt(bc2);

@@ -253,6 +253,7 @@ __device__ __forceinline__ void nb_gemm64_tc_body(const NbGemmArgs& a, unsigned 
 }
 
 __global__ void __launch_bounds__(NB_THREADS, 2) k_gemm64_tc(NbGemmBatch batch, int nsrc_max) {
+  NB_PDL_ENTER();
   const NbGemmArgs& a = batch.job[blockIdx.y];
   const int ntiles = (a.rows + NB_TILE - 1) / NB_TILE;
   if ((int)blockIdx.x >= ntiles) return;
@@ -275,6 +276,7 @@ struct NbWimgBatch {
   unsigned char* out;  // image i at out + i * 2 * NB_TC_TILE_BYTES(64)
 };
 __global__ void __launch_bounds__(256) k_weight_images(NbWimgBatch b) {
+  NB_PDL_ENTER();
   const float* W = b.W[blockIdx.x];
   const int ld = b.ld[blockIdx.x];
   unsigned char* hi = b.out + (size_t)blockIdx.x * 2 * NB_TC_TILE_BYTES(64);
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(256) k_weight_images(NbWimgBatch b) {
 #define NB_WT_SMEM (4 * NB_TC_TILE_BYTES(128) + NB_TILE * 16 + 64 + 1024)
 
 __global__ void __launch_bounds__(NB_THREADS, 3) k_wgrad64_tc(NbWgradBatch batch) {
+  NB_PDL_ENTER();
   const NbWgradArgs& a = batch.job[blockIdx.y];
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
@@ -338,8 +341,8 @@ __global__ void __launch_bounds__(NB_THREADS, 3) k_wgrad64_tc(NbWgradBatch batch
         const int idx = tid + it * NB_THREADS;
         const int r = idx >> 3, j = idx & 7;
         if (r < nv) {
-          const float* gp = pr.G + (int64_t)(r0 + r) * pr.ldg + 8 * j;
-          const float* ap = pr.A + (int64_t)(r0 + r) * pr.lda + 8 * j;
+          const float* gp = nb_wg_row(pr.G, pr.ldg, pr.seg_rows, pr.seg_g, r0 + r) + 8 * j;
+          const float* ap = nb_wg_row(pr.A, pr.lda, pr.seg_rows, pr.seg_a, r0 + r) + 8 * j;
           g0[it] = nb_ld4(gp); g1[it] = nb_ld4(gp + 4); a0[it] = nb_ld4(ap); a1[it] = nb_ld4(ap + 4);
         } else {
           g0[it] = g1[it] = a0[it] = a1[it] = make_float4(0.f, 0.f, 0.f, 0.f);

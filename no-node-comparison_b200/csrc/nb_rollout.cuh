@@ -20,6 +20,7 @@ struct NbFeatArgs {
 };
 
 __global__ void __launch_bounds__(128) k_nbody_features(NbFeatArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);             // [N][4]: x, y, z, q
   __shared__ float mean[3];
   const int N = a.N, tid = threadIdx.x;
@@ -73,6 +74,7 @@ struct NbEnergyArgs {
 };
 
 __global__ void __launch_bounds__(128) k_nbody_energy(NbEnergyArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);             // [N][4] + [128] partials
   float* part = sm + a.N * 4;
   const int N = a.N, tid = threadIdx.x;
@@ -134,6 +136,7 @@ struct NbMseArgs {
 };
 
 __global__ void __launch_bounds__(256) k_traj_mse(NbMseArgs a) {
+  NB_PDL_ENTER();
   __shared__ float part[256];
   const int t = blockIdx.y, tid = threadIdx.x;
   const int64_t n = a.R * 3;   // elements of one frame
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(256) k_traj_mse(NbMseArgs a) {
 }
 
 __global__ void __launch_bounds__(32) k_traj_mse_fin(NbMseArgs a) {
+  NB_PDL_ENTER();
   __shared__ float ls[NB_MAX_T];
   const int t = threadIdx.x;
   if (t < a.T) {

@@ -56,6 +56,7 @@ __device__ __forceinline__ void nb_fs_stage_w(unsigned char* hi, unsigned char* 
 }
 
 __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedArgs a) {
+  NB_PDL_ENTER();
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
   unsigned char* Wt = base + NB_FS_W;  // piece p (hi at 2p, lo at 2p+1): 0 W2, 1 W3, 2 W1r, 3 W1c, 4 W5a, 5 W5b, 6 W6

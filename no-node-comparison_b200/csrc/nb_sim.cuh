@@ -49,6 +49,7 @@ __device__ __forceinline__ void nb_sim_charged_force(const NbSimChargedArgs& a, 
 }
 
 __global__ void __launch_bounds__(NB_SIM_MAX_N) k_sim_charged(NbSimChargedArgs a) {
+  NB_PDL_ENTER();
   __shared__ double sx[3][NB_SIM_MAX_N];
   __shared__ double sn[NB_SIM_MAX_N];
   __shared__ double sq[NB_SIM_MAX_N];
@@ -136,6 +137,7 @@ __device__ __forceinline__ void nb_sim_gravity_acc(const NbSimGravityArgs& a, do
 }
 
 __global__ void __launch_bounds__(NB_SIM_MAX_N) k_sim_gravity(NbSimGravityArgs a) {
+  NB_PDL_ENTER();
   __shared__ double sx[3][NB_SIM_MAX_N];
   __shared__ double sm[NB_SIM_MAX_N];
   const int i = threadIdx.x, N = a.N;

@@ -45,6 +45,7 @@ __device__ __forceinline__ float4 nb_f4_fma(float s, float4 a, float4 b) {
 
 // coef = DFT(x)
 __global__ void __launch_bounds__(256) k_dft_fwd(NbDftArgs a) {
+  NB_PDL_ENTER();
   const int64_t total = (int64_t)a.Nn0 * 16;
   const int64_t plane = (int64_t)a.Nn0 * NB_H;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -99,6 +100,7 @@ __device__ __forceinline__ float nb_dleaky(float v) { return v > 0.f ? 1.f : 0.0
 
 // out = x + LeakyReLU(irfft(ycoef))        (TimeConv.forward, layer_no.py:121-126)
 __global__ void __launch_bounds__(256) k_idft_fwd(NbDftArgs a) {
+  NB_PDL_ENTER();
   const int64_t total = (int64_t)a.Nn0 * 16;
   const int64_t plane = (int64_t)a.Nn0 * NB_H;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(256) k_idft_fwd(NbDftArgs a) {
 
 // gycoef = adjoint of the inverse DFT applied to gout * LeakyReLU'(y)
 __global__ void __launch_bounds__(256) k_idft_bwd(NbDftArgs a) {
+  NB_PDL_ENTER();
   const int64_t total = (int64_t)a.Nn0 * 16;
   const int64_t plane = (int64_t)a.Nn0 * NB_H;
   const float invT = 1.0f / (float)a.tw.T;
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) k_idft_bwd(NbDftArgs a) {
 
 // gx[s] = gout[s] + sum_m gC_m cos(theta s) + gS_m sin(theta s)
 __global__ void __launch_bounds__(256) k_dft_bwd(NbDftArgs a) {
+  NB_PDL_ENTER();
   const int64_t total = (int64_t)a.Nn0 * 16;
   const int64_t plane = (int64_t)a.Nn0 * NB_H;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -202,6 +206,7 @@ __device__ __forceinline__ float nb_tcx_w(const NbTcxArgs& a, int i, int o, int 
 }
 
 __global__ void __launch_bounds__(256) k_tcx_fwd(NbTcxArgs a) {
+  NB_PDL_ENTER();
   const float invT = 1.0f / (float)a.tw.T;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.n3; idx += gridDim.x * blockDim.x) {
     float X[2][NB_MAX_T], Y[2][NB_MAX_T], mean[NB_MAX_T];
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(256) k_tcx_fwd(NbTcxArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_tcx_bwd(NbTcxArgs a) {
+  NB_PDL_ENTER();
   __shared__ float red[8][2 * 2 * NB_MAX_MODES * 2];
   const float invT = 1.0f / (float)a.tw.T;
   const int nw = 2 * 2 * a.tw.modes * 2;
@@ -429,6 +435,7 @@ __device__ __forceinline__ void nb_tconv_mix(const float* As, const float* B0, c
 }
 
 __global__ void __launch_bounds__(256) k_tconv_fwd(NbTconvArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   float* B0 = sm;                    // W[.][.][0][re]
   float* B1 = B0 + NB_H * NB_H;      // W[.][.][1][re]
@@ -480,6 +487,7 @@ __global__ void __launch_bounds__(256) k_tconv_fwd(NbTconvArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_tconv_bwd(NbTconvArgs a) {
+  NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   float* B0 = sm;
   float* B1 = B0 + NB_H * NB_H;

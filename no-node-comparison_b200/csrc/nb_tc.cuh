@@ -248,6 +248,7 @@ __device__ __forceinline__ void nb_tc_issue3(uint32_t tmem_d, uint32_t a_hi, uin
 //      commit observed), out[8193] = cycles of four groups issued back to back
 __global__ void __launch_bounds__(128) k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ W,
                                                      float* __restrict__ out) {
+  NB_PDL_ENTER();
   extern __shared__ __align__(1024) unsigned char tsm[];
   unsigned char* base = (unsigned char*)(((uintptr_t)tsm + 1023) & ~(uintptr_t)1023);
   unsigned char* a_hi = base;

@@ -16,6 +16,7 @@
 #include "nb_edge_sel.cuh"
 #include "nb_node_tc.cuh"
 #include "nb_segno_fused.cuh"
+#include <cstdlib>
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
 #define NB_LAUNCH_COUNTED(...)                             \
@@ -36,6 +37,15 @@ struct NbRange {
 #else
 #define NB_RANGE(name)
 #endif
+
+int nb_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("NB_B200_PDL");   // opt-in: measured neutral in this form (see nb_common.cuh)
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on;
+}
 
 // ============================================================================= errors / device info
 static thread_local char g_err[512] = "";
@@ -469,6 +479,13 @@ static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* 
 static NbWgradPair wpair(const float* G, const float* A, int a_silu = 0, float scale = 1.f) {
   NbWgradPair p;
   p.G = G; p.ldg = NB_H; p.A = A; p.lda = NB_H; p.a_silu = a_silu; p.scale = scale;
+  p.seg_rows = 0; p.seg_g = p.seg_a = 0;
+  return p;
+}
+// the same tensors of `nseg` consecutive blocks (seg_rows rows each, seg_g / seg_a floats apart): rows = nseg * seg_rows
+static NbWgradPair wpair_seg(const float* G, const float* A, int a_silu, int seg_rows, int64_t seg_g, int64_t seg_a) {
+  NbWgradPair p = wpair(G, A, a_silu);
+  p.seg_rows = seg_rows; p.seg_g = seg_g; p.seg_a = seg_a;
   return p;
 }
 
@@ -582,7 +599,27 @@ struct EdgeGradDst {
   int ldw1, col_rad, col_ef;
 };
 
-static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, int accumulate, void* st) {
+// reduction of `nparts` per-CTA partial slices of the edge backward kernel(s) into the parameter gradients
+static int edge_bwd_finalize(float* partial, int nparts, int nef, float* dst, const EdgeGradDst& d, int accumulate, void* st) {
+  NbFinArgs f;
+  memset(&f, 0, sizeof(f));
+  f.partial = partial; f.nparts = nparts; f.plen = NB_EB_PLEN; f.dst = dst; f.accumulate = accumulate;
+  f.nseg = 0;
+  f.seg[f.nseg++] = fseg(NB_EB_GW2, NB_H * NB_H, NB_H, d.W2, NB_H, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GW3, NB_H * NB_H, NB_H, d.W3, NB_H, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GB2, NB_H, NB_H, d.b2, 0, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GB3, NB_H, NB_H, d.b3, 0, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GW4, NB_H, NB_H, d.w4, 0, 1);
+  f.seg[f.nseg++] = fseg(NB_EB_GWR, NB_H, 1, d.w1 + d.col_rad, d.ldw1, 0);            // column col_rad of W1
+  f.seg[f.nseg++] = fseg(NB_EB_GWE, nef * NB_H, NB_H, d.w1 + d.col_ef, 1, d.ldw1);    // (f, c) -> W1[c][col_ef + f]
+  f.seg[f.nseg++] = fseg(NB_EB_GB4, 1, 1, d.b4, 0, 0);
+  return launch_finalize(f, st);
+}
+
+// run: when given, the finalisation is NOT queued here; the partial slices of consecutive launches are contiguous (the
+// caller queues one reduction over all of them, edge_bwd_finalize): *run_base = first slice, *run_parts += this grid
+static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, int accumulate, void* st,
+                           float** run_base = nullptr, int* run_parts = nullptr) {
   bool use_sel = false;
 #ifndef NB_EMU
   if (g_edge_impl == 2) {
@@ -591,9 +628,19 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
   }
 #endif
   int grid = imin(a.g.n_units, use_sel ? nb_num_sms() : edge_bwd_grid_cap());
+  if (run_base && *run_parts > 0 && g_q.pused + ((int64_t)grid * NB_EB_PLEN + 63) / 64 * 64 > g_q.pcap) {
+    // the scratch is full: reduce the run collected so far before q_alloc recycles it
+    NB_TRY(edge_bwd_finalize(*run_base, *run_parts, a.g.nef, dst, d, accumulate, st));
+    NB_TRY(q_flush(st));
+    *run_parts = 0;
+  }
   float* partial = q_alloc((int64_t)grid * NB_EB_PLEN, st);
   if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
   a.partial = partial;
+  if (run_base) {
+    if (*run_parts == 0) *run_base = partial;
+    else if (partial != *run_base + (int64_t)*run_parts * NB_EB_PLEN) { nb_set_error("edge backward partial slices are not contiguous"); return NB_ERR_INVALID; }
+  }
   bool done = false;
 #ifndef NB_EMU
   if (use_sel) {
@@ -628,19 +675,11 @@ static int launch_edge_bwd(NbEdgeBwdArgs& a, float* dst, const EdgeGradDst& d, i
     prof_end(1, pi, st);
     NB_TRY(nb_check_launch("k_edge_bwd"));
   }
-  NbFinArgs f;
-  memset(&f, 0, sizeof(f));
-  f.partial = partial; f.nparts = grid; f.plen = NB_EB_PLEN; f.dst = dst; f.accumulate = accumulate;
-  f.nseg = 0;
-  f.seg[f.nseg++] = fseg(NB_EB_GW2, NB_H * NB_H, NB_H, d.W2, NB_H, 1);
-  f.seg[f.nseg++] = fseg(NB_EB_GW3, NB_H * NB_H, NB_H, d.W3, NB_H, 1);
-  f.seg[f.nseg++] = fseg(NB_EB_GB2, NB_H, NB_H, d.b2, 0, 1);
-  f.seg[f.nseg++] = fseg(NB_EB_GB3, NB_H, NB_H, d.b3, 0, 1);
-  f.seg[f.nseg++] = fseg(NB_EB_GW4, NB_H, NB_H, d.w4, 0, 1);
-  f.seg[f.nseg++] = fseg(NB_EB_GWR, NB_H, 1, d.w1 + d.col_rad, d.ldw1, 0);            // column col_rad of W1
-  f.seg[f.nseg++] = fseg(NB_EB_GWE, a.g.nef * NB_H, NB_H, d.w1 + d.col_ef, 1, d.ldw1);  // (f, c) -> W1[c][col_ef + f]
-  f.seg[f.nseg++] = fseg(NB_EB_GB4, 1, 1, d.b4, 0, 0);
-  return launch_finalize(f, st);
+  if (run_base) {
+    *run_parts += grid;
+    return NB_OK;
+  }
+  return edge_bwd_finalize(partial, grid, a.g.nef, dst, d, accumulate, st);
 }
 
 // ============================================================================= twiddles
@@ -1359,6 +1398,7 @@ static void segno_layout(const NbSegnoConfig* c, SegnoLayout* lo) {
   lo->total = o;
 }
 
+#define SEGNO_PARTIAL_FLOATS ((int64_t)32 * 1024 * 1024)
 #define SEGNO_WIMG 5  /* edge layer 1 (h_row | h_col), node_mlp layer 1 (h | M), layer 2 */
 struct SegnoIterBufs {
   float *h, *M, *U5, *x;
@@ -1388,7 +1428,10 @@ extern "C" int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int mode)
   const int64_t wi = wimg_floats(SEGNO_WIMG);
   if (mode == NB_WS_FORWARD_TRAIN) return wi + 2 * nh /*P,Q*/ + 3 * n3 /*Fsum, v ping-pong*/;
   if (mode == NB_WS_FORWARD_INFER) return wi + 2 * nh + 3 * n3 + 2 * segno_iter_floats(Nn);
-  return wi + 2 * nh + 2 * nh /*gh*/ + 4 * nh /*GU5 gM gP gQ*/ + 4 * n3 + NB_PARTIAL_FLOATS;
+  // backward: gh / GU5 / gP / gQ are kept PER sub-step, so that the weight-gradient reductions of all sub-steps run as a few
+  // large batches at the end of the sweep instead of one small batch (+ finalize) per sub-step
+  return wi + 2 * nh /*P,Q*/ + nh /*gM*/ + (int64_t)(cfg->T + 1) * nh /*gh_k*/ + 3 * (int64_t)cfg->T * nh /*GU5_k gP_k gQ_k*/ + 4 * n3 +
+         SEGNO_PARTIAL_FLOATS;
 }
 
 struct SegnoCtx {
@@ -1547,15 +1590,15 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   w += wimg_floats(SEGNO_WIMG);
   float* P = w; w += nh;
   float* Q = w; w += nh;
-  float* ghb[2]; ghb[0] = w; w += nh; ghb[1] = w; w += nh;
-  float* GU5 = w; w += nh;
   float* gM = w; w += nh;
-  float* gP = w; w += nh;
-  float* gQ = w; w += nh;
+  float* gh_all = w; w += (int64_t)(T + 1) * nh;    // gh entering sub-step k at slot k + 1; slot k receives its output
+  float* GU5_all = w; w += (int64_t)T * nh;
+  float* gP_all = w; w += (int64_t)T * nh;
+  float* gQ_all = w; w += (int64_t)T * nh;
   float* gx = w; w += n3;
   float* gvb[2]; gvb[0] = w; w += n3; gvb[1] = w; w += n3;
   float* gFsum = w; w += n3;
-  q_begin(w, NB_PARTIAL_FLOATS);
+  q_begin(w, SEGNO_PARTIAL_FLOATS);
   cudaStream_t cst = (cudaStream_t)stream;
 
   cudaMemsetAsync(grad_params, 0, lo.total * sizeof(float), cst);
@@ -1564,19 +1607,24 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   const float* gv_in = g_v_out;
   int gvi = 0;
   const float* gh_in = g_h_out;
-  int ghi = 0;
-  if (!gh_in) { cudaMemsetAsync(ghb[1], 0, Nn * NB_H * sizeof(float), cst); gh_in = ghb[1]; }
+  if (!gh_in) { cudaMemsetAsync(gh_all + (int64_t)T * nh, 0, Nn * NB_H * sizeof(float), cst); gh_in = gh_all + (int64_t)T * nh; }
 
+  EdgeGradDst ed;
+  ed.w1 = lo.e_w1; ed.W2 = lo.e_w2; ed.b2 = lo.e_b2; ed.W3 = lo.c_w1; ed.b3 = lo.c_b1; ed.w4 = lo.c_w2; ed.b4 = lo.c_b2;
+  ed.ldw1 = lo.E; ed.col_rad = 2 * NB_H; ed.col_ef = 2 * NB_H + 1; ed.b_unused = 0;
+  float* run_base = nullptr;   // the edge kernels' per-CTA partial slices of consecutive sub-steps are contiguous:
+  int run_parts = 0;           // one reduction over all of them after the sweep
   for (int k = T - 1; k >= 0; --k) {
     SegnoIterBufs b = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)k * itf, Nn);
-    float* gh_new = ghb[ghi];
+    float* gh_new = gh_all + (int64_t)k * nh;
+    float* GU5 = GU5_all + (int64_t)k * nh;
+    float* gP = gP_all + (int64_t)k * nh;
+    float* gQ = gQ_all + (int64_t)k * nh;
     // node_mlp backward
     NbGemmArgs a = gemm_args((int)Nn);  // GU5 = (gh W6) * SiLU'(U5)
     a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + lo.n_w2, NB_H, 1);
     a.epi = NB_EPI_MUL_DSILU; a.U = b.U5; a.out = GU5;
     NB_TRY(launch_gemm(a, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1,
-                    lo.n_b2, 1, stream));
     NbGemmArgs g1 = gemm_args((int)Nn);  // gh = GU5 W5[:, :64] (+ gh: residual)
     g1.nsrc = 1; g1.src[0] = gsrc(GU5, NB_H, 0, params + lo.n_w1, 2 * NB_H, 1);
     if (cfg->recurrent) g1.R = gh_in;
@@ -1586,10 +1634,6 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     g2.out = gM;
     NbGemmArgs g12[2] = {g1, g2};
     NB_TRY(launch_gemm_batch(g12, 2, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.h), wpair(nullptr, nullptr), grad_params, lo.n_w1, 2 * NB_H, 1,
-                    lo.n_b1, 1, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), grad_params, lo.n_w1 + NB_H, 2 * NB_H,
-                    1, -1, 1, stream));
     // integrator backward
     NbIntegArgs ia;
     memset(&ia, 0, sizeof(ia));
@@ -1606,23 +1650,44 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     ea.g = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
     ea.w = segno_edge_w(X);
     ea.x = b.x; ea.P = P; ea.Q = Q; ea.ef = edge_attr; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
-    EdgeGradDst d;
-    d.w1 = lo.e_w1; d.W2 = lo.e_w2; d.b2 = lo.e_b2; d.W3 = lo.c_w1; d.b3 = lo.c_b1; d.w4 = lo.c_w2; d.b4 = lo.c_b2;
-    d.ldw1 = lo.E; d.col_rad = 2 * NB_H; d.col_ef = 2 * NB_H + 1; d.b_unused = 0;
-    NB_TRY(launch_edge_bwd(ea, grad_params, d, 1, stream));
+    NB_TRY(launch_edge_bwd(ea, grad_params, ed, 1, stream, &run_base, &run_parts));
     NbGemmArgs pa = gemm_args((int)Nn);  // gh += gP W1[:, h_row] + gQ W1[:, h_col]
     pa.nsrc = 2;
     pa.src[0] = gsrc(gP, NB_H, 0, params + lo.e_w1, lo.E, 1);
     pa.src[1] = gsrc(gQ, NB_H, 0, params + lo.e_w1 + NB_H, lo.E, 1);
     pa.out = gh_new; pa.accumulate = 1;
     NB_TRY(launch_gemm(pa, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, b.h), wpair(nullptr, nullptr), grad_params, lo.e_w1, lo.E, 1, lo.e_b1,
-                    1, stream));
-    NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, b.h), wpair(nullptr, nullptr), grad_params, lo.e_w1 + NB_H, lo.E, 1,
-                    -1, 1, stream));
-    NB_TRY(q_flush(stream));  // the shared weights accumulate across iterations: one reduction batch per iteration
     gh_in = gh_new;
-    ghi ^= 1;
+  }
+  // ---- weight gradients of the shared layers: ONE reduction per weight block over the rows of all T sub-steps (the
+  // operands of sub-step k sit k blocks apart: saved state at stride itf, the sweep's gradients at stride nh)
+  {
+    if (run_parts > 0) NB_TRY(edge_bwd_finalize(run_base, run_parts, cfg->in_edge_nf, grad_params, ed, 1, stream));
+    const SegnoIterBufs b0 = segno_iter_bufs(const_cast<float*>(saved), Nn);
+    const int rows = (int)(Nn * T), sr = (int)Nn;
+    const float* ghin0 = g_h_out && T == 1 ? nullptr : gh_all + nh;   // gh entering sub-step k = slot k + 1 ...
+    // ... except for the last sub-step when the caller supplied dL/dh_out: that one lives in the caller's buffer
+    if (g_h_out) {
+      if (T > 1)
+        NB_TRY(wgrad_to((int)(Nn * (T - 1)), 1, wpair_seg(ghin0, b0.U5, 1, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w2,
+                        NB_H, 1, lo.n_b2, 1, stream));
+      const SegnoIterBufs bl = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)(T - 1) * itf, Nn);
+      NB_TRY(q_flush_wgrad(stream));   // same destination as the job above: separate reduction batches
+      NB_TRY(q_flush_fin(stream, false));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(g_h_out, bl.U5, 1), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1, lo.n_b2, 1, stream));
+    } else {
+      NB_TRY(wgrad_to(rows, 1, wpair_seg(ghin0, b0.U5, 1, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1,
+                      lo.n_b2, 1, stream));
+    }
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(GU5_all, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w1, 2 * NB_H, 1,
+                    lo.n_b1, 1, stream));
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(GU5_all, b0.M, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w1 + NB_H,
+                    2 * NB_H, 1, -1, 1, stream));
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(gP_all, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.e_w1, lo.E, 1,
+                    lo.e_b1, 1, stream));
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(gQ_all, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.e_w1 + NB_H, lo.E, 1,
+                    -1, 1, stream));
+    NB_TRY(q_flush(stream));
   }
   if (cfg->h_given) {
     NB_TRY(q_flush(stream));
@@ -1832,6 +1897,7 @@ extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float*
 
 // tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.
 __global__ void k_silu_selftest(int64_t n, const float* x, float* a, float* b) {
+  NB_PDL_ENTER();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     a[i] = nb_silu(x[i]);
     b[i] = nb_silu_fma(x[i]);

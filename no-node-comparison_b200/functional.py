@@ -94,6 +94,33 @@ def _maybe_allreduce(grad_flat: torch.Tensor, dp) -> None:
         grad_flat.div_(dist.get_world_size(group))
 
 
+class _AllReduceGrad(torch.autograd.Function):
+    """Identity whose backward all-reduces the incoming gradient over the data-parallel group: for the few parameters that
+    are multiplied on the torch side (multi-input SEGNO: embedding and temporal attention, SEGNO/models/model.py:65-90,
+    127-139) and therefore do not pass through the flat gradient bucket of the C call."""
+
+    @staticmethod
+    def forward(ctx, dp, t):
+        ctx.dp = dp
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+
+        group, average = ctx.dp
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            g.div_(dist.get_world_size(group))
+        return None, g
+
+
+def dp_param(t: torch.Tensor, dp):
+    """`t` itself without data parallelism, else a view whose gradient is reduced over the group before it reaches `t`."""
+    return t if dp is None else _AllReduceGrad.apply(dp, t)
+
+
 class EgnoFunction(torch.autograd.Function):
     """x, v, h = EGNO.forward(...)   (reference: EGNO/model/egno.py:37-111)."""
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .functional import SegnoFunction, _EdgeCache, _ParamPack, _require_cuda_f32
+from .functional import SegnoFunction, _EdgeCache, _ParamPack, _require_cuda_f32, dp_param
 
 _HIDDEN = 64
 
@@ -99,13 +99,17 @@ class SEGNO(nn.Module):
             raise ValueError("multi-input SEGNO needs x, v, his of shape [BN, n_inputs >= 2, .] and in_steps [n_inputs]")
         if self.multiple_agg is None:
             raise ValueError("multi-input SEGNO needs multiple_agg='sum' or 'attn' (main.py:110-114)")
-        if self.process_group is not None:
-            raise NotImplementedError("data-parallel multi-input SEGNO: the torch-side parameters (embedding, attention) "
-                                      "are not part of the flat-bucket all-reduce yet")
         steps = torch.diff(torch.as_tensor(in_steps).cpu()).tolist() + [T]
         if len(steps) != x.shape[1]:
             raise ValueError(f"in_steps has {len(steps)} entries for {x.shape[1]} input frames")
-        h = self.embedding(his)                       # [BN, L, H]
+        # Data parallel: every integration segment all-reduces its flat gradient bucket inside the C call's backward; the
+        # parameters multiplied on the torch side reduce their gradients through dp_param (one small all-reduce each).
+        dp = self.process_group
+        F = torch.nn.functional
+        h = F.linear(his, dp_param(self.embedding.weight, dp), dp_param(self.embedding.bias, dp))     # [BN, L, H]
+        if self.multiple_agg == 'attn':
+            l0, l2 = self.enc_attn_net.attn_mlp[0], self.enc_attn_net.attn_mlp[2]
+            aw0, ab0, aw2, ab2 = (dp_param(t, dp) for t in (l0.weight, l0.bias, l2.weight, l2.bias))
         h_, x_, v_ = h[:, 0, :], x[:, 0, :], v[:, 0, :]
         out = None
         for i, step in enumerate(steps):
@@ -119,7 +123,8 @@ class SEGNO(nn.Module):
                     hs = torch.stack([h[:, i + 1, :], hi], dim=1)
                     xs = torch.stack([x[:, i + 1, :], xi], dim=1)
                     vs = torch.stack([v[:, i + 1, :], vi], dim=1)
-                    attn = self.enc_attn_net(vs, hs)                                   # [BN, 2, 1]
+                    feats = torch.cat([vs.norm(dim=-1, keepdim=True), hs], dim=-1)       # model.py:134-138
+                    attn = F.linear(torch.tanh(F.linear(feats, aw0, ab0)), aw2, ab2).softmax(dim=1)   # [BN, 2, 1]
                     x_, v_, h_ = (attn * xs).sum(1), (attn * vs).sum(1), (attn * hs).sum(1)
         return out
 

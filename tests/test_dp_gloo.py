@@ -29,6 +29,11 @@ def _worker(rank, world, port, out):
     _maybe_allreduce(g, (dist.group.WORLD, True))                   # mean (any optimizer)
     s = torch.arange(10, dtype=torch.float32) * (rank + 1)
     _maybe_allreduce(s, (dist.group.WORLD, False))                  # sum (1 / world rides in FlatAdam's kernel)
+    # parameters multiplied on the torch side (multi-input SEGNO): gradient reduced by dp_param
+    from no_node_comparison_b200.functional import dp_param
+    w = torch.ones(3, requires_grad=True)
+    ((rank + 1.0) * dp_param(w, (dist.group.WORLD, True)).sum() + dp_param(w, None).sum() * 0.0).backward()
+    assert torch.allclose(w.grad, torch.full((3,), 1.5)), w.grad
     lo, hi = shard_range(11, rank, world)
     out.put((rank, g.tolist(), (lo, hi), s.tolist()))
     dist.barrier()

@@ -56,6 +56,6 @@ def to_json(path, key, digest_txt, workload, out='profiles/ncu_digest.json'):
 
 if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == '--json':     # ncu_digest.py rep --json key digest.txt "workload"
-        to_json(sys.argv[1], sys.argv[3], sys.argv[4], sys.argv[5])
+        to_json(sys.argv[1], sys.argv[3], sys.argv[4], sys.argv[5], *(sys.argv[6:7]))
     else:
         main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
