@@ -22,7 +22,16 @@ struct NbGemmSrc {
   // loads.  img_mn = 1: the product uses the block transposed (dgrad), i.e. reads the same image as an MN-major operand.
   const unsigned char* img;
   int img_mn;
+  // segmented rows (seg_rows > 0): logical row r of A lives in block r / seg_rows at offset r % seg_rows, blocks seg_a
+  // floats apart (the same tensor of all SEGNO sub-steps, stored one block per sub-step)
+  int seg_rows;
+  int64_t seg_a;
 };
+__device__ __forceinline__ const float* nb_seg_row(const float* base, int ld, int seg_rows, int64_t seg_stride, int64_t r) {
+  if (seg_rows <= 0) return base + r * ld;
+  const int64_t sgm = r / seg_rows;
+  return base + sgm * seg_stride + (r - sgm * seg_rows) * ld;
+}
 enum { NB_EPI_NONE = 0, NB_EPI_SILU = 1, NB_EPI_MUL_DSILU = 2 };
 struct NbGemmArgs {
   int rows;
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_gemm64(NbGemmBatch batch) {
       int r = idx >> 4, c4 = idx & 15;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < nv) {
-        v = nb_ld4(A + (int64_t)(r0 + r) * lda + c4 * 4);
+        v = nb_ld4(nb_seg_row(A, lda, a.src[s].seg_rows, a.src[s].seg_a, r0 + r) + c4 * 4);
         if (asilu) {
           v.x = nb_silu(v.x);
           v.y = nb_silu(v.y);
@@ -146,11 +155,7 @@ struct NbWgradPair {
   int seg_rows;
   int64_t seg_g, seg_a;
 };
-__device__ __forceinline__ const float* nb_wg_row(const float* base, int ld, int seg_rows, int64_t seg_stride, int64_t r) {
-  if (seg_rows <= 0) return base + r * ld;
-  const int64_t sgm = r / seg_rows;
-  return base + sgm * seg_stride + (r - sgm * seg_rows) * ld;
-}
+#define nb_wg_row nb_seg_row
 struct NbWgradArgs {
   int rows;
   int npair;

@@ -30,7 +30,7 @@ __device__ __forceinline__ void nb_gemm_load_rows(const NbGemmArgs& a, int r0, i
         const int idx = tid + it * NB_THREADS;
         const int r = idx >> 3, j = idx & 7;
         if (r < nv) {
-          const float* p = src.A + (int64_t)(r0 + r) * src.lda + 8 * j;
+          const float* p = nb_seg_row(src.A, src.lda, src.seg_rows, src.seg_a, r0 + r) + 8 * j;
           x0[s][it] = nb_ld4(p);
           x1[s][it] = nb_ld4(p + 4);
         } else {

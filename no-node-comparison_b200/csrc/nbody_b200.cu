@@ -321,7 +321,7 @@ static int launch_gemm(const NbGemmArgs& a, void* st) { return launch_gemm_batch
 static NbGemmSrc gsrc(const float* A, int lda, int a_silu, const float* W, int64_t sk, int64_t sn, float scale = 1.f) {
   NbGemmSrc s;
   s.A = A; s.lda = lda; s.a_silu = a_silu; s.W = W; s.sk = sk; s.sn = sn; s.scale = scale; s.kmax = NB_H;
-  s.img = nullptr; s.img_mn = 0;
+  s.img = nullptr; s.img_mn = 0; s.seg_rows = 0; s.seg_a = 0;
   return s;
 }
 
@@ -1430,8 +1430,8 @@ extern "C" int64_t nb_segno_workspace_floats(const NbSegnoConfig* cfg, int mode)
   if (mode == NB_WS_FORWARD_INFER) return wi + 2 * nh + 3 * n3 + 2 * segno_iter_floats(Nn);
   // backward: gh / GU5 / gP / gQ are kept PER sub-step, so that the weight-gradient reductions of all sub-steps run as a few
   // large batches at the end of the sweep instead of one small batch (+ finalize) per sub-step
-  return wi + 2 * nh /*P,Q*/ + nh /*gM*/ + (int64_t)(cfg->T + 1) * nh /*gh_k*/ + 3 * (int64_t)cfg->T * nh /*GU5_k gP_k gQ_k*/ + 4 * n3 +
-         SEGNO_PARTIAL_FLOATS;
+  return wi + 2 * (int64_t)cfg->T * nh /*P_k, Q_k*/ + nh /*gM*/ + (int64_t)(cfg->T + 1) * nh /*gh_k*/ +
+         3 * (int64_t)cfg->T * nh /*GU5_k gP_k gQ_k*/ + 4 * n3 + SEGNO_PARTIAL_FLOATS;
 }
 
 struct SegnoCtx {
@@ -1449,13 +1449,19 @@ static int segno_weight_images(const SegnoCtx& X, float* scratch) {
   return wimg_prepare(W, ld, SEGNO_WIMG, scratch, X.st);
 }
 
-static int segno_pq(const SegnoCtx& X, const float* h, float* P, float* Q) {
-  NbGemmArgs a = gemm_args((int)X.Nn);  // cols: h_row | h_col | radial | edge_attr  (gcl.py:78)
+// nblocks > 1: h is the first of `nblocks` row blocks of Nn rows, `hstride` floats apart (the saved hidden states of all
+// sub-steps); P, Q are then [nblocks * Nn][64]
+static int segno_pq(const SegnoCtx& X, const float* h, float* P, float* Q, int nblocks = 1, int64_t hstride = 0) {
+  NbGemmArgs a = gemm_args((int)(X.Nn * nblocks));  // cols: h_row | h_col | radial | edge_attr  (gcl.py:78)
   a.nsrc = 1; a.src[0] = gsrc(h, NB_H, 0, X.params + X.lo.e_w1, 1, X.lo.E);
   a.bias = X.params + X.lo.e_b1; a.out = P;
-  NbGemmArgs b = gemm_args((int)X.Nn);
+  NbGemmArgs b = gemm_args((int)(X.Nn * nblocks));
   b.nsrc = 1; b.src[0] = gsrc(h, NB_H, 0, X.params + X.lo.e_w1 + NB_H, 1, X.lo.E);
   b.out = Q;
+  if (nblocks > 1) {
+    a.src[0].seg_rows = b.src[0].seg_rows = (int)X.Nn;
+    a.src[0].seg_a = b.src[0].seg_a = hstride;
+  }
   NbGemmArgs ab[2] = {a, b};
   return launch_gemm_batch(ab, 2, X.st);
 }
@@ -1588,8 +1594,8 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   WimgGuard wimg_guard;
   NB_TRY(segno_weight_images(X, w));
   w += wimg_floats(SEGNO_WIMG);
-  float* P = w; w += nh;
-  float* Q = w; w += nh;
+  float* P_all = w; w += (int64_t)T * nh;   // first edge layer's per-node halves of EVERY sub-step: one GEMM launch over the
+  float* Q_all = w; w += (int64_t)T * nh;   // saved hidden states before the sweep instead of one small launch per sub-step
   float* gM = w; w += nh;
   float* gh_all = w; w += (int64_t)(T + 1) * nh;    // gh entering sub-step k at slot k + 1; slot k receives its output
   float* GU5_all = w; w += (int64_t)T * nh;
@@ -1609,6 +1615,12 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   const float* gh_in = g_h_out;
   if (!gh_in) { cudaMemsetAsync(gh_all + (int64_t)T * nh, 0, Nn * NB_H * sizeof(float), cst); gh_in = gh_all + (int64_t)T * nh; }
 
+  if (align64(Nn * NB_H) == Nn * NB_H) {
+    NB_TRY(segno_pq(X, segno_iter_bufs(const_cast<float*>(saved), Nn).h, P_all, Q_all, T, itf));
+  } else {   // row blocks of P_all / Q_all are padded: one launch per sub-step
+    for (int k = 0; k < T; ++k)
+      NB_TRY(segno_pq(X, segno_iter_bufs(const_cast<float*>(saved) + (int64_t)k * itf, Nn).h, P_all + (int64_t)k * nh, Q_all + (int64_t)k * nh));
+  }
   EdgeGradDst ed;
   ed.w1 = lo.e_w1; ed.W2 = lo.e_w2; ed.b2 = lo.e_b2; ed.W3 = lo.c_w1; ed.b3 = lo.c_b1; ed.w4 = lo.c_w2; ed.b4 = lo.c_b2;
   ed.ldw1 = lo.E; ed.col_rad = 2 * NB_H; ed.col_ef = 2 * NB_H + 1; ed.b_unused = 0;
@@ -1644,12 +1656,11 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     gv_in = gvb[gvi];
     gvi ^= 1;
     // edge tile backward
-    NB_TRY(segno_pq(X, b.h, P, Q));
     NbEdgeBwdArgs ea;
     memset(&ea, 0, sizeof(ea));
     ea.g = edge_geom(cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 1);
     ea.w = segno_edge_w(X);
-    ea.x = b.x; ea.P = P; ea.Q = Q; ea.ef = edge_attr; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
+    ea.x = b.x; ea.P = P_all + (int64_t)k * nh; ea.Q = Q_all + (int64_t)k * nh; ea.ef = edge_attr; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
     NB_TRY(launch_edge_bwd(ea, grad_params, ed, 1, stream, &run_base, &run_parts));
     NbGemmArgs pa = gemm_args((int)Nn);  // gh += gP W1[:, h_row] + gQ W1[:, h_col]
     pa.nsrc = 2;

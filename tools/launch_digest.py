@@ -7,8 +7,9 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 hdr, data = rows[hi], rows[hi + 2:]
 ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
 agg = collections.OrderedDict()
+skip = sys.argv[3].split(',') if len(sys.argv) > 3 else ['k_sim_']   # set-up kernels (data generation) are not part of a step
 for r in data:
-    if len(r) <= vi: continue
+    if len(r) <= vi or any(x in r[ki] for x in skip): continue
     a = agg.setdefault(r[ki][:64], [0, 0.0]); a[0] += 1; a[1] += float(r[vi].replace(',', ''))
 tot = sum(a[1] for a in agg.values())
 for n, a in sorted(agg.items(), key=lambda x: -x[1][1]):

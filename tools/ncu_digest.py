@@ -50,7 +50,8 @@ def to_json(path, key, digest_txt, workload, out='profiles/ncu_digest.json'):
     d[key] = {'dram_bytes': (get('dram__bytes_read.sum') or 0) + (get('dram__bytes_write.sum') or 0),
               'tensor_pipe_active_pct': get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'),
               'xu_pipe_pct': get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'),
-              'duration_us': get('gpu__time_duration.sum'), 'workload': workload, 'source': digest_txt}
+              'duration_us': next((float(v.replace(',', '')) * {'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3, 'second': 1e6}.get(u, 1.0)
+                                  for h, u, v in zip(hdr, units, vals) if h == 'gpu__time_duration.sum'), None), 'workload': workload, 'source': digest_txt}
     json.dump(d, open(out, 'w'), indent=1)
 
 
