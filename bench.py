@@ -246,7 +246,9 @@ def workload_config(args, per_step=None, note=None):
     c = {"workload": f"EGNO charged N-body, {args.n_balls} particles, num_timesteps={args.timesteps}, hidden 64, "
                      f"{args.layers} layers (BASELINE.json configs[2])",
          "batch_per_gpu": per_step if per_step is not None else args.batch, "n_balls": args.n_balls,
-         "num_timesteps": args.timesteps, "n_layers": args.layers, "parallelism": f"dp{args.gpus}", "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per step)",
+         "num_timesteps": args.timesteps, "n_layers": args.layers,
+         "parallelism": f"dp{args.gpus}" + ("" if args.gpus == 1 else (" (NCCL all-reduce of the flat gradient bucket)" if os.environ.get("NB_BENCH_DP", "peer") == "nccl" else
+                                                                       " (gradient sum over NVLink peer memory fused into the Adam kernel, no collective call)")), "launch": "eager" if args.no_graph else "cuda-graph replay (one graph per step)",
          "cache": "per-step activation working set (~270 MB at B=256) exceeds the 126 MB L2; inputs rotate over "
                   "8 distinct batches"}
     if note:
@@ -286,11 +288,14 @@ def run_ours(args):
     torch.manual_seed(1)
     model = nb.EGNO(n_layers=L, in_node_nf=2, in_edge_nf=2, hidden_nf=64, with_v=True, num_modes=2, num_timesteps=T,
                     device=dev)
+    # data parallel: the gradient reduction is fused into the optimizer kernel over peer memory (NB_BENCH_DP=nccl selects
+    # the NCCL flat-bucket all-reduce instead)
+    peer_dp = os.environ.get("NB_BENCH_DP", "peer") != "nccl"
     if world > 1:
         broadcast_parameters(model)
-        model.enable_data_parallel()
+        model.enable_data_parallel(peer_memory=peer_dp)
     use_graph = not args.no_graph
-    opt = nb.FlatAdam(model.parameters(), lr=1e-4, weight_decay=1e-8)   # Adam of model_confs.yaml:15-17, one fused launch
+    opt = nb.FlatAdam(model.parameters(), lr=1e-4, weight_decay=1e-8, peer_bucket=model.peer_bucket)   # model_confs.yaml:15-17
 
     # ---- synthetic data: NB distinct batches per rank, raw states in pinned host memory
     NBATCH = 8
@@ -482,8 +487,8 @@ def run_ours(args):
         seg = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=dev, n_layers=8, recurrent=True)
         if world > 1:
             broadcast_parameters(seg)
-            seg.enable_data_parallel()
-        sopt = nb.FlatAdam(seg.parameters(), lr=5e-3, weight_decay=1e-12)
+            seg.enable_data_parallel(peer_memory=peer_dp)
+        sopt = nb.FlatAdam(seg.parameters(), lr=5e-3, weight_decay=1e-12, peer_bucket=seg.peer_bucket)
         sb, shost = [], []
         for i in range(NBATCH):
             # trajectories of synthetic_sim.py's gravitational system (nb.simulate_gravity): frame 0 in, frame 1 out
@@ -647,8 +652,8 @@ def config5_leg(nb, synth, dev, rank, world, timed, dist, use_graph):
         from no_node_comparison_b200.dataparallel import broadcast_parameters
 
         broadcast_parameters(m5)
-        m5.enable_data_parallel()
-    o5 = nb.FlatAdam(m5.parameters(), lr=1e-4, weight_decay=1e-8)
+        m5.enable_data_parallel(peer_memory=os.environ.get("NB_BENCH_DP", "peer") != "nccl")
+    o5 = nb.FlatAdam(m5.parameters(), lr=1e-4, weight_decay=1e-8, peer_bucket=m5.peer_bucket)
     s5 = synth.sample_state("charged", B5, N5, seed=9 + rank)
     x5, n5, ea5, v5, lm5 = synth.egno_features(s5["loc"].to(dev), s5["vel"].to(dev), s5["charges"].to(dev), e5[0], e5[1])
     tg5 = x5.repeat(T5, 1) + 0.05 * torch.randn(T5 * B5 * N5, 3, device=dev)

@@ -243,6 +243,15 @@ int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_freq, double 
 int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
                  int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                  void* stream);
+/* Data-parallel variant: gradient all-reduce and optimizer update as ONE kernel over peer memory.  peer_grads[r] (host
+ * array of npeer <= 8 device pointers) is rank r's flat gradient buffer as mapped into this process (NVLink / NVSwitch
+ * peer access, e.g. torch's symmetric memory); every rank sums them in rank order (bit-identical replicas) and applies
+ * grad_scale (1 / world for the mean).  The caller orders the launch after every rank's backward (a device-side
+ * barrier) and keeps the buffers unchanged until every rank has passed a second barrier.  Replaces the
+ * dist.all_reduce + optimizer.step pair of a data-parallel main.py:150. */
+int nb_adam_step_peers(int64_t n, float* params, const void* const* peer_grads, int32_t npeer, float* exp_avg,
+                       float* exp_avg_sq, float* step, int32_t tick, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, double grad_scale, void* stream);
 
 /* tcgen05 self test: one 128-thread CTA evaluates, with split-bf16 operands and fp32 TMEM accumulation,
  *   mode 0: A[128x64] * W[64x64]^T   mode 1: A[128x64] * W[64x64]   mode 2: A[128x64]^T * W[128x64]

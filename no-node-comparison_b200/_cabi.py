@@ -42,6 +42,7 @@ EXPORTS = {
     "nb_traj_mse_workspace_floats": (C.c_int64, [C.c_int32]),
     "nb_traj_mse": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [c_f] * 7),
     "nb_adam_step": (C.c_int, [C.c_int64] + [c_f] * 5 + [C.c_int32] + [C.c_double] * 6 + [c_f]),
+    "nb_adam_step_peers": (C.c_int, [C.c_int64, c_f, C.POINTER(C.c_void_p), C.c_int32] + [c_f] * 3 + [C.c_int32] + [C.c_double] * 6 + [c_f]),
     "nb_launch_count": (C.c_longlong, []),
     "nb_profile_enable": (C.c_int, [C.c_int]),
     "nb_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(256) k_check_edges(const int64_t* __restrict__
 __global__ void k_adam_tick(float* step) {
   NB_PDL_ENTER(); *step += 1.0f; }
 
+#define NB_MAX_PEERS 8
 struct NbAdamArgs {
   int64_t n;
   float* p;
@@ -605,6 +606,11 @@ struct NbAdamArgs {
   const float* step;   // already incremented
   double lr, beta1, beta2, eps, weight_decay;   // hyper-parameters in double, like the Python scalars torch uses
   float grad_scale;    // gradients are multiplied by it first (data parallel: 1 / world over the summed bucket)
+  // Data parallel over peer memory (npeer > 0): the gradient is the SUM over the ranks' flat gradient buffers, read in
+  // place through NVLink / NVSwitch (peer[r] = rank r's buffer as mapped into this process), in rank order on every rank
+  // so that the replicas stay bit-identical: the all-reduce and the optimizer update are one kernel, no collective call.
+  const float* peer[NB_MAX_PEERS];
+  int npeer;
 };
 __global__ void __launch_bounds__(256) k_adam(NbAdamArgs a) {
   NB_PDL_ENTER();
@@ -615,7 +621,18 @@ __global__ void __launch_bounds__(256) k_adam(NbAdamArgs a) {
   const float eps = (float)a.eps, wd = (float)a.weight_decay;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
     const float p = a.p[i];
-    const float g = fmaf(wd, p, a.g[i] * a.grad_scale);  // grad.add(param, alpha=weight_decay)
+    float gsum;
+    if (a.npeer > 0) {
+      float pg[NB_MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < NB_MAX_PEERS; ++r) pg[r] = r < a.npeer ? a.peer[r][i] : 0.f;   // all loads in flight together
+      gsum = pg[0];
+#pragma unroll
+      for (int r = 1; r < NB_MAX_PEERS; ++r) gsum += pg[r];
+    } else {
+      gsum = a.g[i];
+    }
+    const float g = fmaf(wd, p, gsum * a.grad_scale);  // grad.add(param, alpha=weight_decay)
     const float m = fmaf(omb1, g - a.m[i], a.m[i]);      // exp_avg.lerp_(grad, 1 - beta1)
     const float v = fmaf(omb2 * g, g, b2 * a.v[i]);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     a.m[i] = m;

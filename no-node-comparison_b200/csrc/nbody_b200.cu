@@ -1888,22 +1888,41 @@ extern "C" int nb_sim_gravity(int32_t B, int32_t N, int32_t T, int32_t sample_fr
 
 // fused Adam: `step` is a device float holding the number of steps taken so far (incremented here when tick != 0);
 // [params, grads, exp_avg, exp_avg_sq] are flat fp32 buffers of n elements
+static int adam_launch(int64_t n, float* params, const float* grads, const void* const* peer_grads, int npeer, float* exp_avg,
+                       float* exp_avg_sq, float* step, int32_t tick, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, double grad_scale, void* stream) {
+  if (n < 0 || !params || (!grads && npeer <= 0) || !exp_avg || !exp_avg_sq || !step) {
+    nb_set_error("nb_adam_step: null pointer or negative size");
+    return NB_ERR_INVALID;
+  }
+  if (npeer < 0 || npeer > NB_MAX_PEERS) { nb_set_error("nb_adam_step_peers: 1 <= npeer <= %d", NB_MAX_PEERS); return NB_ERR_INVALID; }
+  if (tick) NB_LAUNCH_COUNTED(k_adam_tick, 1, 1, 0, stream, step);
+  if (n > 0) {
+    NbAdamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.step = step;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = (float)grad_scale;
+    a.npeer = npeer;
+    for (int r = 0; r < npeer; ++r) {
+      if (!peer_grads || !peer_grads[r]) { nb_set_error("nb_adam_step_peers: null peer buffer %d", r); return NB_ERR_INVALID; }
+      a.peer[r] = (const float*)peer_grads[r];
+    }
+    NB_LAUNCH_COUNTED(k_adam, (unsigned)imin(cdiv(n, 256), 4 * nb_num_sms()), 256, 0, stream, a);
+  }
+  return nb_check_launch("k_adam");
+}
 extern "C" int nb_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
                             int32_t tick, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                             void* stream) {
   NB_RANGE("nb_adam_step");
-  if (n < 0 || !params || !grads || !exp_avg || !exp_avg_sq || !step) {
-    nb_set_error("nb_adam_step: null pointer or negative size");
-    return NB_ERR_INVALID;
-  }
-  if (tick) NB_LAUNCH_COUNTED(k_adam_tick, 1, 1, 0, stream, step);
-  if (n > 0) {
-    NbAdamArgs a;
-    a.n = n; a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.step = step;
-    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = (float)grad_scale;
-    NB_LAUNCH_COUNTED(k_adam, (unsigned)imin(cdiv(n, 256), 4 * nb_num_sms()), 256, 0, stream, a);
-  }
-  return nb_check_launch("k_adam");
+  return adam_launch(n, params, grads, nullptr, 0, exp_avg, exp_avg_sq, step, tick, lr, beta1, beta2, eps, weight_decay, grad_scale, stream);
+}
+extern "C" int nb_adam_step_peers(int64_t n, float* params, const void* const* peer_grads, int32_t npeer, float* exp_avg,
+                                  float* exp_avg_sq, float* step, int32_t tick, double lr, double beta1, double beta2, double eps,
+                                  double weight_decay, double grad_scale, void* stream) {
+  NB_RANGE("nb_adam_step_peers");
+  if (npeer < 1) { nb_set_error("nb_adam_step_peers: npeer must be >= 1"); return NB_ERR_INVALID; }
+  return adam_launch(n, params, nullptr, peer_grads, npeer, exp_avg, exp_avg_sq, step, tick, lr, beta1, beta2, eps, weight_decay, grad_scale, stream);
 }
 
 // tcgen05 self test (see nb_tc.cuh): validates descriptors / layouts of the three MMA forms on the device.

@@ -40,3 +40,35 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0) -> None:
     if dist.is_initialized() and dist.get_world_size() > 1:
         for p in model.parameters():
             dist.broadcast(p.data, src=src)
+
+
+class PeerGradBucket:
+    """The flat gradient buffer of a model in symmetric memory: every rank's buffer is mapped into every process
+    (NVLink / NVSwitch peer access), so the data-parallel reduction needs no collective call — `FlatAdam` reads all
+    ranks' gradients in place and sums them inside its update kernel (`nb_adam_step_peers`), between two device-side
+    barriers.  PyTorch's symmetric-memory allocator is used for the plumbing only (allocation, handle exchange, barrier)."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.group = group
+        self.buf = symm.empty(numel, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        try:
+            self.hdl = symm.rendezvous(self.buf, group)
+        except Exception:                                        # older releases want the group registered first
+            symm.enable_symm_mem_for_group(group.group_name)
+            self.hdl = symm.rendezvous(self.buf, group)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        if self.world > 8:
+            raise ValueError("peer-memory gradient reduction supports at most 8 ranks (one NVSwitch box)")
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]       # rank r's buffer as seen from this process
+        if self.ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric memory: the local buffer pointer does not match its own mapping")
+        self.numel = numel
+
+    def barrier(self) -> None:
+        """All ranks' current streams meet here (device-side signal exchange; enqueue-only, CUDA-graph capturable)."""
+        self.hdl.barrier()

@@ -104,14 +104,29 @@ class EGNO(nn.Module):
         self._pack = _ParamPack(self)
         self._edges = _EdgeCache()
         self.process_group = None   # set by enable_data_parallel(): one flat-bucket all-reduce per backward
+        self.peer_bucket = None
 
-    def enable_data_parallel(self, group=None, average=True):
-        """Reduce parameter gradients over `group` with ONE all-reduce of the flat gradient buffer.  average=True leaves
-        the mean in `.grad` (any optimizer); average=False leaves the sum, for FlatAdam(grad_scale=1 / world), which
-        applies the factor inside its update kernel."""
+    def enable_data_parallel(self, group=None, average=True, peer_memory=False):
+        """Reduce parameter gradients over `group` once per backward.  Default: ONE NCCL all-reduce of the flat gradient
+        buffer; average=True leaves the mean in `.grad` (any optimizer), average=False the sum, for
+        FlatAdam(grad_scale=1 / world).  peer_memory=True: no collective call at all — the flat gradient buffer lives in
+        symmetric memory (dataparallel.PeerGradBucket), `.grad` keeps the LOCAL gradient, and
+        FlatAdam(..., peer_bucket=model.peer_bucket) sums all ranks' buffers over NVLink inside its update kernel
+        (mean over the ranks)."""
         import torch.distributed as dist
 
-        self.process_group = (group if group is not None else dist.group.WORLD, bool(average))
+        group = group if group is not None else dist.group.WORLD
+        self.peer_bucket = None
+        if peer_memory:
+            from .dataparallel import PeerGradBucket
+
+            if any(True for k, _ in self.named_parameters() if self._pack.skip_prefix and k.startswith(self._pack.skip_prefix)):
+                raise ValueError("peer-memory data parallel needs every parameter inside the flat C layout")
+            ps = self._pack.params()
+            self.peer_bucket = PeerGradBucket(sum(p.numel() for p in ps), ps[0].device, group)
+            self.process_group = (group, bool(average), self.peer_bucket)
+        else:
+            self.process_group = (group, bool(average))
         return self
 
     @staticmethod

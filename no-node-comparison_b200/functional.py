@@ -84,14 +84,30 @@ def _maybe_allreduce(grad_flat: torch.Tensor, dp) -> None:
     """Data parallel: ONE all-reduce of the flat gradient bucket (NCCL over NVLink).  `dp` = (group, average): with
     average the bucket is divided by the world size here (any optimizer sees the mean gradient); without, the SUM is left
     in place and the 1 / world factor rides inside the fused optimizer kernel (FlatAdam(grad_scale=1 / world))."""
-    if dp is None:
+    if dp is None or dp_bucket(dp) is not None:   # peer-memory mode: FlatAdam reduces inside its update kernel
         return
     import torch.distributed as dist
 
-    group, average = dp
+    group, average = dp[0], dp[1]
     dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         grad_flat.div_(dist.get_world_size(group))
+
+
+def dp_bucket(dp):
+    """dp = (group, average[, PeerGradBucket]) -> the bucket or None"""
+    return dp[2] if dp is not None and len(dp) > 2 else None
+
+
+def _grad_buffer(flat: torch.Tensor, dp) -> torch.Tensor:
+    """Where the backward writes the flat parameter gradient: a fresh buffer, or — peer-memory data parallel — the model's
+    symmetric-memory bucket (its address is what the other ranks read)."""
+    b = dp_bucket(dp)
+    if b is None:
+        return torch.empty_like(flat)
+    if b.numel != flat.numel() or b.buf.device != flat.device:
+        raise RuntimeError("peer gradient bucket does not match the model's flat parameter buffer")
+    return b.buf
 
 
 class _AllReduceGrad(torch.autograd.Function):
@@ -108,7 +124,7 @@ class _AllReduceGrad(torch.autograd.Function):
     def backward(ctx, g):
         import torch.distributed as dist
 
-        group, average = ctx.dp
+        group, average = ctx.dp[0], ctx.dp[1]
         g = g.contiguous().clone()
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
         if average:
@@ -157,7 +173,7 @@ class EgnoFunction(torch.autograd.Function):
         gx_out = None if gx_out is None else gx_out.contiguous()
         gv_out = None if gv_out is None else gv_out.contiguous()
         gh_out = None if gh_out is None else gh_out.contiguous()
-        grad_flat = torch.empty_like(flat)
+        grad_flat = _grad_buffer(flat, ctx.dp_group)
         in_shape = (cfg.num_inputs, n0, 3) if cfg.num_inputs > 1 else (n0, 3)
         gx_in = torch.empty(in_shape, device=dev, dtype=torch.float32)
         gv_in = torch.empty(in_shape, device=dev, dtype=torch.float32)
@@ -211,7 +227,7 @@ class SegnoFunction(torch.autograd.Function):
         gx_out = None if gx_out is None else gx_out.contiguous()
         gv_out = None if gv_out is None else gv_out.contiguous()
         gh_out = None if gh_out is None else gh_out.contiguous()
-        grad_flat = torch.empty_like(flat)
+        grad_flat = _grad_buffer(flat, ctx.dp_group)
         gx_in = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         gv_in = torch.empty((Nn, 3), device=dev, dtype=torch.float32)
         ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 1), device=dev, dtype=torch.float32)

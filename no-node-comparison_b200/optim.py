@@ -20,12 +20,15 @@ from .functional import _ptr, _stream_ptr
 
 class FlatAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, grad_scale: float = 1.0):
+                 weight_decay: float = 0.0, grad_scale: float = 1.0, peer_bucket=None):
         """`grad_scale`: the gradients are multiplied by it inside the update kernel (data parallel: 1 / world size when
-        the flat gradient bucket holds the SUM over ranks)."""
+        the flat gradient bucket holds the SUM over ranks).  `peer_bucket` (model.peer_bucket after
+        enable_data_parallel(peer_memory=True)): the gradient all-reduce happens INSIDE the update kernel — it sums every
+        rank's flat gradient buffer through peer memory, in rank order, times grad_scale / world."""
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale))
+        self.peer_bucket = peer_bucket
         self._flat = {}     # group index -> dict(m, v, step, offs): flat moment buffers; self.state[p] holds views of them
 
     @staticmethod
@@ -120,11 +123,29 @@ class FlatAdam(torch.optim.Optimizer):
                     self._publish(st, p)
             b1, b2 = group["betas"]
             tick = 1
+            pb = self.peer_bucket
+            if pb is not None:
+                if len(self.param_groups) != 1 or sum(p.numel() for p in ps) != pb.numel:
+                    raise ValueError("peer_bucket needs ONE parameter group holding exactly the model's parameters")
+                pb.barrier()        # every rank's backward has written its bucket
             for first, n in self._runs(ps):
                 o = st["offs"][id(first)]
-                check(lib.nb_adam_step(n, _ptr(first.data), _ptr(first.grad), _ptr(st["m"][o:o + n]), _ptr(st["v"][o:o + n]),
-                                       _ptr(st["step"]), tick, ctypes.c_double(group["lr"]), ctypes.c_double(b1),
-                                       ctypes.c_double(b2), ctypes.c_double(group["eps"]), ctypes.c_double(group["weight_decay"]),
-                                       ctypes.c_double(group.get("grad_scale", 1.0)), _stream_ptr(dev)), "nb_adam_step")
+                hyper = (ctypes.c_double(group["lr"]), ctypes.c_double(b1), ctypes.c_double(b2), ctypes.c_double(group["eps"]),
+                         ctypes.c_double(group["weight_decay"]))
+                if pb is None:
+                    check(lib.nb_adam_step(n, _ptr(first.data), _ptr(first.grad), _ptr(st["m"][o:o + n]), _ptr(st["v"][o:o + n]),
+                                           _ptr(st["step"]), tick, *hyper, ctypes.c_double(group.get("grad_scale", 1.0)),
+                                           _stream_ptr(dev)), "nb_adam_step")
+                else:
+                    if first.grad.data_ptr() != pb.buf.data_ptr() + 4 * o:
+                        raise RuntimeError("peer-memory data parallel: .grad does not alias the model's gradient bucket "
+                                           "(use zero_grad(set_to_none=True) and one backward per step)")
+                    peers = (ctypes.c_void_p * pb.world)(*[ptr + 4 * o for ptr in pb.ptrs])
+                    check(lib.nb_adam_step_peers(n, _ptr(first.data), peers, pb.world, _ptr(st["m"][o:o + n]), _ptr(st["v"][o:o + n]),
+                                                 _ptr(st["step"]), tick, *hyper,
+                                                 ctypes.c_double(group.get("grad_scale", 1.0) / pb.world), _stream_ptr(dev)),
+                          "nb_adam_step_peers")
                 tick = 0
+            if pb is not None:
+                pb.barrier()        # nobody overwrites a bucket (next backward) before every rank has read it
         return loss

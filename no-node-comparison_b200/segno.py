@@ -76,12 +76,29 @@ class SEGNO(nn.Module):
         self._pack = _ParamPack(self, skip_prefix="enc_attn_net")   # the C layout: embedding + module
         self._edges = _EdgeCache()
         self.process_group = None
+        self.peer_bucket = None
 
-    def enable_data_parallel(self, group=None, average=True):
-        """See EGNO.enable_data_parallel: one all-reduce of the flat gradient bucket per backward."""
+    def enable_data_parallel(self, group=None, average=True, peer_memory=False):
+        """Reduce parameter gradients over `group` once per backward.  Default: ONE NCCL all-reduce of the flat gradient
+        buffer; average=True leaves the mean in `.grad` (any optimizer), average=False the sum, for
+        FlatAdam(grad_scale=1 / world).  peer_memory=True: no collective call at all — the flat gradient buffer lives in
+        symmetric memory (dataparallel.PeerGradBucket), `.grad` keeps the LOCAL gradient, and
+        FlatAdam(..., peer_bucket=model.peer_bucket) sums all ranks' buffers over NVLink inside its update kernel
+        (mean over the ranks)."""
         import torch.distributed as dist
 
-        self.process_group = (group if group is not None else dist.group.WORLD, bool(average))
+        group = group if group is not None else dist.group.WORLD
+        self.peer_bucket = None
+        if peer_memory:
+            from .dataparallel import PeerGradBucket
+
+            if any(True for k, _ in self.named_parameters() if self._pack.skip_prefix and k.startswith(self._pack.skip_prefix)):
+                raise ValueError("peer-memory data parallel needs every parameter inside the flat C layout")
+            ps = self._pack.params()
+            self.peer_bucket = PeerGradBucket(sum(p.numel() for p in ps), ps[0].device, group)
+            self.process_group = (group, bool(average), self.peer_bucket)
+        else:
+            self.process_group = (group, bool(average))
         return self
 
     def forward(self, his, x, edges, v, edge_attr, T=10, in_steps=None):

@@ -199,6 +199,33 @@ def test_fused_adam_kernel_vs_torch_adam():
     assert step[0] == 5.0
 
 
+def test_fused_adam_kernel_summing_peer_gradient_buffers():
+    """nb_adam_step_peers (data parallel: the all-reduce is fused into the update kernel, which reads every rank's flat
+    gradient buffer) against torch.optim.Adam fed with the mean of the per-rank gradients; three emulated ranks."""
+    import ctypes
+    L = E.lib()
+    g = torch.Generator().manual_seed(1)
+    n, world = 777, 3
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)
+    p = p0.numpy().copy()
+    m, v, step = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(1, np.float32)
+    for it in range(4):
+        grads = [E.f32(torch.randn(n, generator=g)) for _ in range(world)]
+        ref.grad = torch.tensor((grads[0] + grads[1]) + grads[2]) * np.float32(1.0 / world)     # rank order, like the kernel
+        opt.step()
+        peers = (ctypes.c_void_p * world)(*[E.ptr(a) for a in grads])
+        E.check(L.nb_adam_step_peers(n, E.ptr(p), peers, world, E.ptr(m), E.ptr(v), E.ptr(step), 1, ctypes.c_double(2e-3),
+                                     ctypes.c_double(0.9), ctypes.c_double(0.999), ctypes.c_double(1e-8), ctypes.c_double(1e-3),
+                                     ctypes.c_double(1.0 / world), None))
+        np.testing.assert_allclose(p, ref.detach().numpy(), rtol=5e-7, atol=5e-8)
+    assert step[0] == 4.0
+    assert L.nb_adam_step_peers(n, E.ptr(p), peers, 9, E.ptr(m), E.ptr(v), E.ptr(step), 1, ctypes.c_double(2e-3),
+                                ctypes.c_double(0.9), ctypes.c_double(0.999), ctypes.c_double(1e-8), ctypes.c_double(1e-3),
+                                ctypes.c_double(1.0), None) != 0        # more than 8 peers: refused
+
+
 @pytest.mark.parametrize("T,R,layout,only_first", [(8, 25, 1, False), (10, 400, 0, False), (10, 40, 1, True), (1, 100, 0, False)])
 def test_trajectory_mse_kernel_vs_oracle(T, R, layout, only_first):
     """nb_traj_mse (the callers' loss and its gradient) against the oracle's restatement of

@@ -718,3 +718,42 @@ def test_segno_multi_input_under_data_parallel_matches_the_single_process_result
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_peer_memory_data_parallel_matches_the_plain_optimizer_on_one_rank():
+    """enable_data_parallel(peer_memory=True) + FlatAdam(peer_bucket=...): the gradient bucket lives in symmetric memory and
+    the optimizer kernel sums the ranks' buckets itself (nb_adam_step_peers).  With a world of one rank the run must equal
+    the plain FlatAdam run bit for bit, eagerly and under graph replay (2 / 8 ranks: tools/dp_check.py, bench.py)."""
+    import os
+    import torch.distributed as dist
+
+    d = dev()
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29534")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=d)
+        created = True
+    try:
+        c = _egno_case(8, 5, 6, L=2, seed=21)
+        tgt = torch.randn(6 * 8 * 5, 3, generator=torch.Generator().manual_seed(1)).to(d)
+        finals = {}
+        for kind in ("plain", "peer"):
+            m = make_egno(c, seed=7)
+            if kind == "peer":
+                try:
+                    m.enable_data_parallel(peer_memory=True)
+                except Exception as e:      # symmetric memory unavailable on this box / build
+                    pytest.skip(f"symmetric memory not available: {e}")
+                assert m.peer_bucket is not None and m.peer_bucket.world == 1
+            opt = nb.FlatAdam(m.parameters(), lr=2e-3, weight_decay=1e-4, peer_bucket=m.peer_bucket)
+            for _ in range(3):
+                opt.zero_grad(set_to_none=True)
+                _, _, (xo, vo, ho) = run_egno(m, c, requires_grad=False)
+                ((xo - tgt) ** 2).mean().backward()
+                opt.step()
+            finals[kind] = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu()
+        assert torch.equal(finals["plain"], finals["peer"])
+    finally:
+        if created:
+            dist.destroy_process_group()
