@@ -40,23 +40,51 @@ struct NbSegnoFusedArgs {
 #define NB_FS_HN (NB_FS_F + 2 * NB_TILE * 16)                // h tile hi/lo (64 rows)     2 x 8 KB
 #define NB_FS_UN (NB_FS_HN + 2 * NB_TC_TILE_BYTES(64))       // M / SiLU(U5) tile hi/lo    2 x 8 KB
 #define NB_FS_FL (NB_FS_UN + 2 * NB_TC_TILE_BYTES(64))
-#define NB_FS_NFLOAT (28 * NB_H + 2 * 32 * 3 + 6 * NB_H + 2 * NB_TILE)
+#define NB_FS_NFLOAT (28 * NB_H + 2 * 32 * 3 + 6 * NB_H + 4 * NB_TILE)
 #define NB_SEGNO_FUSED_SMEM(RU) (NB_FS_FL + NB_FS_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
-#define NB_FS_TMEM_COLS 512  // [0,64) pre | [64,128) M sums | [128,136) F sums | [192,256) P / U5 / dh | [256,320) Q
+#define NB_FS_TMEM_COLS 512  // [0,64) pre | [64,128) M sums | [128,136) F sums | [192,256) P / U5 / dh | [256,320) Q |
+                             // [448,480) hi, [480,512) lo pieces of the A operand (z1, then m) as packed bf16 pairs
 
-__device__ __forceinline__ void nb_fs_stage_w(unsigned char* hi, unsigned char* lo, const float* __restrict__ W, int ldw,
-                                              int tid) {
-  for (int idx = tid; idx < 64 * 8; idx += NB_THREADS) {
-    int o = idx >> 3, j = idx & 7;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __ldg(W + (int64_t)o * ldw + 8 * j + i);
-    nb_tc_store8(hi, lo, o, j, v);
+#define NB_FS_WH(p) (Wt + (2 * (p)) * NB_TC_TILE_BYTES(64))
+#define NB_FS_WL(p) (Wt + (2 * (p) + 1) * NB_TC_TILE_BYTES(64))
+#define NB_FS_SWH(p) (sW + (2 * (p)) * NB_TC_TILE_BYTES(64))
+#define NB_FS_SWL(p) (sW + (2 * (p) + 1) * NB_TC_TILE_BYTES(64))
+
+// 512 threads (thread = row x 16 columns, as in k_edge_bwd_sel): the staged weights fill the shared memory, so there is one
+// CTA per SM either way and 16 warps are what hides the latencies of the SiLU stages; the two 64-deep products of an
+// edge tile read their activation operand from tensor memory (z1 has no shared-memory copy; m keeps one for the scatter).
+// Measured against the first version (256 threads, 32 columns per thread, shared-memory A operands): 396 -> 378 us per
+// launch at B = 256, N = 20, T = 10 — the kernel is bound by its ~16 dependent MMA round trips per sub-step, not by the
+// CUDA-core stages.
+
+// 16 consecutive fp32 values of row r (column quarter cq) -> split pieces into this thread's TMEM lane and, when `hi`
+// is given, into the shared-memory tiles
+__device__ __forceinline__ void nb_fs_store16(unsigned char* hi, unsigned char* lo, int r, int cq, const float* v, uint32_t ta_hi,
+                                              uint32_t ta_lo) {
+  uint32_t h0[4], l0[4], h1[4], l1[4];
+  nb_split8(v, h0, l0);
+  nb_split8(v + 8, h1, l1);
+  if (hi) {
+    const uint32_t o0 = nb_tc_chunk_off(r, 2 * cq), o1 = nb_tc_chunk_off(r, 2 * cq + 1);
+    *reinterpret_cast<uint4*>(hi + o0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+    *reinterpret_cast<uint4*>(hi + o1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(lo + o0) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+    *reinterpret_cast<uint4*>(lo + o1) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
   }
+  nb_tmem_st44(ta_hi, h0, h1);
+  nb_tmem_st44(ta_lo, l0, l1);
+}
+__device__ __forceinline__ void nb_fs_stage_w(unsigned char* hi, unsigned char* lo, const float* __restrict__ W, int ldw, int tid) {
+  const int o = tid >> 3, j = tid & 7;   // 64 x 8 chunks = 512 threads
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __ldg(W + (int64_t)o * ldw + 8 * j + i);
+  nb_tc_store8(hi, lo, o, j, v);
 }
 
-__global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedArgs a) {
+__global__ void __launch_bounds__(NB_SB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedArgs a) {
   NB_PDL_ENTER();
+  constexpr int NT = NB_SB_THREADS;
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
   unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
   unsigned char* Wt = base + NB_FS_W;  // piece p (hi at 2p, lo at 2p+1): 0 W2, 1 W3, 2 W1r, 3 W1c, 4 W5a, 5 W5b, 6 W6
@@ -81,22 +109,20 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
   float* vw4 = vb3 + NB_H;
   float* vb5 = vw4 + NB_H;
   float* vb6 = vb5 + NB_H;
-  float* cpart = vb6 + NB_H;         // [2][128]
-  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(cpart + 2 * NB_TILE);
+  float* cpart = vb6 + NB_H;         // [4][128]
+  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(cpart + 4 * NB_TILE);
   const NbEdgeGeom g = a.g;
   const int RU = g.G * g.EPG, GN = g.G * g.N;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hf = warp >> 2;
+  const int q = warp & 3, cq = warp >> 2;
   const int row = 32 * q + lane;
-  const int cb = 32 * hf;
+  const int cb = 16 * cq;
   const int nl = 16 * q + lane;      // node owned in the M = 64 accumulators (lanes < 16 only)
   const bool nown = lane < 16;
 
-#define NB_FS_WH(p) (Wt + (2 * (p)) * NB_TC_TILE_BYTES(64))
-#define NB_FS_WL(p) (Wt + (2 * (p) + 1) * NB_TC_TILE_BYTES(64))
   nb_fs_stage_w(NB_FS_WH(0), NB_FS_WL(0), a.W2, NB_H, tid);
   nb_fs_stage_w(NB_FS_WH(1), NB_FS_WL(1), a.W3, NB_H, tid);
   nb_fs_stage_w(NB_FS_WH(2), NB_FS_WL(2), a.W1, a.ldw1, tid);
@@ -105,9 +131,9 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
   nb_fs_stage_w(NB_FS_WH(5), NB_FS_WL(5), a.W5 + NB_H, 2 * NB_H, tid);
   nb_fs_stage_w(NB_FS_WH(6), NB_FS_WL(6), a.W6, NB_H, tid);
   // zero: node tile, h tile, U tile (rows beyond the unit's nodes must stay finite zeros)
-  for (int idx = tid; idx < 2 * NB_TC_TILE_BYTES(64) / 16; idx += NB_THREADS) reinterpret_cast<uint4*>(Nh)[idx] = make_uint4(0u, 0u, 0u, 0u);
-  for (int idx = tid; idx < 4 * NB_TC_TILE_BYTES(64) / 16; idx += NB_THREADS) reinterpret_cast<uint4*>(Hh)[idx] = make_uint4(0u, 0u, 0u, 0u);
-  nb_sel_build_rowinfo(rowinfo, g, tid, NB_THREADS);
+  for (int idx = tid; idx < 2 * NB_TC_TILE_BYTES(64) / 16; idx += NT) reinterpret_cast<uint4*>(Nh)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  for (int idx = tid; idx < 4 * NB_TC_TILE_BYTES(64) / 16; idx += NT) reinterpret_cast<uint4*>(Hh)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  nb_sel_build_rowinfo(rowinfo, g, tid, NT);
   if (tid < NB_H) {
     vb1[tid] = __ldg(a.b1 + tid);
     vb2[tid] = __ldg(a.b2 + tid);
@@ -122,8 +148,8 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
   }
   if (warp == 0) nb_tmem_alloc(tmem_slot, NB_FS_TMEM_COLS);
   __syncthreads();
-  for (int idx = tid; idx < 10 * 8; idx += NB_THREADS) {  // weight rows of the node tile (w_rad, w_ef)
-    int k = idx >> 3, j = idx & 7;
+  if (tid < 10 * 8) {  // weight rows of the node tile (w_rad, w_ef)
+    int k = tid >> 3, j = tid & 7;
     int f = (k >> 1) - 1;
     float v[8];
 #pragma unroll
@@ -141,6 +167,8 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
   const uint32_t tm = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(32 * q) << 16;
   const uint32_t tm_mine = tm + lane_base + (uint32_t)cb;
+  const uint32_t ta_h = tm + 448, ta_l = tm + 480;
+  const uint32_t ta_hm = ta_h + lane_base + 8u * (uint32_t)cq, ta_lm = ta_l + lane_base + 8u * (uint32_t)cq;
   const uint32_t idesc_fwd = nb_idesc_bf16(128, 64, 0, 0);
   const uint32_t idesc_gat = nb_idesc_bf16(128, 64, 0, 1);
   const uint32_t idesc_sc = nb_idesc_bf16(64, 64, 1, 1);
@@ -149,8 +177,6 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
   const uint32_t sTh = nb_smem_u32(Th), sTl = nb_smem_u32(Tl), sSel = nb_smem_u32(Sel), sNh = nb_smem_u32(Nh),
                  sNl = nb_smem_u32(Nl), sFh = nb_smem_u32(Fh), sFl = nb_smem_u32(Fl), sHh = nb_smem_u32(Hh),
                  sHl = nb_smem_u32(Hl), sUh = nb_smem_u32(Uh), sUl = nb_smem_u32(Ul), sW = nb_smem_u32(Wt);
-#define NB_FS_SWH(p) (sW + (2 * (p)) * NB_TC_TILE_BYTES(64))
-#define NB_FS_SWL(p) (sW + (2 * (p) + 1) * NB_TC_TILE_BYTES(64))
   const float b4 = __ldg(a.b4);
   const float cnt = (float)(g.N - 1 > 1 ? g.N - 1 : 1);
   const int64_t Nn = (int64_t)g.NGT * g.N;
@@ -162,20 +188,19 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
     const int R = ngt * g.EPG;
     const int nnode = ngt * g.N;
     const int64_t node0 = (int64_t)gt0 * g.N;
-    // ---- load the unit's state
-    for (int idx = tid; idx < nnode * 16; idx += NB_THREADS)
-      nb_st4(hs + idx * 4, nb_ld4(a.h_in + node0 * NB_H + idx * 4));
-    for (int idx = tid; idx < nnode * 3; idx += NB_THREADS) {
-      xs[idx] = __ldg(a.x_in + node0 * 3 + idx);
-      vs[idx] = __ldg(a.v_in + node0 * 3 + idx);
+    // ---- load the unit's state (nnode * 16 <= 432 float4, nnode * 3 <= 81 scalars: one each per thread)
+    if (tid < nnode * 16) nb_st4(hs + tid * 4, nb_ld4(a.h_in + node0 * NB_H + tid * 4));
+    if (tid < nnode * 3) {
+      xs[tid] = __ldg(a.x_in + node0 * 3 + tid);
+      vs[tid] = __ldg(a.v_in + node0 * 3 + tid);
     }
     __syncthreads();
 
     for (int it = 0; it < a.T; ++it) {
       float* sv = a.saved ? a.saved + (int64_t)it * a.iter_stride : nullptr;  // h | M | U5 | x
       // ---- (a) h tile <- split(h) ; save h_k, x_k
-      for (int idx = tid; idx < nnode * 8; idx += NB_THREADS) {
-        int n = idx >> 3, j = idx & 7;
+      if (tid < nnode * 8) {
+        int n = tid >> 3, j = tid & 7;
         float4 p0 = nb_ld4(hs + n * NB_H + 8 * j), p1 = nb_ld4(hs + n * NB_H + 8 * j + 4);
         float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
         nb_tc_store8(Hh, Hl, n, j, v);
@@ -184,8 +209,10 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
           nb_st4(sv + (node0 + n) * NB_H + 8 * j + 4, p1);
         }
       }
-      if (sv)
-        for (int idx = tid; idx < nnode * 3; idx += NB_THREADS) sv[3 * Nn * NB_H + node0 * 3 + idx] = xs[idx];
+      if (sv && tid >= NT - nnode * 3) {
+        const int idx = tid - (NT - nnode * 3);
+        sv[3 * Nn * NB_H + node0 * 3 + idx] = xs[idx];
+      }
       nb_fence_async_smem();
       nb_tc_fence_before();
       __syncthreads();
@@ -200,18 +227,18 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       phase ^= 1;
       nb_tc_fence_after();
       {
-        float v[32];
-        nb_tmem_ld32(tm + lane_base + 192 + (uint32_t)cb, v);
+        float v[16];
+        nb_tmem_ld16(tm + lane_base + 192 + (uint32_t)cb, v);
         if (nown && nl < nnode) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += vb1[cb + i];
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Nh, Nl, nl, 4 * hf + jj, v + 8 * jj);
+          for (int i = 0; i < 16; ++i) v[i] += vb1[cb + i];
+          nb_tc_store8(Nh, Nl, nl, 2 * cq, v);
+          nb_tc_store8(Nh, Nl, nl, 2 * cq + 1, v + 8);
         }
-        nb_tmem_ld32(tm + lane_base + 256 + (uint32_t)cb, v);
+        nb_tmem_ld16(tm + lane_base + 256 + (uint32_t)cb, v);
         if (nown && nl < nnode) {
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Nh, Nl, GN + nl, 4 * hf + jj, v + 8 * jj);
+          nb_tc_store8(Nh, Nl, GN + nl, 2 * cq, v);
+          nb_tc_store8(Nh, Nl, GN + nl, 2 * cq + 1, v + 8);
         }
       }
       nb_tc_fence_before();
@@ -235,17 +262,19 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
           dy = xs[li * 3 + 1] - xs[lj * 3 + 1];
           dz = xs[li * 3 + 2] - xs[lj * 3 + 2];
           r2 = dx * dx + dy * dy + dz * dz;
-          const int64_t eoff = ((int64_t)((gt0 + lg) % g.B) * g.EPG + (r0 + row - lg * g.EPG)) * g.nef;
+          if (cq == 1) {  // only the selector's second half carries the scalars
+            const int64_t eoff = ((int64_t)((gt0 + lg) % g.B) * g.EPG + (r0 + row - lg * g.EPG)) * g.nef;
 #pragma unroll
-          for (int f = 0; f < NB_MAX_EF; ++f)
-            if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
+            for (int f = 0; f < NB_MAX_EF; ++f)
+              if (f < g.nef) e[f] = __ldg(a.ef + eoff + f);
+          }
         }
         if (r0 > 0) {  // the scatter MMAs of the previous tile have consumed Sel / T / F
           nb_mbar_wait(bar, phase);
           phase ^= 1;
           nb_tc_fence_after();
         }
-        nb_sel_write_row(Sel, row, hf, valid, li, GN + lj, r2, e);
+        if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, GN + lj, r2, e);
         nb_fence_async_smem();
         nb_tc_fence_before();
         __syncthreads();
@@ -258,38 +287,37 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
         phase ^= 1;
         nb_tc_fence_after();
         {
-          float v[32];
-          nb_tmem_ld32(tm_mine, v);
+          float v[16];
+          nb_tmem_ld16(tm_mine, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Th, Tl, row, 4 * hf + jj, v + 8 * jj);
+          for (int i = 0; i < 16; ++i) v[i] = nb_silu(v[i]);
+          nb_fs_store16(nullptr, nullptr, row, cq, v, ta_hm, ta_lm);  // z1 is only ever an A operand
+          nb_tmem_st_wait();
         }
-        nb_fence_async_smem();
         nb_tc_fence_before();
         __syncthreads();
         if (NB_ISSUER(0)) {
           nb_tc_fence_after();
-          nb_issue_w3(tm, sTh, sTl, NB_FS_SWH(0), NB_FS_SWL(0), false, idesc_fwd, 0u);
+          nb_issue_w3_ta(tm, ta_h, ta_l, NB_FS_SWH(0), NB_FS_SWL(0), false, idesc_fwd, 0u);
           nb_mma_commit(bar);
         }
         nb_mbar_wait(bar, phase);
         phase ^= 1;
         nb_tc_fence_after();
         {
-          float v[32];
-          nb_tmem_ld32(tm_mine, v);
+          float v[16];
+          nb_tmem_ld16(tm_mine, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i] + vb2[cb + i]);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Th, Tl, row, 4 * hf + jj, v + 8 * jj);
+          for (int i = 0; i < 16; ++i) v[i] = nb_silu(v[i] + vb2[cb + i]);
+          nb_fs_store16(Th, Tl, row, cq, v, ta_hm, ta_lm);  // shared-memory copy: B operand of the scatter
+          nb_tmem_st_wait();
         }
         nb_fence_async_smem();
         nb_tc_fence_before();
         __syncthreads();
         if (NB_ISSUER(0)) {
           nb_tc_fence_after();
-          nb_issue_w3(tm, sTh, sTl, NB_FS_SWH(1), NB_FS_SWL(1), false, idesc_fwd, 0u);
+          nb_issue_w3_ta(tm, ta_h, ta_l, NB_FS_SWH(1), NB_FS_SWL(1), false, idesc_fwd, 0u);
           nb_mma_commit(bar);
           nb_issue_scatter(tm + 64, sSel, sTh, sTl, idesc_sc, r0 > 0 ? 1u : 0u);  // M_i += Sel^T m
         }
@@ -297,17 +325,17 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
         phase ^= 1;
         nb_tc_fence_after();
         {
-          float v[32];
-          nb_tmem_ld32(tm_mine, v);
+          float v[16];
+          nb_tmem_ld16(tm_mine, v);
           float cp = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cp = fmaf(vw4[cb + i], nb_silu(v[i] + vb3[cb + i]), cp);
-          cpart[hf * NB_TILE + row] = cp;
+          for (int i = 0; i < 16; ++i) cp = fmaf(vw4[cb + i], nb_silu(v[i] + vb3[cb + i]), cp);
+          cpart[cq * NB_TILE + row] = cp;
         }
         nb_tc_fence_before();
         __syncthreads();
-        if (hf == 0) {
-          float c = cpart[row] + cpart[NB_TILE + row] + b4;
+        if (cq == 0) {
+          float c = (cpart[row] + cpart[NB_TILE + row]) + (cpart[2 * NB_TILE + row] + cpart[3 * NB_TILE + row]) + b4;
           float fx = dx * c, fy = dy * c, fz = dz * c;
           if (g.clamp_edge) {
             fx = fminf(fmaxf(fx, -100.f), 100.f);
@@ -331,20 +359,20 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       phase ^= 1;
       nb_tc_fence_after();
       {
-        float v[32];
-        nb_tmem_ld32(tm + lane_base + 64 + (uint32_t)cb, v);
+        float v[16];
+        nb_tmem_ld16(tm + lane_base + 64 + (uint32_t)cb, v);
         if (nown && nl < nnode) {
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Uh, Ul, nl, 4 * hf + jj, v + 8 * jj);
+          nb_tc_store8(Uh, Ul, nl, 2 * cq, v);
+          nb_tc_store8(Uh, Ul, nl, 2 * cq + 1, v + 8);
           if (sv) {
             float* dst = sv + Nn * NB_H + (node0 + nl) * NB_H + cb;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+            for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
           }
         }
         float f4[4];
         nb_tmem_ld4(tm + lane_base + 128, f4);
-        if (hf == 0 && nown && nl < nnode) {
+        if (cq == 0 && nown && nl < nnode) {
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const float acc = f4[d] / cnt * a.cw;             // gcl.py:101-102
@@ -368,20 +396,20 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       phase ^= 1;
       nb_tc_fence_after();
       {
-        float v[32];
-        nb_tmem_ld32(tm + lane_base + 192 + (uint32_t)cb, v);
+        float v[16];
+        nb_tmem_ld16(tm + lane_base + 192 + (uint32_t)cb, v);
         if (nown && nl < nnode) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += vb5[cb + i];
+          for (int i = 0; i < 16; ++i) v[i] += vb5[cb + i];
           if (sv) {
             float* dst = sv + 2 * Nn * NB_H + (node0 + nl) * NB_H + cb;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+            for (int k = 0; k < 4; ++k) nb_st4(dst + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = nb_silu(v[i]);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) nb_tc_store8(Uh, Ul, nl, 4 * hf + jj, v + 8 * jj);
+          for (int i = 0; i < 16; ++i) v[i] = nb_silu(v[i]);
+          nb_tc_store8(Uh, Ul, nl, 2 * cq, v);
+          nb_tc_store8(Uh, Ul, nl, 2 * cq + 1, v + 8);
         }
       }
       nb_fence_async_smem();
@@ -396,22 +424,22 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_fused_fwd(NbSegnoFusedA
       phase ^= 1;
       nb_tc_fence_after();
       {
-        float v[32];
-        nb_tmem_ld32(tm + lane_base + 192 + (uint32_t)cb, v);
+        float v[16];
+        nb_tmem_ld16(tm + lane_base + 192 + (uint32_t)cb, v);
         if (nown && nl < nnode) {
           float* hp = hs + nl * NB_H + cb;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) hp[i] = (a.recurrent ? hp[i] : 0.f) + (v[i] + vb6[cb + i]);
+          for (int i = 0; i < 16; ++i) hp[i] = (a.recurrent ? hp[i] : 0.f) + (v[i] + vb6[cb + i]);
         }
       }
       nb_tc_fence_before();
       __syncthreads();
     }
     // ---- write the unit's final state
-    for (int idx = tid; idx < nnode * 16; idx += NB_THREADS) nb_st4(a.h_out + node0 * NB_H + idx * 4, nb_ld4(hs + idx * 4));
-    for (int idx = tid; idx < nnode * 3; idx += NB_THREADS) {
-      a.x_out[node0 * 3 + idx] = xs[idx];
-      a.v_out[node0 * 3 + idx] = vs[idx];
+    if (tid < nnode * 16) nb_st4(a.h_out + node0 * NB_H + tid * 4, nb_ld4(hs + tid * 4));
+    if (tid < nnode * 3) {
+      a.x_out[node0 * 3 + tid] = xs[tid];
+      a.v_out[node0 * 3 + tid] = vs[tid];
     }
     __syncthreads();
   }

@@ -1523,7 +1523,7 @@ extern "C" int nb_segno_forward(const NbSegnoConfig* cfg, const float* params, c
       const size_t fsm = NB_SEGNO_FUSED_SMEM(fg.G * fg.EPG);
       NB_SET_SMEM(k_segno_fused_fwd, fsm);
       int pi = prof_begin(5, stream);
-      NB_LAUNCH_COUNTED(k_segno_fused_fwd, (unsigned)imin(fg.n_units, nb_num_sms()), NB_THREADS, fsm, stream, fa);
+      NB_LAUNCH_COUNTED(k_segno_fused_fwd, (unsigned)imin(fg.n_units, nb_num_sms()), NB_SB_THREADS, fsm, stream, fa);
       prof_end(5, pi, stream);
       return nb_check_launch("k_segno_fused_fwd");
     }
