@@ -47,6 +47,54 @@ int nb_pdl_enabled() {
   return on;
 }
 
+// ============================================================================= side stream
+// Independent kernels of a call (EGNO: the 2-channel (x - mean, v) temporal convolution next to the 64-channel one) run on
+// a library-owned second stream between a fork and a join event, so they overlap on the SMs instead of queueing behind
+// each other.  The caller still sees ONE stream: everything forked is joined before the entry point returns, and under
+// stream capture the side stream joins the caller's capture through the events (a fork / join pair in the graph).
+// Created once per device at the first call (never while a capture is open: GraphedStep warms up eagerly first).
+#ifndef NB_EMU
+struct NbSide {
+  cudaStream_t s;
+  cudaEvent_t fork, join;
+  bool ok;
+};
+static NbSide* side_get() {
+  static NbSide tab[64];
+  static bool tried[64];
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("NB_B200_SIDE_STREAM"); off = (e && e[0] == '0') ? 1 : 0; }
+  int dev = 0;
+  if (off || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  NbSide& x = tab[dev];
+  if (!tried[dev]) {
+    tried[dev] = true;
+    x.ok = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!x.ok) cudaGetLastError();
+  }
+  return x.ok ? &x : nullptr;
+}
+// fork: returns the stream to launch the independent work on (the caller's own stream when there is no side stream)
+static void* side_fork(void* main_st) {
+  NbSide* x = side_get();
+  if (!x) return main_st;
+  cudaEventRecord(x->fork, (cudaStream_t)main_st);
+  cudaStreamWaitEvent(x->s, x->fork, 0);
+  return (void*)x->s;
+}
+static void side_join(void* side_st, void* main_st) {
+  if (side_st == main_st) return;
+  NbSide* x = side_get();
+  cudaEventRecord(x->join, (cudaStream_t)side_st);
+  cudaStreamWaitEvent((cudaStream_t)main_st, x->join, 0);
+}
+#else
+static void* side_fork(void* main_st) { return main_st; }
+static void side_join(void*, void*) {}
+#endif
+
 // ============================================================================= errors / device info
 static thread_local char g_err[512] = "";
 
@@ -1025,7 +1073,20 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
     const EgnoLayerOff& L = X.lo.L[l];
     const float* v0 = v_prev;
     float *h1 = b.h1, *x1 = b.x1, *v1 = b.v1;
+    void* side = stream;
     if (cfg->use_time_conv) {
+      // (x - mean, v) <- (x - mean, v) + conv(.)     (egno.py:103-108, layer_no.py:151-178): independent of the h path
+      // until the edge kernel, so it runs on the side stream underneath the 64-channel convolution and the P | Q product
+      {
+        NbTcxArgs t;
+        memset(&t, 0, sizeof(t));
+        t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
+        { const NbFrameMap fmx = egno_frame_map(cfg); for (int tt = 0; tt < NB_MAX_T; ++tt) t.tmap[tt] = fmx.m[tt]; }
+        t.x1 = x1; t.v1 = v1;
+        side = side_fork(stream);
+        NB_LAUNCH_COUNTED(k_tcx_fwd, (unsigned)ew_grid(Nn0 * 3), 256, 0, side, t);
+        NB_TRY(nb_check_launch("k_tcx_fwd"));
+      }
       // h <- h + LeakyReLU(conv(h))      (layer_no.py:96-126)
       if (egno_tconv_fused(X)) {
         NbTconvArgs tc = tconv_args(X, l);
@@ -1045,14 +1106,6 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
         NB_LAUNCH_COUNTED(k_idft_fwd, (unsigned)ew_grid(Nn0 * 16), 256, 0, stream, d);
         NB_TRY(nb_check_launch("k_idft_fwd"));
       }
-      // (x - mean, v) <- (x - mean, v) + conv(.)     (egno.py:103-108, layer_no.py:151-178)
-      NbTcxArgs t;
-      memset(&t, 0, sizeof(t));
-      t.tw = X.tw; t.n3 = (int)(Nn0 * 3); t.x0 = b.x0; t.v0 = v0; t.mean = loc_mean; t.W = params + L.tcx;
-      { const NbFrameMap fmx = egno_frame_map(cfg); for (int tt = 0; tt < NB_MAX_T; ++tt) t.tmap[tt] = fmx.m[tt]; }
-      t.x1 = x1; t.v1 = v1;
-      NB_LAUNCH_COUNTED(k_tcx_fwd, (unsigned)ew_grid(Nn0 * 3), 256, 0, stream, t);
-      NB_TRY(nb_check_launch("k_tcx_fwd"));
     } else {
       h1 = b.h0; x1 = b.x0;
       cudaMemcpyAsync(v1, v0, Nn * 3 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
@@ -1061,6 +1114,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
     float* Pl = saved ? b.P : P;  // training: kept for the backward edge tile
     float* Ql = saved ? b.Q : Q;
     NB_TRY(egno_pq(X, l, h1, Pl, Ql));
+    side_join(side, stream);
     NbEdgeFwdArgs ea;
     ea.g = edge_geom(T * cfg->B, cfg->B, cfg->N, cfg->in_edge_nf, 0);
     egno_geom_frames(cfg, ea.g);
@@ -1224,6 +1278,16 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     // 5. temporal convolutions
     if (cfg->use_time_conv) {
       float* gx0 = gxb[gxi ^ 1];
+      void* side = stream;
+      if (egno_tconv_fused(X)) {
+        // queued weight-gradient jobs read gh_in (= ghB of the layer above), GU5, gP, ...: run them before ghB is
+        // overwritten.  The spectral weight gradients of THIS layer are queued after the kernel that produces their
+        // operands (coef, gycoef) and run with the next flush, before those planes are overwritten again.
+        NB_TRY(q_flush(stream));
+        // the 2-channel convolution's backward is independent of the 64-channel one: side stream, joined after it;
+        // its partial slice is reduced by the next flush (on the caller's stream, after the join)
+        side = side_fork(stream);
+      }
       {
         NbTcxArgs t;
         memset(&t, 0, sizeof(t));
@@ -1234,7 +1298,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         float* partial = q_alloc((int64_t)grid * 2 * 2 * modes * 2, stream);
         if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
         t.partial = partial;
-        NB_LAUNCH_COUNTED(k_tcx_bwd, (unsigned)grid, 256, 0, stream, t);
+        NB_LAUNCH_COUNTED(k_tcx_bwd, (unsigned)grid, 256, 0, side, t);
         NB_TRY(nb_check_launch("k_tcx_bwd"));
         NbFinArgs f;
         memset(&f, 0, sizeof(f));
@@ -1246,10 +1310,6 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       gxi ^= 1;
       gv_in = gvA;
       if (egno_tconv_fused(X)) {
-        // queued weight-gradient jobs read gh_in (= ghB of the layer above), GU5, gP, ...: run them before ghB is
-        // overwritten.  The spectral weight gradients of THIS layer are queued after the kernel that produces their
-        // operands (coef, gycoef) and run with the next flush, before those planes are overwritten again.
-        NB_TRY(q_flush(stream));
         NbTconvArgs tc = tconv_args(X, l);
         tc.x = b.h0; tc.gout = ghA; tc.gx = ghB; tc.coef = coef; tc.gycoef = gycoef;
         NB_SET_SMEM(k_tconv_bwd, NB_TCONV_BWD_SMEM);
@@ -1257,6 +1317,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         NB_LAUNCH_COUNTED(k_tconv_bwd, (unsigned)tconv_grid(X, 2), 256, NB_TCONV_BWD_SMEM, stream, tc);
         prof_end(4, pi, stream);
         NB_TRY(nb_check_launch("k_tconv_bwd"));
+        side_join(side, stream);
         const int64_t plane = Nn0 * NB_H;
         const int64_t tk = (int64_t)modes * 2, tn = (int64_t)NB_H * modes * 2;
         for (int m = 0; m < modes; ++m) {
