@@ -137,6 +137,38 @@ int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, const float
                       const float* saved, const float* g_x_out, const float* g_h_out, const float* g_v_out,
                       float* grad_params, float* g_x_in, float* g_v_in, float* g_h_in, float* workspace, void* stream);
 
+/* Multi-input SEGNO (SEGNO.forward with x[BN, L, 3], SEGNO/models/model.py:65-90): the reference embeds every observed
+ * frame, integrates from frame i to frame i + 1 (forward_step = nb_segno_forward with cfg.h_given = 1) and merges the
+ * integrated state with the observed frame i + 1 ('sum', model.py:82-85; InvariantTemporalAttention +
+ * prepare_node_inputs, model.py:86-90, 105-139).  These entry points are everything around the segments.
+ *   nb_segno_embed_forward : h[rows, H] = his[rows, in_node_nf] embedding.weight^T + embedding.bias   (model.py:73)
+ *   nb_segno_embed_backward: grad_params[embedding.*] = its weight / bias gradients (overwritten; workspace:
+ *                            nb_segno_embed_backward_workspace_floats)
+ *   nb_segno_merge_forward : mode 0 = observed frame `frame` of h_all[n, L, H] / x_all[n, L, 3] / v_all[n, L, 3];
+ *                            mode 1 = observed + integrated; mode 2 = attention-weighted pair, attn_params =
+ *                            attn_mlp.0.weight[H][H+1] | attn_mlp.0.bias[H] | attn_mlp.2.weight[H] | attn_mlp.2.bias,
+ *                            alpha[n, 2] = the softmax weights, kept for the backward
+ *   nb_segno_merge_backward: gradients of the merged state -> slice [:, frame, :] of g_*_all and g_*_int; mode 2 also
+ *                            writes (accumulate = 0) or adds (1) the 64*65 + 64 + 64 + 1 attention-parameter gradients
+ *                            into g_attn (workspace: nb_segno_merge_backward_workspace_floats)
+ *   nb_accumulate          : dst[0:n] += src[0:n] (sum of the segments' gradients of the shared parameters) */
+int nb_segno_embed_forward(const NbSegnoConfig* cfg, const float* params, int64_t rows, const float* his, float* h,
+                           void* stream);
+int64_t nb_segno_embed_backward_workspace_floats(const NbSegnoConfig* cfg, int64_t rows);
+int nb_segno_embed_backward(const NbSegnoConfig* cfg, int64_t rows, const float* his, const float* g_h, float* grad_params,
+                            float* workspace, void* stream);
+int nb_segno_merge_forward(int32_t mode, int64_t n, int32_t L, int32_t frame, const float* h_all, const float* x_all,
+                           const float* v_all, const float* h_int, const float* x_int, const float* v_int,
+                           const float* attn_params, float* h_out, float* x_out, float* v_out, float* alpha, void* stream);
+int64_t nb_segno_merge_backward_workspace_floats(int64_t n);
+int nb_segno_merge_backward(int32_t mode, int64_t n, int32_t L, int32_t frame, const float* h_all, const float* x_all,
+                            const float* v_all, const float* h_int, const float* x_int, const float* v_int,
+                            const float* attn_params, const float* alpha, const float* g_h, const float* g_x,
+                            const float* g_v, float* g_h_all, float* g_x_all, float* g_v_all, float* g_h_int,
+                            float* g_x_int, float* g_v_int, float* g_attn, int32_t accumulate, float* workspace,
+                            void* stream);
+int nb_accumulate(int64_t n, float* dst, const float* src, void* stream);
+
 /* Validates that (row, col) is the canonical fully connected list for B graphs of N bodies.
  * Writes 0 to *flag_dev if so, else the (1-based) index of a mismatching edge.  No host sync. */
 int nb_check_canonical_edges(const int64_t* row, const int64_t* col, int64_t n_edges, int32_t B, int32_t N,

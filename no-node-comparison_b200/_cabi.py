@@ -31,6 +31,13 @@ EXPORTS = {
     "nb_egno_backward": (C.c_int, [C.POINTER(NbEgnoConfig)] + [c_f] * 15),
     "nb_segno_forward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 11),
     "nb_segno_backward": (C.c_int, [C.POINTER(NbSegnoConfig)] + [c_f] * 13),
+    "nb_segno_embed_forward": (C.c_int, [C.POINTER(NbSegnoConfig), c_f, C.c_int64, c_f, c_f, c_f]),
+    "nb_segno_embed_backward_workspace_floats": (C.c_int64, [C.POINTER(NbSegnoConfig), C.c_int64]),
+    "nb_segno_embed_backward": (C.c_int, [C.POINTER(NbSegnoConfig), C.c_int64] + [c_f] * 5),
+    "nb_segno_merge_forward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [c_f] * 12),
+    "nb_segno_merge_backward_workspace_floats": (C.c_int64, [C.c_int64]),
+    "nb_segno_merge_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32] + [c_f] * 18 + [C.c_int32, c_f, c_f]),
+    "nb_accumulate": (C.c_int, [C.c_int64, c_f, c_f, c_f]),
     "nb_check_canonical_edges": (C.c_int, [c_f, c_f, C.c_int64, C.c_int32, C.c_int32, c_f, c_f]),
     "nb_egcl_edge_forward": (C.c_int, [C.c_int32] * 5 + [c_f] * 5 + [C.c_int32] * 3 + [c_f] * 9),
     "nb_egcl_edge_backward_workspace_floats": (C.c_int64, [C.c_int32, C.c_int32]),

@@ -16,6 +16,7 @@
 #include "nb_edge_sel.cuh"
 #include "nb_node_tc.cuh"
 #include "nb_segno_fused.cuh"
+#include "nb_merge.cuh"
 #include <cstdlib>
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
@@ -1792,6 +1793,138 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     else cudaMemsetAsync(g_v_in, 0, Nn * 3 * sizeof(float), cst);
   }
   return nb_check_launch("nb_segno_backward");
+}
+
+// ============================================================================= multi-input SEGNO (model.py:65-90, 105-139)
+// The integration segments are nb_segno_forward / nb_segno_backward with h_given = 1; these entry points cover what the
+// reference does around them: the embedding of every observed frame, the 'sum' / attention merge of an integrated state
+// with the next observed frame, and the sum of the per-segment gradients of the shared parameters.
+extern "C" int nb_segno_embed_forward(const NbSegnoConfig* cfg, const float* params, int64_t rows, const float* his, float* h,
+                                      void* stream) {
+  NB_RANGE("nb_segno_embed_forward");
+  NB_TRY(segno_validate(cfg));
+  if (rows < 1 || rows > 2000000000LL || !params || !his || !h) { nb_set_error("nb_segno_embed_forward: bad rows / null pointer"); return NB_ERR_INVALID; }
+  SegnoLayout lo;
+  segno_layout(cfg, &lo);
+  NbEmbedArgs e;
+  memset(&e, 0, sizeof(e));
+  e.T = 1; e.Nn0 = (int)rows; e.B = 1; e.F0 = cfg->in_node_nf; e.D = 0;
+  e.nodes = his; e.W = params + lo.emb_w; e.bias = params + lo.emb_b; e.out = h;
+  const size_t esm = ((size_t)e.F0 * NB_H + 4 * e.F0) * sizeof(float);
+  NB_LAUNCH_COUNTED(k_embed_fwd, (unsigned)imin(cdiv(rows, 4), 8 * nb_num_sms()), 256, esm, stream, e);
+  return nb_check_launch("k_embed_fwd");
+}
+static int embed_bwd_grid(int64_t rows) { return imin(cdiv(rows, 32), 2 * nb_num_sms()); }
+extern "C" int64_t nb_segno_embed_backward_workspace_floats(const NbSegnoConfig* cfg, int64_t rows) {
+  if (!cfg || rows < 1) return -1;
+  return (int64_t)embed_bwd_grid(rows) * (NB_H * cfg->in_node_nf + NB_H) + 64;
+}
+// grad_params[embedding.weight | embedding.bias] = dL/dW, dL/db of h = his W^T + b over `rows` rows (overwritten)
+extern "C" int nb_segno_embed_backward(const NbSegnoConfig* cfg, int64_t rows, const float* his, const float* g_h,
+                                       float* grad_params, float* workspace, void* stream) {
+  NB_RANGE("nb_segno_embed_backward");
+  NB_TRY(segno_validate(cfg));
+  if (rows < 1 || rows > 2000000000LL || !his || !g_h || !grad_params || !workspace) { nb_set_error("nb_segno_embed_backward: bad rows / null pointer"); return NB_ERR_INVALID; }
+  SegnoLayout lo;
+  segno_layout(cfg, &lo);
+  NbEmbedBwdArgs eb;
+  memset(&eb, 0, sizeof(eb));
+  eb.e.T = 1; eb.e.Nn0 = (int)rows; eb.e.B = 1; eb.e.F0 = cfg->in_node_nf; eb.e.D = 0; eb.e.nodes = his;
+  eb.g = g_h;
+  const int F = cfg->in_node_nf, grid = embed_bwd_grid(rows);
+  q_begin(workspace, nb_segno_embed_backward_workspace_floats(cfg, rows));
+  float* partial = q_alloc((int64_t)grid * (NB_H * F + NB_H), stream);
+  if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+  eb.partial = partial;
+  const size_t smem = (32 * (size_t)F + 32 * NB_H) * sizeof(float);
+  NB_LAUNCH_COUNTED(k_embed_bwd, (unsigned)grid, 256, smem, stream, eb);
+  NB_TRY(nb_check_launch("k_embed_bwd"));
+  NbFinArgs f;
+  memset(&f, 0, sizeof(f));
+  f.partial = partial; f.nparts = grid; f.plen = NB_H * F + NB_H; f.dst = grad_params; f.nseg = 2;
+  f.seg[0] = fseg(0, NB_H * F, NB_H * F, lo.emb_w, 0, 1);
+  f.seg[1] = fseg(NB_H * F, NB_H, NB_H, lo.emb_b, 0, 1);
+  NB_TRY(launch_finalize(f, stream));
+  return q_flush(stream);
+}
+
+static int merge_check(int32_t mode, int64_t n, int32_t L, int32_t frame) {
+  if (mode < NB_MERGE_COPY || mode > NB_MERGE_ATTN || n < 1 || n > 2000000000LL / 64 || L < 1 || frame < 0 || frame >= L) {
+    nb_set_error("nb_segno_merge: unsupported arguments (mode=%d, n=%lld, L=%d, frame=%d)", mode, (long long)n, L, frame);
+    return NB_ERR_INVALID;
+  }
+  return NB_OK;
+}
+// mode 0: (h, x, v)_out = observed frame `frame` of the [n][L][.] tensors; 1: observed + integrated ('sum', model.py:82-85);
+// 2: attention-weighted sum of the pair (model.py:86-90, 105-139; attn_params = attn_mlp.0.weight[64][65] | .0.bias[64] |
+// .2.weight[64] | .2.bias, alpha[n][2] keeps the weights for the backward)
+extern "C" int nb_segno_merge_forward(int32_t mode, int64_t n, int32_t L, int32_t frame, const float* h_all, const float* x_all,
+                                      const float* v_all, const float* h_int, const float* x_int, const float* v_int,
+                                      const float* attn_params, float* h_out, float* x_out, float* v_out, float* alpha,
+                                      void* stream) {
+  NB_RANGE("nb_segno_merge_forward");
+  NB_TRY(merge_check(mode, n, L, frame));
+  if (!h_all || !x_all || !v_all || !h_out || !x_out || !v_out || (mode != NB_MERGE_COPY && (!h_int || !x_int || !v_int)) ||
+      (mode == NB_MERGE_ATTN && (!attn_params || !alpha))) {
+    nb_set_error("nb_segno_merge_forward: null pointer");
+    return NB_ERR_INVALID;
+  }
+  NbMergeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.n = (int)n; a.L = L; a.frame = frame; a.h_all = h_all; a.x_all = x_all; a.v_all = v_all;
+  a.h_int = h_int; a.x_int = x_int; a.v_int = v_int; a.ap = attn_params; a.h_out = h_out; a.x_out = x_out; a.v_out = v_out;
+  a.alpha = alpha;
+  NB_LAUNCH_COUNTED(k_segno_merge_fwd, (unsigned)imin(cdiv(n, 8), 8 * nb_num_sms()), 256, NB_MERGE_SMEM, stream, a);
+  return nb_check_launch("k_segno_merge_fwd");
+}
+static int merge_bwd_grid(int64_t n) { return imin(cdiv(n, 8), 2 * nb_num_sms()); }
+extern "C" int64_t nb_segno_merge_backward_workspace_floats(int64_t n) {
+  return n < 1 ? -1 : (int64_t)merge_bwd_grid(n) * NB_AT_PLEN + 64;
+}
+// gradients of the merged state -> slice [:, frame, :] of g_*_all (observed frame) and g_*_int (integrated state);
+// mode 2 also (accumulate ? adds : writes) the NB_AT_PLEN attention-parameter gradients into g_attn
+extern "C" int nb_segno_merge_backward(int32_t mode, int64_t n, int32_t L, int32_t frame, const float* h_all, const float* x_all,
+                                       const float* v_all, const float* h_int, const float* x_int, const float* v_int,
+                                       const float* attn_params, const float* alpha, const float* g_h, const float* g_x,
+                                       const float* g_v, float* g_h_all, float* g_x_all, float* g_v_all, float* g_h_int,
+                                       float* g_x_int, float* g_v_int, float* g_attn, int32_t accumulate, float* workspace,
+                                       void* stream) {
+  NB_RANGE("nb_segno_merge_backward");
+  NB_TRY(merge_check(mode, n, L, frame));
+  if (!g_h_all || !g_x_all || !g_v_all || (mode != NB_MERGE_COPY && (!g_h_int || !g_x_int || !g_v_int)) ||
+      (mode == NB_MERGE_ATTN && (!h_all || !x_all || !v_all || !h_int || !x_int || !v_int || !attn_params || !alpha || !g_attn || !workspace))) {
+    nb_set_error("nb_segno_merge_backward: null pointer");
+    return NB_ERR_INVALID;
+  }
+  NbMergeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.n = (int)n; a.L = L; a.frame = frame; a.h_all = h_all; a.x_all = x_all; a.v_all = v_all;
+  a.h_int = h_int; a.x_int = x_int; a.v_int = v_int; a.ap = attn_params; a.alpha = const_cast<float*>(alpha);
+  a.g_h = g_h; a.g_x = g_x; a.g_v = g_v; a.g_h_all = g_h_all; a.g_x_all = g_x_all; a.g_v_all = g_v_all;
+  a.g_h_int = g_h_int; a.g_x_int = g_x_int; a.g_v_int = g_v_int;
+  const int grid = mode == NB_MERGE_ATTN ? merge_bwd_grid(n) : imin(cdiv(n, 8), 8 * nb_num_sms());
+  if (mode == NB_MERGE_ATTN) {
+    q_begin(workspace, nb_segno_merge_backward_workspace_floats(n));
+    a.partial = q_alloc((int64_t)grid * NB_AT_PLEN, stream);
+    if (!a.partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+  }
+  NB_LAUNCH_COUNTED(k_segno_merge_bwd, (unsigned)grid, 256, NB_MERGE_SMEM, stream, a);
+  NB_TRY(nb_check_launch("k_segno_merge_bwd"));
+  if (mode != NB_MERGE_ATTN) return NB_OK;
+  NbFinArgs f;
+  memset(&f, 0, sizeof(f));
+  f.partial = a.partial; f.nparts = grid; f.plen = NB_AT_PLEN; f.dst = g_attn; f.nseg = 1; f.accumulate = accumulate ? 1 : 0;
+  f.seg[0] = fseg(0, NB_AT_PLEN, NB_AT_PLEN, 0, 0, 1);
+  NB_TRY(launch_finalize(f, stream));
+  return q_flush(stream);
+}
+// dst[0:n] += src[0:n]: the shared parameters' gradients of the integration segments
+extern "C" int nb_accumulate(int64_t n, float* dst, const float* src, void* stream) {
+  NB_RANGE("nb_accumulate");
+  if (n < 0 || !dst || !src) { nb_set_error("nb_accumulate: null pointer or negative size"); return NB_ERR_INVALID; }
+  if (n == 0) return NB_OK;
+  NB_LAUNCH_COUNTED(k_accumulate, (unsigned)ew_grid(n), 256, 0, stream, dst, src, n);
+  return nb_check_launch("k_accumulate");
 }
 
 // ============================================================================= exported building blocks

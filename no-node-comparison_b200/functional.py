@@ -249,6 +249,128 @@ class SegnoFunction(torch.autograd.Function):
         return (None, None, None, gh_in, gx_in, gv_in, None, *grads)
 
 
+class SegnoMultiFunction(torch.autograd.Function):
+    """x, h, v = SEGNO.forward(his[BN, L, F], x[BN, L, 3], ..., in_steps)   (reference: SEGNO/models/model.py:65-90).
+
+    ONE autograd node for the whole multi-input forward: the embedding of every observed frame, the integration segments
+    (nb_segno_forward with h_given) and the 'sum' / attention merges between them (model.py:82-90, 105-139) are C calls
+    enqueued back to back; the backward walks them in reverse, sums the segments' gradients of the shared parameters on
+    the device and reduces the flat bucket once.  PyTorch only allocates.
+
+    meta = (B, N, steps, in_node_nf, in_edge_nf, recurrent, coords_weight, mode) with mode 1 = 'sum', 2 = 'attn';
+    `attn_flat` is the flat view of enc_attn_net's four tensors (None for 'sum')."""
+
+    @staticmethod
+    def forward(ctx, meta, dp_group, flat, attn_flat, his, x, v, edge_attr, n_params, *params):
+        lib = load_library()
+        B, N, steps, in_nf, in_ef, recurrent, cw, mode = meta
+        dev = x.device
+        n, L = B * N, x.shape[1]
+        st = _stream_ptr(dev)
+        need_grad = any(ctx.needs_input_grad)
+        f32 = dict(device=dev, dtype=torch.float32)
+        cfgs = [_cabi.NbSegnoConfig(B, N, int(T), in_nf, in_ef, recurrent, cw, 1) for T in steps]
+        h_all = torch.empty((n, L, 64), **f32)
+        check(lib.nb_segno_embed_forward(ctypes.byref(cfgs[0]), _ptr(flat), n * L, _ptr(his), _ptr(h_all), st),
+              "nb_segno_embed_forward")
+        cur = [torch.empty((n, 64), **f32), torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)]   # h_, x_, v_
+        check(lib.nb_segno_merge_forward(0, n, L, 0, _ptr(h_all), _ptr(x), _ptr(v), None, None, None, None,
+                                         _ptr(cur[0]), _ptr(cur[1]), _ptr(cur[2]), None, st), "nb_segno_merge_forward")
+        seg_in, seg_saved, seg_out, alphas = [], [], [], []
+        out = None
+        for i, cfg in enumerate(cfgs):
+            xo, ho, vo = (torch.empty((n, 3), **f32), torch.empty((n, 64), **f32), torch.empty((n, 3), **f32))
+            saved = torch.empty(lib.nb_segno_saved_floats(ctypes.byref(cfg)), **f32) if need_grad else None
+            ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 2 if need_grad else 0), **f32)
+            check(lib.nb_segno_forward(ctypes.byref(cfg), _ptr(flat), _ptr(cur[0]), _ptr(cur[1]), _ptr(cur[2]), _ptr(edge_attr),
+                                       _ptr(xo), _ptr(ho), _ptr(vo), _ptr(saved), _ptr(ws), st), "nb_segno_forward")
+            seg_in.append(cur[0])          # the segment's input hidden state (its `his` in the backward)
+            seg_saved.append(saved)
+            seg_out.append((ho, xo, vo))
+            out = (xo, ho, vo)
+            if i < len(cfgs) - 1:
+                nxt = [torch.empty((n, 64), **f32), torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)]
+                alpha = torch.empty((n, 2), **f32) if mode == 2 else None
+                check(lib.nb_segno_merge_forward(mode, n, L, i + 1, _ptr(h_all), _ptr(x), _ptr(v), _ptr(ho), _ptr(xo), _ptr(vo),
+                                                 _ptr(attn_flat), _ptr(nxt[0]), _ptr(nxt[1]), _ptr(nxt[2]), _ptr(alpha), st),
+                      "nb_segno_merge_forward")
+                alphas.append(alpha)
+                cur = nxt
+        ctx.meta, ctx.dp_group, ctx.n_params = meta, dp_group, n_params
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.has_saved = need_grad
+        if need_grad:
+            ctx.save_for_backward(flat, attn_flat, his, x, v, edge_attr, h_all, *seg_in, *seg_saved,
+                                  *[t for o in seg_out[:-1] for t in o], *alphas)
+        return out
+
+    @staticmethod
+    def backward(ctx, gx_out, gh_out, gv_out):
+        if not ctx.has_saved:
+            raise RuntimeError("SEGNO forward ran without autograd state; cannot run backward")
+        lib = load_library()
+        B, N, steps, in_nf, in_ef, recurrent, cw, mode = ctx.meta
+        S = len(steps)
+        t = list(ctx.saved_tensors)
+        flat, attn_flat, his, x, v, edge_attr, h_all = t[:7]
+        seg_in, seg_saved = t[7:7 + S], t[7 + S:7 + 2 * S]
+        rest = t[7 + 2 * S:]
+        seg_out = [tuple(rest[3 * i:3 * i + 3]) for i in range(S - 1)]
+        alphas = rest[3 * (S - 1):] if mode == 2 else [None] * (S - 1)
+        dev = flat.device
+        n, L = B * N, x.shape[1]
+        st = _stream_ptr(dev)
+        f32 = dict(device=dev, dtype=torch.float32)
+        cfgs = [_cabi.NbSegnoConfig(B, N, int(T), in_nf, in_ef, recurrent, cw, 1) for T in steps]
+        grad_flat = _grad_buffer(flat, ctx.dp_group)
+        tmp = torch.empty_like(flat) if S > 1 else None
+        g_h_all, g_x_all, g_v_all = torch.empty((n, L, 64), **f32), torch.empty((n, L, 3), **f32), torch.empty((n, L, 3), **f32)
+        g_attn = torch.empty_like(attn_flat) if mode == 2 else None
+        gh = None if gh_out is None else gh_out.contiguous()
+        gx = None if gx_out is None else gx_out.contiguous()
+        gv = None if gv_out is None else gv_out.contiguous()
+        for i in range(S - 1, -1, -1):
+            cfg = cfgs[i]
+            target = grad_flat if i == S - 1 else tmp
+            gx_in, gv_in, gh_in = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 64), **f32)
+            ws = torch.empty(lib.nb_segno_workspace_floats(ctypes.byref(cfg), 1), **f32)
+            check(lib.nb_segno_backward(ctypes.byref(cfg), _ptr(flat), _ptr(seg_in[i]), _ptr(edge_attr), _ptr(seg_saved[i]),
+                                        _ptr(gx), _ptr(gh), _ptr(gv), _ptr(target), _ptr(gx_in), _ptr(gv_in), _ptr(gh_in),
+                                        _ptr(ws), st), "nb_segno_backward")
+            if i != S - 1:
+                check(lib.nb_accumulate(flat.numel(), _ptr(grad_flat), _ptr(tmp), st), "nb_accumulate")
+            if i > 0:     # the merge that produced this segment's input: observed frame i, integrated state of segment i - 1
+                ho, xo, vo = seg_out[i - 1]
+                gh, gx, gv = torch.empty((n, 64), **f32), torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
+                mws = torch.empty(lib.nb_segno_merge_backward_workspace_floats(n), **f32) if mode == 2 else None
+                check(lib.nb_segno_merge_backward(mode, n, L, i, _ptr(h_all), _ptr(x), _ptr(v), _ptr(ho), _ptr(xo), _ptr(vo),
+                                                  _ptr(attn_flat), _ptr(alphas[i - 1]), _ptr(gh_in), _ptr(gx_in), _ptr(gv_in),
+                                                  _ptr(g_h_all), _ptr(g_x_all), _ptr(g_v_all), _ptr(gh), _ptr(gx), _ptr(gv),
+                                                  _ptr(g_attn), 0 if i == S - 1 else 1, _ptr(mws), st), "nb_segno_merge_backward")
+            else:         # frame 0 was copied into the first segment
+                check(lib.nb_segno_merge_backward(0, n, L, 0, None, None, None, None, None, None, None, None, _ptr(gh_in),
+                                                  _ptr(gx_in), _ptr(gv_in), _ptr(g_h_all), _ptr(g_x_all), _ptr(g_v_all),
+                                                  None, None, None, None, 0, None, st), "nb_segno_merge_backward")
+        ews = torch.empty(lib.nb_segno_embed_backward_workspace_floats(ctypes.byref(cfgs[0]), n * L), **f32)
+        check(lib.nb_segno_embed_backward(ctypes.byref(cfgs[0]), n * L, _ptr(his), _ptr(g_h_all), _ptr(grad_flat), _ptr(ews), st),
+              "nb_segno_embed_backward")
+        _maybe_allreduce(grad_flat, ctx.dp_group)
+        if g_attn is not None and ctx.dp_group is not None:
+            _maybe_allreduce(g_attn, ctx.dp_group[:2])
+        grads, o = [], 0
+        for shp in ctx.param_shapes[:ctx.n_params]:
+            k = shp.numel()
+            grads.append(grad_flat[o:o + k].view(shp))
+            o += k
+        grads[-4:] = [None] * 4      # coord_mlp_vel never enters the computation (gcl.py:64-67)
+        o = 0
+        for shp in ctx.param_shapes[ctx.n_params:]:
+            k = shp.numel()
+            grads.append(g_attn[o:o + k].view(shp))
+            o += k
+        return (None, None, None, None, None, g_x_all, g_v_all, None, None, *grads)
+
+
 class _EdgeCache:
     """Validates `edge_index` against the canonical fully connected list once per distinct tensor OBJECT: the cache holds
     weak references to the validated row / col tensors and their `_version`s, so a new tensor that happens to reuse a

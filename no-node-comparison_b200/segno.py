@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .functional import SegnoFunction, _EdgeCache, _ParamPack, _require_cuda_f32, dp_param
+from .functional import SegnoFunction, SegnoMultiFunction, _EdgeCache, _ParamPack, _require_cuda_f32
 
 _HIDDEN = 64
 
@@ -32,7 +32,9 @@ class _GCLHolder(nn.Module):
 
 
 class InvariantTemporalAttention(nn.Module):
-    """model.py:127-139: softmax over the frames of an MLP on (|v|, h).  Per-node, two frames: plain torch."""
+    """model.py:127-139: softmax over the frames of an MLP on (|v|, h).  SEGNO.forward evaluates it (and its backward)
+    in the merge kernels (csrc/nb_merge.cuh) from the flat view of these parameters; this torch forward is the
+    reference's module interface, kept for callers that use the sub-module on its own."""
 
     def __init__(self, in_dim, hidden_dim=32):
         super().__init__()
@@ -74,6 +76,7 @@ class SEGNO(nn.Module):
         self.module.n_layers = n_layers
         self.to(self.device)
         self._pack = _ParamPack(self, skip_prefix="enc_attn_net")   # the C layout: embedding + module
+        self._attn_pack = None                                       # enc_attn_net's four tensors as one flat buffer
         self._edges = _EdgeCache()
         self.process_group = None
         self.peer_bucket = None
@@ -109,41 +112,54 @@ class SEGNO(nn.Module):
     def _forward_multi(self, his, x, edges, v, edge_attr, T, in_steps):
         """Several input frames (model.py:65-90): integrate from frame i to frame i+1 (`diff(in_steps)` sub-steps),
         merge the result with the observed frame ('sum': add; 'attn': invariant temporal attention over the pair,
-        model.py:105-139), and finally integrate T sub-steps from the last frame.  The integration segments are the
-        fused CUDA path; the embedding Linear and the (tiny, per-node) merges are ordinary torch ops.  Returns the
-        integrated state of the last segment (the intended semantics, see the module docstring)."""
+        model.py:105-139), and finally integrate T sub-steps from the last frame.  Embedding, integration segments and
+        merges are all C calls behind ONE autograd node (functional.SegnoMultiFunction): no torch compute kernel runs.
+        Returns the integrated state of the last segment (the intended semantics, see the module docstring)."""
         if in_steps is None or x.shape[1] < 2:
             raise ValueError("multi-input SEGNO needs x, v, his of shape [BN, n_inputs >= 2, .] and in_steps [n_inputs]")
         if self.multiple_agg is None:
             raise ValueError("multi-input SEGNO needs multiple_agg='sum' or 'attn' (main.py:110-114)")
-        steps = torch.diff(torch.as_tensor(in_steps).cpu()).tolist() + [T]
-        if len(steps) != x.shape[1]:
-            raise ValueError(f"in_steps has {len(steps)} entries for {x.shape[1]} input frames")
-        # Data parallel: every integration segment all-reduces its flat gradient bucket inside the C call's backward; the
-        # parameters multiplied on the torch side reduce their gradients through dp_param (one small all-reduce each).
-        dp = self.process_group
-        F = torch.nn.functional
-        h = F.linear(his, dp_param(self.embedding.weight, dp), dp_param(self.embedding.bias, dp))     # [BN, L, H]
+        steps = [int(t) for t in torch.diff(torch.as_tensor(in_steps).cpu()).tolist()] + [int(T)]
+        n0, L = x.shape[0], x.shape[1]
+        if len(steps) != L:
+            raise ValueError(f"in_steps has {len(steps)} entries for {L} input frames")
+        if min(steps) < 1:
+            raise ValueError(f"in_steps must increase strictly (sub-steps per segment: {steps})")
+        if edge_attr.requires_grad or his.requires_grad:
+            raise ValueError("gradients w.r.t. his / edge_attr are not implemented (the reference callers detach them)")
+        dev = x.device
+        x = _require_cuda_f32("x", x, (n0, L, 3))
+        v = _require_cuda_f32("v", v, (n0, L, 3))
+        his = _require_cuda_f32("his", his, (n0, L, self.in_node_nf))
+        E = edge_attr.shape[0]
+        if n0 == 0 or E % n0 != 0:
+            raise ValueError(f"{E} edges / {n0} nodes is not a batch of fully connected graphs")
+        N = E // n0 + 1
+        if n0 % N != 0:
+            raise ValueError(f"{n0} nodes do not divide into graphs of N={N}")
+        B = n0 // N
+        edge_attr = _require_cuda_f32("edge_attr", edge_attr, (E, self.in_edge_nf))
+        self._edges.validate(edges, B, N, dev)
+        self.module.n_layers = steps[-1]   # forward_step mutates these on every call (model.py:96-97)
+        self.n_layers = steps[-1]
+        from ._lib import load_library, check
+        from . import _cabi
+        import ctypes
+        cfg0 = _cabi.NbSegnoConfig(B, N, steps[0], self.in_node_nf, self.in_edge_nf, 1 if self.recurrent else 0,
+                                   float(self.coords_weight), 1)
+        expected = load_library().nb_segno_param_count(ctypes.byref(cfg0))
+        if expected < 0:
+            check(-1, "SEGNO configuration")
+        flat, params = self._pack.flat_params(expected, dev)
+        attn_flat, attn_params = None, []
         if self.multiple_agg == 'attn':
-            l0, l2 = self.enc_attn_net.attn_mlp[0], self.enc_attn_net.attn_mlp[2]
-            aw0, ab0, aw2, ab2 = (dp_param(t, dp) for t in (l0.weight, l0.bias, l2.weight, l2.bias))
-        h_, x_, v_ = h[:, 0, :], x[:, 0, :], v[:, 0, :]
-        out = None
-        for i, step in enumerate(steps):
-            xi, hi, vi = self._segment(h_.contiguous(), x_.contiguous(), edges, v_.contiguous(), edge_attr, int(step),
-                                       h_given=True)
-            out = (xi, hi, vi)
-            if i < len(steps) - 1:
-                if self.multiple_agg == 'sum':
-                    h_, x_, v_ = h[:, i + 1, :] + hi, x[:, i + 1, :] + xi, v[:, i + 1, :] + vi
-                else:
-                    hs = torch.stack([h[:, i + 1, :], hi], dim=1)
-                    xs = torch.stack([x[:, i + 1, :], xi], dim=1)
-                    vs = torch.stack([v[:, i + 1, :], vi], dim=1)
-                    feats = torch.cat([vs.norm(dim=-1, keepdim=True), hs], dim=-1)       # model.py:134-138
-                    attn = F.linear(torch.tanh(F.linear(feats, aw0, ab0)), aw2, ab2).softmax(dim=1)   # [BN, 2, 1]
-                    x_, v_, h_ = (attn * xs).sum(1), (attn * vs).sum(1), (attn * hs).sum(1)
-        return out
+            if self._attn_pack is None:
+                self._attn_pack = _ParamPack(self.enc_attn_net)
+            attn_flat, attn_params = self._attn_pack.flat_params(_HIDDEN * (_HIDDEN + 1) + 2 * _HIDDEN + 1, dev)
+        meta = (B, N, tuple(steps), self.in_node_nf, self.in_edge_nf, 1 if self.recurrent else 0, float(self.coords_weight),
+                2 if self.multiple_agg == 'attn' else 1)
+        return SegnoMultiFunction.apply(meta, self.process_group, flat, attn_flat, his, x, v, edge_attr, len(params),
+                                        *params, *attn_params)
 
     def _segment(self, his, x, edges, v, edge_attr, T, h_given):
         if edge_attr.requires_grad or (his.requires_grad and not h_given):

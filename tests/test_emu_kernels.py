@@ -246,3 +246,103 @@ def test_trajectory_mse_kernel_vs_oracle(T, R, layout, only_first):
     np.testing.assert_allclose(loss[0], loss_r.item(), rtol=2e-6)
     np.testing.assert_allclose(grad, pred.grad.numpy(), rtol=1e-6, atol=1e-9)
     assert L.nb_traj_mse(0, R, layout, 0, E.ptr(grad), E.ptr(grad), E.ptr(losses), E.ptr(loss), None, E.ptr(ws), None) < 0
+
+
+def _attn_params(g):
+    W0 = torch.randn(64, 65, generator=g) * 0.2
+    b0 = torch.randn(64, generator=g) * 0.1
+    w2 = torch.randn(64, generator=g) * 0.3
+    b2 = torch.randn(1, generator=g) * 0.1
+    return W0, b0, w2, b2
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_segno_merge_kernels_vs_torch(mode):
+    """nb_segno_merge_forward / _backward (multi-input SEGNO between its integration segments, model.py:82-90, 105-139:
+    copy of an observed frame, 'sum', InvariantTemporalAttention + prepare_node_inputs) against torch autograd of the
+    reference's formulas; the weight gradients are accumulated over two calls."""
+    L = E.lib()
+    g = torch.Generator().manual_seed(40 + mode)
+    n, nf, frame = 37, 3, 1
+    h_all = torch.randn(n, nf, 64, generator=g, requires_grad=True)
+    x_all = torch.randn(n, nf, 3, generator=g, requires_grad=True)
+    v_all = (torch.randn(n, nf, 3, generator=g) * 0.5).requires_grad_(True)
+    h_int = torch.randn(n, 64, generator=g, requires_grad=True)
+    x_int = torch.randn(n, 3, generator=g, requires_grad=True)
+    v_int = (torch.randn(n, 3, generator=g) * 0.5).requires_grad_(True)
+    W0, b0, w2, b2 = [t.requires_grad_(True) for t in _attn_params(g)]
+    Gh, Gx, Gv = torch.randn(n, 64, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    ho, xo, vo = h_all[:, frame], x_all[:, frame], v_all[:, frame]
+    if mode == 0:
+        h_r, x_r, v_r = ho, xo, vo
+    elif mode == 1:
+        h_r, x_r, v_r = ho + h_int, xo + x_int, vo + v_int
+    else:
+        hs, xs, vs = torch.stack([ho, h_int], 1), torch.stack([xo, x_int], 1), torch.stack([vo, v_int], 1)
+        feats = torch.cat([vs.norm(dim=-1, keepdim=True), hs], dim=-1)
+        attn = (torch.tanh(feats @ W0.T + b0) @ w2[:, None] + b2).softmax(dim=1)
+        x_r, v_r, h_r = (attn * xs).sum(1), (attn * vs).sum(1), (attn * hs).sum(1)
+    ((h_r * Gh).sum() + (x_r * Gx).sum() + (v_r * Gv).sum()).backward()
+    ap = E.f32(torch.cat([W0.detach().reshape(-1), b0.detach(), w2.detach(), b2.detach()]))
+    arr = lambda t: E.f32(t.detach())
+    h_out, x_out, v_out = np.zeros((n, 64), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    alpha = np.zeros((n, 2), np.float32)
+    intp = (None, None, None) if mode == 0 else (E.ptr(arr(h_int)), E.ptr(arr(x_int)), E.ptr(arr(v_int)))
+    E.check(L.nb_segno_merge_forward(mode, n, nf, frame, E.ptr(arr(h_all)), E.ptr(arr(x_all)), E.ptr(arr(v_all)), *intp,
+                                     E.ptr(ap) if mode == 2 else None, E.ptr(h_out), E.ptr(x_out), E.ptr(v_out),
+                                     E.ptr(alpha) if mode == 2 else None, None))
+    np.testing.assert_allclose(h_out, h_r.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(x_out, x_r.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(v_out, v_r.detach().numpy(), rtol=2e-5, atol=2e-6)
+    gha, gxa, gva = np.full((n, nf, 64), 7.0, np.float32), np.full((n, nf, 3), 7.0, np.float32), np.full((n, nf, 3), 7.0, np.float32)
+    ghi, gxi, gvi = np.zeros((n, 64), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    g_attn = np.zeros(64 * 65 + 129, np.float32)
+    ws = np.zeros(int(L.nb_segno_merge_backward_workspace_floats(n)), np.float32)
+    gint = (None, None, None) if mode == 0 else (E.ptr(ghi), E.ptr(gxi), E.ptr(gvi))
+    for acc in (0, 1):
+        E.check(L.nb_segno_merge_backward(mode, n, nf, frame, E.ptr(arr(h_all)), E.ptr(arr(x_all)), E.ptr(arr(v_all)), *intp,
+                                          E.ptr(ap) if mode == 2 else None, E.ptr(alpha) if mode == 2 else None, E.ptr(E.f32(Gh)),
+                                          E.ptr(E.f32(Gx)), E.ptr(E.f32(Gv)), E.ptr(gha), E.ptr(gxa), E.ptr(gva), *gint,
+                                          E.ptr(g_attn) if mode == 2 else None, acc, E.ptr(ws) if mode == 2 else None, None))
+    tol = dict(rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(gha[:, frame], h_all.grad[:, frame].numpy(), **tol)
+    np.testing.assert_allclose(gxa[:, frame], x_all.grad[:, frame].numpy(), **tol)
+    np.testing.assert_allclose(gva[:, frame], v_all.grad[:, frame].numpy(), **tol)
+    assert (gha[:, 0] == 7.0).all() and (gxa[:, 2] == 7.0).all()      # only the observed frame's slice is written
+    if mode > 0:
+        np.testing.assert_allclose(ghi, h_int.grad.numpy(), **tol)
+        np.testing.assert_allclose(gxi, x_int.grad.numpy(), **tol)
+        np.testing.assert_allclose(gvi, v_int.grad.numpy(), **tol)
+    if mode == 2:
+        ref = torch.cat([W0.grad.reshape(-1), b0.grad, w2.grad, b2.grad]).numpy() * 2.0    # written, then accumulated
+        np.testing.assert_allclose(g_attn[:-1], ref[:-1], rtol=2e-4, atol=2e-5)
+        assert abs(g_attn[-1]) < 1e-4      # softmax is shift invariant: dL/db2 = 0 up to rounding
+
+
+def test_segno_embedding_of_all_frames_and_accumulate_kernels():
+    """nb_segno_embed_forward / _backward over the rows of every observed frame (model.py:73) and nb_accumulate."""
+    L = E.lib()
+    g = torch.Generator().manual_seed(3)
+    rows, F = 150, 1
+    cfg = E.cabi.NbSegnoConfig(5, 5, 4, F, 2, 1, 1.0, 1)
+    import ctypes
+    total = int(L.nb_segno_param_count(ctypes.byref(cfg)))
+    params = E.f32(torch.randn(total, generator=g) * 0.3)
+    his = torch.randn(rows, F, generator=g)
+    W, b = torch.tensor(params[:64 * F]).view(64, F).requires_grad_(True), torch.tensor(params[64 * F:64 * F + 64]).requires_grad_(True)
+    ref = his @ W.T + b
+    Gh = torch.randn(rows, 64, generator=g)
+    (ref * Gh).sum().backward()
+    h = np.zeros((rows, 64), np.float32)
+    E.check(L.nb_segno_embed_forward(ctypes.byref(cfg), E.ptr(params), rows, E.ptr(E.f32(his)), E.ptr(h), None))
+    np.testing.assert_allclose(h, ref.detach().numpy(), rtol=1e-6, atol=1e-6)
+    gp = np.full(total, 3.0, np.float32)
+    ws = np.zeros(int(L.nb_segno_embed_backward_workspace_floats(ctypes.byref(cfg), rows)), np.float32)
+    E.check(L.nb_segno_embed_backward(ctypes.byref(cfg), rows, E.ptr(E.f32(his)), E.ptr(E.f32(Gh)), E.ptr(gp), E.ptr(ws), None))
+    np.testing.assert_allclose(gp[:64 * F], W.grad.reshape(-1).numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(gp[64 * F:64 * F + 64], b.grad.numpy(), rtol=2e-5, atol=2e-5)
+    assert (gp[64 * F + 64:] == 3.0).all()      # only the embedding entries are written
+    a, c = E.f32(torch.randn(1000, generator=g)), E.f32(torch.randn(1000, generator=g))
+    want = a + c
+    E.check(L.nb_accumulate(1000, E.ptr(a), E.ptr(c), None))
+    np.testing.assert_array_equal(a, want)

@@ -563,8 +563,8 @@ def test_flat_adam_matches_torch_adam_and_skips_inert_parameters():
 
 @pytest.mark.parametrize("name", SEGNO_MULTI_CASES)
 def test_segno_multi_input_matches_reference_golden(name):
-    """Several input frames (model.py:65-90): CUDA integration segments (hidden state handed in, dL/dh handed back)
-    composed with the torch-side embedding and 'sum' / attention merges, against golden vectors of the reference."""
+    """Several input frames (model.py:65-90): embedding of every observed frame, CUDA integration segments and the
+    'sum' / attention merges between them (one autograd node, C calls only), against golden vectors of the reference."""
     dd, w, g = load_case(name)
     c = segno_multi_inputs_from_case(dd)
     d = dev()
@@ -588,6 +588,42 @@ def test_segno_multi_input_matches_reference_golden(name):
             continue
         got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g[k])
         assert rel_err(got, g[k]) < TOL_GRAD, k
+
+
+@pytest.mark.parametrize("name", SEGNO_MULTI_CASES)
+def test_segno_multi_input_launches_only_this_librarys_kernels(name):
+    """the multi-input SEGNO forward + backward (embedding, segments, merges, gradient sums) must not
+    run a single torch compute kernel — every kernel in the profiler's list is one of this library's (`k_*`)."""
+    from torch.profiler import ProfilerActivity, profile
+    dd, w, g = load_case(name)
+    c = segno_multi_inputs_from_case(dd)
+    d = dev()
+    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True, multiple_agg=c["agg"])
+    m.load_state_dict(w)
+    his, ea = c["his"].to(d), c["edge_attr"].to(d)
+    G = [torch.tensor(dd[k], device=d) for k in ("Gx", "Gh", "Gv")]
+
+    def run():
+        x, v = c["x"].to(d).requires_grad_(True), c["v"].to(d).requires_grad_(True)
+        torch.cuda.synchronize()
+        return x, v
+
+    x, v = run()
+    out = m(his, x, [c["row"], c["col"]], v, ea, T=c["T"], in_steps=c["in_steps"])      # warm-up: flat views, edge check
+    torch.autograd.backward(out, G)
+    m.zero_grad(set_to_none=True)      # otherwise autograd would ADD the second gradient onto the first (a torch kernel)
+    x, v = run()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        out = m(his, x, [c["row"], c["col"]], v, ea, T=c["T"], in_steps=c["in_steps"])
+        torch.autograd.backward(out, G)
+        torch.cuda.synchronize()
+    names = [e.name for e in prof.events() if getattr(e, "device_type", None) == torch.autograd.DeviceType.CUDA]
+    kernels = [n for n in names if not n.lower().startswith(("memcpy", "memset"))]
+    if not kernels:
+        pytest.skip("the profiler recorded no device activity on this box")
+    foreign = [n for n in kernels if not (n.startswith("k_") or n.startswith("void k_"))]
+    assert not foreign, foreign
+    assert any("k_segno_merge_fwd" in n for n in kernels) and any("k_segno_merge_bwd" in n for n in kernels)
 
 
 @pytest.mark.parametrize("B,N,T,nin", [(4, 20, 10, 2), (2, 37, 6, 3)])
