@@ -447,4 +447,182 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_segno_fused_fwd(NbSegnoFus
   __syncthreads();
   if (warp == 0) nb_tmem_dealloc(tm, NB_FS_TMEM_COLS);
 }
+
+// ----------------------------------------------------------------------------- node-level backward between two edge sweeps
+// SEGNO's backward walks the T sub-steps in reverse; between the edge-tile backward of sub-step k and that of sub-step
+// k - 1 the node-level chain is (gcl.py:78-94 backwards; all products are data gradients, g_in = g_out W):
+//   gh      = gh_k + gP_k W1[:, h_row] + gQ_k W1[:, h_col]          dL/dh entering sub-step k - 1 (edge_mlp.0's h halves)
+//   GU5     = (gh W6) * SiLU'(U5_{k-1})                              node_mlp.2 backwards, through the activation
+//   gh_{k-1} = GU5 W5[:, :64] (+ gh: residual) ;  gM = GU5 W5[:, 64:]  node_mlp.0 backwards: the h and the M halves
+// followed by the integrator's backward (k_segno_integ_bwd).  These were four launches on the critical path of every
+// sub-step (three k_gemm64_tc launches of 40 tiles each + the integrator); here they are ONE: a CTA owns a 128-row tile,
+// stages the five pre-split weight images once (80 KB), and chains the three products through tensor memory — each
+// result is split in registers and written back as the A operand of the next product, so nothing but the tensors the
+// weight-gradient reduction needs later (gh, GU5) and the edge kernel's inputs (gM) goes to HBM.
+// TMEM: [0,64) D1 | [64,128) D3 (h half) | [128,192) D3 (M half) | [192,256) A0 hi|lo | [256,320) A1 hi|lo.
+struct NbSegnoNodeBwdArgs {
+  int rows, recurrent;
+  const unsigned char* img;   // 5 images, 16 KB each: W1 h_row | W1 h_col | W5 h half | W5 M half | W6  (segno_weight_images)
+  const float *gP, *gQ;       // [rows][64], sub-step k
+  float* gh_k;                // in: gh_k (partial) ; out: gh (total)
+  const float* U5;            // [rows][64] pre-activations of sub-step k - 1
+  float *GU5, *gh_km1, *gM;   // out, sub-step k - 1
+  // integrator backward of sub-step k - 1 (gcl.py:101-102,116-117)
+  int64_t n3;
+  int N;
+  float inv_T, cw;
+  const float *gx, *gv;
+  float *gv_out, *gFsum;
+};
+#define NB_SNB_SMEM (5 * 2 * NB_TC_TILE_BYTES(64) + 64 + 1024)
+
+__device__ __forceinline__ void nb_snb_load32(const float* p, bool live, float (&v)[32]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 t = live ? nb_ld4(p + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void nb_snb_store32(float* p, bool live, const float (&v)[32]) {
+  if (!live) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) nb_st4(p + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+}
+
+__global__ void __launch_bounds__(NB_THREADS, 1) k_segno_node_bwd(NbSegnoNodeBwdArgs a) {
+  NB_PDL_ENTER();
+  extern __shared__ __align__(1024) unsigned char nb_smraw[];
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 5 * 2 * NB_TC_TILE_BYTES(64));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int row = 32 * q + lane, cb = 32 * hf;
+  const int ntiles = (a.rows + NB_TILE - 1) / NB_TILE;
+  // the first tile's rows are requested before anything else, the 80 KB of weight images in batches of ten independent
+  // 16-byte loads per thread: the kernel is a latency chain, so every load that can be in flight early is
+  float v[32], r[32], u[32];
+  {
+    const int64_t gr0 = (int64_t)blockIdx.x * NB_TILE + row;
+    const bool live0 = (int)blockIdx.x < ntiles && gr0 < a.rows;
+    nb_snb_load32(a.gP + gr0 * NB_H + cb, live0, v);
+    nb_snb_load32(a.gQ + gr0 * NB_H + cb, live0, u);
+    nb_snb_load32(a.gh_k + gr0 * NB_H + cb, live0, r);
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.img);
+    uint4* dst = reinterpret_cast<uint4*>(base);
+    constexpr int NCOPY = 5 * 2 * (int)NB_TC_TILE_BYTES(64) / 16 / NB_THREADS;   // 20 per thread
+    static_assert(NCOPY == 20, "weight-image copy is unrolled for 20 chunks per thread");
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint4 t[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) t[i] = __ldg(src + tid + (half * 10 + i) * NB_THREADS);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) dst[tid + (half * 10 + i) * NB_THREADS] = t[i];
+    }
+  }
+  if (tid == 0) {
+    nb_mbar_init(bar, 1);
+    nb_mbar_fence_init();
+  }
+  if (warp == 0) nb_tmem_alloc(tmem_slot, 512);
+  {  // integrator backward: independent element-wise work, issued while the weight copies are in flight
+    const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
+    for (int64_t i = (int64_t)blockIdx.x * NB_THREADS + tid; i < a.n3; i += (int64_t)gridDim.x * NB_THREADS) {
+      const float gxi = a.gx ? a.gx[i] : 0.f;
+      const float gvt = (a.gv ? a.gv[i] : 0.f) + gxi * a.inv_T;
+      a.gv_out[i] = gvt;
+      a.gFsum[i] = gvt * a.inv_T * a.cw / cnt;
+    }
+  }
+  nb_fence_async_smem();
+  nb_tc_fence_before();
+  __syncthreads();
+  nb_tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+  const uint32_t d1 = tm + lane_base + (uint32_t)cb;
+  const uint32_t a0h = tm + 192, a0l = tm + 224, a1h = tm + 256, a1l = tm + 288;
+  const uint32_t mine = lane_base + 16u * (uint32_t)hf;
+  const uint32_t idesc_mn = nb_idesc_bf16(128, 64, 0, 1);
+  const uint32_t sW = nb_smem_u32(base);
+#define NB_SNB_WH(i) (sW + (uint32_t)(i) * 2u * (uint32_t)NB_TC_TILE_BYTES(64))
+#define NB_SNB_WL(i) (NB_SNB_WH(i) + (uint32_t)NB_TC_TILE_BYTES(64))
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t gr = (int64_t)tile * NB_TILE + row;
+    const bool live = gr < a.rows;
+    const int64_t off = gr * NB_H + cb;
+    if (tile != (int)blockIdx.x) {   // (the first tile's rows are already in registers)
+      nb_snb_load32(a.gP + off, live, v);
+      nb_snb_load32(a.gQ + off, live, u);
+      nb_snb_load32(a.gh_k + off, live, r);
+    }
+    nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
+    nb_store32_ta(nullptr, nullptr, row, hf, u, a1h + mine, a1l + mine);
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();
+    if (NB_ISSUER(0)) {
+      nb_tc_fence_after();
+      nb_issue_w3_ta(tm, a0h, a0l, NB_SNB_WH(0), NB_SNB_WL(0), true, idesc_mn, 0u);
+      nb_issue_w3_ta(tm, a1h, a1l, NB_SNB_WH(1), NB_SNB_WL(1), true, idesc_mn, 1u);
+      nb_mma_commit(bar);
+    }
+    nb_snb_load32(a.U5 + off, live, u);   // requested under the MMAs
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    // ---- gh = gh_k + gP W1r + gQ W1c
+    nb_tmem_ld32(d1, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] += v[i];
+    nb_snb_store32(a.gh_k + off, live, r);
+    nb_store32_ta(nullptr, nullptr, row, hf, r, a0h + mine, a0l + mine);
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();
+    if (NB_ISSUER(0)) {
+      nb_tc_fence_after();
+      nb_issue_w3_ta(tm, a0h, a0l, NB_SNB_WH(4), NB_SNB_WL(4), true, idesc_mn, 0u);
+      nb_mma_commit(bar);
+    }
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    // ---- GU5 = (gh W6) * SiLU'(U5)
+    nb_tmem_ld32(d1, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = live ? v[i] * nb_dsilu(u[i]) : 0.f;
+    nb_snb_store32(a.GU5 + off, live, v);
+    nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();
+    if (NB_ISSUER(0)) {
+      nb_tc_fence_after();
+      nb_issue_w3_ta(tm + 64, a0h, a0l, NB_SNB_WH(2), NB_SNB_WL(2), true, idesc_mn, 0u);
+      nb_issue_w3_ta(tm + 128, a0h, a0l, NB_SNB_WH(3), NB_SNB_WL(3), true, idesc_mn, 0u);
+      nb_mma_commit(bar);
+    }
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    // ---- gh_{k-1} = GU5 W5a (+ gh) ; gM = GU5 W5b
+    nb_tmem_ld32(d1 + 64, v);
+    if (a.recurrent) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += r[i];
+    }
+    nb_snb_store32(a.gh_km1 + off, live, v);
+    nb_tmem_ld32(d1 + 128, v);
+    nb_snb_store32(a.gM + off, live, v);
+    nb_tc_fence_before();
+  }
+  nb_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nb_tmem_dealloc(tm, 512);
+}
 #endif  // NB_EMU

@@ -1688,12 +1688,25 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   ed.ldw1 = lo.E; ed.col_rad = 2 * NB_H; ed.col_ef = 2 * NB_H + 1; ed.b_unused = 0;
   float* run_base = nullptr;   // the edge kernels' per-CTA partial slices of consecutive sub-steps are contiguous:
   int run_parts = 0;           // one reduction over all of them after the sweep
+  // The node-level chain between the edge sweeps of sub-steps k and k - 1 (edge layer 1's h halves backwards, node_mlp
+  // backwards, integrator backwards) is ONE launch (k_segno_node_bwd) when the tcgen05 node kernels and their weight images
+  // are in use; the first sub-step of the sweep (k = T - 1) and the tail (k = 0) keep the separate launches.
+  bool chain = false;
+#ifndef NB_EMU
+  {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("NB_B200_SEGNO_CHAIN"); off = (e && e[0] == '0') ? 1 : 0; }
+    chain = !off && g_node_impl == 1 && g_wimg.n == SEGNO_WIMG;
+  }
+#endif
+  bool head_done = false;   // the node_mlp / integrator backward of sub-step k already ran (inside the chain launch)
   for (int k = T - 1; k >= 0; --k) {
     SegnoIterBufs b = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)k * itf, Nn);
     float* gh_new = gh_all + (int64_t)k * nh;
     float* GU5 = GU5_all + (int64_t)k * nh;
     float* gP = gP_all + (int64_t)k * nh;
     float* gQ = gQ_all + (int64_t)k * nh;
+    if (!head_done) {
     // node_mlp backward
     NbGemmArgs a = gemm_args((int)Nn);  // GU5 = (gh W6) * SiLU'(U5)
     a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + lo.n_w2, NB_H, 1);
@@ -1717,6 +1730,8 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     NB_TRY(nb_check_launch("k_segno_integ_bwd"));
     gv_in = gvb[gvi];
     gvi ^= 1;
+    }
+    head_done = false;
     // edge tile backward
     NbEdgeBwdArgs ea;
     memset(&ea, 0, sizeof(ea));
@@ -1724,6 +1739,28 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     ea.w = segno_edge_w(X);
     ea.x = b.x; ea.P = P_all + (int64_t)k * nh; ea.Q = Q_all + (int64_t)k * nh; ea.ef = edge_attr; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
     NB_TRY(launch_edge_bwd(ea, grad_params, ed, 1, stream, &run_base, &run_parts));
+#ifndef NB_EMU
+    if (chain && k > 0) {
+      const SegnoIterBufs bm = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)(k - 1) * itf, Nn);
+      NbSegnoNodeBwdArgs na;
+      memset(&na, 0, sizeof(na));
+      na.rows = (int)Nn; na.recurrent = cfg->recurrent; na.img = g_wimg.img[0];
+      na.gP = gP; na.gQ = gQ; na.gh_k = gh_new; na.U5 = bm.U5;
+      na.GU5 = GU5_all + (int64_t)(k - 1) * nh; na.gh_km1 = gh_all + (int64_t)(k - 1) * nh; na.gM = gM;
+      na.n3 = Nn * 3; na.N = cfg->N; na.inv_T = (float)(1.0 / (double)T); na.cw = cfg->coords_weight;
+      na.gx = gx; na.gv = gv_in; na.gv_out = gvb[gvi]; na.gFsum = gFsum;
+      NB_SET_SMEM(k_segno_node_bwd, NB_SNB_SMEM);
+      int pi = prof_begin(2, stream);
+      NB_LAUNCH_COUNTED(k_segno_node_bwd, (unsigned)imin(cdiv(Nn, NB_TILE), nb_num_sms()), NB_THREADS, NB_SNB_SMEM, stream, na);
+      prof_end(2, pi, stream);
+      NB_TRY(nb_check_launch("k_segno_node_bwd"));
+      gv_in = gvb[gvi];
+      gvi ^= 1;
+      gh_in = gh_new;
+      head_done = true;
+      continue;
+    }
+#endif
     NbGemmArgs pa = gemm_args((int)Nn);  // gh += gP W1[:, h_row] + gQ W1[:, h_col]
     pa.nsrc = 2;
     pa.src[0] = gsrc(gP, NB_H, 0, params + lo.e_w1, lo.E, 1);
