@@ -463,8 +463,9 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_segno_fused_fwd(NbSegnoFus
 struct NbSegnoNodeBwdArgs {
   int rows, recurrent;
   const unsigned char* img;   // 5 images, 16 KB each: W1 h_row | W1 h_col | W5 h half | W5 M half | W6  (segno_weight_images)
-  const float *gP, *gQ;       // [rows][64], sub-step k
+  const float *gP, *gQ;       // [rows][64], sub-step k  (unused by the HEAD instantiation: gh = gh_in as it is)
   float* gh_k;                // in: gh_k (partial) ; out: gh (total)
+  const float* gh_in;         // HEAD only: dL/dh of the call's output (read-only; null = zero)
   const float* U5;            // [rows][64] pre-activations of sub-step k - 1
   float *GU5, *gh_km1, *gM;   // out, sub-step k - 1
   // integrator backward of sub-step k - 1 (gcl.py:101-102,116-117)
@@ -489,6 +490,8 @@ __device__ __forceinline__ void nb_snb_store32(float* p, bool live, const float 
   for (int k = 0; k < 8; ++k) nb_st4(p + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
 }
 
+// HEAD: the first sub-step of the sweep — no edge gradients yet, gh = gh_in as it is (the first product is skipped)
+template <bool HEAD>
 __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_node_bwd(NbSegnoNodeBwdArgs a) {
   NB_PDL_ENTER();
   extern __shared__ __align__(1024) unsigned char nb_smraw[];
@@ -505,9 +508,13 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_node_bwd(NbSegnoNodeBwd
   {
     const int64_t gr0 = (int64_t)blockIdx.x * NB_TILE + row;
     const bool live0 = (int)blockIdx.x < ntiles && gr0 < a.rows;
-    nb_snb_load32(a.gP + gr0 * NB_H + cb, live0, v);
-    nb_snb_load32(a.gQ + gr0 * NB_H + cb, live0, u);
-    nb_snb_load32(a.gh_k + gr0 * NB_H + cb, live0, r);
+    if (!HEAD) {
+      nb_snb_load32(a.gP + gr0 * NB_H + cb, live0, v);
+      nb_snb_load32(a.gQ + gr0 * NB_H + cb, live0, u);
+      nb_snb_load32(a.gh_k + gr0 * NB_H + cb, live0, r);
+    } else {
+      nb_snb_load32(a.gh_in + gr0 * NB_H + cb, live0 && a.gh_in, r);
+    }
   }
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.img);
@@ -556,30 +563,38 @@ __global__ void __launch_bounds__(NB_THREADS, 1) k_segno_node_bwd(NbSegnoNodeBwd
     const bool live = gr < a.rows;
     const int64_t off = gr * NB_H + cb;
     if (tile != (int)blockIdx.x) {   // (the first tile's rows are already in registers)
-      nb_snb_load32(a.gP + off, live, v);
-      nb_snb_load32(a.gQ + off, live, u);
-      nb_snb_load32(a.gh_k + off, live, r);
+      if (!HEAD) {
+        nb_snb_load32(a.gP + off, live, v);
+        nb_snb_load32(a.gQ + off, live, u);
+        nb_snb_load32(a.gh_k + off, live, r);
+      } else {
+        nb_snb_load32(a.gh_in + off, live && a.gh_in, r);
+      }
     }
-    nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
-    nb_store32_ta(nullptr, nullptr, row, hf, u, a1h + mine, a1l + mine);
-    nb_tmem_st_wait();
-    nb_tc_fence_before();
-    __syncthreads();
-    if (NB_ISSUER(0)) {
+    if (!HEAD) {
+      nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
+      nb_store32_ta(nullptr, nullptr, row, hf, u, a1h + mine, a1l + mine);
+      nb_tmem_st_wait();
+      nb_tc_fence_before();
+      __syncthreads();
+      if (NB_ISSUER(0)) {
+        nb_tc_fence_after();
+        nb_issue_w3_ta(tm, a0h, a0l, NB_SNB_WH(0), NB_SNB_WL(0), true, idesc_mn, 0u);
+        nb_issue_w3_ta(tm, a1h, a1l, NB_SNB_WH(1), NB_SNB_WL(1), true, idesc_mn, 1u);
+        nb_mma_commit(bar);
+      }
+      nb_snb_load32(a.U5 + off, live, u);   // requested under the MMAs
+      nb_mbar_wait(bar, phase);
+      phase ^= 1;
       nb_tc_fence_after();
-      nb_issue_w3_ta(tm, a0h, a0l, NB_SNB_WH(0), NB_SNB_WL(0), true, idesc_mn, 0u);
-      nb_issue_w3_ta(tm, a1h, a1l, NB_SNB_WH(1), NB_SNB_WL(1), true, idesc_mn, 1u);
-      nb_mma_commit(bar);
-    }
-    nb_snb_load32(a.U5 + off, live, u);   // requested under the MMAs
-    nb_mbar_wait(bar, phase);
-    phase ^= 1;
-    nb_tc_fence_after();
-    // ---- gh = gh_k + gP W1r + gQ W1c
-    nb_tmem_ld32(d1, v);
+      // ---- gh = gh_k + gP W1r + gQ W1c
+      nb_tmem_ld32(d1, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] += v[i];
-    nb_snb_store32(a.gh_k + off, live, r);
+      for (int i = 0; i < 32; ++i) r[i] += v[i];
+      nb_snb_store32(a.gh_k + off, live, r);
+    } else {
+      nb_snb_load32(a.U5 + off, live, u);
+    }
     nb_store32_ta(nullptr, nullptr, row, hf, r, a0h + mine, a0l + mine);
     nb_tmem_st_wait();
     nb_tc_fence_before();

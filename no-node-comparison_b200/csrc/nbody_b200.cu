@@ -249,8 +249,9 @@ extern "C" int nb_set_node_impl(int impl) {
 }
 extern "C" int nb_get_node_impl(void) { return g_node_impl; }
 
-// SEGNO forward: 1 = all T sub-steps in one kernel with the node state resident in shared memory (nb_segno_fused.cuh;
-// needs the tcgen05 variants and N <= 27), 0 = one kernel sequence per sub-step
+// SEGNO: 1 = forward with all T sub-steps in one kernel, the node state resident in shared memory (nb_segno_fused.cuh;
+// needs the tcgen05 variants and N <= 27), and backward with the node-level chain between two edge sweeps as one kernel
+// (k_segno_node_bwd); 0 = one kernel sequence per sub-step in both directions (the cross-check)
 #ifdef NB_EMU
 static int g_segno_fused = 0;
 #else
@@ -1696,7 +1697,7 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   {
     static int off = -1;
     if (off < 0) { const char* e = getenv("NB_B200_SEGNO_CHAIN"); off = (e && e[0] == '0') ? 1 : 0; }
-    chain = !off && g_node_impl == 1 && g_wimg.n == SEGNO_WIMG;
+    chain = !off && g_segno_fused && g_node_impl == 1 && g_wimg.n == SEGNO_WIMG;   // nb_set_segno_fused(0): stepwise both ways
   }
 #endif
   bool head_done = false;   // the node_mlp / integrator backward of sub-step k already ran (inside the chain launch)
@@ -1706,6 +1707,25 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     float* GU5 = GU5_all + (int64_t)k * nh;
     float* gP = gP_all + (int64_t)k * nh;
     float* gQ = gQ_all + (int64_t)k * nh;
+#ifndef NB_EMU
+    if (!head_done && chain) {   // first sub-step of the sweep: the chain without its first product
+      NbSegnoNodeBwdArgs na;
+      memset(&na, 0, sizeof(na));
+      na.rows = (int)Nn; na.recurrent = cfg->recurrent; na.img = g_wimg.img[0];
+      na.gh_in = g_h_out; na.U5 = b.U5;      // g_h_out == null: dL/dh_out = 0
+      na.GU5 = GU5; na.gh_km1 = gh_new; na.gM = gM;
+      na.n3 = Nn * 3; na.N = cfg->N; na.inv_T = (float)(1.0 / (double)T); na.cw = cfg->coords_weight;
+      na.gx = gx; na.gv = gv_in; na.gv_out = gvb[gvi]; na.gFsum = gFsum;
+      NB_SET_SMEM(k_segno_node_bwd<true>, NB_SNB_SMEM);
+      int pi = prof_begin(2, stream);
+      NB_LAUNCH_COUNTED(k_segno_node_bwd<true>, (unsigned)imin(cdiv(Nn, NB_TILE), nb_num_sms()), NB_THREADS, NB_SNB_SMEM, stream, na);
+      prof_end(2, pi, stream);
+      NB_TRY(nb_check_launch("k_segno_node_bwd"));
+      gv_in = gvb[gvi];
+      gvi ^= 1;
+      head_done = true;
+    }
+#endif
     if (!head_done) {
     // node_mlp backward
     NbGemmArgs a = gemm_args((int)Nn);  // GU5 = (gh W6) * SiLU'(U5)
@@ -1749,9 +1769,9 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
       na.GU5 = GU5_all + (int64_t)(k - 1) * nh; na.gh_km1 = gh_all + (int64_t)(k - 1) * nh; na.gM = gM;
       na.n3 = Nn * 3; na.N = cfg->N; na.inv_T = (float)(1.0 / (double)T); na.cw = cfg->coords_weight;
       na.gx = gx; na.gv = gv_in; na.gv_out = gvb[gvi]; na.gFsum = gFsum;
-      NB_SET_SMEM(k_segno_node_bwd, NB_SNB_SMEM);
+      NB_SET_SMEM(k_segno_node_bwd<false>, NB_SNB_SMEM);
       int pi = prof_begin(2, stream);
-      NB_LAUNCH_COUNTED(k_segno_node_bwd, (unsigned)imin(cdiv(Nn, NB_TILE), nb_num_sms()), NB_THREADS, NB_SNB_SMEM, stream, na);
+      NB_LAUNCH_COUNTED(k_segno_node_bwd<false>, (unsigned)imin(cdiv(Nn, NB_TILE), nb_num_sms()), NB_THREADS, NB_SNB_SMEM, stream, na);
       prof_end(2, pi, stream);
       NB_TRY(nb_check_launch("k_segno_node_bwd"));
       gv_in = gvb[gvi];

@@ -414,32 +414,39 @@ def test_kernel_variants_agree_on_golden_case(edge_impl, node_impl):
 
 
 def test_segno_fused_forward_matches_stepwise_kernels():
-    """The fused T-sub-step SEGNO forward (node state resident in shared memory, nb_segno_fused.cuh) against the
-    one-kernel-sequence-per-sub-step path, at BASELINE.json configs[3] shape: outputs, and gradients through the
-    backward that consumes the state each of them saved."""
+    """The fused T-sub-step SEGNO forward (node state resident in shared memory, nb_segno_fused.cuh) and the backward
+    whose node-level chain between two edge sweeps is one kernel (k_segno_node_bwd) against the
+    one-kernel-sequence-per-sub-step path in both directions, at BASELINE.json configs[3] shape: outputs, input and
+    parameter gradients; recurrent and non-recurrent node updates."""
     lib = nb.load_library()
     d = dev()
     B, N, T = 64, 20, 10
     s = synth.sample_state("gravity", B, N, seed=5)
     row, col = synth.canonical_edges(B, N)
     his, x, v, ea = synth.segno_features(s["loc"], s["vel"], s["charges"], row, col)
-    torch.manual_seed(3)
-    m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=True)
-    out = {}
-    for fused in (1, 0):
-        assert lib.nb_set_segno_fused(fused) == 0
-        try:
-            m.zero_grad(set_to_none=True)
-            xg = x.to(d).requires_grad_(True)
-            xo, ho, vo = m(his.to(d), xg, [row, col], v.to(d), ea.to(d), T=T)
-            (xo.square().sum() + 0.1 * ho.sum() + vo.square().sum()).backward()
-            out[fused] = [xo.detach().cpu(), ho.detach().cpu(), vo.detach().cpu(), xg.grad.cpu()] + \
-                [p.grad.cpu().clone() for p in m.parameters() if p.grad is not None]
-        finally:
-            lib.nb_set_segno_fused(1)
-    assert lib.nb_get_segno_fused() == 1
-    for a, b in zip(out[1], out[0]):
-        assert rel_err(a, b) < 2e-5
+    for recurrent in (True, False):
+        torch.manual_seed(3)
+        m = nb.SEGNO(in_node_nf=1, in_edge_nf=2, hidden_nf=64, device=d, n_layers=8, recurrent=recurrent)
+        out = {}
+        for fused in (1, 0):
+            assert lib.nb_set_segno_fused(fused) == 0
+            try:
+                m.zero_grad(set_to_none=True)
+                xg = x.to(d).requires_grad_(True)
+                vg = v.to(d).requires_grad_(True)
+                n0 = lib.nb_launch_count()
+                xo, ho, vo = m(his.to(d), xg, [row, col], vg, ea.to(d), T=T)
+                (xo.square().sum() + 0.1 * ho.sum() + vo.square().sum()).backward()
+                launches = lib.nb_launch_count() - n0
+                out[fused] = [xo.detach().cpu(), ho.detach().cpu(), vo.detach().cpu(), xg.grad.cpu(), vg.grad.cpu()] + \
+                    [p.grad.cpu().clone() for p in m.parameters() if p.grad is not None]
+                out[fused, "launches"] = launches
+            finally:
+                lib.nb_set_segno_fused(1)
+        assert lib.nb_get_segno_fused() == 1
+        assert out[1, "launches"] < out[0, "launches"] - 4 * (T - 1)   # T - 1 chain launches replace 4 (T - 1) + the fused forward
+        for a, b in zip(out[1], out[0]):
+            assert rel_err(a, b) < 2e-5
 
 
 def test_cuda_graph_training_step_matches_eager():
