@@ -1,0 +1,185 @@
+// nb_egno_node.cuh — EGNO's node-level work after an edge sweep as ONE kernel per layer (forward).
+//
+// Reference: EGNN_Layer.forward after the aggregation (EGNO/model/basic.py:172-185):
+//   U5 = [h, M] W5^T + b5 ; h' = SiLU(U5) W6^T + b6                      node_net     (basic.py:183-185)
+//   UV = h Wv1^T + bv1    ; s  = w_v2 . SiLU(UV) + b_v2                   node_v_net   (basic.py:172-176)
+//   x' = x + s v + clamp(Fsum / (N - 1), +-100)                                         (basic.py:177-178)
+// These were three launches per layer (a two-job k_gemm64_tc batch, a second k_gemm64_tc, k_egno_xupd_fwd), each of
+// which streams a 13 MB node tensor through HBM again.  Here a CTA owns a 128-row tile: h and M rows are split in
+// registers and written to tensor memory as the A operands (no shared-memory copy of activations), the four weight
+// blocks come from the call's pre-split images (64 KB, staged once per CTA), SiLU(U5) goes back into tensor memory as
+// the A operand of the second product, and the 64 -> 1 head of node_v_net is a per-row dot finished through shared
+// memory.  HBM: reads h, M, x, v, Fsum once; writes U5, UV (kept for the backward), h', x' once.
+// Two CTAs per SM (66 KB of shared memory, 256 of 512 TMEM columns each): [0,64) D1 (U5, then h') | [64,128) D2 (UV) |
+// [128,192) A0 hi|lo (h, then SiLU(U5)) | [192,256) A1 hi|lo (M).
+#pragma once
+#ifndef NB_EMU
+#include "nb_edge_sel.cuh"
+
+struct NbEgnoNodeFwdArgs {
+  int rows, N;
+  const unsigned char* img;   // 4 images, 16 KB each: W5 h half | W5 M half | W6 | Wv1   (egno_weight_images, slots 2..5)
+  const float *h, *M;         // [rows][64]
+  const float *b5, *b6, *bv1, *wv2, *bv2;
+  const float *x, *v, *Fsum;  // [rows][3]
+  float *U5, *UV;             // [rows][64] pre-activations (the backward's saved state)
+  float *h_out, *x_out;
+};
+#define NB_ENF_W_BYTES (4 * 2 * NB_TC_TILE_BYTES(64))
+#define NB_ENF_SMEM (NB_ENF_W_BYTES + (4 * NB_H + 2 * NB_TILE) * 4 + 64 + 1024)
+
+__device__ __forceinline__ void nb_enf_load32(const float* p, bool live, float (&v)[32]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 t = live ? nb_ld4(p + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void nb_enf_store32(float* p, bool live, const float (&v)[32]) {
+  if (!live) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) nb_st4(p + 4 * k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+}
+
+__global__ void __launch_bounds__(NB_THREADS, 2) k_egno_node_fwd(NbEgnoNodeFwdArgs a) {
+  NB_PDL_ENTER();
+  extern __shared__ __align__(1024) unsigned char nb_smraw[];
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
+  float* sb5 = reinterpret_cast<float*>(base + NB_ENF_W_BYTES);
+  float* sb6 = sb5 + NB_H;
+  float* sbv1 = sb6 + NB_H;
+  float* swv2 = sbv1 + NB_H;
+  float* cpart = swv2 + NB_H;   // [2][128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(cpart + 2 * NB_TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int row = 32 * q + lane, cb = 32 * hf;
+  const int ntiles = (a.rows + NB_TILE - 1) / NB_TILE;
+  const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+  const uint32_t mine = lane_base + 16u * (uint32_t)hf;
+  float v[32];
+  // the first tile's h rows are requested before the weight copy (the kernel is a latency chain)
+  {
+    const int64_t gr0 = (int64_t)blockIdx.x * NB_TILE + row;
+    nb_enf_load32(a.h + gr0 * NB_H + cb, (int)blockIdx.x < ntiles && gr0 < a.rows, v);
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.img);
+    uint4* dst = reinterpret_cast<uint4*>(base);
+    constexpr int NCOPY = (int)NB_ENF_W_BYTES / 16 / NB_THREADS;   // 16 per thread
+    static_assert(NCOPY == 16, "weight-image copy is unrolled for 16 chunks per thread");
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint4 t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = __ldg(src + tid + (half * 8 + i) * NB_THREADS);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[tid + (half * 8 + i) * NB_THREADS] = t[i];
+    }
+  }
+  if (tid < NB_H) {
+    sb5[tid] = __ldg(a.b5 + tid);
+    sb6[tid] = __ldg(a.b6 + tid);
+    sbv1[tid] = __ldg(a.bv1 + tid);
+    swv2[tid] = __ldg(a.wv2 + tid);
+  }
+  if (tid == 0) {
+    nb_mbar_init(bar, 1);
+    nb_mbar_fence_init();
+  }
+  if (warp == 0) nb_tmem_alloc(tmem_slot, 256);
+  nb_fence_async_smem();
+  nb_tc_fence_before();
+  __syncthreads();
+  nb_tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t d1 = tm + lane_base + (uint32_t)cb;
+  const uint32_t a0h = tm + 128, a0l = tm + 160, a1h = tm + 192, a1l = tm + 224;
+  const uint32_t idesc_fwd = nb_idesc_bf16(128, 64, 0, 0);
+  const uint32_t sW = nb_smem_u32(base);
+#define NB_ENF_WH(i) (sW + (uint32_t)(i) * 2u * (uint32_t)NB_TC_TILE_BYTES(64))
+#define NB_ENF_WL(i) (NB_ENF_WH(i) + (uint32_t)NB_TC_TILE_BYTES(64))
+  const float bv2 = __ldg(a.bv2);
+  const float cnt = (float)(a.N - 1 > 1 ? a.N - 1 : 1);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t gr = (int64_t)tile * NB_TILE + row;
+    const bool live = gr < a.rows;
+    const int64_t off = gr * NB_H + cb;
+    if (tile != (int)blockIdx.x) nb_enf_load32(a.h + off, live, v);
+    nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
+    nb_enf_load32(a.M + off, live, v);
+    nb_store32_ta(nullptr, nullptr, row, hf, v, a1h + mine, a1l + mine);
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();   // (also: every thread has finished the previous tile's reads of D1 / cpart)
+    if (NB_ISSUER(0)) {
+      nb_tc_fence_after();
+      nb_issue_w3_ta(tm, a0h, a0l, NB_ENF_WH(0), NB_ENF_WL(0), false, idesc_fwd, 0u);        // U5  = h W5a^T
+      nb_issue_w3_ta(tm, a1h, a1l, NB_ENF_WH(1), NB_ENF_WL(1), false, idesc_fwd, 1u);        //     + M W5b^T
+      nb_issue_w3_ta(tm + 64, a0h, a0l, NB_ENF_WH(3), NB_ENF_WL(3), false, idesc_fwd, 0u);   // UV  = h Wv1^T
+      nb_mma_commit(bar);
+    }
+    // coordinate operands of this row, requested under the MMAs (one thread per row)
+    float xr[3] = {0.f, 0.f, 0.f}, vr[3] = {0.f, 0.f, 0.f}, fr[3] = {0.f, 0.f, 0.f};
+    if (hf == 0 && live) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        xr[d] = a.x[gr * 3 + d];
+        vr[d] = a.v[gr * 3 + d];
+        fr[d] = a.Fsum[gr * 3 + d];
+      }
+    }
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    // ---- U5 (kept for the backward) ; SiLU(U5) -> A operand of the second product
+    nb_tmem_ld32(d1, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += sb5[cb + i];
+    nb_enf_store32(a.U5 + off, live, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = live ? nb_silu(v[i]) : 0.f;
+    nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
+    // ---- UV (kept for the backward) ; this half's share of s = w_v2 . SiLU(UV)
+    nb_tmem_ld32(d1 + 64, v);
+    float cp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] += sbv1[cb + i];
+      cp = fmaf(swv2[cb + i], nb_silu(v[i]), cp);
+    }
+    nb_enf_store32(a.UV + off, live, v);
+    cpart[hf * NB_TILE + row] = cp;
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();
+    if (NB_ISSUER(0)) {
+      nb_tc_fence_after();
+      nb_issue_w3_ta(tm, a0h, a0l, NB_ENF_WH(2), NB_ENF_WL(2), false, idesc_fwd, 0u);        // h' = SiLU(U5) W6^T
+      nb_mma_commit(bar);
+    }
+    if (hf == 0 && live) {   // x' = x + s v + clamp(mean force)      (basic.py:176-178)
+      const float s = (cpart[row] + cpart[NB_TILE + row]) + bv2;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float f = fr[d] / cnt;
+        f = fminf(fmaxf(f, -100.f), 100.f);
+        a.x_out[gr * 3 + d] = xr[d] + s * vr[d] + f;
+      }
+    }
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    nb_tmem_ld32(d1, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += sb6[cb + i];
+    nb_enf_store32(a.h_out + off, live, v);
+    nb_tc_fence_before();
+  }
+  nb_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nb_tmem_dealloc(tm, 256);
+}
+#endif  // NB_EMU

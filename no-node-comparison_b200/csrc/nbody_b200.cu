@@ -17,6 +17,7 @@
 #include "nb_node_tc.cuh"
 #include "nb_segno_fused.cuh"
 #include "nb_merge.cuh"
+#include "nb_egno_node.cuh"
 #include <cstdlib>
 
 // every kernel launch of this library is counted (bench.py reports it as gpu_launches)
@@ -1125,7 +1126,28 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
     NB_TRY(launch_edge_fwd(ea, stream));
     float* h_next = (l + 1 < Ln) ? bufs(l + 1).h0 : h_out;
     float* x_next = (l + 1 < Ln) ? bufs(l + 1).x0 : x_out;
+    bool node_fused = false;
+#ifndef NB_EMU
     {
+      static int off = -1;   // A/B switch: NB_B200_EGNO_NODE_FUSED=0 keeps the three separate launches
+      if (off < 0) { const char* e = getenv("NB_B200_EGNO_NODE_FUSED"); off = (e && e[0] == '0') ? 1 : 0; }
+      node_fused = !off && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * Ln;
+    }
+    if (node_fused) {   // node_net, node_v_net and the coordinate update in one pass over the rows (nb_egno_node.cuh)
+      NbEgnoNodeFwdArgs na;
+      memset(&na, 0, sizeof(na));
+      na.rows = (int)Nn; na.N = cfg->N; na.img = g_wimg.img[EGNO_WIMG_PER_LAYER * l + 2];
+      na.h = h1; na.M = b.M; na.b5 = params + L.n_b1; na.b6 = params + L.n_b2; na.bv1 = params + L.v_b1;
+      na.wv2 = params + L.v_w2; na.bv2 = params + L.v_b2; na.x = x1; na.v = v1; na.Fsum = b.Fsum;
+      na.U5 = b.U5; na.UV = b.UV; na.h_out = h_next; na.x_out = x_next;
+      NB_SET_SMEM(k_egno_node_fwd, NB_ENF_SMEM);
+      int pi = prof_begin(2, stream);
+      NB_LAUNCH_COUNTED(k_egno_node_fwd, (unsigned)imin(cdiv(Nn, NB_TILE), 2 * nb_num_sms()), NB_THREADS, NB_ENF_SMEM, stream, na);
+      prof_end(2, pi, stream);
+      NB_TRY(nb_check_launch("k_egno_node_fwd"));
+    }
+#endif
+    if (!node_fused) {
       NbGemmArgs a = gemm_args((int)Nn);  // U5 = [h, M] W5^T + b5      (basic.py:183-185)
       a.nsrc = 2;
       a.src[0] = gsrc(h1, NB_H, 0, params + L.n_w1, 1, 2 * NB_H);
