@@ -1229,8 +1229,48 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     const float* x1 = cfg->use_time_conv ? b.x1 : b.x0;
     const float* v0 = (l == 0) ? b.v0 : egno_layer_bufs(const_cast<float*>(saved) + (int64_t)(l - 1) * lf, Nn).v1;
     float* gx = gxb[gxi];
-    // 1. x' = x + s v + clamp(mean f): gv1, gFsum, dL/dUV, and the 64->1 head of node_v_net
+    bool node_fused = false;
+#ifndef NB_EMU
     {
+      static int off = -1;   // A/B switch: NB_B200_EGNO_NODE_FUSED=0 keeps the separate launches
+      if (off < 0) { const char* e = getenv("NB_B200_EGNO_NODE_FUSED"); off = (e && e[0] == '0') ? 1 : 0; }
+      node_fused = !off && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * Ln;
+    }
+    if (node_fused) {
+      // 1 + 2. coordinate update, node_v_net head and node_net backwards in one pass over the rows (nb_egno_node.cuh)
+      NbEgnoNodeBwdArgs na;
+      memset(&na, 0, sizeof(na));
+      na.rows = (int)Nn; na.N = cfg->N; na.img = g_wimg.img[EGNO_WIMG_PER_LAYER * l + 2];
+      na.gh = gh_in; na.U5 = b.U5; na.UV = b.UV; na.wv2 = params + L.v_w2; na.bv2 = params + L.v_b2;
+      na.gx = gx; na.gv = gv_in; na.v = b.v1; na.Fsum = b.Fsum; na.gv_out = gvB; na.gFsum = gFsum;
+      na.GU5 = GU5; na.GUV = GUV; na.gh1 = ghA; na.gM = gM;
+      const int grid = imin(cdiv(Nn, NB_TILE), 2 * nb_num_sms());
+      float* partial = q_alloc((int64_t)grid * 65, stream);
+      if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
+      na.partial = partial;
+      NB_SET_SMEM(k_egno_node_bwd, NB_ENB_SMEM);
+      int pi = prof_begin(2, stream);
+      NB_LAUNCH_COUNTED(k_egno_node_bwd, (unsigned)grid, NB_THREADS, NB_ENB_SMEM, stream, na);
+      prof_end(2, pi, stream);
+      NB_TRY(nb_check_launch("k_egno_node_bwd"));
+      NbFinArgs f;
+      memset(&f, 0, sizeof(f));
+      f.partial = partial; f.nparts = grid; f.plen = 65; f.dst = grad_params; f.nseg = 2;
+      f.seg[0] = fseg(0, NB_H, NB_H, L.v_w2, 0, 1);
+      f.seg[1] = fseg(NB_H, 1, 1, L.v_b2, 0, 0);
+      NB_TRY(launch_finalize(f, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, b.U5, 1), wpair(nullptr, nullptr), grad_params, L.n_w2, NB_H, 1,
+                      L.n_b2, 0, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, h1), wpair(nullptr, nullptr), grad_params, L.n_w1, 2 * NB_H, 1,
+                      L.n_b1, 0, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GU5, b.M), wpair(nullptr, nullptr), grad_params, L.n_w1 + NB_H,
+                      2 * NB_H, 1, -1, 0, stream));
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(GUV, h1), wpair(nullptr, nullptr), grad_params, L.v_w1, NB_H, 1,
+                      L.v_b1, 0, stream));
+    }
+#endif
+    // 1. x' = x + s v + clamp(mean f): gv1, gFsum, dL/dUV, and the 64->1 head of node_v_net
+    if (!node_fused) {
       NbXupdArgs xa;
       memset(&xa, 0, sizeof(xa));
       xa.rows = Nn; xa.N = cfg->N; xa.v = b.v1; xa.UV = b.UV; xa.w2 = params + L.v_w2; xa.b2 = params + L.v_b2;
@@ -1249,7 +1289,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       NB_TRY(launch_finalize(f, stream));
     }
     // 2. node_net backward
-    {
+    if (!node_fused) {
       NbGemmArgs a = gemm_args((int)Nn);  // GU5 = (gh W6) * SiLU'(U5)
       a.nsrc = 1; a.src[0] = gsrc(gh_in, NB_H, 0, params + L.n_w2, NB_H, 1);
       a.epi = NB_EPI_MUL_DSILU; a.U = b.U5; a.out = GU5;
