@@ -372,4 +372,111 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_egno_node_bwd(NbEgnoNodeBwdAr
   if (tid == 0) a.partial[(int64_t)blockIdx.x * 65 + 64] = (red[8 * 32 + 0] + red[8 * 32 + 1]) + (red[8 * 32 + 2] + red[8 * 32 + 3]);
   if (warp == 0) nb_tmem_dealloc(tm, 256);
 }
+
+// ----------------------------------------------------------------------------- the first edge layer's node halves
+// PQ = true  (forward):  P = h W1[:, h_row]^T + b1 ; Q = h W1[:, h_col]^T      one A operand, two products, two outputs
+// PQ = false (backward): gh += gP W1[:, h_row] + gQ W1[:, h_col]               two A operands, one accumulated output
+// The same tile scheme as above with 32 KB of weight images: 192 of 256 TMEM columns, two CTAs per SM.  (The generic
+// k_gemm64_tc ran these as two-job / two-source launches through shared-memory A tiles: 21 us per launch at 51 200 rows.)
+struct NbEgnoPairArgs {
+  int rows;
+  const unsigned char* img;   // W1 h_row | W1 h_col
+  const float *A0, *A1;       // [rows][64]  (PQ: A1 unused)
+  const float* bias;          // PQ: b1 (added to the first output)
+  float *O0, *O1;             // PQ: P, Q ; else O0 = gh (read-modify-write), O1 unused
+};
+#define NB_EPR_W_BYTES (2 * 2 * NB_TC_TILE_BYTES(64))
+#define NB_EPR_SMEM (NB_EPR_W_BYTES + NB_H * 4 + 64 + 1024)
+
+template <bool PQ>
+__global__ void __launch_bounds__(NB_THREADS, 2) k_egno_pair(NbEgnoPairArgs a) {
+  NB_PDL_ENTER();
+  extern __shared__ __align__(1024) unsigned char nb_smraw[];
+  unsigned char* base = nb_smraw + ((1024u - (nb_smem_u32(nb_smraw) & 1023u)) & 1023u);
+  float* sbias = reinterpret_cast<float*>(base + NB_EPR_W_BYTES);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + NB_H);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int row = 32 * q + lane, cb = 32 * hf;
+  const int ntiles = (a.rows + NB_TILE - 1) / NB_TILE;
+  const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+  const uint32_t mine = lane_base + 16u * (uint32_t)hf;
+  float v[32];
+  {
+    const int64_t gr0 = (int64_t)blockIdx.x * NB_TILE + row;
+    nb_enf_load32(a.A0 + gr0 * NB_H + cb, (int)blockIdx.x < ntiles && gr0 < a.rows, v);
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.img);
+    uint4* dst = reinterpret_cast<uint4*>(base);
+    uint4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __ldg(src + tid + i * NB_THREADS);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[tid + i * NB_THREADS] = t[i];
+  }
+  if (tid < NB_H) sbias[tid] = (PQ && a.bias) ? __ldg(a.bias + tid) : 0.f;
+  if (tid == 0) {
+    nb_mbar_init(bar, 1);
+    nb_mbar_fence_init();
+  }
+  if (warp == 0) nb_tmem_alloc(tmem_slot, 256);
+  nb_fence_async_smem();
+  nb_tc_fence_before();
+  __syncthreads();
+  nb_tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t d1 = tm + lane_base + (uint32_t)cb;
+  const uint32_t a0h = tm + 128, a0l = tm + 160, a1h = tm + 192, a1l = tm + 224;
+  const uint32_t idesc = PQ ? nb_idesc_bf16(128, 64, 0, 0) : nb_idesc_bf16(128, 64, 0, 1);
+  const uint32_t sW = nb_smem_u32(base);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t gr = (int64_t)tile * NB_TILE + row;
+    const bool live = gr < a.rows;
+    const int64_t off = gr * NB_H + cb;
+    if (tile != (int)blockIdx.x) nb_enf_load32(a.A0 + off, live, v);
+    nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
+    if (!PQ) {
+      nb_enf_load32(a.A1 + off, live, v);
+      nb_store32_ta(nullptr, nullptr, row, hf, v, a1h + mine, a1l + mine);
+    }
+    nb_tmem_st_wait();
+    nb_tc_fence_before();
+    __syncthreads();
+    if (NB_ISSUER(0)) {
+      nb_tc_fence_after();
+      if (PQ) {
+        nb_issue_w3_ta(tm, a0h, a0l, NB_ENF_WH(0), NB_ENF_WL(0), false, idesc, 0u);
+        nb_issue_w3_ta(tm + 64, a0h, a0l, NB_ENF_WH(1), NB_ENF_WL(1), false, idesc, 0u);
+      } else {
+        nb_issue_w3_ta(tm, a0h, a0l, NB_ENF_WH(0), NB_ENF_WL(0), true, idesc, 0u);
+        nb_issue_w3_ta(tm, a1h, a1l, NB_ENF_WH(1), NB_ENF_WL(1), true, idesc, 1u);
+      }
+      nb_mma_commit(bar);
+    }
+    float r[32];
+    if (!PQ) nb_enf_load32(a.O0 + off, live, r);   // the accumulate target, requested under the MMAs
+    nb_mbar_wait(bar, phase);
+    phase ^= 1;
+    nb_tc_fence_after();
+    nb_tmem_ld32(d1, v);
+    if (PQ) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += sbias[cb + i];
+      nb_enf_store32(a.O0 + off, live, v);
+      nb_tmem_ld32(d1 + 64, v);
+      nb_enf_store32(a.O1 + off, live, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += r[i];
+      nb_enf_store32(a.O0 + off, live, v);
+    }
+    nb_tc_fence_before();
+  }
+  nb_tc_fence_before();
+  __syncthreads();
+  if (warp == 0) nb_tmem_dealloc(tm, 256);
+}
 #endif  // NB_EMU

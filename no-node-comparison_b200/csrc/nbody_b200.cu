@@ -1005,9 +1005,34 @@ static inline int tconv_grid(const EgnoCtx& X, int per_sm) {
   return imin(cdiv(X.Nn0, NB_TCV_ROWS), (int64_t)per_sm * nb_num_sms());
 }
 
+// the fused per-layer node kernels (nb_egno_node.cuh) need the tcgen05 variants and this call's weight images;
+// NB_B200_EGNO_NODE_FUSED=0 keeps the generic GEMM launches (A/B switch)
+static bool egno_node_fused(const EgnoCtx& X) {
+#ifndef NB_EMU
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("NB_B200_EGNO_NODE_FUSED"); off = (e && e[0] == '0') ? 1 : 0; }
+  return !off && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * X.c->n_layers;
+#else
+  (void)X;
+  return false;
+#endif
+}
+
 static int egno_pq(const EgnoCtx& X, int l, const float* h1, float* P, float* Q) {
   const EgnoLayerOff& L = X.lo.L[l];
   const int E = X.lo.E;
+#ifndef NB_EMU
+  if (egno_node_fused(X)) {
+    NbEgnoPairArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.rows = (int)X.Nn; pa.img = g_wimg.img[EGNO_WIMG_PER_LAYER * l]; pa.A0 = h1; pa.bias = X.params + L.e_b1; pa.O0 = P; pa.O1 = Q;
+    NB_SET_SMEM(k_egno_pair<true>, NB_EPR_SMEM);
+    int pi = prof_begin(2, X.st);
+    NB_LAUNCH_COUNTED(k_egno_pair<true>, (unsigned)imin(cdiv(X.Nn, NB_TILE), 2 * nb_num_sms()), NB_THREADS, NB_EPR_SMEM, X.st, pa);
+    prof_end(2, pi, X.st);
+    return nb_check_launch("k_egno_pair");
+  }
+#endif
   NbGemmArgs a = gemm_args((int)X.Nn);  // P = h W1[:, h_row]^T + b1   (cols 1..64, basic.py:98,170)
   a.nsrc = 1; a.src[0] = gsrc(h1, NB_H, 0, X.params + L.e_w1 + 1, 1, E);
   a.bias = X.params + L.e_b1; a.out = P;
@@ -1128,11 +1153,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
     float* x_next = (l + 1 < Ln) ? bufs(l + 1).x0 : x_out;
     bool node_fused = false;
 #ifndef NB_EMU
-    {
-      static int off = -1;   // A/B switch: NB_B200_EGNO_NODE_FUSED=0 keeps the three separate launches
-      if (off < 0) { const char* e = getenv("NB_B200_EGNO_NODE_FUSED"); off = (e && e[0] == '0') ? 1 : 0; }
-      node_fused = !off && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * Ln;
-    }
+    node_fused = egno_node_fused(X);
     if (node_fused) {   // node_net, node_v_net and the coordinate update in one pass over the rows (nb_egno_node.cuh)
       NbEgnoNodeFwdArgs na;
       memset(&na, 0, sizeof(na));
@@ -1231,11 +1252,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     float* gx = gxb[gxi];
     bool node_fused = false;
 #ifndef NB_EMU
-    {
-      static int off = -1;   // A/B switch: NB_B200_EGNO_NODE_FUSED=0 keeps the separate launches
-      if (off < 0) { const char* e = getenv("NB_B200_EGNO_NODE_FUSED"); off = (e && e[0] == '0') ? 1 : 0; }
-      node_fused = !off && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * Ln;
-    }
+    node_fused = egno_node_fused(X);
     if (node_fused) {
       // 1 + 2. coordinate update, node_v_net head and node_net backwards in one pass over the rows (nb_egno_node.cuh)
       NbEgnoNodeBwdArgs na;
@@ -1328,12 +1345,26 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     }
     // 4. pre-projection backward: gh1 += gP W1[:, h_row] + gQ W1[:, h_col]
     {
+#ifndef NB_EMU
+      if (egno_node_fused(X)) {
+        NbEgnoPairArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.rows = (int)Nn; pa.img = g_wimg.img[EGNO_WIMG_PER_LAYER * l]; pa.A0 = gP; pa.A1 = gQ; pa.O0 = ghA;
+        NB_SET_SMEM(k_egno_pair<false>, NB_EPR_SMEM);
+        int pi = prof_begin(2, stream);
+        NB_LAUNCH_COUNTED(k_egno_pair<false>, (unsigned)imin(cdiv(Nn, NB_TILE), 2 * nb_num_sms()), NB_THREADS, NB_EPR_SMEM, stream, pa);
+        prof_end(2, pi, stream);
+        NB_TRY(nb_check_launch("k_egno_pair"));
+      } else
+#endif
+      {
       NbGemmArgs a = gemm_args((int)Nn);
       a.nsrc = 2;
       a.src[0] = gsrc(gP, NB_H, 0, params + L.e_w1 + 1, X.lo.E, 1);
       a.src[1] = gsrc(gQ, NB_H, 0, params + L.e_w1 + 1 + NB_H, X.lo.E, 1);
       a.out = ghA; a.accumulate = 1;
       NB_TRY(launch_gemm(a, stream));
+      }
       NB_TRY(wgrad_to((int)Nn, 1, wpair(gP, h1), wpair(nullptr, nullptr), grad_params, L.e_w1 + 1, X.lo.E, 1,
                       L.e_b1, 0, stream));
       NB_TRY(wgrad_to((int)Nn, 1, wpair(gQ, h1), wpair(nullptr, nullptr), grad_params, L.e_w1 + 1 + NB_H,

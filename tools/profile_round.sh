@@ -8,7 +8,7 @@ cd ${GRAFT_REPO_ROOT:-.}
 timeout 120 python bench.py --quick --no-graph --steps 2 --warmup 3 > gpurun_out/${R}_quick.json 2> gpurun_out/${R}_quick.err || exit 1
 cat gpurun_out/${R}_quick.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_launches.csv python bench.py --quick --no-graph --steps 2 --warmup 3 > gpurun_out/ncu_l.log 2>&1
-for K in k_edge_bwd_sel k_edge_fwd_sel k_gemm64_tc k_wgrad64_tc k_tconv_bwd; do
+for K in k_edge_bwd_sel k_edge_fwd_sel k_egno_node_fwd k_egno_node_bwd k_gemm64_tc k_wgrad64_tc k_tconv_bwd; do
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:$K -s 8 -c 1 -f -o gpurun_out/${R}_$K python bench.py --quick --no-graph --steps 1 --warmup 3 > gpurun_out/ncu_$K.log 2>&1
 done
 # SEGNO (configs[3] shape) and the blocked walk (configs[4] shape): tools/profile_shapes.py runs one training step of each
