@@ -434,7 +434,7 @@ __device__ __forceinline__ void nb_tconv_mix(const float* As, const float* B0, c
   }
 }
 
-__global__ void __launch_bounds__(256) k_tconv_fwd(NbTconvArgs a) {
+__global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
   NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   float* B0 = sm;                    // W[.][.][0][re]
@@ -444,18 +444,29 @@ __global__ void __launch_bounds__(256) k_tconv_fwd(NbTconvArgs a) {
   const int tid = threadIdx.x, r = tid >> 4, c4 = tid & 15;
   const NbTwiddle& tw = a.tw;
   const bool has1 = tw.modes > 1, pair1 = has1 && tw.nyq != 1;
-  nb_tconv_stage_w(B0, B1, B2, nullptr, nullptr, nullptr, a.W, tw.modes, tid);
   const int64_t plane = (int64_t)a.Nn0 * NB_H;
   const float invT = 1.0f / (float)tw.T;
   const int ngroups = (a.Nn0 + NB_TCV_ROWS - 1) / NB_TCV_ROWS;
+  // the first group's rows are requested BEFORE the weight staging, so the two memory round trips overlap
+  float4 xs[NB_MAX_T];
+  {
+    const int row = blockIdx.x * NB_TCV_ROWS + r;
+    const bool act = (int)blockIdx.x < ngroups && row < a.Nn0;
+    const int64_t off = (int64_t)row * NB_H + c4 * 4;
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) xs[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  nb_tconv_stage_w(B0, B1, B2, nullptr, nullptr, nullptr, a.W, tw.modes, tid);
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int row = grp * NB_TCV_ROWS + r;
     const bool act = row < a.Nn0;
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
-    float4 xs[NB_MAX_T];
+    if (grp != (int)blockIdx.x) {
 #pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
-      if (t < tw.T) xs[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < NB_MAX_T; ++t)
+        if (t < tw.T) xs[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0;
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
@@ -486,7 +497,7 @@ __global__ void __launch_bounds__(256) k_tconv_fwd(NbTconvArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_tconv_bwd(NbTconvArgs a) {
+__global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
   NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
   float* B0 = sm;
@@ -499,25 +510,45 @@ __global__ void __launch_bounds__(256) k_tconv_bwd(NbTconvArgs a) {
   const int tid = threadIdx.x, r = tid >> 4, c4 = tid & 15;
   const NbTwiddle& tw = a.tw;
   const bool has1 = tw.modes > 1, pair1 = has1 && tw.nyq != 1;
-  nb_tconv_stage_w(B0, B1, B2, T0, T1, T2, a.W, tw.modes, tid);
   const int64_t plane = (int64_t)a.Nn0 * NB_H;
   const float invT = 1.0f / (float)tw.T;
   const float s1 = pair1 ? 2.f * invT : invT;
   const int ngroups = (a.Nn0 + NB_TCV_ROWS - 1) / NB_TCV_ROWS;
+  // Memory round trips overlap instead of queueing behind each other: the first group's x rows are requested before the
+  // weight staging, and a group's gout rows are requested before its forward mix (they are needed only after it) and
+  // kept in registers for the residual path, so gout crosses the memory system once.
+  float4 gq[NB_MAX_T];   // x rows of the group, then its gout rows
+  {
+    const int row = blockIdx.x * NB_TCV_ROWS + r;
+    const bool act = (int)blockIdx.x < ngroups && row < a.Nn0;
+    const int64_t off = (int64_t)row * NB_H + c4 * 4;
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) gq[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  nb_tconv_stage_w(B0, B1, B2, T0, T1, T2, a.W, tw.modes, tid);
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int row = grp * NB_TCV_ROWS + r;
     const bool act = row < a.Nn0;
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
+    if (grp != (int)blockIdx.x) {
+#pragma unroll
+      for (int t = 0; t < NB_MAX_T; ++t)
+        if (t < tw.T) gq[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // ---- recompute: coefficients of x, mixed coefficients, y
     float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0;
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
       if (t < tw.T) {
-        const float4 xv = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 xv = gq[t];
         C0 = nb_f4_fma(tw.c[0][t], xv, C0);
         if (has1) C1 = nb_f4_fma(tw.c[1][t], xv, C1);
         if (pair1) S1 = nb_f4_fma(tw.s[1][t], xv, S1);
       }
+#pragma unroll
+    for (int t = 0; t < NB_MAX_T; ++t)
+      if (t < tw.T) gq[t] = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);   // in flight under the mix
     if (act) {
       nb_st4(a.coef + off, C0);
       if (has1) nb_st4(a.coef + plane + off, C1);
@@ -538,7 +569,7 @@ __global__ void __launch_bounds__(256) k_tconv_bwd(NbTconvArgs a) {
         float4 y = make_float4(P0.x * invT, P0.y * invT, P0.z * invT, P0.w * invT);
         if (has1) y = nb_f4_fma(s1 * tw.c[1][t], P1, y);
         if (pair1) y = nb_f4_fma(-s1 * tw.s[1][t], Q1, y);
-        const float4 g = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 g = gq[t];
         const float4 gy = make_float4(g.x * nb_dleaky(y.x), g.y * nb_dleaky(y.y), g.z * nb_dleaky(y.z), g.w * nb_dleaky(y.w));
         gP0 = nb_f4_fma(invT * tw.c[0][t], gy, gP0);
         if (has1) gP1 = nb_f4_fma(s1 * tw.c[1][t], gy, gP1);
@@ -561,7 +592,7 @@ __global__ void __launch_bounds__(256) k_tconv_bwd(NbTconvArgs a) {
 #pragma unroll
       for (int t = 0; t < NB_MAX_T; ++t)
         if (t < tw.T) {
-          float4 g = nb_ld4(a.gout + t * plane + off);  // residual path
+          float4 g = gq[t];  // residual path
           g = nb_f4_fma(tw.c[0][t], gC0, g);
           if (has1) g = nb_f4_fma(tw.c[1][t], gC1, g);
           if (pair1) g = nb_f4_fma(tw.s[1][t], gS1, g);
