@@ -399,7 +399,7 @@ def run_ours(args):
         qm, qc = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
         lib.nb_profile_read(qm, qc)
         lib.nb_profile_enable(0)
-        per = {c: round(1e3 * qm[i] / max(qc[i], 1), 1) for i, c in enumerate(["edge_fwd", "edge_bwd", "gemm64", "wgrad64", "tconv"])}
+        per = {c: round(1e3 * qm[i] / max(qc[i], 1), 1) for i, c in enumerate(["edge_fwd", "edge_bwd", "node", "wgrad64", "tconv"])}
         if rank == 0:
             emit(dict({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                               "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True,
@@ -421,7 +421,7 @@ def run_ours(args):
     pc = (ctypes.c_longlong * 8)()
     lib.nb_profile_read(pm, pc)
     lib.nb_profile_enable(0)
-    cats = ["edge_fwd", "edge_bwd", "gemm64", "wgrad64", "tconv"]
+    cats = ["edge_fwd", "edge_bwd", "node", "wgrad64", "tconv"]
     kern = {c: {"ms_total": pm[i], "launches": int(pc[i]), "ms_per_launch": (pm[i] / pc[i]) if pc[i] else None,
                 "share_of_step": pm[i] / ms_prof if ms_prof else None} for i, c in enumerate(cats)}
 
@@ -550,7 +550,7 @@ def run_ours(args):
         sm_, sc_ = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
         lib.nb_profile_read(sm_, sc_)
         lib.nb_profile_enable(0)
-        scat = {"edge_bwd": 1, "segno_fused_fwd": 5, "gemm64": 2, "wgrad64": 3}
+        scat = {"edge_bwd": 1, "segno_fused_fwd": 5, "node": 2, "wgrad64": 3}
         skern = {c: {"ms_total": sm_[i], "launches": int(sc_[i]), "ms_per_launch": (sm_[i] / sc_[i]) if sc_[i] else None,
                      "share_of_step": sm_[i] / ms_sprof if ms_sprof else None} for c, i in scat.items()}
         ne_s = B * N * (N - 1)                                    # edges per sub-step

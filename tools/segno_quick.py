@@ -63,7 +63,7 @@ timed(eager, 10)
 sm_, sc_ = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
 lib.nb_profile_read(sm_, sc_)
 lib.nb_profile_enable(0)
-cat = {"edge_bwd": 1, "segno_fused_fwd": 5, "gemm64": 2, "wgrad64": 3}
+cat = {"edge_bwd": 1, "segno_fused_fwd": 5, "node": 2, "wgrad64": 3}
 print(json.dumps({"train_ms": round(ms_train, 4), "train_traj_per_s": round(B / ms_train * 1e3), "infer_ms": round(ms_inf, 4),
                   "infer_traj_per_s": round(B / ms_inf * 1e3), "launches_per_step": g.launches_per_replay,
                   "us_per_launch": {c: (round(sm_[i] / sc_[i] * 1e3, 1), int(sc_[i]) // 10) for c, i in cat.items() if sc_[i]}}))
