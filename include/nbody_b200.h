@@ -225,6 +225,9 @@ int nb_get_edge_impl(void);
  * kernels (cross-check; the variant the host emulator runs). */
 int nb_set_node_impl(int impl);
 int nb_get_node_impl(void);
+/* EGNO: 1 (default) = one fused node kernel per layer and direction, 0 = the generic node GEMM launches (cross-check). */
+int nb_set_node_fused(int on);
+int nb_get_node_fused(void);
 /* SEGNO forward: 1 = all T integration sub-steps fused into one kernel, node state resident in shared memory (default;
  * needs edge impl 2, node impl 1 and N <= 27), 0 = one kernel sequence per sub-step. */
 int nb_set_segno_fused(int on);

@@ -56,6 +56,8 @@ EXPORTS = {
     "nb_set_edge_impl": (C.c_int, [C.c_int]),
     "nb_set_node_impl": (C.c_int, [C.c_int]),
     "nb_get_node_impl": (C.c_int, []),
+    "nb_set_node_fused": (C.c_int, [C.c_int]),
+    "nb_get_node_fused": (C.c_int, []),
     "nb_set_segno_fused": (C.c_int, [C.c_int]),
     "nb_get_segno_fused": (C.c_int, []),
     "nb_get_edge_impl": (C.c_int, []),

@@ -249,6 +249,11 @@ extern "C" int nb_set_node_impl(int impl) {
   return NB_OK;
 }
 extern "C" int nb_get_node_impl(void) { return g_node_impl; }
+// EGNO: 1 = one node kernel per layer and direction (nb_egno_node.cuh; needs the tcgen05 node kernels), 0 = the generic
+// GEMM launches + coordinate-update kernels they replaced (the cross-check)
+static int g_node_fused = 1;
+extern "C" int nb_set_node_fused(int on) { g_node_fused = on ? 1 : 0; return NB_OK; }
+extern "C" int nb_get_node_fused(void) { return g_node_fused; }
 
 // SEGNO: 1 = forward with all T sub-steps in one kernel, the node state resident in shared memory (nb_segno_fused.cuh;
 // needs the tcgen05 variants and N <= 27), and backward with the node-level chain between two edge sweeps as one kernel
@@ -1011,7 +1016,7 @@ static bool egno_node_fused(const EgnoCtx& X) {
 #ifndef NB_EMU
   static int off = -1;
   if (off < 0) { const char* e = getenv("NB_B200_EGNO_NODE_FUSED"); off = (e && e[0] == '0') ? 1 : 0; }
-  return !off && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * X.c->n_layers;
+  return !off && g_node_fused && g_node_impl == 1 && g_wimg.n == EGNO_WIMG_PER_LAYER * X.c->n_layers;
 #else
   (void)X;
   return false;

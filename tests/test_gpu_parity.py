@@ -449,6 +449,39 @@ def test_segno_fused_forward_matches_stepwise_kernels():
             assert rel_err(a, b) < 2e-5
 
 
+@pytest.mark.parametrize("B,N,T,L", [(16, 20, 10, 4), (7, 5, 8, 2), (2, 37, 5, 1)])
+def test_egno_fused_node_kernels_match_generic_launches(B, N, T, L):
+    """The per-layer node kernels (nb_egno_node.cuh: node_net + node_v_net + coordinate update forward and backward,
+    the first edge layer's node halves; operands chained through tensor memory) against the generic node GEMM launches
+    and coordinate-update kernels they replaced (`nb_set_node_fused(0)`): outputs, input and parameter gradients, and
+    the launch count (3 + 1 launches less per layer forward... 16 per 4-layer step)."""
+    lib = nb.load_library()
+    c = _egno_case(B, N, T, L=L, seed=31 + N)
+    gen = torch.Generator().manual_seed(9)
+    n = T * B * N
+    Gx, Gv, Gh = torch.randn(n, 3, generator=gen).to(dev()), torch.randn(n, 3, generator=gen).to(dev()), 0.1 * torch.randn(n, 64, generator=gen).to(dev())
+    out = {}
+    for fused in (1, 0):
+        assert lib.nb_set_node_fused(fused) == 0
+        try:
+            m = make_egno(c, seed=12)
+            n0 = lib.nb_launch_count()
+            x, v, (xo, vo, ho) = run_egno(m, c)
+            ((xo * Gx).sum() + (vo * Gv).sum() + (ho * Gh).sum()).backward()
+            torch.cuda.synchronize()
+            out[fused, "launches"] = lib.nb_launch_count() - n0
+            out[fused] = [xo.detach().cpu(), vo.detach().cpu(), ho.detach().cpu(), x.grad.cpu(), v.grad.cpu()] + \
+                [p.grad.cpu().clone() for p in m.parameters()]
+        finally:
+            lib.nb_set_node_fused(1)
+    assert lib.nb_get_node_fused() == 1
+    assert out[1, "launches"] == out[0, "launches"] - 4 * L      # 2 launches less per layer in each direction
+    for a, b in zip(out[1][:5], out[0][:5]):
+        assert rel_err(a, b) < 2e-5
+    for a, b in zip(out[1][5:], out[0][5:]):
+        assert rel_err(a, b) < 1e-3      # parameter gradients: LeakyReLU-kink flips under any rounding change (see the header)
+
+
 def test_cuda_graph_training_step_matches_eager():
     """GraphedStep (forward + loss + backward + Adam captured in one CUDA graph) follows the eager step bit for bit:
     the C ABI is enqueue-only and allocation-free, so capture must not change any result."""
