@@ -40,7 +40,7 @@ struct NbSegnoFusedArgs {
 #define NB_FS_HN (NB_FS_F + 2 * NB_TILE * 16)                // h tile hi/lo (64 rows)     2 x 8 KB
 #define NB_FS_UN (NB_FS_HN + 2 * NB_TC_TILE_BYTES(64))       // M / SiLU(U5) tile hi/lo    2 x 8 KB
 #define NB_FS_FL (NB_FS_UN + 2 * NB_TC_TILE_BYTES(64))
-#define NB_FS_NFLOAT (28 * NB_H + 2 * 32 * 3 + 6 * NB_H + 4 * NB_TILE)
+#define NB_FS_NFLOAT (28 * NB_H + 2 * 32 * 3 + 6 * NB_H)
 #define NB_SEGNO_FUSED_SMEM(RU) (NB_FS_FL + NB_FS_NFLOAT * 4 + (RU) * 4 + 64 + 1024)
 #define NB_FS_TMEM_COLS 512  // [0,64) pre | [64,128) M sums | [128,136) F sums | [192,256) P / U5 / dh | [256,320) Q |
                              // [448,480) hi, [480,512) lo pieces of the A operand (z1, then m) as packed bf16 pairs
@@ -109,8 +109,12 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_segno_fused_fwd(NbSegnoFus
   float* vw4 = vb3 + NB_H;
   float* vb5 = vw4 + NB_H;
   float* vb6 = vb5 + NB_H;
-  float* cpart = vb6 + NB_H;         // [4][128]
-  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(cpart + 4 * NB_TILE);
+  // [4][128] partial dots of the phi_x head: lives in the first 2 KB of the M / SiLU(U5) tile, which is idle during the
+  // edge tiles (rows 0..15 of its hi piece; they are rewritten by the read-out (d) before the node MMAs read them, and a
+  // node row beyond the unit's nodes only ever feeds accumulator rows nobody reads) — with its own 2 KB the kernel does
+  // not fit the 227 KB of a CTA at G * N = 27
+  float* cpart = reinterpret_cast<float*>(Uh);
+  uint32_t* rowinfo = reinterpret_cast<uint32_t*>(vb6 + NB_H);
   const NbEdgeGeom g = a.g;
   const int RU = g.G * g.EPG, GN = g.G * g.N;
   uint64_t* bar = reinterpret_cast<uint64_t*>(rowinfo + RU + (RU & 1));

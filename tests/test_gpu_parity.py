@@ -158,7 +158,7 @@ def test_egno_vs_oracle_various_shapes(B, N, T, L):
     param_grads_within_kink_budget(m, p, n_rows=T * B * N, tol=TOL_GRAD)
 
 
-@pytest.mark.parametrize("B,N,T", [(16, 20, 10), (2, 100, 2), (9, 3, 5)])
+@pytest.mark.parametrize("B,N,T", [(16, 20, 10), (2, 100, 2), (9, 3, 5), (3, 27, 4), (2, 28, 3)])   # 27: largest fused unit; 28: blocked walk
 def test_segno_vs_oracle_various_shapes(B, N, T):
     d = dev()
     s = synth.sample_state("gravity", B, N, seed=B)
