@@ -46,25 +46,33 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize("B,N,T,L", [(3, 20, 10, 2), (2, 37, 4, 1), (5, 5, 8, 2)])
-def test_egno_c_abi_never_writes_outside_its_buffers(B, N, T, L):
+@pytest.mark.parametrize("B,N,T,L,modes,nin", [(3, 20, 10, 2, 2, 1), (2, 37, 4, 1, 2, 1), (5, 5, 8, 2, 2, 1), (2, 5, 6, 2, 4, 1),
+                                                (3, 5, 10, 2, 2, 3), (1, 100, 2, 1, 1, 1), (2, 20, 16, 1, 2, 2)])
+def test_egno_c_abi_never_writes_outside_its_buffers(B, N, T, L, modes, nin):
+    """whole-graph and blocked selector walks, the fused (modes <= 2) and the general temporal convolution, several input
+    frames, the longest supported horizon"""
     import no_node_comparison_b200 as nb
     from no_node_comparison_b200 import _cabi, synth
     d = _dev()
     lib = nb.load_library()
-    s = synth.sample_state("charged", B, N, seed=7)
     row, col = synth.canonical_edges(B, N)
-    x, nodes, ea, v, lm = [t.to(d).contiguous() for t in synth.egno_features(s["loc"], s["vel"], s["charges"], row, col)]
-    cfg = _cabi.NbEgnoConfig(B, N, T, L, 2, 2, 2, 32, 1, 1)
+    fr = []
+    for i in range(nin):
+        s = synth.sample_state("charged", B, N, seed=7 + i)
+        fr.append([t.to(d) for t in synth.egno_features(s["loc"], s["vel"], s["charges"], row, col)])
+    x, nodes, ea, v, lm = [(torch.stack([f[k] for f in fr]) if nin > 1 else fr[0][k]).contiguous() for k in range(5)]
+    cfg = _cabi.NbEgnoConfig(B, N, T, L, modes, 2, 2, 32, 1, nin)
     npar = lib.nb_egno_param_count(ctypes.byref(cfg))
+    assert npar > 0, lib.nb_last_error()
     params = (0.1 * torch.randn(npar, generator=torch.Generator().manual_seed(1))).to(d)
     ts = torch.arange(1, T + 1, device=d)[None].repeat(B, 1).contiguous()
+    ts_in = torch.arange(-nin + 1, 1, device=d)[None].repeat(B, 1).contiguous() if nin > 1 else None
     Nn = T * B * N
     st = ctypes.c_void_p(torch.cuda.current_stream(d).cuda_stream)
     A = Arena(dict(x_out=Nn * 3, v_out=Nn * 3, h_out=Nn * 64, saved=lib.nb_egno_saved_floats(ctypes.byref(cfg)),
                    ws_f=lib.nb_egno_workspace_floats(ctypes.byref(cfg), 2), ws_b=lib.nb_egno_workspace_floats(ctypes.byref(cfg), 1),
-                   grad=npar, gx_in=B * N * 3, gv_in=B * N * 3), d)
-    rc = lib.nb_egno_forward(ctypes.byref(cfg), _p(params), _p(x), _p(nodes), _p(ea), _p(v), _p(lm), _p(ts), None, A.ptr("x_out"),
+                   grad=npar, gx_in=nin * B * N * 3, gv_in=nin * B * N * 3), d)
+    rc = lib.nb_egno_forward(ctypes.byref(cfg), _p(params), _p(x), _p(nodes), _p(ea), _p(v), _p(lm), _p(ts), _p(ts_in), A.ptr("x_out"),
                              A.ptr("v_out"), A.ptr("h_out"), A.ptr("saved"), A.ptr("ws_f"), st)
     assert rc == 0, lib.nb_last_error()
     torch.cuda.synchronize()
@@ -74,7 +82,7 @@ def test_egno_c_abi_never_writes_outside_its_buffers(B, N, T, L):
         assert bool(torch.isfinite(A.view(k)).all()), k
     g = torch.Generator().manual_seed(2)
     Gx, Gv, Gh = [torch.randn(Nn, c, generator=g).to(d) for c in (3, 3, 64)]
-    rc = lib.nb_egno_backward(ctypes.byref(cfg), _p(params), _p(nodes), _p(ea), _p(lm), _p(ts), None, A.ptr("saved"), _p(Gx), _p(Gv),
+    rc = lib.nb_egno_backward(ctypes.byref(cfg), _p(params), _p(nodes), _p(ea), _p(lm), _p(ts), _p(ts_in), A.ptr("saved"), _p(Gx), _p(Gv),
                               _p(Gh), A.ptr("grad"), A.ptr("gx_in"), A.ptr("gv_in"), A.ptr("ws_b"), st)
     assert rc == 0, lib.nb_last_error()
     torch.cuda.synchronize()
