@@ -128,3 +128,49 @@ def test_segno_c_abi_never_writes_outside_its_buffers(B, N, T, h_given):
     for k in ("grad", "gx_in", "gv_in") + (("gh_in",) if h_given else ()):
         assert not bool((A.view(k) == SENT).any()), k
         assert bool(torch.isfinite(A.view(k)).all()), k
+
+
+@pytest.mark.parametrize("mode,n,nf", [(0, 37, 2), (1, 100, 2), (2, 333, 3), (2, 5, 2)])
+def test_segno_merge_and_embedding_entry_points_stay_inside_their_buffers(mode, n, nf):
+    import no_node_comparison_b200 as nb
+    from no_node_comparison_b200 import _cabi
+    d = _dev()
+    lib = nb.load_library()
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(d).contiguous()
+    frame = nf - 1
+    h_all, x_all, v_all = rnd(n, nf, 64), rnd(n, nf, 3), rnd(n, nf, 3)
+    h_int, x_int, v_int = rnd(n, 64), rnd(n, 3), rnd(n, 3)
+    ap = (0.2 * torch.randn(64 * 65 + 129, generator=g)).to(d)
+    st = ctypes.c_void_p(torch.cuda.current_stream(d).cuda_stream)
+    cfg = _cabi.NbSegnoConfig(1, 5, 2, 1, 2, 1, 1.0, 1)      # the embedding entry points take their row count separately
+    A = Arena(dict(h_out=n * 64, x_out=n * 3, v_out=n * 3, alpha=n * 2, g_h_all=n * nf * 64, g_x_all=n * nf * 3, g_v_all=n * nf * 3,
+                   g_h_int=n * 64, g_x_int=n * 3, g_v_int=n * 3, g_attn=64 * 65 + 129,
+                   ws=max(lib.nb_segno_merge_backward_workspace_floats(n), 64), emb=n * nf * 64,
+                   ews=lib.nb_segno_embed_backward_workspace_floats(ctypes.byref(cfg), n * nf),
+                   gpar=lib.nb_segno_param_count(ctypes.byref(cfg))), d)
+    intp = (None, None, None) if mode == 0 else (_p(h_int), _p(x_int), _p(v_int))
+    rc = lib.nb_segno_merge_forward(mode, n, nf, frame, _p(h_all), _p(x_all), _p(v_all), *intp, _p(ap) if mode == 2 else None,
+                                    A.ptr("h_out"), A.ptr("x_out"), A.ptr("v_out"), A.ptr("alpha") if mode == 2 else None, st)
+    assert rc == 0, lib.nb_last_error()
+    gint = (None, None, None) if mode == 0 else (A.ptr("g_h_int"), A.ptr("g_x_int"), A.ptr("g_v_int"))
+    rc = lib.nb_segno_merge_backward(mode, n, nf, frame, _p(h_all), _p(x_all), _p(v_all), *intp, _p(ap) if mode == 2 else None,
+                                     A.ptr("alpha") if mode == 2 else None, _p(rnd(n, 64)), _p(rnd(n, 3)), _p(rnd(n, 3)),
+                                     A.ptr("g_h_all"), A.ptr("g_x_all"), A.ptr("g_v_all"), *gint,
+                                     A.ptr("g_attn") if mode == 2 else None, 0, A.ptr("ws") if mode == 2 else None, st)
+    assert rc == 0, lib.nb_last_error()
+    params = (0.1 * torch.randn(A.off["gpar"][1], generator=g)).to(d)
+    his = rnd(n * nf, 1)
+    rc = lib.nb_segno_embed_forward(ctypes.byref(cfg), _p(params), n * nf, _p(his), A.ptr("emb"), st)
+    assert rc == 0, lib.nb_last_error()
+    rc = lib.nb_segno_embed_backward(ctypes.byref(cfg), n * nf, _p(his), _p(rnd(n * nf, 64)), A.ptr("gpar"), A.ptr("ews"), st)
+    assert rc == 0, lib.nb_last_error()
+    torch.cuda.synchronize()
+    assert A.guards_intact()
+    for k in ("h_out", "x_out", "v_out", "emb"):
+        assert not bool((A.view(k) == SENT).any()), k
+    # only the observed frame's slice of the *_all gradients is written
+    gh = A.view("g_h_all").view(n, nf, 64)
+    assert not bool((gh[:, frame] == SENT).any()) and bool((gh[:, :frame] == SENT).all())
+    if mode == 2:
+        assert not bool((A.view("g_attn") == SENT).any()) and not bool((A.view("alpha") == SENT).any())
