@@ -399,7 +399,8 @@ def run_ours(args):
         qm, qc = (ctypes.c_double * 8)(), (ctypes.c_longlong * 8)()
         lib.nb_profile_read(qm, qc)
         lib.nb_profile_enable(0)
-        per = {c: round(1e3 * qm[i] / max(qc[i], 1), 1) for i, c in enumerate(["edge_fwd", "edge_bwd", "node", "wgrad64", "tconv"])}
+        per = {c: round(1e3 * qm[i] / max(qc[i], 1), 1)
+               for c, i in {"edge_fwd": 0, "edge_bwd": 1, "node": 2, "wgrad64": 3, "tconv": 4, "node_fwd": 6, "node_bwd": 7}.items()}
         if rank == 0:
             emit(dict({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                               "ms_per_step": ms / K, "gpu_launches": int(launches), "quick": True,
@@ -421,9 +422,9 @@ def run_ours(args):
     pc = (ctypes.c_longlong * 8)()
     lib.nb_profile_read(pm, pc)
     lib.nb_profile_enable(0)
-    cats = ["edge_fwd", "edge_bwd", "node", "wgrad64", "tconv"]
+    cats = {"edge_fwd": 0, "edge_bwd": 1, "node": 2, "wgrad64": 3, "tconv": 4, "node_fwd": 6, "node_bwd": 7}
     kern = {c: {"ms_total": pm[i], "launches": int(pc[i]), "ms_per_launch": (pm[i] / pc[i]) if pc[i] else None,
-                "share_of_step": pm[i] / ms_prof if ms_prof else None} for i, c in enumerate(cats)}
+                "share_of_step": pm[i] / ms_prof if ms_prof else None} for c, i in cats.items()}
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
@@ -471,6 +472,24 @@ def run_ours(args):
                     "bytes_per_launch_fwd": tconv_bytes_fwd, "bytes_per_launch_bwd": tconv_bytes_bwd,
                     "note": "mean over the forward and backward launches of a step (CUDA events); algorithmic bytes = "
                             "2*T*64*4 B per node-trajectory forward, (3*T + 6)*64*4 B backward"}
+
+    # the per-layer node kernels (nb_egno_node.cuh): every tensor crosses HBM once per kernel
+    rows = T * nn0
+    nf_bytes = rows * 4 * (2 * 64 + 3 * 3 + 3 * 64 + 3)           # reads h, M, x, v, Fsum ; writes U5, UV, h', x'
+    nb_bytes = rows * 4 * (3 * 64 + 4 * 3 + 4 * 64 + 2 * 3)       # reads gh, U5, UV, gx, gv, v, Fsum ; writes GUV, GU5, gh1, gM, gv, gFsum
+    t_nf, t_nb = kern["node_fwd"]["ms_per_launch"], kern["node_bwd"]["ms_per_launch"]
+    roofline_node = None
+    if t_nf and t_nb:
+        roofline_node = {"kernel": "k_egno_node_fwd / k_egno_node_bwd (node_net + node_v_net + coordinate update of a layer, "
+                                   "operands chained through tensor memory)",
+                         "bound": "hbm", "peak": hbm, "unit": "GB/s",
+                         "achieved_fwd": nf_bytes / (t_nf * 1e-3) / 1e9, "achieved_bwd": nb_bytes / (t_nb * 1e-3) / 1e9,
+                         "frac_fwd": nf_bytes / (t_nf * 1e-3) / 1e9 / hbm, "frac_bwd": nb_bytes / (t_nb * 1e-3) / 1e9 / hbm,
+                         "bytes_per_launch_fwd": nf_bytes, "bytes_per_launch_bwd": nb_bytes,
+                         "traffic_fwd": (digest.get("k_egno_node_fwd") or {}).get("dram_bytes"),
+                         "traffic_bwd": (digest.get("k_egno_node_bwd") or {}).get("dram_bytes"),
+                         "ncu_source": (digest.get("k_egno_node_fwd") or {}).get("source"),
+                         "note": "algorithmic bytes = the kernel's inputs and outputs once (rows = T*B*N); live CUDA-event time per launch"}
 
     extras, segno = {}, None
     if not args.no_extras:
@@ -632,7 +651,7 @@ def run_ours(args):
                 "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
-                "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_node": roofline_node,
                 "cpu_baseline": cpu_baseline,
                 "kernels": kern, "segno": segno, "config5": cfg5, "extras": extras}
         emit(line)

@@ -205,11 +205,12 @@ int nb_egcl_edge_backward(int32_t n_gt, int32_t B, int32_t N, int32_t n_edge_fea
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long nb_launch_count(void);
 /* CUDA-event timing of the dominant kernels on their launch stream: categories
- * 0 = edge tile forward, 1 = edge tile backward, 2 = gemm64, 3 = wgrad64, 4 = fused temporal convolution,
- * 5 = fused SEGNO forward (all T sub-steps in one kernel).
+ * 0 = edge tile forward, 1 = edge tile backward, 2 = node GEMMs (k_gemm64_tc, k_egno_pair, SEGNO node chain), 3 = wgrad64,
+ * 4 = fused temporal convolution, 5 = fused SEGNO forward (all T sub-steps in one kernel), 6 = EGNO per-layer node kernel
+ * forward, 7 = its backward.
  * enable(1) resets the counters; read() synchronises the recorded events and returns total milliseconds and launch
  * counts per category (arrays of NB_PROFILE_CATEGORIES entries). */
-#define NB_PROFILE_CATEGORIES 6
+#define NB_PROFILE_CATEGORIES 8
 int nb_profile_enable(int enable);
 int nb_profile_read(double* ms /*[NB_PROFILE_CATEGORIES]*/, long long* counts /*[NB_PROFILE_CATEGORIES]*/);
 

@@ -137,7 +137,8 @@ int nb_num_sms() {
 }
 
 // ---- launch accounting and optional per-kernel CUDA-event timing (used by bench.py for the roofline)
-#define NB_PROF_CATS 6  /* 0 edge_fwd, 1 edge_bwd, 2 gemm64, 3 wgrad64, 4 temporal conv, 5 fused SEGNO forward */
+#define NB_PROF_CATS 8  /* 0 edge_fwd, 1 edge_bwd, 2 node GEMMs / pair / SEGNO chain, 3 wgrad64, 4 temporal conv, 5 fused SEGNO forward,
+                           6 k_egno_node_fwd, 7 k_egno_node_bwd */
 #define NB_PROF_MAX 8192
 #ifndef NB_EMU
 static int g_prof_on = 0;
@@ -1167,9 +1168,9 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       na.wv2 = params + L.v_w2; na.bv2 = params + L.v_b2; na.x = x1; na.v = v1; na.Fsum = b.Fsum;
       na.U5 = b.U5; na.UV = b.UV; na.h_out = h_next; na.x_out = x_next;
       NB_SET_SMEM(k_egno_node_fwd, NB_ENF_SMEM);
-      int pi = prof_begin(2, stream);
+      int pi = prof_begin(6, stream);
       NB_LAUNCH_COUNTED(k_egno_node_fwd, (unsigned)imin(cdiv(Nn, NB_TILE), 2 * nb_num_sms()), NB_THREADS, NB_ENF_SMEM, stream, na);
-      prof_end(2, pi, stream);
+      prof_end(6, pi, stream);
       NB_TRY(nb_check_launch("k_egno_node_fwd"));
     }
 #endif
@@ -1271,9 +1272,9 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       if (!partial) { nb_set_error("partial-sum workspace too small"); return NB_ERR_INVALID; }
       na.partial = partial;
       NB_SET_SMEM(k_egno_node_bwd, NB_ENB_SMEM);
-      int pi = prof_begin(2, stream);
+      int pi = prof_begin(7, stream);
       NB_LAUNCH_COUNTED(k_egno_node_bwd, (unsigned)grid, NB_THREADS, NB_ENB_SMEM, stream, na);
-      prof_end(2, pi, stream);
+      prof_end(7, pi, stream);
       NB_TRY(nb_check_launch("k_egno_node_bwd"));
       NbFinArgs f;
       memset(&f, 0, sizeof(f));
