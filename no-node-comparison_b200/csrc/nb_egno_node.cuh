@@ -22,7 +22,7 @@ struct NbEgnoNodeFwdArgs {
   const float *h, *M;         // [rows][64]
   const float *b5, *b6, *bv1, *wv2, *bv2;
   const float *x, *v, *Fsum;  // [rows][3]
-  float *U5, *UV;             // [rows][64] pre-activations (the backward's saved state)
+  float *U5, *UV;             // [rows][64] pre-activations (the backward's saved state; null: not stored)
   float *h_out, *x_out;
 };
 #define NB_ENF_W_BYTES (4 * 2 * NB_TC_TILE_BYTES(64))
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_egno_node_fwd(NbEgnoNodeFwdAr
     nb_tmem_ld32(d1, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += sb5[cb + i];
-    nb_enf_store32(a.U5 + off, live, v);
+    if (a.U5) nb_enf_store32(a.U5 + off, live, v);   // inference keeps nothing for a backward
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = live ? nb_silu(v[i]) : 0.f;
     nb_store32_ta(nullptr, nullptr, row, hf, v, a0h + mine, a0l + mine);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2) k_egno_node_fwd(NbEgnoNodeFwdAr
       v[i] += sbv1[cb + i];
       cp = fmaf(swv2[cb + i], nb_silu(v[i]), cp);
     }
-    nb_enf_store32(a.UV + off, live, v);
+    if (a.UV) nb_enf_store32(a.UV + off, live, v);
     cpart[hf * NB_TILE + row] = cp;
     nb_tmem_st_wait();
     nb_tc_fence_before();

@@ -1166,7 +1166,8 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       na.rows = (int)Nn; na.N = cfg->N; na.img = g_wimg.img[EGNO_WIMG_PER_LAYER * l + 2];
       na.h = h1; na.M = b.M; na.b5 = params + L.n_b1; na.b6 = params + L.n_b2; na.bv1 = params + L.v_b1;
       na.wv2 = params + L.v_w2; na.bv2 = params + L.v_b2; na.x = x1; na.v = v1; na.Fsum = b.Fsum;
-      na.U5 = b.U5; na.UV = b.UV; na.h_out = h_next; na.x_out = x_next;
+      na.U5 = saved ? b.U5 : nullptr; na.UV = saved ? b.UV : nullptr;   // inference: the pre-activations stay on chip
+      na.h_out = h_next; na.x_out = x_next;
       NB_SET_SMEM(k_egno_node_fwd, NB_ENF_SMEM);
       int pi = prof_begin(6, stream);
       NB_LAUNCH_COUNTED(k_egno_node_fwd, (unsigned)imin(cdiv(Nn, NB_TILE), 2 * nb_num_sms()), NB_THREADS, NB_ENF_SMEM, stream, na);
