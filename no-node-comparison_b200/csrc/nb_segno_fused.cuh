@@ -227,26 +227,8 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_segno_fused_fwd(NbSegnoFus
         nb_issue_w3(tm + 256, sHh, sHl, NB_FS_SWH(3), NB_FS_SWL(3), false, idesc_node, 0u);
         nb_mma_commit(bar);
       }
-      nb_mbar_wait(bar, phase);
-      phase ^= 1;
-      nb_tc_fence_after();
-      {
-        float v[16];
-        nb_tmem_ld16(tm + lane_base + 192 + (uint32_t)cb, v);
-        if (nown && nl < nnode) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += vb1[cb + i];
-          nb_tc_store8(Nh, Nl, nl, 2 * cq, v);
-          nb_tc_store8(Nh, Nl, nl, 2 * cq + 1, v + 8);
-        }
-        nb_tmem_ld16(tm + lane_base + 256 + (uint32_t)cb, v);
-        if (nown && nl < nnode) {
-          nb_tc_store8(Nh, Nl, GN + nl, 2 * cq, v);
-          nb_tc_store8(Nh, Nl, GN + nl, 2 * cq + 1, v + 8);
-        }
-      }
-      nb_tc_fence_before();
-      // (the selector write below is followed by fence + __syncthreads before the gather reads the node tile)
+      // (the products are read out inside the first edge tile, after its geometry and edge-feature loads have been
+      //  issued: those do not depend on P / Q, so their latency hides under the MMAs)
 
       // ---- (c) edge tiles
       for (int r0 = 0; r0 < R; r0 += NB_TILE) {
@@ -277,6 +259,25 @@ __global__ void __launch_bounds__(NB_SB_THREADS, 1) k_segno_fused_fwd(NbSegnoFus
           nb_mbar_wait(bar, phase);
           phase ^= 1;
           nb_tc_fence_after();
+        } else {       // (b) read-out: P + b1 and Q rows of the unit's nodes -> node tile
+          nb_mbar_wait(bar, phase);
+          phase ^= 1;
+          nb_tc_fence_after();
+          float v[16];
+          nb_tmem_ld16(tm + lane_base + 192 + (uint32_t)cb, v);
+          if (nown && nl < nnode) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += vb1[cb + i];
+            nb_tc_store8(Nh, Nl, nl, 2 * cq, v);
+            nb_tc_store8(Nh, Nl, nl, 2 * cq + 1, v + 8);
+          }
+          nb_tmem_ld16(tm + lane_base + 256 + (uint32_t)cb, v);
+          if (nown && nl < nnode) {
+            nb_tc_store8(Nh, Nl, GN + nl, 2 * cq, v);
+            nb_tc_store8(Nh, Nl, GN + nl, 2 * cq + 1, v + 8);
+          }
+          nb_tc_fence_before();
+          // (the selector write below is followed by fence + __syncthreads before the gather reads the node tile)
         }
         if (cq < 2) nb_sel_write_row(Sel, row, cq, valid, li, GN + lj, r2, e);
         nb_fence_async_smem();
