@@ -366,9 +366,12 @@ struct NbTconvArgs {
   float* gx;           // [T][Nn0][64]
   float* coef;         // [ncoef][Nn0][64]  C0 | C1 | S1   (backward: written for the weight-gradient jobs)
   float* gycoef;       // [ncoef][Nn0][64]  gP0 | gP1 | gQ1
+  // [Nn0][16][2] words: bit 4 t + c of word pair (row, c4) = [y_t[4 c4 + c] > 0], the LeakyReLU mask of the forward.
+  // Training forward writes it, the backward reads it: no recompute of the mode mixing (and none of its rounding) there.
+  uint32_t* mask;
 };
 #define NB_TCONV_FWD_SMEM ((3 * NB_H * NB_H + 3 * NB_TCV_ROWS * NB_TCV_LDA) * sizeof(float))
-#define NB_TCONV_BWD_SMEM ((3 * NB_H * NB_H + 3 * NB_H * 68 + 3 * NB_TCV_ROWS * NB_TCV_LDA) * sizeof(float))
+#define NB_TCONV_BWD_SMEM ((3 * NB_H * 68 + 3 * NB_TCV_ROWS * NB_TCV_LDA) * sizeof(float))
 
 // De-interleave W[i][o][m][re/im] (modes <= 2) into the k-major planes B0 = Re W_0, B1 = Re W_1, B2 = Im W_1
 // (Bq[i][o], row stride 64) and, when Tq != nullptr, their transposes Tq[o][i] (row stride NB_TCV_LDT).
@@ -390,9 +393,11 @@ __device__ __forceinline__ void nb_tconv_stage_w(float* B0, float* B1, float* B2
     for (int it = 0; it < 8; ++it) {
       const int idx = tid + (half * 8 + it) * 256;
       const int i = idx >> 6, o = idx & 63;
-      B0[idx] = w0[it].x;
-      B1[idx] = w1[it].x;
-      B2[idx] = w1[it].y;
+      if (B0) {
+        B0[idx] = w0[it].x;
+        B1[idx] = w1[it].x;
+        B2[idx] = w1[it].y;
+      }
       if (T0) {
         T0[o * NB_TCV_LDT + i] = w0[it].x;
         T1[o * NB_TCV_LDT + i] = w1[it].x;
@@ -484,6 +489,7 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
     nb_tconv_mix(As, B0, B1, B2, NB_H, r, c4, has1, pair1, P0, P1, Q1);
     if (act) {
       const float s1 = pair1 ? 2.f * invT : invT;
+      uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
       for (int t = 0; t < NB_MAX_T; ++t)
         if (t < tw.T) {
@@ -492,7 +498,14 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
           if (pair1) y = nb_f4_fma(-s1 * tw.s[1][t], Q1, y);
           nb_st4(a.out + t * plane + off, make_float4(xs[t].x + nb_leaky(y.x), xs[t].y + nb_leaky(y.y),
                                                       xs[t].z + nb_leaky(y.z), xs[t].w + nb_leaky(y.w)));
+          const uint32_t bits = (y.x > 0.f ? 1u : 0u) | (y.y > 0.f ? 2u : 0u) | (y.z > 0.f ? 4u : 0u) | (y.w > 0.f ? 8u : 0u);
+          if (t < 8) m0 |= bits << (4 * t);
+          else m1 |= bits << (4 * (t - 8));
         }
+      if (a.mask) {
+        a.mask[((int64_t)row * 16 + c4) * 2] = m0;
+        a.mask[((int64_t)row * 16 + c4) * 2 + 1] = m1;
+      }
     }
   }
 }
@@ -500,10 +513,7 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
 __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
   NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
-  float* B0 = sm;
-  float* B1 = B0 + NB_H * NB_H;
-  float* B2 = B1 + NB_H * NB_H;
-  float* T0 = B2 + NB_H * NB_H;      // transposed copies for the data gradient, row stride NB_TCV_LDT
+  float* T0 = sm;                      // transposed weight planes for the data gradient, row stride NB_TCV_LDT
   float* T1 = T0 + NB_H * NB_TCV_LDT;
   float* T2 = T1 + NB_H * NB_TCV_LDT;
   float* As = T2 + NB_H * NB_TCV_LDT;  // [3][16][68]
@@ -514,19 +524,20 @@ __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
   const float invT = 1.0f / (float)tw.T;
   const float s1 = pair1 ? 2.f * invT : invT;
   const int ngroups = (a.Nn0 + NB_TCV_ROWS - 1) / NB_TCV_ROWS;
-  // Memory round trips overlap instead of queueing behind each other: the first group's x rows are requested before the
-  // weight staging, and a group's gout rows are requested before its forward mix (they are needed only after it) and
-  // kept in registers for the residual path, so gout crosses the memory system once.
-  float4 gq[NB_MAX_T];   // x rows of the group, then its gout rows
+  // The LeakyReLU mask comes from the forward (a.mask), so nothing of the forward mixing is recomputed here: one pass over
+  // the frames gives the coefficients of x (for the weight gradients) and the adjoint of the inverse DFT applied to
+  // gout * LeakyReLU'(y); ONE mixing GEMM (transposed weights) turns that into the coefficient gradients.  The first
+  // group's gout rows are requested before the weight staging and stay in registers for the residual path.
+  float4 gq[NB_MAX_T];
   {
     const int row = blockIdx.x * NB_TCV_ROWS + r;
     const bool act = (int)blockIdx.x < ngroups && row < a.Nn0;
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
-      if (t < tw.T) gq[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < tw.T) gq[t] = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  nb_tconv_stage_w(B0, B1, B2, T0, T1, T2, a.W, tw.modes, tid);
+  nb_tconv_stage_w(nullptr, nullptr, nullptr, T0, T1, T2, a.W, tw.modes, tid);
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int row = grp * NB_TCV_ROWS + r;
     const bool act = row < a.Nn0;
@@ -534,53 +545,34 @@ __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
     if (grp != (int)blockIdx.x) {
 #pragma unroll
       for (int t = 0; t < NB_MAX_T; ++t)
-        if (t < tw.T) gq[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < tw.T) gq[t] = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // ---- recompute: coefficients of x, mixed coefficients, y
-    float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0;
+    const uint32_t mk0 = act ? a.mask[((int64_t)row * 16 + c4) * 2] : 0u, mk1 = act ? a.mask[((int64_t)row * 16 + c4) * 2 + 1] : 0u;
+    float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0, gP0 = C0, gP1 = C0, gQ1 = C0;
 #pragma unroll
     for (int t = 0; t < NB_MAX_T; ++t)
       if (t < tw.T) {
-        const float4 xv = gq[t];
+        const float4 xv = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         C0 = nb_f4_fma(tw.c[0][t], xv, C0);
         if (has1) C1 = nb_f4_fma(tw.c[1][t], xv, C1);
         if (pair1) S1 = nb_f4_fma(tw.s[1][t], xv, S1);
-      }
-#pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
-      if (t < tw.T) gq[t] = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);   // in flight under the mix
-    if (act) {
-      nb_st4(a.coef + off, C0);
-      if (has1) nb_st4(a.coef + plane + off, C1);
-      if (pair1) nb_st4(a.coef + 2 * plane + off, S1);
-    }
-    __syncthreads();
-    nb_st4(As + r * NB_TCV_LDA + c4 * 4, C0);
-    nb_st4(As + (NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, C1);
-    nb_st4(As + (2 * NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, S1);
-    __syncthreads();
-    float4 P0, P1, Q1;
-    nb_tconv_mix(As, B0, B1, B2, NB_H, r, c4, has1, pair1, P0, P1, Q1);
-    // ---- gy = gout * LeakyReLU'(y) ; adjoint of the inverse DFT -> gP0, gP1, gQ1
-    float4 gP0 = make_float4(0.f, 0.f, 0.f, 0.f), gP1 = gP0, gQ1 = gP0;
-#pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
-      if (t < tw.T) {
-        float4 y = make_float4(P0.x * invT, P0.y * invT, P0.z * invT, P0.w * invT);
-        if (has1) y = nb_f4_fma(s1 * tw.c[1][t], P1, y);
-        if (pair1) y = nb_f4_fma(-s1 * tw.s[1][t], Q1, y);
+        const uint32_t bits = (t < 8 ? mk0 >> (4 * t) : mk1 >> (4 * (t - 8))) & 15u;
         const float4 g = gq[t];
-        const float4 gy = make_float4(g.x * nb_dleaky(y.x), g.y * nb_dleaky(y.y), g.z * nb_dleaky(y.z), g.w * nb_dleaky(y.w));
+        const float4 gy = make_float4(g.x * ((bits & 1u) ? 1.f : 0.01f), g.y * ((bits & 2u) ? 1.f : 0.01f),
+                                      g.z * ((bits & 4u) ? 1.f : 0.01f), g.w * ((bits & 8u) ? 1.f : 0.01f));
         gP0 = nb_f4_fma(invT * tw.c[0][t], gy, gP0);
         if (has1) gP1 = nb_f4_fma(s1 * tw.c[1][t], gy, gP1);
         if (pair1) gQ1 = nb_f4_fma(-s1 * tw.s[1][t], gy, gQ1);
       }
     if (act) {
+      nb_st4(a.coef + off, C0);
+      if (has1) nb_st4(a.coef + plane + off, C1);
+      if (pair1) nb_st4(a.coef + 2 * plane + off, S1);
       nb_st4(a.gycoef + off, gP0);
       if (has1) nb_st4(a.gycoef + plane + off, gP1);
       if (pair1) nb_st4(a.gycoef + 2 * plane + off, gQ1);
     }
-    __syncthreads();  // the forward mix has finished reading As
+    __syncthreads();  // the previous group's mix has finished reading As (also orders the weight staging)
     nb_st4(As + r * NB_TCV_LDA + c4 * 4, gP0);
     nb_st4(As + (NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, gP1);
     nb_st4(As + (2 * NB_TCV_ROWS + r) * NB_TCV_LDA + c4 * 4, gQ1);

@@ -824,15 +824,17 @@ static void egno_layout(const NbEgnoConfig* c, EgnoLayout* lo) {
 
 struct EgnoLayerBufs {
   float *h0, *h1, *M, *U5, *UV, *P, *Q, *x0, *v0, *x1, *v1, *Fsum;
+  uint32_t* tmask;   // [Nn0][16][2]: sign bits of the temporal convolution's pre-activation (bit 4 t + channel), see k_tconv_fwd
 };
 // P, Q (the per-node halves of the first edge layer) are kept for the backward edge tile: 26 MB per layer at B = 256
 // instead of one more two-job GEMM launch per layer in the backward pass
-static inline int64_t egno_layer_floats(int64_t Nn) { return Nn * (7 * NB_H + 5 * 3); }
+static inline int64_t egno_layer_floats(int64_t Nn, int64_t Nn0) { return Nn * (7 * NB_H + 5 * 3) + Nn0 * 32; }
 static EgnoLayerBufs egno_layer_bufs(float* base, int64_t Nn) {
   EgnoLayerBufs b;
   b.h0 = base; b.h1 = b.h0 + Nn * NB_H; b.M = b.h1 + Nn * NB_H; b.U5 = b.M + Nn * NB_H; b.UV = b.U5 + Nn * NB_H;
   b.P = b.UV + Nn * NB_H; b.Q = b.P + Nn * NB_H;
   b.x0 = b.Q + Nn * NB_H; b.v0 = b.x0 + Nn * 3; b.x1 = b.v0 + Nn * 3; b.v1 = b.x1 + Nn * 3; b.Fsum = b.v1 + Nn * 3;
+  b.tmask = reinterpret_cast<uint32_t*>(b.Fsum + Nn * 3);
   return b;
 }
 static inline int64_t align64(int64_t v) { return (v + 63) / 64 * 64; }
@@ -847,7 +849,7 @@ extern "C" int64_t nb_egno_param_count(const NbEgnoConfig* cfg) {
 extern "C" int64_t nb_egno_saved_floats(const NbEgnoConfig* cfg) {
   if (egno_validate(cfg) != NB_OK) return -1;
   int64_t Nn = (int64_t)cfg->T * cfg->B * cfg->N;
-  return align64(egno_layer_floats(Nn)) * cfg->n_layers;
+  return align64(egno_layer_floats(Nn, (int64_t)cfg->B * cfg->N)) * cfg->n_layers;
 }
 
 // two tables (output times, input times) of T*B*D floats each: first region of the workspace
@@ -910,7 +912,7 @@ extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int mode) {
   int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
   const int64_t tab = egno_table_floats(cfg) + wimg_floats(EGNO_WIMG_PER_LAYER * cfg->n_layers);   // + weight images
   if (mode == NB_WS_FORWARD_TRAIN) return tab + 2 * nh + 2 * cf;                     // `saved` holds the layer sets
-  if (mode == NB_WS_FORWARD_INFER) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn));  // + ping-pong
+  if (mode == NB_WS_FORWARD_INFER) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn, (int64_t)cfg->B * cfg->N));  // + ping-pong
   return tab + 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
          NB_PARTIAL_FLOATS;
 }
@@ -1067,7 +1069,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
   NB_TRY(egno_ctx_init(&X, cfg, params, stream));
   const int T = cfg->T, Ln = cfg->n_layers;
   const int64_t Nn = X.Nn, Nn0 = X.Nn0;
-  const int64_t nh = align64(Nn * NB_H), cf = egno_coef_floats(cfg), lf = align64(egno_layer_floats(Nn));
+  const int64_t nh = align64(Nn * NB_H), cf = egno_coef_floats(cfg), lf = align64(egno_layer_floats(Nn, X.Nn0));
   WimgGuard wimg_guard;
   NB_TRY(egno_weight_images(X, workspace));
   float* ttab = workspace + wimg_floats(EGNO_WIMG_PER_LAYER * Ln);
@@ -1124,7 +1126,7 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       // h <- h + LeakyReLU(conv(h))      (layer_no.py:96-126)
       if (egno_tconv_fused(X)) {
         NbTconvArgs tc = tconv_args(X, l);
-        tc.x = b.h0; tc.out = h1;
+        tc.x = b.h0; tc.out = h1; tc.mask = saved ? b.tmask : nullptr;   // training: the LeakyReLU mask for the backward
         NB_SET_SMEM(k_tconv_fwd, NB_TCONV_FWD_SMEM);
         int pi = prof_begin(4, stream);
         NB_LAUNCH_COUNTED(k_tconv_fwd, (unsigned)tconv_grid(X, 3), 256, NB_TCONV_FWD_SMEM, stream, tc);
@@ -1214,7 +1216,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   const int T = cfg->T, Ln = cfg->n_layers, modes = cfg->num_modes;
   const int64_t Nn = X.Nn, Nn0 = X.Nn0;
   const int64_t nh = align64(Nn * NB_H), n3 = align64(Nn * 3), cf = egno_coef_floats(cfg);
-  const int64_t lf = align64(egno_layer_floats(Nn));
+  const int64_t lf = align64(egno_layer_floats(Nn, Nn0));
   float* w = workspace;
   WimgGuard wimg_guard;
   NB_TRY(egno_weight_images(X, w));
@@ -1413,7 +1415,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       gv_in = gvA;
       if (egno_tconv_fused(X)) {
         NbTconvArgs tc = tconv_args(X, l);
-        tc.x = b.h0; tc.gout = ghA; tc.gx = ghB; tc.coef = coef; tc.gycoef = gycoef;
+        tc.x = b.h0; tc.gout = ghA; tc.gx = ghB; tc.coef = coef; tc.gycoef = gycoef; tc.mask = b.tmask;
         NB_SET_SMEM(k_tconv_bwd, NB_TCONV_BWD_SMEM);
         int pi = prof_begin(4, stream);
         NB_LAUNCH_COUNTED(k_tconv_bwd, (unsigned)tconv_grid(X, 2), 256, NB_TCONV_BWD_SMEM, stream, tc);
