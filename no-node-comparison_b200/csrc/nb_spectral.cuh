@@ -439,6 +439,9 @@ __device__ __forceinline__ void nb_tconv_mix(const float* As, const float* B0, c
   }
 }
 
+// MAXT: compile-time bound of the frame loops (T <= MAXT): the per-frame register arrays are sized by it, so the
+// configured T = 10 does not pay for 16 frames
+template <int MAXT>
 __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
   NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
@@ -453,13 +456,13 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
   const float invT = 1.0f / (float)tw.T;
   const int ngroups = (a.Nn0 + NB_TCV_ROWS - 1) / NB_TCV_ROWS;
   // the first group's rows are requested BEFORE the weight staging, so the two memory round trips overlap
-  float4 xs[NB_MAX_T];
+  float4 xs[MAXT];
   {
     const int row = blockIdx.x * NB_TCV_ROWS + r;
     const bool act = (int)blockIdx.x < ngroups && row < a.Nn0;
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
 #pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
+    for (int t = 0; t < MAXT; ++t)
       if (t < tw.T) xs[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   nb_tconv_stage_w(B0, B1, B2, nullptr, nullptr, nullptr, a.W, tw.modes, tid);
@@ -469,12 +472,12 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
     if (grp != (int)blockIdx.x) {
 #pragma unroll
-      for (int t = 0; t < NB_MAX_T; ++t)
+      for (int t = 0; t < MAXT; ++t)
         if (t < tw.T) xs[t] = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0;
 #pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
+    for (int t = 0; t < MAXT; ++t)
       if (t < tw.T) {
         C0 = nb_f4_fma(tw.c[0][t], xs[t], C0);
         if (has1) C1 = nb_f4_fma(tw.c[1][t], xs[t], C1);
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
       const float s1 = pair1 ? 2.f * invT : invT;
       uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
-      for (int t = 0; t < NB_MAX_T; ++t)
+      for (int t = 0; t < MAXT; ++t)
         if (t < tw.T) {
           float4 y = make_float4(P0.x * invT, P0.y * invT, P0.z * invT, P0.w * invT);
           if (has1) y = nb_f4_fma(s1 * tw.c[1][t], P1, y);
@@ -510,6 +513,7 @@ __global__ void __launch_bounds__(256, 3) k_tconv_fwd(NbTconvArgs a) {
   }
 }
 
+template <int MAXT>
 __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
   NB_PDL_ENTER();
   NB_DYN_SMEM(sm);
@@ -528,13 +532,13 @@ __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
   // the frames gives the coefficients of x (for the weight gradients) and the adjoint of the inverse DFT applied to
   // gout * LeakyReLU'(y); ONE mixing GEMM (transposed weights) turns that into the coefficient gradients.  The first
   // group's gout rows are requested before the weight staging and stay in registers for the residual path.
-  float4 gq[NB_MAX_T];
+  float4 gq[MAXT];
   {
     const int row = blockIdx.x * NB_TCV_ROWS + r;
     const bool act = (int)blockIdx.x < ngroups && row < a.Nn0;
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
 #pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
+    for (int t = 0; t < MAXT; ++t)
       if (t < tw.T) gq[t] = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   nb_tconv_stage_w(nullptr, nullptr, nullptr, T0, T1, T2, a.W, tw.modes, tid);
@@ -544,13 +548,13 @@ __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
     const int64_t off = (int64_t)row * NB_H + c4 * 4;
     if (grp != (int)blockIdx.x) {
 #pragma unroll
-      for (int t = 0; t < NB_MAX_T; ++t)
+      for (int t = 0; t < MAXT; ++t)
         if (t < tw.T) gq[t] = act ? nb_ld4(a.gout + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const uint32_t mk0 = act ? a.mask[((int64_t)row * 16 + c4) * 2] : 0u, mk1 = act ? a.mask[((int64_t)row * 16 + c4) * 2 + 1] : 0u;
     float4 C0 = make_float4(0.f, 0.f, 0.f, 0.f), C1 = C0, S1 = C0, gP0 = C0, gP1 = C0, gQ1 = C0;
 #pragma unroll
-    for (int t = 0; t < NB_MAX_T; ++t)
+    for (int t = 0; t < MAXT; ++t)
       if (t < tw.T) {
         const float4 xv = act ? nb_ld4(a.x + t * plane + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         C0 = nb_f4_fma(tw.c[0][t], xv, C0);
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(256, 2) k_tconv_bwd(NbTconvArgs a) {
     nb_tconv_mix(As, T0, T1, T2, NB_TCV_LDT, r, c4, has1, pair1, gC0, gC1, gS1);
     if (act) {
 #pragma unroll
-      for (int t = 0; t < NB_MAX_T; ++t)
+      for (int t = 0; t < MAXT; ++t)
         if (t < tw.T) {
           float4 g = gq[t];  // residual path
           g = nb_f4_fma(tw.c[0][t], gC0, g);

@@ -1127,9 +1127,14 @@ extern "C" int nb_egno_forward(const NbEgnoConfig* cfg, const float* params, con
       if (egno_tconv_fused(X)) {
         NbTconvArgs tc = tconv_args(X, l);
         tc.x = b.h0; tc.out = h1; tc.mask = saved ? b.tmask : nullptr;   // training: the LeakyReLU mask for the backward
-        NB_SET_SMEM(k_tconv_fwd, NB_TCONV_FWD_SMEM);
         int pi = prof_begin(4, stream);
-        NB_LAUNCH_COUNTED(k_tconv_fwd, (unsigned)tconv_grid(X, 3), 256, NB_TCONV_FWD_SMEM, stream, tc);
+        if (T <= 10) {
+          NB_SET_SMEM(k_tconv_fwd<10>, NB_TCONV_FWD_SMEM);
+          NB_LAUNCH_COUNTED(k_tconv_fwd<10>, (unsigned)tconv_grid(X, 3), 256, NB_TCONV_FWD_SMEM, stream, tc);
+        } else {
+          NB_SET_SMEM(k_tconv_fwd<NB_MAX_T>, NB_TCONV_FWD_SMEM);
+          NB_LAUNCH_COUNTED(k_tconv_fwd<NB_MAX_T>, (unsigned)tconv_grid(X, 3), 256, NB_TCONV_FWD_SMEM, stream, tc);
+        }
         prof_end(4, pi, stream);
         NB_TRY(nb_check_launch("k_tconv_fwd"));
       } else {
@@ -1416,9 +1421,14 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
       if (egno_tconv_fused(X)) {
         NbTconvArgs tc = tconv_args(X, l);
         tc.x = b.h0; tc.gout = ghA; tc.gx = ghB; tc.coef = coef; tc.gycoef = gycoef; tc.mask = b.tmask;
-        NB_SET_SMEM(k_tconv_bwd, NB_TCONV_BWD_SMEM);
         int pi = prof_begin(4, stream);
-        NB_LAUNCH_COUNTED(k_tconv_bwd, (unsigned)tconv_grid(X, 2), 256, NB_TCONV_BWD_SMEM, stream, tc);
+        if (T <= 10) {
+          NB_SET_SMEM(k_tconv_bwd<10>, NB_TCONV_BWD_SMEM);
+          NB_LAUNCH_COUNTED(k_tconv_bwd<10>, (unsigned)tconv_grid(X, 2), 256, NB_TCONV_BWD_SMEM, stream, tc);
+        } else {
+          NB_SET_SMEM(k_tconv_bwd<NB_MAX_T>, NB_TCONV_BWD_SMEM);
+          NB_LAUNCH_COUNTED(k_tconv_bwd<NB_MAX_T>, (unsigned)tconv_grid(X, 2), 256, NB_TCONV_BWD_SMEM, stream, tc);
+        }
         prof_end(4, pi, stream);
         NB_TRY(nb_check_launch("k_tconv_bwd"));
         side_join(side, stream);
