@@ -59,6 +59,8 @@ int nb_pdl_enabled() {
 struct NbSide {
   cudaStream_t s;
   cudaEvent_t fork, join;
+  cudaStream_t s2;               // deferred weight-gradient reductions of the EGNO backward (defer_flush)
+  cudaEvent_t fork2, done2[2];
   bool ok;
 };
 static NbSide* side_get() {
@@ -73,7 +75,11 @@ static NbSide* side_get() {
     tried[dev] = true;
     x.ok = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&x.s2, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.fork2, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.done2[0], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&x.done2[1], cudaEventDisableTiming) == cudaSuccess;
     if (!x.ok) cudaGetLastError();
   }
   return x.ok ? &x : nullptr;
@@ -517,6 +523,56 @@ static int q_flush(void* st) {
   return q_flush_fin(st);
 }
 
+// ---- deferred flush (EGNO backward).  The weight-gradient GEMMs and partial-sum finalisations of a layer feed nothing
+// but the optimizer, yet launched on the caller's stream they sit between two layers of the dependent chain (one
+// k_wgrad64_tc + one k_finalize per layer, ~50 us of a 3.3 ms step each).  Here a flush runs on a library-owned second
+// stream (NbSide::s2), forked after the kernels that produced its operands, underneath the NEXT layer's backward.  What
+// makes that legal: every buffer a queued job reads and a later layer rewrites exists twice (gh, GU5, GUV, gP, gQ, the
+// spectral planes, the partial-sum arena), layer l uses set l & 1, and the caller's stream waits for flush k - 1 before
+// it goes on past flush k — so a set is rewritten only after the flush that read it has completed.  The side stream is
+// in order, the destinations are the same as before and every reduction keeps its fixed order: results are bitwise
+// those of the synchronous flush.  Joined before the entry point returns; under stream capture fork / done events become
+// graph edges.  NB_B200_WGRAD_DEFER=0 keeps the synchronous flush (A/B switch).
+struct DeferState {
+  bool on;
+  int k;              // flushes issued so far
+  float* arena[2];    // partial-sum arenas, NB_PARTIAL_FLOATS each
+};
+static bool defer_available() {
+#ifndef NB_EMU
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("NB_B200_WGRAD_DEFER"); off = (e && e[0] == '0') ? 1 : 0; }
+  return !off && side_get() != nullptr;
+#else
+  return false;
+#endif
+}
+static int defer_flush(DeferState& D, void* main_st) {
+#ifndef NB_EMU
+  if (D.on) {
+    NbSide* x = side_get();
+    cudaStream_t ms = (cudaStream_t)main_st;
+    cudaEventRecord(x->fork2, ms);
+    cudaStreamWaitEvent(x->s2, x->fork2, 0);
+    NB_TRY(q_flush((void*)x->s2));
+    cudaEventRecord(x->done2[D.k & 1], x->s2);
+    if (D.k > 0) cudaStreamWaitEvent(ms, x->done2[(D.k - 1) & 1], 0);   // set (k + 1) & 1 is free again
+    ++D.k;
+    g_q.pbase = D.arena[D.k & 1];
+    g_q.pused = 0;
+    return nb_check_launch("deferred flush");
+  }
+#endif
+  return q_flush(main_st);
+}
+static void defer_join(DeferState& D, void* main_st) {
+#ifndef NB_EMU
+  if (D.on && D.k > 0) cudaStreamWaitEvent((cudaStream_t)main_st, side_get()->done2[(D.k - 1) & 1], 0);
+#else
+  (void)D; (void)main_st;
+#endif
+}
+
 // dst[w_off + o*so + k*si] (+)= sum_rows sum_p scale_p G_p[r][o] A_p[r][k];  dst[b_off + o] (+)= colsum(G_0) if b_off >= 0
 // (queued; executed at the next q_flush)
 static int wgrad_to(int rows, int npair, NbWgradPair p0, NbWgradPair p1, float* dst, int64_t w_off, int64_t so,
@@ -914,7 +970,8 @@ extern "C" int64_t nb_egno_workspace_floats(const NbEgnoConfig* cfg, int mode) {
   if (mode == NB_WS_FORWARD_TRAIN) return tab + 2 * nh + 2 * cf;                     // `saved` holds the layer sets
   if (mode == NB_WS_FORWARD_INFER) return tab + 2 * nh + 2 * cf + 2 * align64(egno_layer_floats(Nn, (int64_t)cfg->B * cfg->N));  // + ping-pong
   return tab + 2 * nh /*P,Q*/ + 4 * cf + 2 * nh /*gh*/ + 5 * nh /*GU5 GUV gM gP gQ*/ + 4 * n3 /*gx, gv*/ + n3 /*gFsum*/ +
-         NB_PARTIAL_FLOATS;
+         NB_PARTIAL_FLOATS +
+         5 * nh + 2 * cf + NB_PARTIAL_FLOATS;   // second set of gh, GU5, GUV, gP, gQ, coef, gycoef, arena (defer_flush)
 }
 
 struct EgnoCtx {
@@ -1244,7 +1301,20 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   float* gvA = w; w += n3;
   float* gvB = w; w += n3;
   float* gFsum = w; w += n3;
-  q_begin(w, NB_PARTIAL_FLOATS);
+  float* arena0 = w; w += NB_PARTIAL_FLOATS;
+  // second set of everything a queued weight-gradient job reads and the next layer rewrites (defer_flush)
+  float* ghB_s[2]; ghB_s[0] = ghB; ghB_s[1] = w; w += nh;
+  float* GU5_s[2]; GU5_s[0] = GU5; GU5_s[1] = w; w += nh;
+  float* GUV_s[2]; GUV_s[0] = GUV; GUV_s[1] = w; w += nh;
+  float* gP_s[2]; gP_s[0] = gP; gP_s[1] = w; w += nh;
+  float* gQ_s[2]; gQ_s[0] = gQ; gQ_s[1] = w; w += nh;
+  float* coef_s[2]; coef_s[0] = coef; coef_s[1] = w; w += cf;
+  float* gycoef_s[2]; gycoef_s[0] = gycoef; gycoef_s[1] = w; w += cf;
+  DeferState D;
+  D.on = cfg->use_time_conv && egno_tconv_fused(X) && defer_available();
+  D.k = 0;
+  D.arena[0] = arena0; D.arena[1] = w;
+  q_begin(arena0, NB_PARTIAL_FLOATS);
   cudaStream_t cst = (cudaStream_t)stream;
 
   cudaMemsetAsync(grad_params, 0, X.lo.total * sizeof(float), cst);
@@ -1255,10 +1325,15 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   const float* gv_in = g_v_out;
   if (!gv_in) { cudaMemsetAsync(gvA, 0, Nn * 3 * sizeof(float), cst); gv_in = gvA; }
   const float* gh_in = g_h_out;
+  if (D.on) ghB = ghB_s[Ln & 1];   // the set "layer Ln" would have written
   if (!gh_in) { cudaMemsetAsync(ghB, 0, Nn * NB_H * sizeof(float), cst); gh_in = ghB; }
 
   for (int l = Ln - 1; l >= 0; --l) {
     const EgnoLayerOff& L = X.lo.L[l];
+    if (D.on) {   // layer l writes set l & 1; its queued jobs read that set and the gh / spectral planes of set (l + 1) & 1
+      const int ps = l & 1;
+      ghB = ghB_s[ps]; GU5 = GU5_s[ps]; GUV = GUV_s[ps]; gP = gP_s[ps]; gQ = gQ_s[ps]; coef = coef_s[ps]; gycoef = gycoef_s[ps];
+    }
     EgnoLayerBufs b = egno_layer_bufs(const_cast<float*>(saved) + (int64_t)l * lf, Nn);
     const float* h1 = cfg->use_time_conv ? b.h1 : b.h0;
     const float* x1 = cfg->use_time_conv ? b.x1 : b.x0;
@@ -1392,7 +1467,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
         // queued weight-gradient jobs read gh_in (= ghB of the layer above), GU5, gP, ...: run them before ghB is
         // overwritten.  The spectral weight gradients of THIS layer are queued after the kernel that produces their
         // operands (coef, gycoef) and run with the next flush, before those planes are overwritten again.
-        NB_TRY(q_flush(stream));
+        NB_TRY(defer_flush(D, stream));
         // the 2-channel convolution's backward is independent of the 64-channel one: side stream, joined after it;
         // its partial slice is reduced by the next flush (on the caller's stream, after the join)
         side = side_fork(stream);
@@ -1523,11 +1598,12 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
     if (F > NB_H)
       NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, Q), wpair(nullptr, nullptr), grad_params, X.lo.emb_w + NB_H, F, 1, -1, 0,
                       stream, F - NB_H));
-    NB_TRY(q_flush(stream));
+    NB_TRY(defer_flush(D, stream));
   }
   const NbFrameMap fm = egno_frame_map(cfg);
   if (g_x_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3 * fm.L), 256, 0, stream, (const float*)gxb[gxi], g_x_in, (int)(Nn0 * 3), T, fm);
   if (g_v_in) NB_LAUNCH_COUNTED(k_sum_over_t, (unsigned)ew_grid(Nn0 * 3 * fm.L), 256, 0, stream, gv_in, g_v_in, (int)(Nn0 * 3), T, fm);
+  defer_join(D, stream);
   return nb_check_launch("nb_egno_backward");
 }
 
