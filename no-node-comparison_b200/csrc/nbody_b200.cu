@@ -1855,7 +1855,11 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
   float* gx = w; w += n3;
   float* gvb[2]; gvb[0] = w; w += n3; gvb[1] = w; w += n3;
   float* gFsum = w; w += n3;
-  q_begin(w, SEGNO_PARTIAL_FLOATS);
+  // the last quarter of the partial-sum scratch belongs to the deferred reductions (below); it is only ever touched on
+  // the second stream, which is in order, so one arena serves every deferred flush
+  const int64_t def_cap = SEGNO_PARTIAL_FLOATS / 4;
+  float* def_arena = w + (SEGNO_PARTIAL_FLOATS - def_cap);
+  q_begin(w, SEGNO_PARTIAL_FLOATS - def_cap);
   cudaStream_t cst = (cudaStream_t)stream;
 
   cudaMemsetAsync(grad_params, 0, lo.total * sizeof(float), cst);
@@ -1888,6 +1892,46 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     chain = !off && g_segno_fused && g_node_impl == 1 && g_wimg.n == SEGNO_WIMG;   // nb_set_segno_fused(0): stepwise both ways
   }
 #endif
+  // ---- weight gradients of the shared layers: ONE reduction per weight block over the rows of sub-steps [k0, k1) (the
+  // operands of sub-step k sit k blocks apart: saved state at stride itf, the sweep's gradients at stride nh); queued on
+  // `st`, every job accumulates onto grad_params
+  auto queue_wgrads = [&](int k0, int k1, void* st) -> int {
+    const SegnoIterBufs b0 = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)k0 * itf, Nn);
+    const int rows = (int)(Nn * (k1 - k0)), sr = (int)Nn;
+    const float* ghin0 = gh_all + (int64_t)(k0 + 1) * nh;   // gh entering sub-step k = slot k + 1 ...
+    // ... except for the last sub-step when the caller supplied dL/dh_out: that one lives in the caller's buffer
+    if (g_h_out && k1 == T) {
+      if (k1 - 1 > k0) {
+        NB_TRY(wgrad_to((int)(Nn * (k1 - 1 - k0)), 1, wpair_seg(ghin0, b0.U5, 1, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w2,
+                        NB_H, 1, lo.n_b2, 1, st));
+        NB_TRY(q_flush_wgrad(st));   // same destination as the job below: separate reduction batches
+        NB_TRY(q_flush_fin(st, false));
+      }
+      const SegnoIterBufs bl = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)(T - 1) * itf, Nn);
+      NB_TRY(wgrad_to((int)Nn, 1, wpair(g_h_out, bl.U5, 1), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1, lo.n_b2, 1, st));
+    } else {
+      NB_TRY(wgrad_to(rows, 1, wpair_seg(ghin0, b0.U5, 1, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1,
+                      lo.n_b2, 1, st));
+    }
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(GU5_all + (int64_t)k0 * nh, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w1,
+                    2 * NB_H, 1, lo.n_b1, 1, st));
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(GU5_all + (int64_t)k0 * nh, b0.M, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params,
+                    lo.n_w1 + NB_H, 2 * NB_H, 1, -1, 1, st));
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(gP_all + (int64_t)k0 * nh, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.e_w1,
+                    lo.E, 1, lo.e_b1, 1, st));
+    NB_TRY(wgrad_to(rows, 1, wpair_seg(gQ_all + (int64_t)k0 * nh, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params,
+                    lo.e_w1 + NB_H, lo.E, 1, -1, 1, st));
+    return NB_OK;
+  };
+  // Deferred reductions.  A sweep leaves most of the GPU idle (the node chain runs 40 CTAs; the second half of every edge
+  // launch 108 of 148), and the reductions above used to run after it, alone.  With the second stream (defer_available)
+  // the sub-steps the sweep has finished are reduced every NB_SEGNO_DEFER_CHUNK sub-steps underneath the rest of the
+  // sweep: their operands are per-sub-step buffers nobody rewrites, the partial slices live in their own arena, every
+  // reduction still has a fixed order.  The caller's stream joins before its own last reduction touches grad_params.
+  const int DEFER_CHUNK = 3;
+  const bool defer = chain && defer_available();
+  int k_hi = T;             // sub-steps [0, k_hi) still have to be reduced
+  bool deferred_any = false;
   bool head_done = false;   // the node_mlp / integrator backward of sub-step k already ran (inside the chain launch)
   for (int k = T - 1; k >= 0; --k) {
     SegnoIterBufs b = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)k * itf, Nn);
@@ -1948,6 +1992,23 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     ea.x = b.x; ea.P = P_all + (int64_t)k * nh; ea.Q = Q_all + (int64_t)k * nh; ea.ef = edge_attr; ea.gM = gM; ea.gFsum = gFsum; ea.gP = gP; ea.gQ = gQ; ea.gx = gx;
     NB_TRY(launch_edge_bwd(ea, grad_params, ed, 1, stream, &run_base, &run_parts));
 #ifndef NB_EMU
+    if (defer && k > 0 && k_hi - k >= DEFER_CHUNK) {   // sub-steps [k, k_hi): every operand is final once this launch is done
+      NbSide* sd = side_get();
+      cudaEventRecord(sd->fork2, cst);
+      cudaStreamWaitEvent(sd->s2, sd->fork2, 0);
+      float* const sv_base = g_q.pbase;
+      const int64_t sv_cap = g_q.pcap, sv_used = g_q.pused;
+      g_q.pbase = def_arena; g_q.pcap = def_cap; g_q.pused = 0;
+      int rc = edge_bwd_finalize(run_base, run_parts, cfg->in_edge_nf, grad_params, ed, 1, (void*)sd->s2);
+      run_parts = 0;   // the next launch starts a new run right behind this one
+      if (rc == NB_OK) rc = queue_wgrads(k, k_hi, (void*)sd->s2);
+      if (rc == NB_OK) rc = q_flush((void*)sd->s2);
+      g_q.pbase = sv_base; g_q.pcap = sv_cap; g_q.pused = sv_used;
+      NB_TRY(rc);
+      cudaEventRecord(sd->done2[0], sd->s2);
+      k_hi = k;
+      deferred_any = true;
+    }
     if (chain && k > 0) {
       const SegnoIterBufs bm = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)(k - 1) * itf, Nn);
       NbSegnoNodeBwdArgs na;
@@ -1977,34 +2038,14 @@ extern "C" int nb_segno_backward(const NbSegnoConfig* cfg, const float* params, 
     NB_TRY(launch_gemm(pa, stream));
     gh_in = gh_new;
   }
-  // ---- weight gradients of the shared layers: ONE reduction per weight block over the rows of all T sub-steps (the
-  // operands of sub-step k sit k blocks apart: saved state at stride itf, the sweep's gradients at stride nh)
+  // ---- what the deferred flushes have not taken: the remaining sub-steps' reductions on the caller's stream, after the
+  // second stream's last finalisation (both accumulate onto grad_params)
   {
+#ifndef NB_EMU
+    if (deferred_any) cudaStreamWaitEvent(cst, side_get()->done2[0], 0);
+#endif
     if (run_parts > 0) NB_TRY(edge_bwd_finalize(run_base, run_parts, cfg->in_edge_nf, grad_params, ed, 1, stream));
-    const SegnoIterBufs b0 = segno_iter_bufs(const_cast<float*>(saved), Nn);
-    const int rows = (int)(Nn * T), sr = (int)Nn;
-    const float* ghin0 = g_h_out && T == 1 ? nullptr : gh_all + nh;   // gh entering sub-step k = slot k + 1 ...
-    // ... except for the last sub-step when the caller supplied dL/dh_out: that one lives in the caller's buffer
-    if (g_h_out) {
-      if (T > 1)
-        NB_TRY(wgrad_to((int)(Nn * (T - 1)), 1, wpair_seg(ghin0, b0.U5, 1, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w2,
-                        NB_H, 1, lo.n_b2, 1, stream));
-      const SegnoIterBufs bl = segno_iter_bufs(const_cast<float*>(saved) + (int64_t)(T - 1) * itf, Nn);
-      NB_TRY(q_flush_wgrad(stream));   // same destination as the job above: separate reduction batches
-      NB_TRY(q_flush_fin(stream, false));
-      NB_TRY(wgrad_to((int)Nn, 1, wpair(g_h_out, bl.U5, 1), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1, lo.n_b2, 1, stream));
-    } else {
-      NB_TRY(wgrad_to(rows, 1, wpair_seg(ghin0, b0.U5, 1, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w2, NB_H, 1,
-                      lo.n_b2, 1, stream));
-    }
-    NB_TRY(wgrad_to(rows, 1, wpair_seg(GU5_all, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w1, 2 * NB_H, 1,
-                    lo.n_b1, 1, stream));
-    NB_TRY(wgrad_to(rows, 1, wpair_seg(GU5_all, b0.M, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.n_w1 + NB_H,
-                    2 * NB_H, 1, -1, 1, stream));
-    NB_TRY(wgrad_to(rows, 1, wpair_seg(gP_all, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.e_w1, lo.E, 1,
-                    lo.e_b1, 1, stream));
-    NB_TRY(wgrad_to(rows, 1, wpair_seg(gQ_all, b0.h, 0, sr, nh, itf), wpair(nullptr, nullptr), grad_params, lo.e_w1 + NB_H, lo.E, 1,
-                    -1, 1, stream));
+    NB_TRY(queue_wgrads(0, k_hi, stream));
     NB_TRY(q_flush(stream));
   }
   if (cfg->h_given) {
