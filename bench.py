@@ -653,7 +653,11 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_node": roofline_node,
                 "cpu_baseline": cpu_baseline,
-                "kernels": kern, "segno": segno, "config5": cfg5, "extras": extras}
+                "kernels": kern,
+                "kernels_note": "CUDA-event time per launch category of an eager pass; wgrad64 (and the finalisations) run on "
+                                "the library's second stream underneath the next layer's kernels, so its launch time is "
+                                "stretched by the overlap, node_bwd shares the SMs with it, and the shares need not add up to 1",
+                "segno": segno, "config5": cfg5, "extras": extras}
         emit(line)
     finish(world, dist)
 
