@@ -1324,6 +1324,19 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   else cudaMemsetAsync(gxb[0], 0, Nn * 3 * sizeof(float), cst);
   const float* gv_in = g_v_out;
   if (!gv_in) { cudaMemsetAsync(gvA, 0, Nn * 3 * sizeof(float), cst); gv_in = gvA; }
+  // the embedding layer's inputs (re-materialised for its weight gradient at the very end) depend on nothing but the
+  // call's inputs: with the second stream they are built there now, off the dependent chain
+  NbEmbedArgs emb_args;
+  bool embed_built = false;
+#ifndef NB_EMU
+  if (D.on) {
+    NbSide* sd = side_get();
+    cudaEventRecord(sd->fork2, cst);
+    cudaStreamWaitEvent(sd->s2, sd->fork2, 0);
+    NB_TRY(egno_embed_inputs(cfg, X.lo, emb_args, nodes, timesteps_out, timesteps_in, ttab, P, Q, (void*)sd->s2));
+    embed_built = true;
+  }
+#endif
   const float* gh_in = g_h_out;
   if (D.on) ghB = ghB_s[Ln & 1];   // the set "layer Ln" would have written
   if (!gh_in) { cudaMemsetAsync(ghB, 0, Nn * NB_H * sizeof(float), cst); gh_in = ghB; }
@@ -1590,8 +1603,7 @@ extern "C" int nb_egno_backward(const NbEgnoConfig* cfg, const float* params, co
   {
     // dW_emb = gh^T [nodes | time embeddings], db_emb = column sums of gh: the inputs are re-materialised 64 wide
     // (scratch: P, Q, free by now) and reduced by the weight-gradient kernel; columns >= F are not written.
-    NbEmbedArgs e;
-    NB_TRY(egno_embed_inputs(cfg, X.lo, e, nodes, timesteps_out, timesteps_in, ttab, P, Q, stream));
+    if (!embed_built) NB_TRY(egno_embed_inputs(cfg, X.lo, emb_args, nodes, timesteps_out, timesteps_in, ttab, P, Q, stream));
     const int F = X.lo.F;
     NB_TRY(wgrad_to((int)Nn, 1, wpair(gh_in, P), wpair(nullptr, nullptr), grad_params, X.lo.emb_w, F, 1, X.lo.emb_b, 0,
                     stream, F < NB_H ? F : NB_H));
