@@ -70,6 +70,22 @@ __device__ __forceinline__ bool nb_elect_one() {
   return pred != 0;
 }
 #define NB_ISSUER(w) (warp == (w) && nb_elect_one())
+
+// One thread hands a contiguous global -> shared copy (16-byte aligned, a multiple of 16 bytes) to the TMA engine
+// (cp.async.bulk, UBLKCP in SASS); `bar` (initialised with count 1) completes when all `bytes` have landed.  The weight
+// images of the node kernels are stored in global memory in their shared-memory tile layout, so a whole set of tiles is
+// one such copy: no register staging, and the copy runs underneath the first tile's row loads.  The data is written and
+// (by tcgen05.mma) read through the async proxy: the reader only has to wait for the barrier.
+#ifndef NB_WIMG_BULK
+#define NB_WIMG_BULK 1
+#endif
+__device__ __forceinline__ void nb_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = nb_smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(nb_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(b)
+               : "memory");
+}
 __device__ __forceinline__ void nb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread l of warp w reads TMEM lane 32*(w%4)+l
