@@ -469,8 +469,13 @@ static int q_flush_wgrad(void* st) {
     if (wb.job[j].rows > maxrows) maxrows = wb.job[j].rows;
   int grid = imin(cdiv(maxrows, NB_TILE), wgrad_grid_cap());
 #ifndef NB_EMU
-  if (g_node_impl == 1) {  // 3 co-resident CTAs per SM over all jobs of the batch
-    int per_job = 3 * nb_num_sms() / wb.njobs;
+  if (g_node_impl == 1) {
+    // CTAs per SM over all jobs of the batch.  Three fit (and were the choice while the launch had the GPU to itself); on
+    // the second stream, sharing the SMs with the next layer's kernels, two measured better (same box, alternating:
+    // 3.241 / 3.241 ms per EGNO step with 3, 3.207 / 3.225 with 2, 3.277 with 1; NB_B200_WGRAD_CTAS for A/B).
+    static int ctas = 0;
+    if (!ctas) { const char* e = getenv("NB_B200_WGRAD_CTAS"); ctas = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; }
+    int per_job = ctas * nb_num_sms() / wb.njobs;
     if (per_job < 16) per_job = 16;
     if (per_job > nb_num_sms()) per_job = nb_num_sms();
     grid = imin(cdiv(maxrows, NB_TILE), per_job);
